@@ -1,0 +1,110 @@
+"""Pins oracle/distmesh_oracle.py against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+from conftest import load_golden, load_sdf_specs, relerr
+
+from oracle import distmesh_oracle as orc
+
+SPECS = load_sdf_specs()
+
+
+@pytest.mark.parametrize("i", range(len(SPECS)))
+def test_sdf_matches_reference(i):
+    g = load_golden("sdf_cases.npz")
+    d = orc.sdf(SPECS[i], g[f"x{i}"])
+    # un-rotated trees are bit-identical; rotated/stretched ones differ by BLAS rounding only
+    assert relerr(d, g[f"d{i}"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["interp_2d.npz", "interp_3d.npz", "r0m_values.npz"])
+def test_interp_bit_exact(name):
+    g = load_golden(name)
+    axes = [g[k] for k in ("axis0", "axis1", "axis2") if k in g]
+    h = orc.interp_grid(axes, g["grid"], g["x"])
+    assert np.array_equal(h, g["h"])
+
+
+def test_r0m_pinned_values():
+    g = load_golden("r0m_values.npz")
+    h = orc.interp_grid([g["axis0"], g["axis1"]], g["grid"], g["x"])
+    assert h[0] == 100 and h[1] == 150  # reference tests/test_2dmesher_r0m_values.py:42-43
+
+
+def _fd_fh(name, g):
+    if name == "loop_2d.npz":
+        spec = ("disk", dict(x0=[0.0, 0.0], r=1.0))
+        levels = [spec]
+    elif name == "loop_2d_levels.npz":
+        spec = ("rectangle", dict(bbox=(0.0, 1.0, 0.0, 1.0)))
+        levels = [spec, ("disk", dict(x0=[0.5, 0.5], r=0.25))]
+    elif name == "loop_3d.npz":
+        spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0))
+        levels = [spec]
+    elif name == "loop_2d_grid.npz":
+        spec = ("rectangle", dict(bbox=tuple(g["bbox"])))
+        levels = [spec]
+    else:
+        spec = ("cube", dict(bbox=tuple(g["bbox"])))
+        levels = [spec]
+    if "grid" in g:
+        axes = [g[k] for k in ("axis0", "axis1", "axis2") if k in g]
+        fh = lambda x: orc.interp_grid(axes, g["grid"], x)  # noqa: E731
+    else:
+        h0 = float(g["h0"])
+        fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    return [(lambda x, s=s: orc.sdf(s, x)) for s in levels], fh
+
+
+LOOPS = ["loop_2d.npz", "loop_2d_levels.npz", "loop_3d.npz", "loop_2d_grid.npz", "loop_3d_grid.npz"]
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_loop_body(name):
+    g = load_golden(name)
+    levels, fh = _fd_fh(name, g)
+    p, t, h0 = g["p"], g["t"], float(g["h0"])
+    geps = 0.1 * h0
+    deps = np.sqrt(np.finfo(np.double).eps) * h0
+    out = orc.force_iteration(p, t, levels, fh, h0, geps, deps)
+    assert np.array_equal(t[out["keep"]], g["t_kept"])          # cull: bit exact
+    assert np.array_equal(out["bars"], g["bars"])                # bars: bit exact
+    assert out["bars"].dtype == np.int32
+    assert np.array_equal(out["h"], g["hbars"])
+    assert relerr(out["Ftot"], g["Ftot"]) < 1e-12
+    assert relerr(out["p"], g["p_new"]) < 1e-12
+    assert abs(out["maxdp"] - float(g["maxdp"])) <= 1e-12 * max(1.0, float(g["maxdp"]))
+
+
+def test_scatter_order_is_bit_exact():
+    """The sequential COO accumulation order (generation/utils.py:48-68) is restated exactly."""
+    g = load_golden("loop_2d.npz")
+    p, tk = g["p"], g["t_kept"]
+    F = orc.compute_forces(p, tk, lambda x: np.array([float(g["h0"])] * len(x)), 1.2)
+    assert np.array_equal(F, g["Ftot"])
+
+
+def test_sliver_blocks():
+    g = load_golden("sliver_3d.npz")
+    p, t = g["p"], g["t"]
+    dh = orc.dihedral_angles(p, t)
+    assert relerr(dh, g["dh"]) < 1e-12
+    ele = orc.sliver_cells(p, t, float(g["min_dh"]), float(g["max_dh"]))
+    assert np.array_equal(ele, g["ele"])
+    s = t[ele]
+    gr = orc.circumsphere_grad(p[s[:, 0]], p[s[:, 1]], p[s[:, 2]], p[s[:, 3]])
+    assert np.allclose(gr, g["grad"], rtol=1e-10, atol=0)
+    pn = orc.sliver_perturbation(p, t, ele, float(g["step"]), float(g["h0"]))
+    assert relerr(pn, g["p_new"]) < 1e-12
+
+
+def test_initial_points():
+    g = load_golden("init_points.npz")
+    disk = lambda x: orc.sdf(("disk", dict(x0=[0.0, 0.0], r=1.0)), x)  # noqa: E731
+    p = orc.initial_points(0.05, 0.005, 2, np.array([[-1.0, 1.0], [-1.0, 1.0]]), lambda x: np.array([0.05] * len(x)),
+                           disk, np.empty((0, 2)))
+    assert np.array_equal(p, g["disk"])
+    ball = lambda x: orc.sdf(("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)), x)  # noqa: E731
+    p = orc.initial_points(0.2, 0.02, 3, np.array([[-1.0, 1.0]] * 3), lambda x: np.array([0.2] * len(x)),
+                           ball, np.empty((0, 3)))
+    assert np.array_equal(p, g["ball"])
