@@ -1,0 +1,233 @@
+/*
+ * distmesh_b200.h -- C ABI of libdistmesh_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for ONE hot path of krober10nd/SeismicMesh: the DistMesh force-iteration
+ * loop inside generate_mesh (SeismicMesh/generation/mesh_generator.py:460-527) and the sibling
+ * loop of sliver_removal (:204-286).  Delaunay retriangulation stays on the host.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - coordinates are float64, row-major (N, dim); connectivity is int32, row-major (T, dim+1)
+ *     (the reference's native modules use C `double` / `int`, geometry/cpp/fast_geometry.cpp);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no hidden allocation, no global state: all scratch lives in a caller-provided workspace
+ *     (query its size with dm_plan_bytes), so one host thread per device can call concurrently;
+ *   - return value: 0 = ok, <0 = DM_ERR_* (argument / capacity errors), >0 = cudaError_t.
+ *   - all arithmetic is IEEE fp64 without FMA contraction (nvcc -fmad=false) so that stages
+ *     whose NumPy counterpart is elementwise are bit-identical to the reference.
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef DISTMESH_B200_H
+#define DISTMESH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_OK 0
+#define DM_ERR_ARG (-1)       /* bad argument (dim, null pointer, negative size) */
+#define DM_ERR_WORKSPACE (-2) /* workspace too small */
+#define DM_ERR_PROGRAM (-3)   /* malformed SDF program */
+
+#define DM_MAX_LEVELS 8
+
+/* ---------------------------------------------------------------------------------------------
+ * SDF program: the reference evaluates a tree of Python objects with one NumPy pass per node
+ * (SeismicMesh/geometry/signed_distance_functions.py:283-623).  Here the tree is lowered on the
+ * host to a postfix program (float64 words in device memory) that ONE kernel evaluates per point.
+ *
+ *   prog[0]            = number of instructions n
+ *   prog[1 + 24*i ...] = instruction i, 24 float64 words:
+ *       [0] opcode   [1] transform flags   [2..7] parameters   [8..10] translation
+ *       [11..16] cos,sin of the x / y / z rotation angles   [17..19] unit stretch vector
+ *       [20] stretch factor alpha   [21..23] reserved
+ * ------------------------------------------------------------------------------------------- */
+#define DM_SDF_WORDS 24
+enum {
+  DM_OP_DISK = 1,      /* params xc,yc,r            (:429-444, :596-598) */
+  DM_OP_BALL = 2,      /* params xc,yc,zc,r         (:450-468, :601-603) */
+  DM_OP_RECT = 3,      /* params x1,x2,y1,y2        (:474-489; fast_geometry.cpp:165-185) */
+  DM_OP_CUBE = 4,      /* params x1,x2,y1,y2,z1,z2  (:495-516; fast_geometry.cpp:104-134) */
+  DM_OP_TORUS = 5,     /* params r1,r2              (:522-540) */
+  DM_OP_PRISM = 6,     /* params b,h                (:546-563) */
+  DM_OP_CYLINDER = 7,  /* params r,h/2              (:569-590) */
+  DM_OP_UNION = 16,    /* pops b,a ; pushes min(a,b)                        (:336-339) */
+  DM_OP_SUNION = 17,   /* params k ; smooth union                           (:332-334) */
+  DM_OP_INTER = 18,    /* max(a,b)                                          (:376-379) */
+  DM_OP_SINTER = 19,   /* params k ; smooth intersection                    (:372-374) */
+  DM_OP_DIFF = 20,     /* max(a,-b)                                         (:416-420) */
+  DM_OP_SDIFF = 21,    /* params k ; max(-a,b)+h^2/4k on the reversed list  (:412-414,421-423) */
+  DM_OP_REPEAT_BEGIN = 24, /* params Px,Py,Pz : push point, x <- floormod(x+P/2,P)-P/2 (:292-293) */
+  DM_OP_REPEAT_END = 25    /* params bbox6    : pop point, v <- max(v, cube(x))        (:294) */
+};
+#define DM_TF_TRANSLATE 1
+#define DM_TF_ROT0 2 /* 2-D rotation, or rotation about x in 3-D */
+#define DM_TF_ROT1 4 /* about y */
+#define DM_TF_ROT2 8 /* about z */
+#define DM_TF_STRETCH 16
+
+/* ---------------------------------------------------------------------------------------------
+ * Mesh-size function fh (SeismicMesh/sizing/size_function.py:1-12; gridded interpolant built at
+ * sizing/mesh_size_function.py:391-408 with float32-rounded axes, :514-523).
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  DM_SIZE_CONST = 0,    /* scalar edge_length (mesh_generator.py:574-585) */
+  DM_SIZE_GRID = 1,     /* scipy RegularGridInterpolator(linear, extrapolating) semantics */
+  DM_SIZE_EXTERNAL = 2  /* h per bar supplied by the caller (opaque Python callable) */
+};
+typedef struct DmSizeFn {
+  int32_t kind;
+  int32_t dim;
+  int32_t n[3];          /* nodes per axis */
+  int32_t _pad;
+  const double *axis[3]; /* DEVICE: the ACTUAL axis vectors (float64 of the float32 linspace) */
+  const double *grid;    /* DEVICE: (n0,n1[,n2]) float64, C order */
+  double hconst;         /* DM_SIZE_CONST */
+} DmSizeFn;
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone stage kernels (parity-testable one by one)
+ * ------------------------------------------------------------------------------------------- */
+
+/* fd(x): replaces `domain.eval(x)` (signed_distance_functions.py, all classes) and the natives
+ * drectangle_fast / dblock_fast (fast_geometry.cpp:187,136).  x (M,dim) -> out (M). */
+int dm_sdf_eval(const double *prog, const double *x, int64_t M, int dim, double *out, void *stream);
+
+/* fh(x) on a grid: replaces SizeFunction.eval -> RegularGridInterpolator.__call__
+ * (size_function.py:11-12).  x (M,dim) -> out (M). */
+int dm_size_eval(const DmSizeFn *fh_host, const double *x, int64_t M, double *out, void *stream);
+
+/* centroids p[t].sum(1)/(dim+1) (mesh_generator.py:737) -> out (T,dim); for opaque-callable fd. */
+int dm_centroids(const double *p, const int32_t *t, int64_t T, int dim, double *out, void *stream);
+
+/* keep[i] = fd(centroid_i) < -geps   (mesh_generator.py:734-738, _remove_triangles_outside). */
+int dm_cull_cells(const double *prog, const double *p, const int32_t *t, int64_t T, int dim,
+                  double geps, uint8_t *keep, void *stream);
+
+/* order-preserving compaction t[keep] -> t_out ; *T_out_dev receives the kept count.
+ * scratch: (T+1) int32 + dm_scan_scratch_bytes(T+1). */
+int dm_compact_cells(const int32_t *t, const uint8_t *keep, int64_t T, int dim, int32_t *t_out,
+                     int32_t *T_out_dev, void *scratch, size_t scratch_bytes, void *stream);
+size_t dm_compact_scratch_bytes(int64_t T);
+
+/* 6 dihedral angles per tet, cell-major (replaces _fast_geometry.calc_dihedral_angles,
+ * fast_geometry.cpp:351-452) and the out-of-bounds test of mesh_generator.py:532-540.
+ * angles (6T) may be NULL; flags (T) u8 = 1 if any angle < min_dh or > max_dh. */
+int dm_dihedral(const double *p, const int32_t *t, int64_t T, double min_dh, double max_dh,
+                double *angles, uint8_t *flags, void *stream);
+
+/* gradient of the circumsphere radius wrt vertex 0 of the listed tets (replaces
+ * _fast_geometry.calc_circumsphere_grad, fast_geometry.cpp:580-703).  ele (S) int32 cell ids
+ * (NULL = all T cells, S=T) -> grad (S,3). */
+int dm_circumsphere_grad(const double *p, const int32_t *t, const int32_t *ele, int64_t S,
+                         double *grad, void *stream);
+
+/* sliver perturbation (mesh_generator.py:245-274): p[t[ele,0]] += step*h0*unit(grad), inf->1,
+ * last sliver wins for a repeated vertex.  winner (N) int32 and delta (S,3) f64 are scratch.
+ * p updated in place (all gradients are taken from the pre-update positions). */
+int dm_sliver_perturb(double *p, int64_t N, const int32_t *t, const int32_t *ele, int64_t S,
+                      double step_h0, int32_t *winner, double *delta, void *stream);
+
+/* 5 damped Newton steps onto the zero level set for the listed vertices (replaces
+ * _improve_level_set_newton, mesh_generator.py:741-759).  p updated in place. */
+int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64_t nb, int dim,
+                        double deps, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The force iteration (mesh_generator.py:482, 497-521) as a plan over a caller workspace
+ * ------------------------------------------------------------------------------------------- */
+typedef struct DmPlan {
+  int64_t N, T;      /* vertices, cells handed over by the host Delaunay */
+  int32_t dim, nb;   /* nb = bars per cell (3 | 6) */
+  int64_t K;         /* nb*T : capacity for raw / unique bars */
+  /* device arrays carved from the workspace */
+  uint8_t *keep;       /* (T)   cull flags                                                    */
+  int32_t *bucket_end; /* (N+1) raw-bar count per min vertex -> bucket start -> bucket end    */
+  int32_t *raw;        /* (K)   max endpoints bucketed by min endpoint                        */
+  int32_t *rowptr;     /* (N+1) CSR of unique bars by min vertex  == reference's sorted (E,2) */
+  int32_t *col;        /* (K)   max vertex of bar e, e < E                                    */
+  int32_t *lrowptr;    /* (N+1) CSR of the transposed list (lower neighbours)                 */
+  uint64_t *low;       /* (K)   (u << 32 | e), ascending per vertex                           */
+  double *hbar;        /* (K)   fh at bar midpoints                                           */
+  double *partials;    /* (2*DM_MAX_PARTIALS) block partial sums / maxima                     */
+  double *scalars;     /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp            */
+  int32_t *counters;   /* [0]=E [1]=T' (kept cells)                                           */
+  void *scan_tmp;      /* scan scratch                                                        */
+  size_t scan_tmp_bytes;
+} DmPlan;
+
+size_t dm_plan_bytes(int64_t N, int64_t T, int dim);
+/* carve `ws` (device, 256-B aligned, >= dm_plan_bytes) into *plan (host struct). */
+int dm_plan_init(DmPlan *plan_host, int64_t N, int64_t T, int dim, void *ws, size_t ws_bytes);
+
+/* stage A: keep flags (fd on centroids) + raw-bar counts per min vertex.
+ * prog == NULL: plan->keep was filled by the caller (opaque fd), only count.
+ * use_keep == 0: every cell is kept (plain _get_edges(t) semantics, mesh_generator.py:680-688). */
+int dm_stage_cull_count(const DmPlan *plan_host, const double *prog, const double *p,
+                        const int32_t *t, double geps, int use_keep, void *stream);
+/* stage B: unique bars (replaces _fast_geometry.unique_edges, fast_geometry.cpp:30-77, bit-exact)
+ * as CSR by min vertex + transposed lower-neighbour lists. */
+int dm_stage_build_bars(const DmPlan *plan_host, const int32_t *t, int use_keep, void *stream);
+/* (E,2) int32 pairs in the reference's order, for parity checks / API users. */
+int dm_bars_pairs(const DmPlan *plan_host, int32_t *pairs, void *stream);
+/* bar midpoints (E,dim) for an opaque fh (mesh_generator.py:699). */
+int dm_bar_midpoints(const DmPlan *plan_host, const double *p, double *mid, void *stream);
+/* stage C: h at bar midpoints + the global scale ((sum L^d)/(sum h^d))^(1/d)
+ * (mesh_generator.py:696-700).  DM_SIZE_EXTERNAL: plan->hbar already holds h. */
+int dm_stage_bar_pass(const DmPlan *plan_host, const double *p, const DmSizeFn *fh_host,
+                      void *stream);
+/* stage D: forces gathered per vertex in the reference's accumulation order, pfix mask, update,
+ * Newton projection per level, max|F| (mesh_generator.py:701-712, 499-521).
+ * progs_host: nlevels device program pointers (0 levels = no projection, opaque fd);
+ * nfix: the first nfix vertices are fixed; fixed (N) u8 optional extra mask (may be NULL);
+ * Ftot (N,dim) optional output (may be NULL). p_out must not alias p. */
+int dm_stage_vertex_update(const DmPlan *plan_host, const double *p, double *p_out,
+                           const double *const *progs_host, int nlevels, double L0mult,
+                           double delta_t, double deps, double h0, int64_t nfix,
+                           const uint8_t *fixed, double *Ftot, void *stream);
+/* projection only (for opaque fd the host does it; for tests): p in place, level idx semantics
+ * of _project_points_back_newton (mesh_generator.py:762-784). */
+int dm_project_points(const double *prog, double *p, int64_t N, int dim, double deps, double h0,
+                      int level_idx, void *stream);
+
+/* A+B+C+D in one call: one DistMesh force iteration on (p, t). */
+int dm_force_iteration(const DmPlan *plan_host, const double *const *progs_host, int nlevels,
+                       const DmSizeFn *fh_host, const double *p, const int32_t *t, double *p_out,
+                       double geps, double L0mult, double delta_t, double deps, double h0,
+                       int64_t nfix, const uint8_t *fixed, double *Ftot, void *stream);
+
+/* dm_force_iteration with a CUDA event recorded after every kernel (measurement only, used by
+ * bench.py for the per-kernel roofline table; synchronises the stream).  ms_host[i] and the
+ * NUL-terminated names_host[i*names_stride ...] describe the i-th timed span; *n_host = count. */
+int dm_force_iteration_profiled(const DmPlan *plan_host, const double *const *progs_host, int nlevels,
+                                const DmSizeFn *fh_host, const double *p, const int32_t *t,
+                                double *p_out, double geps, double L0mult, double delta_t,
+                                double deps, double h0, int64_t nfix, const uint8_t *fixed,
+                                void *stream, float *ms_host, char *names_host, int names_stride,
+                                int cap, int *n_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU slab halo (replaces migration/cpp/cpputils.cpp where_to2/3 :85-200,:247-383 and
+ * migration.enqueue, migration.py:116-145): flag vertices whose incident-cell circumball touches
+ * the slab box below / above.  boxes_host: 2 boxes x (2*dim) doubles (min..., max...);
+ * flags (N) u8: bit0 = export below, bit1 = export above.
+ * ------------------------------------------------------------------------------------------- */
+int dm_halo_select(const double *p, const int32_t *t, int64_t T, int64_t N, int dim,
+                   const double *boxes_host, int has_below, int has_above, uint8_t *flags,
+                   void *stream);
+
+/* utilities */
+size_t dm_scan_scratch_bytes(int64_t n);
+/* exclusive scan of int32 in[0..n) -> out[0..n], out[n] = total (in == out allowed) */
+int dm_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void *scratch,
+                          size_t scratch_bytes, void *stream);
+const char *dm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTMESH_B200_H */

@@ -1,0 +1,93 @@
+// Shared device helpers: warp/block scans and reductions, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DM_CUDA_TRY(x)                      \
+  do {                                      \
+    cudaError_t e__ = (x);                  \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+#define DM_LAUNCH_CHECK()                       \
+  do {                                          \
+    cudaError_t e__ = cudaGetLastError();       \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+
+namespace dm {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// Exclusive scan of one int per thread across the block (blockDim.x multiple of 32, <= 1024).
+// `total` receives the block sum in every thread. smem: >= 33 ints.
+__device__ __forceinline__ int block_exclusive_scan(int v, int& total, int* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int inc = warp_inclusive_scan(v);
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? smem[lane] : 0;
+    const int winc = warp_inclusive_scan(w);
+    smem[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  const int off = smem[wid];
+  total = smem[32];
+  __syncthreads();  // smem reusable by the caller
+  return off + inc - v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_down_sync(FULL, v, d));
+  return v;
+}
+
+// Deterministic block reductions (fixed shuffle tree). Result valid in thread 0. smem >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = lane < nw ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = lane < nw ? smem[lane] : 0.0;
+    r = warp_max(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+}  // namespace dm

@@ -48,3 +48,28 @@ def relerr(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
     return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
+# --------------------------------------------------------------------------------------------
+# hostsim: the per-point arithmetic header of the CUDA library compiled for the host (g++), so
+# the SDF lowering + interpreter arithmetic can be unit-tested without a GPU.  Test-only.
+# --------------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+import subprocess  # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+    hdr = os.path.join(ROOT, "seismicmesh_b200", "csrc", "dm_sdf.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(
+            ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+             "-I" + os.path.join(ROOT, "include"), src, "-o", out]
+        )
+    return C.CDLL(out)
+
+
+def np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,440 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI (ctypes, seismicmesh_b200._lib),
+against (i) golden vectors produced by the unmodified reference and (ii) the NumPy oracle on
+seeded inputs.  Bars / connectivity / flags are bit-exact; floating point within the stated
+tolerance (north_star: 1e-6 relative; we assert far tighter where the arithmetic allows)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, load_golden, load_sdf_specs, relerr
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import distmesh_oracle as orc  # noqa: E402
+
+SPECS = load_sdf_specs()
+TOL = 1e-12  # relative, fp64 (north_star allows 1e-6)
+
+
+@pytest.fixture(scope="module")
+def sm():
+    import seismicmesh_b200 as sm
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return sm
+
+
+def dev(a, dtype):
+    from seismicmesh_b200 import device as D
+
+    return D.to_dev(a, dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# utilities
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 100003, 3_000_001])
+def test_exclusive_scan(sm, n):
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 50, size=n, dtype=np.int32)
+    ad = dev(np.concatenate([a, [0]]).astype(np.int32), torch.int32)
+    nb = lib.dm_scan_scratch_bytes(n)
+    scr = torch.empty(nb, dtype=torch.uint8, device=ad.device)
+    check(lib.dm_exclusive_scan_i32(D.ptr(ad), D.ptr(ad), n, D.ptr(scr), nb, D.stream_ptr()), "scan")
+    ref = np.concatenate([[0], np.cumsum(a, dtype=np.int64)]).astype(np.int32)
+    assert np.array_equal(ad.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# fd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("i", range(len(SPECS)))
+def test_sdf_eval_vs_reference(sm, i):
+    g = load_golden("sdf_cases.npz")
+    obj = sm.geometry.from_spec(SPECS[i])
+    d = obj.eval(g[f"x{i}"])
+    assert relerr(d, g[f"d{i}"]) < 1e-13
+    assert relerr(d, orc.sdf(SPECS[i], g[f"x{i}"])) < 1e-13
+    prm = SPECS[i][1] if isinstance(SPECS[i][1], dict) else {}
+    plain = isinstance(SPECS[i][1], dict) and not any(prm.get("rotate") or [0]) and prm.get("stretch") is None
+    if plain:  # un-rotated primitives: bit-identical to the reference
+        assert np.array_equal(d, g[f"d{i}"])
+
+
+def test_sdf_eval_edge_cases(sm):
+    disk = sm.Disk([0.0, 0.0], 1.0)
+    assert disk.eval(np.zeros((0, 2))).shape == (0,)
+    x = torch.rand((1000, 2), dtype=torch.float64, device="cuda")
+    out = disk.eval(x)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), orc.sdf(("disk", dict(x0=[0.0, 0.0], r=1.0)), x.cpu().numpy()))
+
+
+# ------------------------------------------------------------------------------------------------
+# fh
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["interp_2d.npz", "interp_3d.npz", "r0m_values.npz"])
+def test_size_eval_bit_exact(sm, name):
+    g = load_golden(name)
+    axes = [g[k] for k in ("axis0", "axis1", "axis2") if k in g]
+    gi = sm.GridInterpolant(axes, g["grid"])
+    h = gi(g["x"])
+    assert np.array_equal(h, g["h"])  # identical to scipy RegularGridInterpolator as the reference builds it
+    if name == "r0m_values.npz":
+        assert h[0] == 100 and h[1] == 150  # reference tests/test_2dmesher_r0m_values.py:42-43
+
+
+def test_size_function_accepts_scipy_rgi(sm):
+    from scipy.interpolate import RegularGridInterpolator
+
+    g = load_golden("interp_3d.npz")
+    axes = [g["axis0"], g["axis1"], g["axis2"]]
+    rgi = RegularGridInterpolator(tuple(axes), g["grid"], bounds_error=False, fill_value=None)
+    sf = sm.SizeFunction(tuple(g["bbox"].tolist()), rgi, float(g["hmin"]))
+    assert sf.interpolant() is not None
+    assert np.array_equal(sf.eval(g["x"]), rgi(g["x"]))
+    assert np.array_equal(sf.eval(g["x"]), g["h"])
+
+
+# ------------------------------------------------------------------------------------------------
+# unique bars (integer work: bit exact)
+# ------------------------------------------------------------------------------------------------
+def _random_mesh(dim, n, seed):
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    p = rng.random((n, dim))
+    return p, Delaunay(p).simplices.astype(np.int32)
+
+
+@pytest.mark.parametrize("dim,n,seed", [(2, 50, 0), (2, 5000, 1), (3, 40, 2), (3, 3000, 3), (2, 200000, 4), (3, 60000, 5)])
+def test_unique_bars_random_meshes(sm, dim, n, seed):
+    from seismicmesh_b200.engine import unique_bars
+
+    p, t = _random_mesh(dim, n, seed)
+    bars = unique_bars(t, N=n)
+    ref = orc.unique_bars(t)
+    assert bars.dtype == np.int32 and np.array_equal(bars, ref)
+
+
+def test_unique_bars_matches_reference_native(sm):
+    """oracle/_ref/_fast_geometry is the reference's own compiled unique_edges (if built)."""
+    from oracle import ref_harness
+    from seismicmesh_b200.engine import unique_bars
+
+    if not ref_harness.native_available():
+        pytest.skip("oracle/_ref not built")
+    fg = ref_harness.load_native()
+    p, t = _random_mesh(3, 20000, 11)
+    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]], t[:, [0, 3]], t[:, [1, 3]], t[:, [2, 3]]])
+    assert np.array_equal(unique_bars(t, N=len(p)), fg.unique_edges(e))
+
+
+def test_unique_bars_edge_cases(sm):
+    from seismicmesh_b200.engine import unique_bars
+
+    # empty cell list
+    assert unique_bars(np.zeros((0, 3), dtype=np.int32), N=5).shape == (0, 2)
+    assert unique_bars(np.zeros((0, 4), dtype=np.int32), N=5).shape == (0, 2)
+    # duplicated cells, permuted vertex order, degenerate cells with a repeated vertex
+    t = np.array([[0, 1, 2], [2, 1, 0], [1, 2, 3], [3, 3, 4], [4, 4, 4], [0, 1, 2]], dtype=np.int32)
+    assert np.array_equal(unique_bars(t, N=6), orc.unique_bars(t))
+    t = np.array([[0, 1, 2, 3], [3, 2, 1, 0], [1, 1, 2, 5], [7, 7, 7, 7]], dtype=np.int32)
+    assert np.array_equal(unique_bars(t, N=9), orc.unique_bars(t))
+    # a hub vertex with a very large raw bucket (forces the non-staged fallback of the sorter)
+    n = 6000
+    hub = np.zeros(n - 2, dtype=np.int32)
+    a = np.arange(1, n - 1, dtype=np.int32)
+    t = np.column_stack([hub, a, a + 1]).astype(np.int32)
+    assert np.array_equal(unique_bars(t, N=n), orc.unique_bars(t))
+
+
+def test_compact_cells_preserves_order(sm):
+    from seismicmesh_b200.engine import compact_cells
+
+    rng = np.random.default_rng(3)
+    for dim in (2, 3):
+        t = rng.integers(0, 1000, size=(100001, dim + 1), dtype=np.int32)
+        keep = rng.random(len(t)) < 0.6
+        out = compact_cells(dev(t, torch.int32), dev(keep.astype(np.uint8), torch.uint8), dim).cpu().numpy()
+        assert np.array_equal(out, t[keep])
+
+
+# ------------------------------------------------------------------------------------------------
+# one loop body against the reference's own stage outputs
+# ------------------------------------------------------------------------------------------------
+def _loop_setup(sm, name, g):
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dim = g["p"].shape[1]
+    h0 = float(g["h0"])
+    if name == "loop_2d.npz":
+        doms = [sm.Disk([0.0, 0.0], 1.0)]
+    elif name == "loop_2d_levels.npz":
+        doms = [sm.Rectangle((0.0, 1.0, 0.0, 1.0)), sm.Disk([0.5, 0.5], 0.25)]
+    elif name == "loop_3d.npz":
+        doms = [sm.Ball([0.0, 0.0, 0.0], 1.0)]
+    elif name == "loop_2d_grid.npz":
+        doms = [sm.Rectangle(tuple(g["bbox"].tolist()))]
+    else:
+        doms = [sm.Cube(tuple(g["bbox"].tolist()))]
+    if "grid" in g:
+        axes = [g[k] for k in ("axis0", "axis1", "axis2") if k in g]
+        size = SizeSpec(dim, interp=sm.GridInterpolant(axes, g["grid"]))
+    else:
+        size = SizeSpec(dim, const=h0)
+    geps = 0.1 * h0
+    deps = np.sqrt(np.finfo(np.double).eps) * h0
+    return ForceLoop(dim, [Level(d, dim) for d in doms], size, h0, geps, deps), dim, h0
+
+
+LOOPS = ["loop_2d.npz", "loop_2d_levels.npz", "loop_3d.npz", "loop_2d_grid.npz", "loop_3d_grid.npz"]
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_force_iteration_vs_reference(sm, name):
+    g = load_golden(name)
+    loop, dim, h0 = _loop_setup(sm, name, g)
+    p = dev(g["p"], torch.float64)
+    t = dev(g["t"], torch.int32)
+    p_new, Ftot = loop.iterate(p, t, want_forces=True)
+    torch.cuda.synchronize()
+    T = len(g["t"])
+    keep = loop.plan.keep()[:T].cpu().numpy().astype(bool)
+    assert np.array_equal(g["t"][keep], g["t_kept"])              # cull: bit exact
+    bars = loop.bars().cpu().numpy()
+    assert np.array_equal(bars, g["bars"])                        # bars: bit exact
+    E = len(bars)
+    assert loop.plan.num_bars() == E
+    assert np.array_equal(loop.plan.hbar(E).cpu().numpy(), g["hbars"])   # fh at midpoints: bit exact
+    assert relerr(Ftot.cpu().numpy(), g["Ftot"]) < TOL
+    assert relerr(p_new.cpu().numpy(), g["p_new"]) < TOL
+    assert abs(loop.maxdp() - float(g["maxdp"])) <= TOL * max(1.0, float(g["maxdp"]))
+    # kept_cells = order preserving compaction of the cull
+    assert np.array_equal(loop.kept_cells(p, t).cpu().numpy(), g["t_kept"])
+
+
+@pytest.mark.parametrize("name", ["loop_2d.npz", "loop_3d_grid.npz"])
+def test_staged_path_with_opaque_callables(sm, name):
+    """Opaque Python callables for fd / fh go through the staged path (host evaluation of the USER
+    code only); results must agree with the fused device path."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    g = load_golden(name)
+    loop, dim, h0 = _loop_setup(sm, name, g)
+    p = dev(g["p"], torch.float64)
+    t = dev(g["t"], torch.int32)
+    fused, _ = loop.iterate(p, t)
+    spec = loop.levels[0].obj.spec()
+    fd = lambda x: orc.sdf(spec, x)  # noqa: E731
+    if "grid" in g:
+        axes = [g[k] for k in ("axis0", "axis1", "axis2") if k in g]
+        fh = lambda x: orc.interp_grid(axes, g["grid"], x)  # noqa: E731
+    else:
+        fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    staged = ForceLoop(dim, [Level(fd, dim)], SizeSpec(dim, func=fh), h0, loop.geps, loop.deps)
+    assert not staged.all_lowered
+    out, _ = staged.iterate(p, t)
+    assert relerr(out.cpu().numpy(), fused.cpu().numpy()) < TOL
+    assert relerr(out.cpu().numpy(), g["p_new"]) < TOL
+    assert staged.host_seconds > 0
+
+
+def test_fixed_points_and_projection_kernel(sm):
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+
+    g = load_golden("loop_2d.npz")
+    loop, dim, h0 = _loop_setup(sm, "loop_2d.npz", g)
+    loop.nfix = 7
+    p = dev(g["p"], torch.float64)
+    t = dev(g["t"], torch.int32)
+    p_new, F = loop.iterate(p, t, want_forces=True)
+    assert np.all(F.cpu().numpy()[:7] == 0)
+    ref = g["Ftot"].copy()
+    ref[:7] = 0
+    assert relerr(F.cpu().numpy(), ref) < TOL
+    # stand-alone projection kernel == reference _project_points_back_newton
+    q = dev(g["p_upd"], torch.float64)
+    prog = loop.levels[0].prog
+    check(lib.dm_project_points(D.ptr(prog), D.ptr(q), q.shape[0], 2, loop.deps, h0, 0, D.stream_ptr()), "project")
+    assert np.array_equal(q.cpu().numpy(), g["p_new"])
+    # idempotence: projected points are (numerically) inside, a second pass moves almost nothing
+    q2 = q.clone()
+    check(lib.dm_project_points(D.ptr(prog), D.ptr(q2), q2.shape[0], 2, loop.deps, h0, 0, D.stream_ptr()), "project")
+    assert relerr(q2.cpu().numpy(), q.cpu().numpy()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# sliver kernels
+# ------------------------------------------------------------------------------------------------
+def test_sliver_kernels(sm):
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+
+    g = load_golden("sliver_3d.npz")
+    p = dev(g["p"], torch.float64)
+    t = dev(g["t"], torch.int32)
+    T = t.shape[0]
+    ang = torch.empty(6 * T, dtype=torch.float64, device="cuda")
+    flags = torch.empty(T, dtype=torch.uint8, device="cuda")
+    st = D.stream_ptr()
+    check(lib.dm_dihedral(D.ptr(p), D.ptr(t), T, float(g["min_dh"]), float(g["max_dh"]), D.ptr(ang), D.ptr(flags), st), "dihedral")
+    assert relerr(ang.cpu().numpy(), g["dh"]) < TOL
+    ele = np.nonzero(flags.cpu().numpy())[0]
+    assert np.array_equal(ele, g["ele"])
+    ed = dev(ele.astype(np.int32), torch.int32)
+    S = len(ele)
+    grad = torch.empty((S, 3), dtype=torch.float64, device="cuda")
+    check(lib.dm_circumsphere_grad(D.ptr(p), D.ptr(t), D.ptr(ed), S, D.ptr(grad), st), "grad")
+    assert np.array_equal(grad.cpu().numpy(), g["grad"])  # pure +-*/ arithmetic: bit exact
+    winner = torch.empty(p.shape[0], dtype=torch.int32, device="cuda")
+    delta = torch.empty((S, 3), dtype=torch.float64, device="cuda")
+    q = p.clone()
+    check(lib.dm_sliver_perturb(D.ptr(q), q.shape[0], D.ptr(t), D.ptr(ed), S, float(g["step"]) * float(g["h0"]),
+                                D.ptr(winner), D.ptr(delta), st), "perturb")
+    assert relerr(q.cpu().numpy(), g["p_new"]) < TOL
+
+
+def test_level_set_newton_kernel(sm):
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+
+    g = load_golden("loop_3d.npz")
+    ball = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    h0 = float(g["h0"])
+    deps = np.sqrt(np.finfo(np.double).eps) * h0
+    rng = np.random.default_rng(0)
+    bid = np.sort(rng.choice(len(g["p"]), size=50, replace=False)).astype(np.int32)
+    ref = orc.improve_level_set_newton(g["p"], bid, lambda x: orc.sdf(ball.spec(), x), deps)
+    p = dev(g["p"], torch.float64)
+    check(lib.dm_level_set_newton(D.ptr(ball.device_program()), D.ptr(p), D.ptr(dev(bid, torch.int32)), len(bid), 3, deps,
+                                  D.stream_ptr()), "newton")
+    assert relerr(p.cpu().numpy(), ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-size checks through size-independent properties + the oracle
+# ------------------------------------------------------------------------------------------------
+def _lattice_mesh(sm, dom, h0, dim, seed=0):
+    from scipy.spatial import Delaunay
+    from seismicmesh_b200.generation import _staggered_grid
+
+    rng = np.random.default_rng(seed)
+    p = _staggered_grid(h0, dim, np.array(dom.bbox).reshape(-1, 2))
+    p = p[dom.eval(p) < 0.1 * h0]
+    p = p + rng.uniform(-0.15 * h0, 0.15 * h0, size=p.shape)
+    return np.ascontiguousarray(p), Delaunay(p).simplices.astype(np.int32)
+
+
+@pytest.mark.parametrize("dim,h0", [(2, 0.01), (3, 0.05)])
+def test_full_size_iteration_vs_oracle(sm, dim, h0):
+    """BASELINE configs[0] (Disk h0=0.01, N~3.6e4 lattice points) and the 3-D ball at the size the
+    oracle finishes in seconds: full iteration vs the oracle + structural properties."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dom = sm.Disk([0.0, 0.0], 1.0) if dim == 2 else sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _lattice_mesh(sm, dom, h0, dim)
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+    p_new, F = loop.iterate(dev(p, torch.float64), dev(t, torch.int32), want_forces=True)
+    spec = dom.spec()
+    ref = orc.force_iteration(p, t, [lambda x: orc.sdf(spec, x)], lambda x: np.array([h0] * len(x)), h0, geps, deps)
+    bars = loop.bars().cpu().numpy()
+    assert np.array_equal(bars, ref["bars"])
+    key = bars[:, 0].astype(np.int64) << 32 | bars[:, 1]
+    assert np.all(np.diff(key) > 0) and np.all(bars[:, 0] < bars[:, 1])      # strictly sorted, min<max
+    Fh = F.cpu().numpy()
+    assert relerr(Fh, ref["Ftot"]) < TOL
+    assert relerr(p_new.cpu().numpy(), ref["p"]) < TOL
+    # Newton's third law: internal bar forces sum to zero
+    assert np.abs(Fh.sum(0)).max() < 1e-9 * np.abs(Fh).sum()
+    # every output vertex is inside or on the boundary (to first order)
+    assert dom.eval(p_new.cpu().numpy()).max() < 0.05 * h0
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end through the public API
+# ------------------------------------------------------------------------------------------------
+def _e2e():
+    with open(os.path.join(GOLDEN, "e2e.json")) as f:
+        return json.load(f)
+
+
+def test_generate_mesh_disk_matches_reference(sm):
+    from seismicmesh_b200 import meshutil
+
+    ref = _e2e()["disk_h0.05"]
+    p, t = sm.generate_mesh(sm.Disk([0.0, 0.0], 1.0), 0.05, max_iter=25, verbose=0)
+    q = meshutil.simp_qual(p, t)
+    assert abs(len(p) - ref["nverts"]) <= 0.01 * ref["nverts"]
+    assert abs(len(t) - ref["ncells"]) <= 0.01 * ref["ncells"]
+    assert abs(q.mean() - ref["mean_q"]) <= 0.01 * ref["mean_q"]
+    assert q.min() >= ref["min_q"] * 0.99 or q.min() > 0.6
+    assert abs(meshutil.simp_vol(p, t).sum() - ref["area"]) < 0.01 * ref["area"]
+    assert sm.last_run_stats["iterations"] == 24  # max_iter=K means K-1 force iterations
+
+
+def test_generate_mesh_gridded_rectangle(sm):
+    from seismicmesh_b200 import meshutil
+
+    ref = _e2e()["grid2d"]
+    g = load_golden("interp_2d.npz")
+    bbox = tuple(g["bbox"].tolist())
+    ef = sm.SizeFunction(bbox, sm.GridInterpolant([g["axis0"], g["axis1"]], g["grid"]), float(g["hmin"]))
+    p, t = sm.generate_mesh(sm.Rectangle(bbox), ef, max_iter=25, verbose=0)
+    q = meshutil.simp_qual(p, t)
+    assert abs(len(p) - ref["nverts"]) <= 0.01 * ref["nverts"]
+    assert abs(q.mean() - ref["mean_q"]) <= 0.01 * ref["mean_q"]
+    assert abs(meshutil.simp_vol(p, t).sum() - ref["area"]) < 1e-6 * ref["area"]
+
+
+def test_generate_mesh_annulus_min_quality(sm):
+    """reference tests/test_2d_min_qual.py: min quality > 0.6 is NOT reached at every h by the
+    reference itself with Qhull; we pin against the reference's own outcome for this case."""
+    from seismicmesh_b200 import meshutil
+
+    ref = _e2e()["annulus_h0.05"]
+    rect = sm.Rectangle((0.0, 1.0, 0.0, 1.0))
+    ann = sm.Intersection([rect, sm.Difference([sm.Disk([0.0, 0.0], 1.0), sm.Disk([0.0, 0.0], 0.5)])])
+    p, t = sm.generate_mesh(ann, 0.05, max_iter=25, verbose=0)
+    q = meshutil.simp_qual(p, t)
+    assert abs(len(p) - ref["nverts"]) <= max(3, 0.01 * ref["nverts"])
+    assert abs(q.mean() - ref["mean_q"]) <= 0.01 * ref["mean_q"]
+    assert abs(meshutil.simp_vol(p, t).sum() - ref["area"]) < 0.01 * ref["area"]
+
+
+def test_ball_generate_and_sliver_removal(sm):
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200 import meshutil
+    from seismicmesh_b200._lib import check, lib
+
+    ref = _e2e()["ball_h0.2"]
+    ball = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = sm.generate_mesh(ball, 0.2, max_iter=25, verbose=0)
+    assert abs(len(p) - ref["nverts_generate"]) <= max(3, 0.01 * ref["nverts_generate"])
+    p, t = sm.sliver_removal(points=p, domain=ball, edge_length=0.2, verbose=0)
+    assert abs(len(p) - ref["nverts"]) <= max(3, 0.01 * ref["nverts"])
+    dh = orc.dihedral_angles(p, t.astype(np.int64))
+    assert dh.min() * 180 / np.pi >= 10.0            # reference tests/test_3d_sliver.py: no slivers left
+    assert abs(meshutil.simp_vol(p, t).sum() - ref["volume"]) < 0.02 * ref["volume"]
+
+
+def test_api_errors(sm):
+    disk = sm.Disk([0.0, 0.0], 1.0)
+    with pytest.raises(ValueError):
+        sm.generate_mesh(disk, 0.1, bogus_option=1)
+    with pytest.raises(ValueError):
+        sm.generate_mesh(disk, "not a size")
+    with pytest.raises(ValueError):
+        sm.generate_mesh(42, 0.1)
+    with pytest.raises(ValueError):
+        sm.generate_mesh(lambda x: x, 0.1, bbox=(0, 1, 0, 1))  # ints in bbox
+    with pytest.raises(Exception):
+        sm.sliver_removal(points=np.zeros((4, 2)), domain=disk, edge_length=0.1)
