@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- DistMesh force-iteration throughput (vertex-updates/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ball|disk] [--impl ours|reference]
+
+A *step* is one pass of the hot path (cull -> unique bars -> forces -> update -> projection ->
+max|dp|, i.e. one iteration of the loop body of SeismicMesh generate_mesh AFTER its Delaunay
+call) over one synthetic (p, t).  Delaunay is host work in the reference's design and is done
+once in the untimed set-up; it is reported separately (`delaunay_s`).
+
+Prints ONE JSON line (contract in the task statement): `value` = vertex-updates/s with inputs
+resident in HBM, `e2e` = the same through the public host-buffer call (H2D of p and t from pinned
+memory + D2H of the new positions inside the timed region), `roofline` for the dominant kernel
+(algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json), `cpu_baseline` = the oracle
+port of the reference's NumPy loop body timed on one host core.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DistMesh vertex-updates/sec (verts x iters / s), device-resident force iteration"
+UNIT = "vertex-updates/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# ------------------------------------------------------------------------------------------------
+def _lattice(h0, dim, bbox):
+    axes = [np.arange(int(np.ceil((hi + h0 - lo) / h0)), dtype=float) * h0 + lo for lo, hi in bbox]
+    g = [a.copy() for a in np.meshgrid(*axes, indexing="ij")]
+    g[1][1::2] += h0 / 2
+    if dim == 3:
+        g[2][1::2] += h0 / 2
+    return np.stack([a.ravel() for a in g], axis=1)
+
+
+def make_points(workload, h0, seed=0, shift=0.0):
+    """Synthetic input of BASELINE.json configs[1] (ball) / configs[0] (disk): the reference's
+    initial lattice inside the domain (uniform h => no rejection), jittered by 0.1*h0 (seeded) so
+    the host Delaunay is non-degenerate, as in a mid-run iteration."""
+    dim = 3 if workload == "ball" else 2
+    bbox = np.array([[-1.0, 1.0]] * dim)
+    p = _lattice(h0, dim, bbox)
+    r = np.sqrt((p**2).sum(1))
+    p = p[r - 1.0 < 0.1 * h0]
+    rng = np.random.default_rng(seed)
+    p = p + rng.uniform(-0.1 * h0, 0.1 * h0, p.shape)
+    p[:, 1] += shift
+    return np.ascontiguousarray(p), dim
+
+
+def triangulate(p):
+    from scipy.spatial import Delaunay
+
+    t0 = time.perf_counter()
+    t = np.ascontiguousarray(Delaunay(p).simplices, dtype=np.int32)
+    return t, time.perf_counter() - t0
+
+
+def oracle_step_fn(workload, h0, dim):
+    """The reference's loop body (oracle port, + the reference's own native unique_edges from
+    oracle/_ref when it was built) as a closure step(p, t) -> p_new."""
+    from oracle import distmesh_oracle as orc
+    from oracle import ref_harness
+
+    spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)) if workload == "ball" else ("disk", dict(x0=[0.0, 0.0], r=1.0))
+    native = None
+    if ref_harness.native_available():
+        try:
+            native = ref_harness.load_native()
+        except Exception:
+            native = None
+    if native is not None:
+        def unique_bars(t):  # mesh_generator.py:680-688 calling the reference's compiled unique_edges
+            e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+            if t.shape[1] == 4:
+                e = np.concatenate((e, t[:, [0, 3]], t[:, [1, 3]], t[:, [2, 3]]), axis=0)
+            return native.unique_edges(e)
+        orc.unique_bars = unique_bars
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    fd = lambda x: orc.sdf(spec, x)  # noqa: E731
+    fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+
+    def step(p, t):
+        return orc.force_iteration(p, t, [fd], fh, h0, geps, deps)["p"]
+
+    return step, ("reference-native unique_edges + NumPy port" if native is not None else "NumPy port")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, T, Tk, E, dim):
+    """Compulsory HBM traffic per kernel launch (each input read once, each output written once;
+    DESIGN.md section 5 / SURVEY section 8d), from the ACTUAL sizes of the run."""
+    c, nb, d = dim + 1, (3 if dim == 2 else 6), dim
+    Kp = nb * Tk
+    return {
+        "memset_counts": 4 * (N + 1),
+        "cull_count": 4 * c * T + 8 * d * N + T + 4 * (N + 1),
+        "scan_bucket(3 kernels)": 8 * (N + 1),
+        "bar_fill": 4 * c * T + T + 4 * Kp + 4 * (N + 1),
+        "memset_lower": 4 * (N + 1),
+        "sort_unique": 4 * Kp + 4 * E + 12 * (N + 1),
+        "scan_rowptrs(6 kernels)": 16 * (N + 1),
+        "compact_transpose": 4 * E + 8 * (N + 1) + 4 * E + 8 * E,
+        "lower_sort": 16 * E + 4 * (N + 1),
+        "bar_pass": 8 * d * N + 4 * (N + 1) + 4 * E + 8 * E,
+        "scale": 0,
+        "vertex_update": 16 * d * N + 8 * (N + 1) + 4 * E + 8 * E + 16 * E,
+        "maxdp": 0,
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path, on the host cores of this box."""
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    workload = args.workload
+    base_h0 = 0.02 if workload == "ball" else 0.01
+    # bounded sample: coarsen h0 until (K+W) steps + set-up fit in ~150 s (cost ~ 1/h0^dim)
+    dim = 3 if workload == "ball" else 2
+    est_full = 8.0 if workload == "ball" else 0.12
+    h0 = base_h0
+    for cand in (1.0, 1.25, 1.5, 2.0, 3.0):
+        h0 = base_h0 * cand
+        if (K + W) * est_full / cand**dim + (30.0 if workload == "ball" else 1.0) / cand**dim <= 150.0:
+            break
+    p, dim = make_points(workload, h0)
+    t, tq = triangulate(p)
+    step, kind = oracle_step_fn(workload, h0, dim)
+    for _ in range(W):
+        step(p, t)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step(p, t)
+    dt = time.perf_counter() - t0
+    N = len(p)
+    val = N * K / dt
+    sample = f"{workload} h0={h0:g} (N={N}, T={len(t)}), {K} steps of the full loop body on 1 core"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{workload}_h0={base_h0:g}", "sample_h0": h0, "delaunay": "excluded (host, set-up)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "detail": kind},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "delaunay_s": tq,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ball", choices=["ball", "disk"])
+    ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing (scale-up runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    workload = args.workload
+    h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
+    K, W = args.steps, args.warmup
+
+    # ---- set-up (untimed): points + ONE host Delaunay per rank (weak scaling: one slab per GPU) ----
+    p, dim = make_points(workload, h0, seed=rank, shift=2.0 * rank)
+    t, t_delaunay = triangulate(p)
+    N, T = len(p), len(t)
+    dom = (sm.Ball([0.0, 2.0 * rank, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 2.0 * rank], 1.0))
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+
+    p_dev = D.to_dev(p, torch.float64)
+    t_dev = D.to_dev(t, torch.int32)
+    p_out = torch.empty_like(p_dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=p_dev.device)  # > 126 MB L2
+
+    halo = None
+    if world > 1:
+        from seismicmesh_b200.parallel import RingHalo
+
+        halo = RingHalo(p_dev, t_dev, dim, h0, axis=1, rank=rank, world=world)
+
+    def one_step():
+        loop.iterate(p_dev, t_dev, p_out=p_out)
+        if halo is not None:
+            halo.exchange(p_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
+        ev[i][0].record()
+        one_step()
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=p_dev.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+        nn = torch.tensor([N], dtype=torch.float64, device=p_dev.device)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        N_all = int(nn.item())
+    else:
+        N_all = N
+    clocks = sampler.stop() if rank == 0 else None
+    value = N_all * K / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----
+    p_pin = torch.from_numpy(p).pin_memory()
+    t_pin = torch.from_numpy(t).pin_memory()
+    out_pin = torch.empty_like(p_pin).pin_memory()
+    sc_pin = torch.empty(8, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        p_dev.copy_(p_pin, non_blocking=True)
+        t_dev.copy_(t_pin, non_blocking=True)
+        one_step()
+        out_pin.copy_(p_out, non_blocking=True)
+        sc_pin.copy_(loop.plan.scalars(), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        ev2[i][0].record()
+        e2e_step()
+        ev2[i][1].record()
+    barrier()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=p_dev.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = N_all * K / (e2e_ms * 1e-3)
+    maxdp = float(sc_pin[4])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing (CUDA events recorded inside the library, same stream) ----
+    E = loop.plan.num_bars()
+    Tk = int(loop.plan.keep()[:T].sum().item())
+    cap, stride = 32, 48
+    acc, names = None, None
+    reps = 5
+    f = loop.size.struct()
+    progs = D.prog_array(loop._progs)
+    for r in range(reps):
+        flush.fill_(r)
+        ms = (C.c_float * cap)()
+        nm = C.create_string_buffer(cap * stride)
+        n = C.c_int(0)
+        check(lib.dm_force_iteration_profiled(
+            C.byref(loop.plan.c), progs, len(loop._progs), C.byref(f), D.ptr(p_dev), D.ptr(t_dev), D.ptr(p_out),
+            geps, loop.L0mult, loop.delta_t, deps, h0, 0, None, D.stream_ptr(), ms, nm, stride, cap, C.byref(n)), "profiled")
+        cur = np.array(ms[: n.value], dtype=np.float64)
+        acc = cur if acc is None else acc + cur
+        names = [nm.raw[i * stride : (i + 1) * stride].split(b"\0")[0].decode() for i in range(n.value)]
+    kern_ms = acc / reps
+    alg = algorithmic_bytes(N, T, Tk, E, dim)
+    peak, peak_src = measured_peak()
+    table = []
+    for nme, msv in zip(names, kern_ms):
+        b = alg.get(nme, 0)
+        gbs = b / (msv * 1e-3) / 1e9 if msv > 0 else 0.0
+        table.append({"kernel": nme, "ms": float(msv), "share": float(msv / kern_ms.sum()), "alg_bytes": int(b),
+                      "achieved_gbs": gbs, "frac": gbs / peak})
+    dom_k = max(table, key=lambda r: r["ms"])
+    step_bytes = sum(alg.values())
+    roofline = {
+        "bound": "hbm", "kernel": dom_k["kernel"], "achieved": dom_k["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        "frac": dom_k["frac"], "traffic": None, "peak_source": peak_src,
+        "whole_step": {"alg_bytes": int(step_bytes), "achieved": step_bytes / (kern_ms.sum() * 1e-3) / 1e9,
+                       "frac": step_bytes / (kern_ms.sum() * 1e-3) / 1e9 / peak,
+                       "alg_bytes_per_vertex_update": step_bytes / N},
+    }
+    if args.kernel_table:
+        os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
+        with open(args.kernel_table, "w") as fo:
+            json.dump({"workload": workload, "h0": h0, "N": N, "T": T, "T_kept": Tk, "E": E, "peak_gbs": peak,
+                       "kernels": table}, fo, indent=1)
+    for row in table:
+        print("  %-26s %8.4f ms  %5.1f%%  %8.1f GB/s  %5.1f%% of peak" % (
+            row["kernel"], row["ms"], 100 * row["share"], row["achieved_gbs"], 100 * row["frac"]), file=sys.stderr)
+
+    # ---- CPU baseline: the reference's loop body (oracle port) on one host core, same (p, t) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        step, kind = oracle_step_fn(workload, h0, dim)
+        p0 = make_points(workload, h0, seed=0)[0] if world > 1 else p
+        t0_ = triangulate(p0)[0] if world > 1 else t
+        nrep = 1 if N > 200000 else max(1, int(2e5 // N))
+        c0 = time.perf_counter()
+        for _ in range(nrep):
+            ref_p = step(p0, t0_)
+        cdt = time.perf_counter() - c0
+        cpu = {"value": len(p0) * nrep / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{nrep} step(s) of the same (p,t): N={len(p0)}, T={len(t0_)}; {cdt:.1f} s", "detail": kind}
+        if world == 1:  # parity of the benchmarked step against the oracle
+            perr = float(np.abs(out_pin.numpy() - ref_p).max())
+            cpu["max_abs_dp_vs_oracle"] = perr
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{workload}_h0={h0:g}", "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
+                   "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
+                   "parallelism": f"slab x{world}" if world > 1 else "single"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
+                "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
+        "gpu_launches": 18 * K,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

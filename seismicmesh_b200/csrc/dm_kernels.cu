@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(1024) scale_kernel(const double* __restrict__ 
     scalars[0] = tl;
     scalars[1] = th;
     const double r = tl / th;
-    scalars[2] = dim == 2 ? sqrt(r) : cbrt(r);
+    scalars[2] = dim == 2 ? sqrt(r) : pow(r, 1.0 / 3.0);  // ** (1.0 / dim), mesh_generator.py:700
   }
 }
 
@@ -821,8 +821,9 @@ int dm_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scra
 }
 
 int dm_sdf_eval(const double* prog, const double* x, int64_t M, int dim, double* out, void* stream) {
-  if (check_prog_host_side(prog) || !x || !out || M < 0 || (dim != 2 && dim != 3)) return DM_ERR_ARG;
-  if (M == 0) return DM_OK;
+  if (check_prog_host_side(prog) || M < 0 || (dim != 2 && dim != 3)) return DM_ERR_ARG;
+  if (M == 0) return DM_OK;  // empty input: pointers may be NULL
+  if (!x || !out) return DM_ERR_ARG;
   if (dim == 2)
     sdf_eval_kernel<2><<<nblk(M, 256), 256, 0, S(stream)>>>(prog, x, M, out);
   else
@@ -832,12 +833,13 @@ int dm_sdf_eval(const double* prog, const double* x, int64_t M, int dim, double*
 }
 
 int dm_size_eval(const DmSizeFn* f, const double* x, int64_t M, double* out, void* stream) {
-  if (!f || !x || !out || M < 0 || (f->dim != 2 && f->dim != 3)) return DM_ERR_ARG;
+  if (!f || M < 0 || (f->dim != 2 && f->dim != 3)) return DM_ERR_ARG;
   if (f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
   if (f->kind == DM_SIZE_GRID)
     for (int k = 0; k < f->dim; ++k)
       if (f->n[k] < 2 || !f->axis[k]) return DM_ERR_ARG;
-  if (M == 0) return DM_OK;
+  if (M == 0) return DM_OK;  // empty input: pointers may be NULL
+  if (!x || !out) return DM_ERR_ARG;
   if (f->dim == 2)
     size_eval_kernel<2><<<nblk(M, 256), 256, 0, S(stream)>>>(*f, x, M, out);
   else
@@ -1011,7 +1013,7 @@ int dm_plan_init(DmPlan* plan, int64_t N, int64_t T, int dim, void* ws, size_t w
 
 int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
                         int use_keep, void* stream) {
-  if (!pl || !t || (use_keep && prog && !p)) return DM_ERR_ARG;
+  if (!pl || (!t && pl->T > 0) || (use_keep && prog && !p)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
   DM_CUDA_TRY(cudaMemsetAsync(pl->bucket_end, 0, (size_t)(pl->N + 1) * 4, st));
   mark("memset_counts", st);
@@ -1027,7 +1029,7 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
 }
 
 int dm_stage_build_bars(const DmPlan* pl, const int32_t* t, int use_keep, void* stream) {
-  if (!pl || !t) return DM_ERR_ARG;
+  if (!pl || (!t && pl->T > 0)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
   const int64_t N = pl->N, T = pl->T;
   int rc = exclusive_scan(pl->bucket_end, pl->bucket_end, N, pl->scan_tmp, pl->scan_tmp_bytes, st);

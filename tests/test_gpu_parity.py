@@ -16,7 +16,11 @@ pytestmark = pytest.mark.gpu
 from oracle import distmesh_oracle as orc  # noqa: E402
 
 SPECS = load_sdf_specs()
-TOL = 1e-12  # relative, fp64 (north_star allows 1e-6)
+TOL = 1e-12  # relative, fp64: forces, h, SDF, angles (north_star allows 1e-6)
+# Positions AFTER the Newton projection: the reference's forward-difference gradient divides an
+# O(ulp) change of fd by deps = sqrt(eps)*h0, so a last-bit difference in the global force scale
+# (NumPy pairwise summation vs our fixed reduction tree) is amplified ~1e8x.  north_star: 1e-6.
+PTOL = 1e-7
 
 
 @pytest.fixture(scope="module")
@@ -214,7 +218,8 @@ def test_force_iteration_vs_reference(sm, name):
     assert loop.plan.num_bars() == E
     assert np.array_equal(loop.plan.hbar(E).cpu().numpy(), g["hbars"])   # fh at midpoints: bit exact
     assert relerr(Ftot.cpu().numpy(), g["Ftot"]) < TOL
-    assert relerr(p_new.cpu().numpy(), g["p_new"]) < TOL
+    assert relerr(g["p"] + 0.30 * Ftot.cpu().numpy(), g["p_upd"]) < TOL
+    assert relerr(p_new.cpu().numpy(), g["p_new"]) < PTOL
     assert abs(loop.maxdp() - float(g["maxdp"])) <= TOL * max(1.0, float(g["maxdp"]))
     # kept_cells = order preserving compaction of the cull
     assert np.array_equal(loop.kept_cells(p, t).cpu().numpy(), g["t_kept"])
@@ -241,8 +246,8 @@ def test_staged_path_with_opaque_callables(sm, name):
     staged = ForceLoop(dim, [Level(fd, dim)], SizeSpec(dim, func=fh), h0, loop.geps, loop.deps)
     assert not staged.all_lowered
     out, _ = staged.iterate(p, t)
-    assert relerr(out.cpu().numpy(), fused.cpu().numpy()) < TOL
-    assert relerr(out.cpu().numpy(), g["p_new"]) < TOL
+    assert relerr(out.cpu().numpy(), fused.cpu().numpy()) < PTOL
+    assert relerr(out.cpu().numpy(), g["p_new"]) < PTOL
     assert staged.host_seconds > 0
 
 
@@ -352,7 +357,7 @@ def test_full_size_iteration_vs_oracle(sm, dim, h0):
     assert np.all(np.diff(key) > 0) and np.all(bars[:, 0] < bars[:, 1])      # strictly sorted, min<max
     Fh = F.cpu().numpy()
     assert relerr(Fh, ref["Ftot"]) < TOL
-    assert relerr(p_new.cpu().numpy(), ref["p"]) < TOL
+    assert relerr(p_new.cpu().numpy(), ref["p"]) < PTOL
     # Newton's third law: internal bar forces sum to zero
     assert np.abs(Fh.sum(0)).max() < 1e-9 * np.abs(Fh).sum()
     # every output vertex is inside or on the boundary (to first order)
