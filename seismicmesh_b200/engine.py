@@ -214,7 +214,8 @@ class ForceLoop:
         """(E,2) int32 unique bars of the last iteration, in the reference's order."""
         E = self.plan.num_bars()
         pairs = torch.empty((E, 2), dtype=torch.int32, device=D.device())
-        check(lib.dm_bars_pairs(C.byref(self.plan.c), D.ptr(pairs), D.stream_ptr()), "bars_pairs")
+        if E > 0:
+            check(lib.dm_bars_pairs(C.byref(self.plan.c), D.ptr(pairs), D.stream_ptr()), "bars_pairs")
         return pairs
 
 
@@ -245,5 +246,6 @@ def unique_bars(t, N=None):
     check(lib.dm_stage_build_bars(C.byref(pl.c), D.ptr(td), 0, st), "build_bars")
     E = pl.num_bars()
     pairs = torch.empty((E, 2), dtype=torch.int32, device=td.device)
-    check(lib.dm_bars_pairs(C.byref(pl.c), D.ptr(pairs), st), "bars_pairs")
+    if E > 0:
+        check(lib.dm_bars_pairs(C.byref(pl.c), D.ptr(pairs), st), "bars_pairs")
     return pairs if as_torch else pairs.cpu().numpy()
