@@ -147,25 +147,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, T, Tk, E, dim):
-    """Compulsory HBM traffic per kernel launch (each input read once, each output written once;
-    DESIGN.md section 5 / SURVEY section 8d), from the ACTUAL sizes of the run."""
-    c, nb, d = dim + 1, (3 if dim == 2 else 6), dim
-    Kp = nb * Tk
+def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
+    """Compulsory HBM traffic per kernel launch (each input read once, each output written once,
+    gathers counted once per distinct element; DESIGN.md section 4 / SURVEY section 8d), from the
+    ACTUAL sizes of the run."""
+    c, d = dim + 1, dim
+    hs = 8 * E if grid_fh else 0
     return {
-        "memset_counts": 4 * (N + 1),
+        "memset_zero_region": 4 * (N + 1),
         "cull_count": 4 * c * T + 8 * d * N + T + 4 * (N + 1),
-        "scan_bucket(3 kernels)": 8 * (N + 1),
-        "bar_fill": 4 * c * T + T + 4 * Kp + 4 * (N + 1),
-        "memset_lower": 4 * (N + 1),
-        "sort_unique": 4 * Kp + 4 * E + 12 * (N + 1),
-        "scan_rowptrs(6 kernels)": 16 * (N + 1),
-        "compact_transpose": 4 * E + 8 * (N + 1) + 4 * E + 8 * E,
-        "lower_sort": 16 * E + 4 * (N + 1),
-        "bar_pass": 8 * d * N + 4 * (N + 1) + 4 * E + 8 * E,
-        "scale": 0,
-        "vertex_update": 16 * d * N + 8 * (N + 1) + 4 * E + 8 * E + 16 * E,
-        "maxdp": 0,
+        "scan_incidence": 8 * (N + 1),
+        "inc_fill": 4 * c * T + T + 4 * c * Tk + 4 * (N + 1),
+        "adjacency_build": 4 * c * Tk + 4 * c * T + 4 * (N + 1) + 8 * E + 8 * N,
+        "bar_pass+scale": 8 * d * N + 4 * E + 12 * N + hs,
+        "vertex_update+maxdp": 16 * d * N + 8 * E + 12 * N + hs,
     }
 
 
@@ -423,7 +418,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 18 * K,
+        "gpu_launches": 6 * K,
         "roofline": roofline, "cpu_baseline": cpu,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
     }

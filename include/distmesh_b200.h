@@ -137,26 +137,42 @@ int dm_sliver_perturb(double *p, int64_t N, const int32_t *t, const int32_t *ele
 int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64_t nb, int dim,
                         double deps, void *stream);
 
+
 /* ---------------------------------------------------------------------------------------------
  * The force iteration (mesh_generator.py:482, 497-521) as a plan over a caller workspace
+ *
+ * Per-iteration device structures (all int32 / float64, carved from the workspace):
+ *   keep     (T)            cull flags
+ *   inc_end  (N+1)          kept cells incident to each vertex: count -> list start -> list end
+ *   inc      ((dim+1)*T)    incident cell ids grouped by vertex
+ *   adj      (K)            sorted unique neighbour ids of vertex v at adj[dim*inc_start(v) ...],
+ *                           deg[v] of them, the first nlow[v] are < v.  The upper parts (>= v) of
+ *                           all rows in vertex order ARE the reference's sorted unique (E,2) bars.
+ *   rowptr   (N+1)          bar ids = exclusive scan of deg-nlow (built on demand)
+ *   hslot    (K)            gridded fh at the midpoint of bar (v,w), stored at its upper slot
+ *   hbar     (K/2)          fh per bar id, for DM_SIZE_EXTERNAL
  * ------------------------------------------------------------------------------------------- */
 typedef struct DmPlan {
   int64_t N, T;      /* vertices, cells handed over by the host Delaunay */
-  int32_t dim, nb;   /* nb = bars per cell (3 | 6) */
-  int64_t K;         /* nb*T : capacity for raw / unique bars */
-  /* device arrays carved from the workspace */
-  uint8_t *keep;       /* (T)   cull flags                                                    */
-  int32_t *bucket_end; /* (N+1) raw-bar count per min vertex -> bucket start -> bucket end    */
-  int32_t *raw;        /* (K)   max endpoints bucketed by min endpoint                        */
-  int32_t *rowptr;     /* (N+1) CSR of unique bars by min vertex  == reference's sorted (E,2) */
-  int32_t *col;        /* (K)   max vertex of bar e, e < E                                    */
-  int32_t *lrowptr;    /* (N+1) CSR of the transposed list (lower neighbours)                 */
-  uint64_t *low;       /* (K)   (u << 32 | e), ascending per vertex                           */
-  double *hbar;        /* (K)   fh at bar midpoints                                           */
-  double *partials;    /* (2*DM_MAX_PARTIALS) block partial sums / maxima                     */
-  double *scalars;     /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp            */
-  int32_t *counters;   /* [0]=E [1]=T' (kept cells)                                           */
-  void *scan_tmp;      /* scan scratch                                                        */
+  int32_t dim, _pad0;
+  int64_t K;         /* dim*(dim+1)*T : capacity of the directed adjacency */
+  uint8_t *keep;
+  void *zero_base;   /* [inc_end | scan descriptors | sync | counters]: ONE memset per iteration */
+  size_t zero_bytes;
+  int32_t *inc_end;
+  uint64_t *scan_desc;
+  int32_t *sync;     /* [0] scan ticket [1] bar-pass blocks done [2] update blocks done */
+  int32_t *counters; /* [0]=E unique bars [1]=T' kept cells */
+  int32_t *inc;
+  int32_t *adj;
+  int32_t *deg;
+  int32_t *nlow;
+  int32_t *rowptr;
+  double *hslot;
+  double *hbar;
+  double *partials;  /* per-block partial sums / maxima */
+  double *scalars;   /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp */
+  void *scan_tmp;    /* scratch of the on-demand scans */
   size_t scan_tmp_bytes;
 } DmPlan;
 
@@ -164,20 +180,25 @@ size_t dm_plan_bytes(int64_t N, int64_t T, int dim);
 /* carve `ws` (device, 256-B aligned, >= dm_plan_bytes) into *plan (host struct). */
 int dm_plan_init(DmPlan *plan_host, int64_t N, int64_t T, int dim, void *ws, size_t ws_bytes);
 
-/* stage A: keep flags (fd on centroids) + raw-bar counts per min vertex.
+/* stage A: keep flags (fd on centroids) + incident-cell counts per vertex.
  * prog == NULL: plan->keep was filled by the caller (opaque fd), only count.
  * use_keep == 0: every cell is kept (plain _get_edges(t) semantics, mesh_generator.py:680-688). */
 int dm_stage_cull_count(const DmPlan *plan_host, const double *prog, const double *p,
                         const int32_t *t, double geps, int use_keep, void *stream);
-/* stage B: unique bars (replaces _fast_geometry.unique_edges, fast_geometry.cpp:30-77, bit-exact)
- * as CSR by min vertex + transposed lower-neighbour lists. */
-int dm_stage_build_bars(const DmPlan *plan_host, const int32_t *t, int use_keep, void *stream);
-/* (E,2) int32 pairs in the reference's order, for parity checks / API users. */
+/* stage B: sorted unique neighbour rows (replaces _fast_geometry.unique_edges,
+ * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs). */
+int dm_stage_build_adjacency(const DmPlan *plan_host, const int32_t *t, int use_keep, void *stream);
+/* bar ids (rowptr) for dm_bars_pairs / dm_bar_midpoints / DM_SIZE_EXTERNAL. */
+int dm_stage_bar_index(const DmPlan *plan_host, void *stream);
+/* (E,2) int32 pairs in the reference's order (needs dm_stage_bar_index). */
 int dm_bars_pairs(const DmPlan *plan_host, int32_t *pairs, void *stream);
-/* bar midpoints (E,dim) for an opaque fh (mesh_generator.py:699). */
+/* bar midpoints (E,dim) for an opaque fh (mesh_generator.py:699; needs dm_stage_bar_index). */
 int dm_bar_midpoints(const DmPlan *plan_host, const double *p, double *mid, void *stream);
+/* h of every unique bar of the last bar pass, in bar order (E) -- diagnostics / parity tests
+ * (the reference's `hedges`, mesh_generator.py:699; needs dm_stage_bar_index). */
+int dm_bar_sizes(const DmPlan *plan_host, const DmSizeFn *fh_host, double *out, void *stream);
 /* stage C: h at bar midpoints + the global scale ((sum L^d)/(sum h^d))^(1/d)
- * (mesh_generator.py:696-700).  DM_SIZE_EXTERNAL: plan->hbar already holds h. */
+ * (mesh_generator.py:696-700).  DM_SIZE_EXTERNAL: plan->hbar already holds h per bar id. */
 int dm_stage_bar_pass(const DmPlan *plan_host, const double *p, const DmSizeFn *fh_host,
                       void *stream);
 /* stage D: forces gathered per vertex in the reference's accumulation order, pfix mask, update,
@@ -186,8 +207,8 @@ int dm_stage_bar_pass(const DmPlan *plan_host, const double *p, const DmSizeFn *
  * nfix: the first nfix vertices are fixed; fixed (N) u8 optional extra mask (may be NULL);
  * Ftot (N,dim) optional output (may be NULL). p_out must not alias p. */
 int dm_stage_vertex_update(const DmPlan *plan_host, const double *p, double *p_out,
-                           const double *const *progs_host, int nlevels, double L0mult,
-                           double delta_t, double deps, double h0, int64_t nfix,
+                           const double *const *progs_host, int nlevels, const DmSizeFn *fh_host,
+                           double L0mult, double delta_t, double deps, double h0, int64_t nfix,
                            const uint8_t *fixed, double *Ftot, void *stream);
 /* projection only (for opaque fd the host does it; for tests): p in place, level idx semantics
  * of _project_points_back_newton (mesh_generator.py:762-784). */

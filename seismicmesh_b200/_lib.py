@@ -36,19 +36,24 @@ class DmPlan(C.Structure):
         ("N", C.c_int64),
         ("T", C.c_int64),
         ("dim", C.c_int32),
-        ("nb", C.c_int32),
+        ("_pad0", C.c_int32),
         ("K", C.c_int64),
         ("keep", C.c_void_p),
-        ("bucket_end", C.c_void_p),
-        ("raw", C.c_void_p),
+        ("zero_base", C.c_void_p),
+        ("zero_bytes", C.c_size_t),
+        ("inc_end", C.c_void_p),
+        ("scan_desc", C.c_void_p),
+        ("sync", C.c_void_p),
+        ("counters", C.c_void_p),
+        ("inc", C.c_void_p),
+        ("adj", C.c_void_p),
+        ("deg", C.c_void_p),
+        ("nlow", C.c_void_p),
         ("rowptr", C.c_void_p),
-        ("col", C.c_void_p),
-        ("lrowptr", C.c_void_p),
-        ("low", C.c_void_p),
+        ("hslot", C.c_void_p),
         ("hbar", C.c_void_p),
         ("partials", C.c_void_p),
         ("scalars", C.c_void_p),
-        ("counters", C.c_void_p),
         ("scan_tmp", C.c_void_p),
         ("scan_tmp_bytes", C.c_size_t),
     ]
@@ -74,13 +79,15 @@ _SIGNATURES = {
     "dm_plan_bytes": (_SZ, [_I64, _I64, _INT]),
     "dm_plan_init": (_INT, [C.POINTER(DmPlan), _I64, _I64, _INT, _P, _SZ]),
     "dm_stage_cull_count": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _D, _INT, _P]),
-    "dm_stage_build_bars": (_INT, [C.POINTER(DmPlan), _P, _INT, _P]),
+    "dm_stage_build_adjacency": (_INT, [C.POINTER(DmPlan), _P, _INT, _P]),
+    "dm_stage_bar_index": (_INT, [C.POINTER(DmPlan), _P]),
     "dm_bars_pairs": (_INT, [C.POINTER(DmPlan), _P, _P]),
     "dm_bar_midpoints": (_INT, [C.POINTER(DmPlan), _P, _P, _P]),
+    "dm_bar_sizes": (_INT, [C.POINTER(DmPlan), C.POINTER(DmSizeFn), _P, _P]),
     "dm_stage_bar_pass": (_INT, [C.POINTER(DmPlan), _P, C.POINTER(DmSizeFn), _P]),
     "dm_stage_vertex_update": (
         _INT,
-        [C.POINTER(DmPlan), _P, _P, C.POINTER(_P), _INT, _D, _D, _D, _D, _I64, _P, _P, _P],
+        [C.POINTER(DmPlan), _P, _P, C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _D, _D, _D, _D, _I64, _P, _P, _P],
     ),
     "dm_project_points": (_INT, [_P, _P, _I64, _INT, _D, _D, _INT, _P]),
     "dm_force_iteration": (

@@ -1,0 +1,266 @@
+// Stand-alone kernels: fd / fh evaluation, centroids, projection, level-set Newton, cell
+// compaction, sliver kernels, halo selection.
+#pragma once
+#include "dm_device.cuh"
+
+namespace dm {
+
+// =============================================================================================
+// elementwise kernels: fd, fh, centroids, cull
+// =============================================================================================
+template <int DIM>
+__global__ void sdf_eval_kernel(const double* __restrict__ prog, const double* __restrict__ x, int64_t M,
+                                double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double x0, x1, x2;
+  load_pt<DIM>(x, i, x0, x1, x2);
+  out[i] = sdf_eval(prog, DIM, x0, x1, x2);
+}
+
+template <int DIM>
+__global__ void size_eval_kernel(const DmSizeFn f, const double* __restrict__ x, int64_t M,
+                                 double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double x0, x1, x2;
+  load_pt<DIM>(x, i, x0, x1, x2);
+  out[i] = size_eval(f, x0, x1, x2);
+}
+
+template <int DIM>
+__global__ void centroid_kernel(const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
+                                double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int v[4];
+  load_cell<DIM>(t, c, v);
+  double c0, c1, c2;
+  cell_centroid<DIM>(p, v, c0, c1, c2);
+  store_pt<DIM>(out, c, c0, c1, c2);
+}
+
+template <int DIM>
+__global__ void project_kernel(const double* __restrict__ prog, double* __restrict__ p, int64_t N, double deps,
+                               double h0, int level_idx) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  double x0, x1, x2;
+  load_pt<DIM>(p, v, x0, x1, x2);
+  if (sdf_project(prog, DIM, deps, h0, level_idx, x0, x1, x2)) store_pt<DIM>(p, v, x0, x1, x2);
+}
+
+// _improve_level_set_newton (mesh_generator.py:741-759): alpha = 1,1,1/2,1/6,1/24
+template <int DIM>
+__global__ void level_set_newton_kernel(const double* __restrict__ prog, double* __restrict__ p,
+                                        const int32_t* __restrict__ bid, int64_t nb, double deps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const int64_t v = bid[i];
+  double x0, x1, x2;
+  load_pt<DIM>(p, v, x0, x1, x2);
+  double alpha = 1.0;
+  for (int it = 0; it < 5; ++it) {
+    const double d = sdf_eval(prog, DIM, x0, x1, x2);
+    const double g0 = (sdf_eval(prog, DIM, x0 + deps, x1, x2) - d) / deps;
+    const double g1 = (sdf_eval(prog, DIM, x0, x1 + deps, x2) - d) / deps;
+    double g2 = 0.0;
+    double s = 0.0 + g0 * g0;
+    s = s + g1 * g1;
+    if (DIM == 3) {
+      g2 = (sdf_eval(prog, DIM, x0, x1, x2 + deps) - d) / deps;
+      s = s + g2 * g2;
+    }
+    if (s < deps) s = deps;
+    x0 = x0 - alpha * (d * g0 / s);
+    x1 = x1 - alpha * (d * g1 / s);
+    if (DIM == 3) x2 = x2 - alpha * (d * g2 / s);
+    alpha = alpha / (double)(it + 1);
+  }
+  store_pt<DIM>(p, v, x0, x1, x2);
+}
+
+// =============================================================================================
+// cell compaction, sliver kernels, halo selection
+// =============================================================================================
+__global__ void flags_to_int_kernel(const uint8_t* __restrict__ keep, int64_t T, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) out[i] = keep[i] ? 1 : 0;
+}
+template <int C>
+__global__ void compact_cells_kernel(const int32_t* __restrict__ t, const uint8_t* __restrict__ keep,
+                                     const int32_t* __restrict__ pos, int64_t T, int32_t* __restrict__ t_out,
+                                     int32_t* __restrict__ T_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *T_out = pos[T];
+  if (i >= T || !keep[i]) return;
+  const int64_t o = pos[i];
+#pragma unroll
+  for (int k = 0; k < C; ++k) t_out[C * o + k] = t[C * i + k];
+}
+
+__global__ void dihedral_kernel(const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
+                                double min_dh, double max_dh, double* __restrict__ angles,
+                                uint8_t* __restrict__ flags) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int v[4];
+  load_cell<3>(t, c, v);
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double a = dihedral_angle(P, i);
+    if (angles != nullptr) angles[6 * c + i] = a;
+    bad = bad || (a < min_dh) || (a > max_dh);
+  }
+  if (flags != nullptr) flags[c] = bad ? 1 : 0;
+}
+
+__global__ void circumsphere_grad_kernel(const double* __restrict__ p, const int32_t* __restrict__ t,
+                                         const int32_t* __restrict__ ele, int64_t S_, double* __restrict__ grad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S_) return;
+  const int64_t c = ele != nullptr ? ele[i] : i;
+  int v[4];
+  load_cell<3>(t, c, v);
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
+  double g[3];
+  circumsphere_grad(P[0], P[1], P[2], P[3], g);
+  grad[3 * i] = g[0];
+  grad[3 * i + 1] = g[1];
+  grad[3 * i + 2] = g[2];
+}
+
+// fancy-index `p[move] += ...` keeps the LAST sliver for a repeated vertex (mesh_generator.py:274)
+__global__ void sliver_winner_kernel(const int32_t* __restrict__ t, const int32_t* __restrict__ ele, int64_t S_,
+                                     int32_t* __restrict__ winner) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S_) return;
+  atomicMax(winner + t[4 * (int64_t)ele[i]], (int)i);
+}
+// phase 1: displacement of every winning sliver from the PRE-update positions
+__global__ void sliver_delta_kernel(const double* __restrict__ p, const int32_t* __restrict__ t,
+                                    const int32_t* __restrict__ ele, int64_t S_, double step_h0,
+                                    const int32_t* __restrict__ winner, double* __restrict__ delta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S_) return;
+  const int64_t c = ele[i];
+  int v[4];
+  load_cell<3>(t, c, v);
+  if (winner[v[0]] != (int)i) return;
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
+  double g[3];
+  circumsphere_grad(P[0], P[1], P[2], P[3], g);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (isinf(g[k])) g[k] = 1.0;  // mesh_generator.py:254
+  // np.sum(np.abs(g)**2, axis=-1) ** 0.5  (:257)
+  const double nrm = sqrt(fabs(g[0]) * fabs(g[0]) + fabs(g[1]) * fabs(g[1]) + fabs(g[2]) * fabs(g[2]));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) delta[3 * i + k] = step_h0 * (g[k] / nrm);
+}
+// phase 2: apply
+__global__ void sliver_apply_kernel(double* __restrict__ p, const int32_t* __restrict__ t,
+                                    const int32_t* __restrict__ ele, int64_t S_,
+                                    const int32_t* __restrict__ winner, const double* __restrict__ delta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S_) return;
+  const int64_t v0 = t[4 * (int64_t)ele[i]];
+  if (winner[v0] != (int)i) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[3 * v0 + k] = p[3 * v0 + k] + delta[3 * i + k];
+}
+
+// circumball of each cell vs the padded slab boxes of the rank below / above
+// (migration/cpp/cpputils.cpp:85-200, 247-383).  boxes: [min(dim), max(dim)] x 2.
+struct HaloBoxes {
+  double lo[2][3];
+  double hi[2][3];
+  int has[2];
+};
+template <int DIM>
+__global__ void halo_select_kernel(const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
+                                   HaloBoxes hb, uint8_t* __restrict__ flags) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int v[4];
+  load_cell<DIM>(t, c, v);
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k <= DIM; ++k) load_pt<DIM>(p, v[k], P[k][0], P[k][1], P[k][2]);
+  double mn[3], mx[3];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) {
+    mn[j] = P[0][j];
+    mx[j] = P[0][j];
+#pragma unroll
+    for (int k = 1; k <= DIM; ++k) {
+      mn[j] = fmin(mn[j], P[k][j]);
+      mx[j] = fmax(mx[j], P[k][j]);
+    }
+  }
+  // circumcentre relative to vertex 0
+  double cc[3] = {0, 0, 0}, r2;
+  bool degenerate = false;
+  if (DIM == 2) {
+    const double ax = P[1][0] - P[0][0], ay = P[1][1] - P[0][1];
+    const double bx = P[2][0] - P[0][0], by = P[2][1] - P[0][1];
+    const double det = 2.0 * (ax * by - ay * bx);
+    degenerate = det == 0.0;
+    const double a2 = ax * ax + ay * ay, b2 = bx * bx + by * by;
+    cc[0] = (by * a2 - ay * b2) / det;
+    cc[1] = (ax * b2 - bx * a2) / det;
+  } else {
+    const double a[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
+    const double b[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
+    const double cv[3] = {P[3][0] - P[0][0], P[3][1] - P[0][1], P[3][2] - P[0][2]};
+    const double a2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    const double b2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    const double c2 = cv[0] * cv[0] + cv[1] * cv[1] + cv[2] * cv[2];
+    const double bxc[3] = {b[1] * cv[2] - b[2] * cv[1], b[2] * cv[0] - b[0] * cv[2], b[0] * cv[1] - b[1] * cv[0]};
+    const double cxa[3] = {cv[1] * a[2] - cv[2] * a[1], cv[2] * a[0] - cv[0] * a[2], cv[0] * a[1] - cv[1] * a[0]};
+    const double axb[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    const double det = 2.0 * (a[0] * bxc[0] + a[1] * bxc[1] + a[2] * bxc[2]);
+    degenerate = det == 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cc[j] = (a2 * bxc[j] + b2 * cxa[j] + c2 * axb[j]) / det;
+  }
+  if (degenerate) return;  // the reference skips collinear / coplanar cells
+  r2 = cc[0] * cc[0] + cc[1] * cc[1] + cc[2] * cc[2];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) cc[j] += P[0][j];
+  unsigned f = 0;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!hb.has[s]) continue;
+    bool overlap = true;
+    double d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) {
+      overlap = overlap && !(mx[j] < hb.lo[s][j] || mn[j] > hb.hi[s][j]);
+      const double d = cc[j] < hb.lo[s][j] ? hb.lo[s][j] - cc[j] : (cc[j] > hb.hi[s][j] ? cc[j] - hb.hi[s][j] : 0.0);
+      d2 += d * d;
+    }
+    if (overlap && d2 <= r2) f |= (1u << s);
+  }
+  if (f) {
+#pragma unroll
+    for (int k = 0; k <= DIM; ++k) {
+      // byte-wide OR through a 32-bit atomic on the containing word
+      uint8_t* addr = flags + v[k];
+      unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(addr) & ~uintptr_t(3));
+      const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(addr) & 3) * 8;
+      atomicOr(word, f << shift);
+    }
+  }
+}
+
+
+}  // namespace dm

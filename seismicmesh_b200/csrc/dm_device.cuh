@@ -1,0 +1,84 @@
+// Device helpers shared by all kernels: point / cell loads, centroid, bar length.
+#pragma once
+#include <float.h>
+
+#include "dm_common.cuh"
+#include "dm_sdf.cuh"
+
+namespace dm {
+
+template <int DIM>
+__device__ __forceinline__ void load_pt(const double* __restrict__ p, int64_t i, double& x0, double& x1,
+                                        double& x2) {
+  if (DIM == 2) {
+    const double2 v = *reinterpret_cast<const double2*>(p + 2 * i);  // 16-B aligned rows
+    x0 = v.x;
+    x1 = v.y;
+    x2 = 0.0;
+  } else {
+    const double* q = p + 3 * i;
+    x0 = q[0];
+    x1 = q[1];
+    x2 = q[2];
+  }
+}
+template <int DIM>
+__device__ __forceinline__ void store_pt(double* __restrict__ p, int64_t i, double x0, double x1, double x2) {
+  if (DIM == 2) {
+    *reinterpret_cast<double2*>(p + 2 * i) = make_double2(x0, x1);
+  } else {
+    double* q = p + 3 * i;
+    q[0] = x0;
+    q[1] = x1;
+    q[2] = x2;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void load_cell(const int32_t* __restrict__ t, int64_t c, int (&v)[4]) {
+  if (DIM == 3) {
+    const int4 q = *reinterpret_cast<const int4*>(t + 4 * c);  // 16-B aligned rows
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    const int32_t* q = t + 3 * c;
+    v[0] = q[0]; v[1] = q[1]; v[2] = q[2]; v[3] = 0;
+  }
+}
+
+// centroid p[t].sum(1)/(dim+1), vertices added in order (mesh_generator.py:737)
+template <int DIM>
+__device__ __forceinline__ void cell_centroid(const double* __restrict__ p, const int (&v)[4], double& c0,
+                                              double& c1, double& c2) {
+  double a0, a1, a2, b0, b1, b2;
+  load_pt<DIM>(p, v[0], a0, a1, a2);
+#pragma unroll
+  for (int k = 1; k <= DIM; ++k) {
+    load_pt<DIM>(p, v[k], b0, b1, b2);
+    a0 = a0 + b0;
+    a1 = a1 + b1;
+    a2 = a2 + b2;
+  }
+  c0 = a0 / (double)(DIM + 1);
+  c1 = a1 / (double)(DIM + 1);
+  c2 = a2 / (double)(DIM + 1);
+}
+
+// barvec = a - b ; L = sqrt(sum barvec^2) ; L==0 -> eps   (mesh_generator.py:696-698)
+template <int DIM>
+__device__ __forceinline__ double bar_length(double a0, double a1, double a2, double b0, double b1, double b2,
+                                             double& d0, double& d1, double& d2) {
+  d0 = a0 - b0;
+  d1 = a1 - b1;
+  d2 = a2 - b2;
+  double s = d0 * d0 + d1 * d1;
+  if (DIM == 3) s = s + d2 * d2;
+  double L = sqrt(s);
+  if (L == 0.0) L = DBL_EPSILON;
+  return L;
+}
+
+static inline unsigned nblk(int64_t n, int threads) { return (unsigned)(n <= 0 ? 1 : cdiv(n, threads)); }
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace dm

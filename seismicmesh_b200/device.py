@@ -76,14 +76,14 @@ class Plan:
     def keep(self):
         return self._view(self.c.keep, self.T, torch.uint8)
 
-    def rowptr(self):
-        return self._view(self.c.rowptr, (self.N + 1) * 4, torch.int32)
-
-    def col(self, E):
-        return self._view(self.c.col, E * 4, torch.int32)
-
     def hbar(self, E):
         return self._view(self.c.hbar, E * 8, torch.float64)
+
+    def deg(self):
+        return self._view(self.c.deg, self.N * 4, torch.int32)
+
+    def nlow(self):
+        return self._view(self.c.nlow, self.N * 4, torch.int32)
 
     def scalars(self):
         return self._view(self.c.scalars, 8 * 8, torch.float64)

@@ -116,7 +116,7 @@ class ForceLoop:
             self.plan = D.Plan(N, cap, self.dim)
         # the C plan is sized for capacity; the live cell count is set per call
         self.plan.c.T = T
-        self.plan.c.K = self.plan.c.nb * T
+        self.plan.c.K = self.dim * (self.dim + 1) * T
         return self.plan
 
     # -- the iteration --------------------------------------------------------------------
@@ -159,10 +159,11 @@ class ForceLoop:
             return p_out, Ftot
         # ---- staged path: at least one opaque user callable ----
         self.cull(p, t)
-        check(lib.dm_stage_build_bars(C.byref(pl.c), D.ptr(t), 1, st), "build_bars")
+        check(lib.dm_stage_build_adjacency(C.byref(pl.c), D.ptr(t), 1, st), "build_bars")
         f = self.size.struct()
         if not self.size.lowered:
             t0 = time.perf_counter()
+            check(lib.dm_stage_bar_index(C.byref(pl.c), st), "bar_index")
             E = pl.num_bars()
             mid = torch.empty((E, self.dim), dtype=torch.float64, device=p.device)
             check(lib.dm_bar_midpoints(C.byref(pl.c), D.ptr(p), D.ptr(mid), st), "bar_midpoints")
@@ -174,7 +175,7 @@ class ForceLoop:
         progs = D.prog_array(self._progs if fused else [])
         check(
             lib.dm_stage_vertex_update(
-                C.byref(pl.c), D.ptr(p), D.ptr(p_out), progs, len(self._progs) if fused else 0, self.L0mult,
+                C.byref(pl.c), D.ptr(p), D.ptr(p_out), progs, len(self._progs) if fused else 0, C.byref(f), self.L0mult,
                 self.delta_t, self.deps, self.h0, self.nfix, D.ptr(self.fixed_mask), D.ptr(Ftot), st,
             ),
             "vertex_update",
@@ -212,11 +213,24 @@ class ForceLoop:
 
     def bars(self):
         """(E,2) int32 unique bars of the last iteration, in the reference's order."""
+        check(lib.dm_stage_bar_index(C.byref(self.plan.c), D.stream_ptr()), "bar_index")
         E = self.plan.num_bars()
         pairs = torch.empty((E, 2), dtype=torch.int32, device=D.device())
         if E > 0:
             check(lib.dm_bars_pairs(C.byref(self.plan.c), D.ptr(pairs), D.stream_ptr()), "bars_pairs")
         return pairs
+
+
+def bar_sizes(loop):
+    """h of every unique bar of the last iteration, in bar order (tests / diagnostics)."""
+    pl = loop.plan
+    check(lib.dm_stage_bar_index(C.byref(pl.c), D.stream_ptr()), "bar_index")
+    E = pl.num_bars()
+    out = torch.empty(E, dtype=torch.float64, device=D.device())
+    f = loop.size.struct()
+    if E > 0:
+        check(lib.dm_bar_sizes(C.byref(pl.c), C.byref(f), D.ptr(out), D.stream_ptr()), "bar_sizes")
+    return out
 
 
 def compact_cells(t, keep, dim):
@@ -243,7 +257,8 @@ def unique_bars(t, N=None):
     pl = D.Plan(N, td.shape[0], dim)
     st = D.stream_ptr()
     check(lib.dm_stage_cull_count(C.byref(pl.c), None, None, D.ptr(td), 0.0, 0, st), "cull_count")
-    check(lib.dm_stage_build_bars(C.byref(pl.c), D.ptr(td), 0, st), "build_bars")
+    check(lib.dm_stage_build_adjacency(C.byref(pl.c), D.ptr(td), 0, st), "build_bars")
+    check(lib.dm_stage_bar_index(C.byref(pl.c), st), "bar_index")
     E = pl.num_bars()
     pairs = torch.empty((E, 2), dtype=torch.int32, device=td.device)
     if E > 0:

@@ -216,7 +216,9 @@ def test_force_iteration_vs_reference(sm, name):
     assert np.array_equal(bars, g["bars"])                        # bars: bit exact
     E = len(bars)
     assert loop.plan.num_bars() == E
-    assert np.array_equal(loop.plan.hbar(E).cpu().numpy(), g["hbars"])   # fh at midpoints: bit exact
+    from seismicmesh_b200.engine import bar_sizes
+
+    assert np.array_equal(bar_sizes(loop).cpu().numpy(), g["hbars"])   # fh at midpoints: bit exact
     assert relerr(Ftot.cpu().numpy(), g["Ftot"]) < TOL
     assert relerr(g["p"] + 0.30 * Ftot.cpu().numpy(), g["p_upd"]) < TOL
     assert relerr(p_new.cpu().numpy(), g["p_new"]) < PTOL
