@@ -82,26 +82,46 @@ template <int DIM>
 struct HashCfg {
   static constexpr int LOGH = DIM == 3 ? 6 : 5;
   static constexpr int H = 1 << LOGH;       // slots per vertex (3-D: 64, 2-D: 32)
-  static constexpr int MAXLOAD = H - H / 4;  // beyond this the vertex takes the slow path
+  static constexpr int MAXLOAD = H - H / 4 - 4;  // beyond this the vertex takes the slow path
 };
 
 // thread-private open-addressing set; slot k of thread tid lives at col[k * AB_THREADS]
-// (bank = tid % 32 for every k -> conflict free).  Returns false if the table is too full.
+// (bank = tid % 32 for every k -> conflict free).  ~80 % of the candidates are duplicates that
+// hit on the first probe, so that is the straight-line path; new keys / collisions branch out.
 template <int DIM>
-__device__ __forceinline__ bool hash_insert(int32_t* col, int x, int& m) {
+__device__ __forceinline__ void hash_insert(int32_t* col, int x, int& m) {
   constexpr int LOGH = HashCfg<DIM>::LOGH, H = HashCfg<DIM>::H;
   unsigned h = ((unsigned)x * 2654435761u) >> (32 - LOGH);
-  while (true) {
-    const int cur = col[h * AB_THREADS];
-    if (cur == x) return true;
-    if (cur == -1) {
-      if (m >= HashCfg<DIM>::MAXLOAD) return false;
+  int cur = col[h * AB_THREADS];
+  if (cur != x) {
+    bool dup = false;
+    while (cur != -1 && !dup) {
+      h = (h + 1) & (H - 1);
+      cur = col[h * AB_THREADS];
+      dup = cur == x;
+    }
+    if (!dup) {
       col[h * AB_THREADS] = x;
       ++m;
-      return true;
     }
-    h = (h + 1) & (H - 1);
   }
+}
+
+// the DIM candidates one incident cell contributes to vertex v: every OTHER position of the cell.
+// Branch-free: the position holding v is replaced by the last id.  A cell that repeats v (never
+// produced by a Delaunay code, but legal input for unique_edges) yields the self bar (v,v),
+// exactly like the reference's pair list: reported through `selfbar`.
+template <int DIM>
+__device__ __forceinline__ void cell_candidates(const int (&ids)[4], int v, int (&x)[3], bool& selfbar) {
+  const int last = ids[DIM];
+  int self = last == v ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) {
+    const bool isv = ids[j] == v;
+    self += isv ? 1 : 0;
+    x[j] = isv ? last : ids[j];
+  }
+  selfbar = selfbar || self >= 2;
 }
 
 // the neighbours a cell contributes to vertex v: every OTHER position of the cell (a repeated
@@ -149,22 +169,43 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_build_kernel(const int32
                                                                      int32_t* __restrict__ nlow,
                                                                      int32_t* __restrict__ counters) {
   constexpr int H = HashCfg<DIM>::H;
+  constexpr int G = 4;  // incident cells gathered per batch (memory-level parallelism)
   __shared__ int32_t tab[H * AB_THREADS];
   __shared__ int sm[33];
+  __shared__ int heavy[AB_THREADS];
+  __shared__ int nheavy;
+  __shared__ int hcount[3];
   const int tid = threadIdx.x;
   const int64_t v = (int64_t)blockIdx.x * AB_THREADS + tid;
   int m = 0, lo = 0;
+  if (tid == 0) nheavy = 0;
+  __syncthreads();
   if (v < N) {
     const int s = inc_start(inc_end, v), e = inc_end[v];
     int32_t* col = tab + tid;
-#pragma unroll 8
+#pragma unroll
     for (int k = 0; k < H; ++k) col[k * AB_THREADS] = -1;
-    bool ok = true;
-    for (int k = s; k < e && ok; ++k) {
-      int ids[4];
-      load_cell<DIM>(t, inc[k], ids);
-      for_each_neighbour<DIM>(ids, (int)v, [&](int x) { ok = ok && hash_insert<DIM>(col, x, m); });
+    bool ok = true, selfbar = false;
+    for (int k = s; k < e && ok; k += G) {
+      int c[G];
+      int ids[G][4];
+#pragma unroll
+      for (int u = 0; u < G; ++u) c[u] = k + u < e ? inc[k + u] : -1;
+#pragma unroll
+      for (int u = 0; u < G; ++u)
+        if (c[u] >= 0) load_cell<DIM>(t, c[u], ids[u]);
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        if (c[u] >= 0) {
+          int x[3];
+          cell_candidates<DIM>(ids[u], (int)v, x, selfbar);
+#pragma unroll
+          for (int j = 0; j < DIM; ++j) hash_insert<DIM>(col, x[j], m);
+        }
+      }
+      ok = m <= HashCfg<DIM>::MAXLOAD;  // at most G*DIM = 12 new keys per batch: the table never fills
     }
+    if (ok && selfbar) hash_insert<DIM>(col, (int)v, m);
     int32_t* row = adj + (int64_t)DIM * s;
     if (ok) {
       // compact the occupied slots to the top of the column, then insertion-sort them
@@ -192,14 +233,88 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_build_kernel(const int32
         lo += (x < (int)v) ? 1 : 0;
       }
     } else {
-      m = adjacency_row_slow<DIM>(t, inc, s, e, (int)v, row);
-      for (int i = 0; i < m; ++i) lo += (row[i] < (int)v) ? 1 : 0;
+      // neighbour set too large for the private hash (hull / hub vertices): queue the vertex for
+      // the cooperative path below
+      heavy[atomicAdd(&nheavy, 1)] = tid;
+      m = 0;
     }
-    deg[v] = m;
-    nlow[v] = lo;
+    if (ok) {
+      deg[v] = m;
+      nlow[v] = lo;
+    }
+  }
+  __syncthreads();
+  // ---- heavy vertices: the whole block de-duplicates one vertex at a time by rank counting ----
+  const int nh = nheavy;
+  int heavy_bars = 0;
+  for (int ih = 0; ih < nh; ++ih) {
+    const int64_t hv = (int64_t)blockIdx.x * AB_THREADS + heavy[ih];
+    const int s = inc_start(inc_end, hv), e = inc_end[hv];
+    const int n = DIM * (e - s);
+    int32_t* row = adj + (int64_t)DIM * s;
+    __syncthreads();  // tab / counters free
+    if (tid == 0) {
+      hcount[0] = 0;
+      hcount[1] = 0;
+      hcount[2] = 0;
+    }
+    if (2 * (n + 1) <= H * AB_THREADS) {
+      int32_t* val = tab;
+      int32_t* first = tab + (n + 1);
+      __syncthreads();
+      for (int k = s + tid; k < e; k += AB_THREADS) {
+        int ids[4], x[3];
+        bool sb = false;
+        load_cell<DIM>(t, inc[k], ids);
+        cell_candidates<DIM>(ids, (int)hv, x, sb);
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) val[(k - s) * DIM + j] = x[j];
+        if (sb) hcount[2] = 1;
+      }
+      __syncthreads();
+      const int nn = n + (hcount[2] ? 1 : 0);
+      if (tid == 0 && hcount[2]) val[n] = (int)hv;
+      __syncthreads();
+      for (int i = tid; i < nn; i += AB_THREADS) {
+        const int x = val[i];
+        int f = 1;
+        for (int j = 0; j < i; ++j)
+          if (val[j] == x) {
+            f = 0;
+            break;
+          }
+        first[i] = f;
+      }
+      __syncthreads();
+      for (int i = tid; i < nn; i += AB_THREADS) {
+        if (!first[i]) continue;
+        const int x = val[i];
+        int r = 0;
+        for (int j = 0; j < nn; ++j) r += (first[j] && val[j] < x) ? 1 : 0;
+        row[r] = x;
+        atomicAdd(&hcount[0], 1);
+        if (x < (int)hv) atomicAdd(&hcount[1], 1);
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if (tid == 0) {  // beyond the cooperative capacity: sequential last resort
+        const int mm = adjacency_row_slow<DIM>(t, inc, s, e, (int)hv, row);
+        int ll = 0;
+        for (int i = 0; i < mm; ++i) ll += (row[i] < (int)hv) ? 1 : 0;
+        hcount[0] = mm;
+        hcount[1] = ll;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      deg[hv] = hcount[0];
+      nlow[hv] = hcount[1];
+      heavy_bars += hcount[0] - hcount[1];
+    }
   }
   int total;
-  block_exclusive_scan(m - lo, total, sm);  // unique bars owned by this block's vertices
+  block_exclusive_scan(m - lo + heavy_bars, total, sm);  // unique bars owned by this block's vertices
   if (tid == 0 && total) atomicAdd(counters, total);
 }
 
