@@ -250,10 +250,22 @@ def main():
     K, W = args.steps, args.warmup
 
     # ---- set-up (untimed): points + ONE host Delaunay per rank (weak scaling: one slab per GPU) ----
-    p, dim = make_points(workload, h0, seed=rank, shift=2.0 * rank)
+    layout = None
+    if world == 1:
+        p, dim = make_points(workload, h0)
+        dom = sm.Ball([0.0, 0.0, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 0.0], 1.0)
+        n_owned = len(p)
+    else:
+        # weak scaling: a cylinder (3-D) / rectangle (2-D) of `world` slabs along axis 1, each slab
+        # with the volume of the N=1 ball / disk; every rank meshes its slab + ghost layers
+        from seismicmesh_b200.parallel import make_slab_workload
+
+        p, dim, dom, layout = make_slab_workload(workload, h0, rank, world)
+        n_owned = layout.n_owned
     t, t_delaunay = triangulate(p)
+    if layout is not None:  # cells made only of ghost vertices belong to the neighbours
+        t = np.ascontiguousarray(t[(t < n_owned).any(axis=1)])
     N, T = len(p), len(t)
-    dom = (sm.Ball([0.0, 2.0 * rank, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 2.0 * rank], 1.0))
     geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
     loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
 
@@ -266,7 +278,7 @@ def main():
     if world > 1:
         from seismicmesh_b200.parallel import RingHalo
 
-        halo = RingHalo(p_dev, t_dev, dim, h0, axis=1, rank=rank, world=world)
+        halo = RingHalo(layout, dim, p_dev.device, rank=rank, world=world)
 
     def one_step():
         loop.iterate(p_dev, t_dev, p_out=p_out)
@@ -301,11 +313,11 @@ def main():
         tt = torch.tensor([total_ms], dtype=torch.float64, device=p_dev.device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-        nn = torch.tensor([N], dtype=torch.float64, device=p_dev.device)
+        nn = torch.tensor([n_owned], dtype=torch.float64, device=p_dev.device)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
         N_all = int(nn.item())
     else:
-        N_all = N
+        N_all = n_owned
     clocks = sampler.stop() if rank == 0 else None
     value = N_all * K / (total_ms * 1e-3)
 
@@ -393,7 +405,7 @@ def main():
 
     # ---- CPU baseline: the reference's loop body (oracle port) on one host core, same (p, t) ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         step, kind = oracle_step_fn(workload, h0, dim)
         p0 = make_points(workload, h0, seed=0)[0] if world > 1 else p
         t0_ = triangulate(p0)[0] if world > 1 else t
@@ -414,7 +426,9 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"{workload}_h0={h0:g}", "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
                    "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
-                   "parallelism": f"slab x{world}" if world > 1 else "single"},
+                   "parallelism": (f"{world} slabs along axis 1 (owned+ghost per GPU), NCCL P2P halo exchange per step; "
+                                   f"halo bytes/step/rank={halo.bytes_per_exchange}") if world > 1 else "single",
+                   "N_owned_total": N_all},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},

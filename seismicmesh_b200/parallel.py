@@ -116,6 +116,45 @@ class RingHalo:
             p[self.ghost_a] = self.recv_a
 
 
+def make_slab_workload(workload, h0, rank, world, halo_layers=5, seed=0):
+    """Synthetic weak-scaling input for bench.py --gpus N: `world` slabs along axis 1 of a
+    cylinder (3-D, axis = y) / rectangle (2-D), each slab with the volume (area) of the unit ball
+    (disk), i.e. the per-GPU work of the N=1 workload.  Returns (local points [owned|ghosts],
+    dim, domain object, SlabLayout).  The reference pads slab extents by 5*h0
+    (mesh_generator.py:873-874), hence halo_layers=5.  Every rank builds the same global jittered
+    lattice (seeded), so owners and ghost holders agree on positions without communication."""
+    from . import geometry
+
+    if workload == "ball":
+        dim, ell = 3, 4.0 / 3.0
+    else:
+        dim, ell = 2, np.pi / 2.0
+    Ly = world * ell
+    lo = [-1.0] * dim
+    hi = [1.0] * dim
+    lo[1], hi[1] = -Ly / 2, Ly / 2
+    axes = [np.arange(int(np.ceil((b + h0 - a) / h0)), dtype=float) * h0 + a for a, b in zip(lo, hi)]
+    g = [a.copy() for a in np.meshgrid(*axes, indexing="ij")]
+    g[1][1::2] += h0 / 2
+    if dim == 3:
+        g[2][1::2] += h0 / 2
+    p = np.stack([a.ravel() for a in g], axis=1)
+    if dim == 3:
+        dom = geometry.Cylinder(h=Ly, r=1.0)
+        rad = np.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2)
+        inside = (rad - 1.0 < 0.1 * h0) & (np.abs(p[:, 1]) - Ly / 2 < 0.1 * h0)
+    else:
+        dom = geometry.Rectangle((-1.0, 1.0, -Ly / 2, Ly / 2))
+        inside = (np.abs(p[:, 0]) - 1.0 < 0.1 * h0) & (np.abs(p[:, 1]) - Ly / 2 < 0.1 * h0)
+    p = p[inside]
+    rng = np.random.default_rng(seed)
+    p = p + rng.uniform(-0.1 * h0, 0.1 * h0, p.shape)
+    faces = slab_bounds(-Ly / 2 - h0, Ly / 2 + h0, world)
+    faces[1:-1] = np.linspace(-Ly / 2, Ly / 2, world + 1)[1:-1]
+    layout = slab_partition(p[:, 1], faces, rank, width=halo_layers * h0)
+    return np.ascontiguousarray(p[layout.local_ids]), dim, dom, layout
+
+
 def allreduce_force_scale(sum_L, sum_h, group=None):
     """Optional: global (sum L^d, sum h^d) so that every slab uses the single-GPU force scale
     (the reference uses rank-local sums, mesh_generator.py:700)."""
