@@ -155,12 +155,13 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
     hs = 8 * E if grid_fh else 0
     return {
         "memset_zero_region": 4 * (N + 1),
-        "cull_count": 4 * c * T + 8 * d * N + T + 4 * (N + 1),
-        "scan_incidence": 8 * (N + 1),
-        "inc_fill": 4 * c * T + T + 4 * c * Tk + 4 * (N + 1),
-        "adjacency_build": 4 * c * Tk + 4 * c * T + 4 * (N + 1) + 8 * E + 8 * N,
-        "bar_pass+scale": 8 * d * N + 4 * E + 12 * N + hs,
-        "vertex_update+maxdp": 16 * d * N + 8 * E + 12 * N + hs,
+        # t and p read once, keep flags + the kept cells handed to the bar stage written once
+        "cull_scatter": 4 * c * T + 8 * d * N + T + 4 * c * Tk,
+        # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends)
+        "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E,
+        "adjacency_heavy": 0,
+        "bar_pass+scale": 8 * d * N + 4 * E + 8 * N + hs,
+        "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + 2 * hs,
     }
 
 
@@ -432,7 +433,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 6 * K,
+        "gpu_launches": 5 * K,
         "roofline": roofline, "cpu_baseline": cpu,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
     }

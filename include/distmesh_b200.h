@@ -141,32 +141,42 @@ int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64
 /* ---------------------------------------------------------------------------------------------
  * The force iteration (mesh_generator.py:482, 497-521) as a plan over a caller workspace
  *
- * Per-iteration device structures (all int32 / float64, carved from the workspace):
+ * Per-iteration device structures (all int32 / float64, carved from the workspace).  The layout is
+ * built around the observation that every scattered 4..16-byte access costs one 128-byte line
+ * wavefront: per-vertex structures are fixed-stride, line-aligned rows.
  *   keep     (T)            cull flags
- *   inc_end  (N+1)          kept cells incident to each vertex: count -> list start -> list end
- *   inc      ((dim+1)*T)    incident cell ids grouped by vertex
- *   adj      (K)            sorted unique neighbour ids of vertex v at adj[dim*inc_start(v) ...],
- *                           deg[v] of them, the first nlow[v] are < v.  The upper parts (>= v) of
- *                           all rows in vertex order ARE the reference's sorted unique (E,2) bars.
+ *   cnt      (N+1)          kept cells incident to each vertex
+ *   bucket   (N*CAP)        per vertex: the OTHER vertex ids of each incident kept cell
+ *                           (3-D: CAP=48 entries of 4 ints; 2-D: CAP=16 entries of 2 ints)
+ *   ovf_v/e  ((dim+1)*T)    spill records (vertex, entry) of buckets that overflowed
+ *   hv       (N)            vertices handled by the heavy path (spilled / very high degree)
+ *   adj      (N*RS)         sorted unique neighbour ids of vertex v at adj[v*RS ...] (RS = 32 ints
+ *                           in 3-D = one 128-B line, 16 in 2-D); degs[v] = {deg, nlow}: the first
+ *                           nlow are < v.  deg > RS: the row lives in `heap` at offset adj[v*RS].
+ *                           The upper parts (>= v) of all rows in vertex order ARE the reference's
+ *                           sorted unique (E,2) bars.
  *   rowptr   (N+1)          bar ids = exclusive scan of deg-nlow (built on demand)
- *   hslot    (K)            gridded fh at the midpoint of bar (v,w), stored at its upper slot
+ *   hslot    (N*RS + heap)  gridded fh at the midpoint of bar (v,w), stored at its upper slot
  *   hbar     (K/2)          fh per bar id, for DM_SIZE_EXTERNAL
  * ------------------------------------------------------------------------------------------- */
 typedef struct DmPlan {
   int64_t N, T;      /* vertices, cells handed over by the host Delaunay */
   int32_t dim, _pad0;
-  int64_t K;         /* dim*(dim+1)*T : capacity of the directed adjacency */
+  int64_t K;         /* dim*(dim+1)*T : directed (vertex, neighbour) candidates */
   uint8_t *keep;
-  void *zero_base;   /* [inc_end | scan descriptors | sync | counters]: ONE memset per iteration */
+  void *zero_base;   /* [cnt | sync | counters]: ONE memset per iteration */
   size_t zero_bytes;
-  int32_t *inc_end;
-  uint64_t *scan_desc;
-  int32_t *sync;     /* [0] scan ticket [1] bar-pass blocks done [2] update blocks done */
-  int32_t *counters; /* [0]=E unique bars [1]=T' kept cells */
-  int32_t *inc;
+  int32_t *cnt;
+  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done */
+  int32_t *counters; /* [0]=E unique bars [1]=T' kept cells [2]=spill records [3]=heavy vertices
+                        [4]=heap cursor (ints) */
+  void *bucket;
+  int32_t *ovf_v;
+  void *ovf_e;
+  int32_t *hv;
   int32_t *adj;
-  int32_t *deg;
-  int32_t *nlow;
+  int32_t *heap;
+  int32_t *degs;     /* (N) pairs {deg, nlow} */
   int32_t *rowptr;
   double *hslot;
   double *hbar;
@@ -180,13 +190,14 @@ size_t dm_plan_bytes(int64_t N, int64_t T, int dim);
 /* carve `ws` (device, 256-B aligned, >= dm_plan_bytes) into *plan (host struct). */
 int dm_plan_init(DmPlan *plan_host, int64_t N, int64_t T, int dim, void *ws, size_t ws_bytes);
 
-/* stage A: keep flags (fd on centroids) + incident-cell counts per vertex.
+/* stage A: keep flags (fd on centroids) + scatter of every kept cell to its vertices' buckets.
  * prog == NULL: plan->keep was filled by the caller (opaque fd), only count.
  * use_keep == 0: every cell is kept (plain _get_edges(t) semantics, mesh_generator.py:680-688). */
 int dm_stage_cull_count(const DmPlan *plan_host, const double *prog, const double *p,
                         const int32_t *t, double geps, int use_keep, void *stream);
 /* stage B: sorted unique neighbour rows (replaces _fast_geometry.unique_edges,
- * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs). */
+ * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs).  `t` and `use_keep` are unused since
+ * stage A already scattered the kept cells (kept for call compatibility). */
 int dm_stage_build_adjacency(const DmPlan *plan_host, const int32_t *t, int use_keep, void *stream);
 /* bar ids (rowptr) for dm_bars_pairs / dm_bar_midpoints / DM_SIZE_EXTERNAL. */
 int dm_stage_bar_index(const DmPlan *plan_host, void *stream);

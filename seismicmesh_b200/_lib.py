@@ -41,14 +41,16 @@ class DmPlan(C.Structure):
         ("keep", C.c_void_p),
         ("zero_base", C.c_void_p),
         ("zero_bytes", C.c_size_t),
-        ("inc_end", C.c_void_p),
-        ("scan_desc", C.c_void_p),
+        ("cnt", C.c_void_p),
         ("sync", C.c_void_p),
         ("counters", C.c_void_p),
-        ("inc", C.c_void_p),
+        ("bucket", C.c_void_p),
+        ("ovf_v", C.c_void_p),
+        ("ovf_e", C.c_void_p),
+        ("hv", C.c_void_p),
         ("adj", C.c_void_p),
-        ("deg", C.c_void_p),
-        ("nlow", C.c_void_p),
+        ("heap", C.c_void_p),
+        ("degs", C.c_void_p),
         ("rowptr", C.c_void_p),
         ("hslot", C.c_void_p),
         ("hbar", C.c_void_p),

@@ -12,6 +12,7 @@
 //   dm_aux.cuh       stand-alone kernels (fd/fh eval, projection, compaction, sliver, halo)
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dm_aux.cuh"
@@ -50,10 +51,14 @@ int check_size_fn(const DmSizeFn* f, int dim) {
   return DM_OK;
 }
 
-size_t plan_layout(DmPlan* pl, int64_t N, int64_t T, int dim, char* base) {
-  const int64_t K = (int64_t)dim * (dim + 1) * T;
+template <int DIM>
+size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
+  constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS;
+  const size_t esz = sizeof(typename PCfg<DIM>::entry_t);
+  const int64_t K = (int64_t)DIM * (DIM + 1) * T;
   const int64_t K1 = K > 0 ? K : 1, T1 = T > 0 ? T : 1;
-  const int64_t nblocks = cdiv(N > 0 ? N : 1, PL_THREADS < AB_THREADS ? PL_THREADS : AB_THREADS);
+  const int64_t heap_ints = K1 + 4 * (N + 1);
+  const int64_t nblocks = cdiv(N > 0 ? N : 1, PL_THREADS);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* ptr = base ? base + off : nullptr;
@@ -61,20 +66,22 @@ size_t plan_layout(DmPlan* pl, int64_t N, int64_t T, int dim, char* base) {
     return ptr;
   };
   char* keep = take((size_t)T1);
-  // ---- zero region (contiguous): inc_end | scan descriptors | sync | counters
+  // ---- zero region (contiguous): cnt | sync | counters : ONE memset per iteration
   const size_t z0 = off;
-  char* inc_end = take((size_t)(N + 1) * 4);
-  char* desc = take((size_t)(scan_tiles(N) + 2) * 8);
+  char* cnt = take((size_t)(N + 1) * 4);
   char* sync = take(8 * 4);
   char* counters = take(8 * 4);
   const size_t zbytes = off - z0;
   // ----
-  char* inc = take((size_t)(dim + 1) * T1 * 4);
-  char* adj = take((size_t)K1 * 4);
-  char* deg = take((size_t)(N + 1) * 4);
-  char* nlow = take((size_t)(N + 1) * 4);
+  char* bucket = take((size_t)(N + 1) * CAP * esz);
+  char* ovf_v = take((size_t)(DIM + 1) * T1 * 4);
+  char* ovf_e = take((size_t)(DIM + 1) * T1 * esz);
+  char* hv = take((size_t)(N + 1) * 4);
+  char* adj = take((size_t)(N + 1) * RS * 4);
+  char* heap = take((size_t)heap_ints * 4);
+  char* degs = take((size_t)(N + 1) * 8);
   char* rowptr = take((size_t)(N + 1) * 4);
-  char* hslot = take((size_t)K1 * 8);
+  char* hslot = take((size_t)((N + 1) * RS + heap_ints) * 8);
   char* hbar = take((size_t)(K1 / 2 + 1) * 8);
   char* partials = take((size_t)(2 * nblocks) * 8);
   char* scalars = take(8 * 8);
@@ -83,20 +90,22 @@ size_t plan_layout(DmPlan* pl, int64_t N, int64_t T, int dim, char* base) {
   if (pl) {
     pl->N = N;
     pl->T = T;
-    pl->dim = dim;
+    pl->dim = DIM;
     pl->_pad0 = 0;
     pl->K = K;
     pl->keep = reinterpret_cast<uint8_t*>(keep);
-    pl->zero_base = inc_end;
+    pl->zero_base = cnt;
     pl->zero_bytes = zbytes;
-    pl->inc_end = reinterpret_cast<int32_t*>(inc_end);
-    pl->scan_desc = reinterpret_cast<uint64_t*>(desc);
+    pl->cnt = reinterpret_cast<int32_t*>(cnt);
     pl->sync = reinterpret_cast<int32_t*>(sync);
     pl->counters = reinterpret_cast<int32_t*>(counters);
-    pl->inc = reinterpret_cast<int32_t*>(inc);
+    pl->bucket = bucket;
+    pl->ovf_v = reinterpret_cast<int32_t*>(ovf_v);
+    pl->ovf_e = ovf_e;
+    pl->hv = reinterpret_cast<int32_t*>(hv);
     pl->adj = reinterpret_cast<int32_t*>(adj);
-    pl->deg = reinterpret_cast<int32_t*>(deg);
-    pl->nlow = reinterpret_cast<int32_t*>(nlow);
+    pl->heap = reinterpret_cast<int32_t*>(heap);
+    pl->degs = reinterpret_cast<int32_t*>(degs);
     pl->rowptr = reinterpret_cast<int32_t*>(rowptr);
     pl->hslot = reinterpret_cast<double*>(hslot);
     pl->hbar = reinterpret_cast<double*>(hbar);
@@ -108,13 +117,26 @@ size_t plan_layout(DmPlan* pl, int64_t N, int64_t T, int dim, char* base) {
   return off;
 }
 
+size_t plan_layout(DmPlan* pl, int64_t N, int64_t T, int dim, char* base) {
+  return dim == 2 ? plan_layout_dim<2>(pl, N, T, base) : plan_layout_dim<3>(pl, N, T, base);
+}
+
+template <int DIM>
+Rows<DIM> rows_of(const DmPlan* pl) {
+  Rows<DIM> R;
+  R.adj = pl->adj;
+  R.heap = pl->heap;
+  R.degs = reinterpret_cast<const int2*>(pl->degs);
+  R.N = pl->N;
+  return R;
+}
+
 template <int DIM>
 int launch_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn& f, int hmode, double* mid, cudaStream_t st) {
   const unsigned nb = nblk(pl->N, PL_THREADS);
 #define DM_BP(H)                                                                                              \
-  bar_pass_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, pl->inc_end, pl->adj, pl->deg, pl->nlow, pl->rowptr, \
-                                                     pl->N, pl->hslot, pl->hbar, mid, pl->partials,           \
-                                                     pl->sync + 1, pl->scalars)
+  bar_pass_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, rows_of<DIM>(pl), pl->rowptr, pl->N, pl->hslot,     \
+                                                     pl->hbar, mid, pl->partials, pl->sync + 1, pl->scalars)
   switch (hmode) {
     case 0: DM_BP(0); break;
     case 1: DM_BP(1); break;
@@ -131,16 +153,45 @@ int launch_vertex_update(const DmPlan* pl, const double* p, double* p_out, const
                          const uint8_t* fixed, double* Ftot, cudaStream_t st) {
   const unsigned nb = nblk(pl->N, PL_THREADS);
 #define DM_VU(H)                                                                                                  \
-  vertex_update_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, p_out, pl->inc_end, pl->adj, pl->deg, pl->nlow,    \
-                                                          pl->rowptr, pl->hslot, pl->hbar, pl->scalars, pl->N, lv, \
-                                                          L0mult, delta_t, deps, h0, nfix, fixed, Ftot,            \
-                                                          pl->partials, pl->sync + 2, pl->scalars)
+  vertex_update_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, p_out, rows_of<DIM>(pl), pl->rowptr, pl->hslot,   \
+                                                          pl->hbar, pl->scalars, pl->N, lv, L0mult, delta_t, deps, \
+                                                          h0, nfix, fixed, Ftot, pl->partials, pl->sync + 2,       \
+                                                          pl->scalars)
   switch (hmode) {
     case 0: DM_VU(0); break;
     case 1: DM_VU(1); break;
     default: DM_VU(2); break;
   }
 #undef DM_VU
+  return (int)cudaGetLastError();
+}
+
+template <int DIM>
+static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
+                              int mode, cudaStream_t st) {
+  typedef typename PCfg<DIM>::entry_t entry_t;
+  cull_scatter_kernel<DIM, true><<<nblk(pl->T, PL_THREADS), PL_THREADS, 0, st>>>(
+      prog, p, t, pl->T, geps, mode, pl->keep, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
+      static_cast<entry_t*>(pl->ovf_e), pl->counters);
+  return (int)cudaGetLastError();
+}
+
+template <int DIM>
+static int stage_adjacency(const DmPlan* pl, cudaStream_t st) {
+  typedef typename PCfg<DIM>::entry_t entry_t;
+  constexpr int VPB = AB_THREADS / PCfg<DIM>::G;
+  const int64_t N = pl->N;
+  int2* degs = reinterpret_cast<int2*>(pl->degs);
+  adjacency_kernel<DIM><<<nblk(N, VPB), AB_THREADS, 0, st>>>(pl->cnt, static_cast<const entry_t*>(pl->bucket), N, pl->adj,
+                                                             pl->heap, degs, pl->hv, pl->counters);
+  mark("adjacency", st);
+#ifdef DM_DEBUG_HEAVY
+  if (getenv("DM_SKIP_HEAVY")) return (int)cudaGetLastError();
+#endif
+  adjacency_heavy_kernel<DIM><<<HV_BLOCKS, HV_THREADS, 0, st>>>(pl->cnt, static_cast<const entry_t*>(pl->bucket), pl->ovf_v,
+                                                                static_cast<const entry_t*>(pl->ovf_e), N, pl->adj,
+                                                                pl->heap, degs, pl->hv, pl->counters);
+  mark("adjacency_heavy", st);
   return (int)cudaGetLastError();
 }
 
@@ -151,7 +202,7 @@ int launch_vertex_update(const DmPlan* pl, const double* p, double* p_out, const
 // =============================================================================================
 extern "C" {
 
-const char* dm_version(void) { return "distmesh_b200 0.2 (sm_100a)"; }
+const char* dm_version(void) { return "distmesh_b200 0.3 (sm_100a)"; }
 
 size_t dm_scan_scratch_bytes(int64_t n) { return scan_scratch_bytes(n); }
 
@@ -204,11 +255,11 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (T == 0) return DM_OK;
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
-    cull_count_kernel<2><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(prog, p, t, T, geps, 0, keep, nullptr,
-                                                                            nullptr);
+    cull_scatter_kernel<2, false><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   else
-    cull_count_kernel<3><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(prog, p, t, T, geps, 0, keep, nullptr,
-                                                                            nullptr);
+    cull_scatter_kernel<3, false><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }
@@ -321,57 +372,33 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
   mark("memset_zero_region", st);
   if (pl->T == 0) return DM_OK;
   const int mode = !use_keep ? 2 : (prog ? 0 : 1);
-  const unsigned nb = nblk(pl->T, PL_THREADS);
-  if (pl->dim == 2)
-    cull_count_kernel<2><<<nb, PL_THREADS, 0, st>>>(prog, p, t, pl->T, geps, mode, pl->keep, pl->inc_end, pl->counters);
-  else
-    cull_count_kernel<3><<<nb, PL_THREADS, 0, st>>>(prog, p, t, pl->T, geps, mode, pl->keep, pl->inc_end, pl->counters);
-  mark("cull_count", st);
-  DM_LAUNCH_CHECK();
-  return DM_OK;
+  const int rc = pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t, geps, mode, st)
+                              : stage_cull_scatter<3>(pl, prog, p, t, geps, mode, st);
+  mark("cull_scatter", st);
+  return rc;
 }
 
 int dm_stage_build_adjacency(const DmPlan* pl, const int32_t* t, int use_keep, void* stream) {
-  if (!pl || (!t && pl->T > 0)) return DM_ERR_ARG;
+  (void)t;
+  (void)use_keep;  // the kept cells were already scattered to the vertex buckets by stage A
+  if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  const int64_t N = pl->N, T = pl->T;
-  int rc = scan_launch(pl->inc_end, pl->inc_end, N, reinterpret_cast<unsigned long long*>(pl->scan_desc), pl->sync, st);
-  if (rc) return rc;
-  mark("scan_incidence", st);
-  const uint8_t* keep = use_keep ? pl->keep : nullptr;
-  if (T > 0) {
-    if (pl->dim == 2)
-      inc_fill_kernel<2><<<nblk(T, PL_THREADS), PL_THREADS, 0, st>>>(t, T, keep, pl->inc_end, pl->inc);
-    else
-      inc_fill_kernel<3><<<nblk(T, PL_THREADS), PL_THREADS, 0, st>>>(t, T, keep, pl->inc_end, pl->inc);
-  }
-  mark("inc_fill", st);
-  if (pl->dim == 2)
-    adjacency_build_kernel<2><<<nblk(N, AB_THREADS), AB_THREADS, 0, st>>>(t, pl->inc_end, pl->inc, N, pl->adj, pl->deg,
-                                                                          pl->nlow, pl->counters);
-  else
-    adjacency_build_kernel<3><<<nblk(N, AB_THREADS), AB_THREADS, 0, st>>>(t, pl->inc_end, pl->inc, N, pl->adj, pl->deg,
-                                                                          pl->nlow, pl->counters);
-  mark("adjacency_build", st);
-  DM_LAUNCH_CHECK();
-  return DM_OK;
+  return pl->dim == 2 ? stage_adjacency<2>(pl, st) : stage_adjacency<3>(pl, st);
 }
 
 int dm_stage_bar_index(const DmPlan* pl, void* stream) {
   if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  upper_count_kernel<<<nblk(pl->N, 256), 256, 0, st>>>(pl->deg, pl->nlow, pl->N, pl->rowptr);
+  upper_count_kernel<<<nblk(pl->N, 256), 256, 0, st>>>(reinterpret_cast<const int2*>(pl->degs), pl->N, pl->rowptr);
   return exclusive_scan(pl->rowptr, pl->rowptr, pl->N, pl->scan_tmp, pl->scan_tmp_bytes, st);
 }
 
 int dm_bars_pairs(const DmPlan* pl, int32_t* pairs, void* stream) {
   if (!pl || !pairs) return DM_ERR_ARG;
   if (pl->dim == 2)
-    bars_pairs_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(pl->inc_end, pl->adj, pl->deg, pl->nlow, pl->rowptr,
-                                                                  pl->N, pairs);
+    bars_pairs_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(rows_of<2>(pl), pl->rowptr, pl->N, pairs);
   else
-    bars_pairs_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(pl->inc_end, pl->adj, pl->deg, pl->nlow, pl->rowptr,
-                                                                  pl->N, pairs);
+    bars_pairs_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(rows_of<3>(pl), pl->rowptr, pl->N, pairs);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }
@@ -379,11 +406,11 @@ int dm_bars_pairs(const DmPlan* pl, int32_t* pairs, void* stream) {
 int dm_bar_sizes(const DmPlan* pl, const DmSizeFn* f, double* out, void* stream) {
   if (!pl || !f || !out) return DM_ERR_ARG;
   if (pl->dim == 2)
-    bar_sizes_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, pl->inc_end, pl->deg, pl->nlow, pl->rowptr,
-                                                                 pl->hslot, pl->hbar, pl->N, out);
+    bar_sizes_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, rows_of<2>(pl), pl->rowptr, pl->hslot, pl->hbar,
+                                                                 pl->N, out);
   else
-    bar_sizes_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, pl->inc_end, pl->deg, pl->nlow, pl->rowptr,
-                                                                 pl->hslot, pl->hbar, pl->N, out);
+    bar_sizes_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, rows_of<3>(pl), pl->rowptr, pl->hslot, pl->hbar,
+                                                                 pl->N, out);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }

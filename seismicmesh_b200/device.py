@@ -79,11 +79,13 @@ class Plan:
     def hbar(self, E):
         return self._view(self.c.hbar, E * 8, torch.float64)
 
-    def deg(self):
-        return self._view(self.c.deg, self.N * 4, torch.int32)
+    def degs(self):
+        """(N,2) int32: {degree, number of lower neighbours} per vertex."""
+        return self._view(self.c.degs, self.N * 8, torch.int32).view(self.N, 2)
 
-    def nlow(self):
-        return self._view(self.c.nlow, self.N * 4, torch.int32)
+    def cnt(self):
+        """(N,) int32: kept cells incident to each vertex."""
+        return self._view(self.c.cnt, self.N * 4, torch.int32)
 
     def scalars(self):
         return self._view(self.c.scalars, 8 * 8, torch.float64)
