@@ -60,11 +60,26 @@ def make_points(workload, h0, seed=0, shift=0.0):
 
 
 def triangulate(p):
+    """Host Delaunay (Qhull).  DM_BENCH_CACHE=<dir> re-uses the cells of an identical point set
+    between runs of one profiling session (the set-up is untimed either way)."""
     from scipy.spatial import Delaunay
 
+    cache = os.environ.get("DM_BENCH_CACHE")
+    key = None
+    if cache:
+        import hashlib
+
+        key = os.path.join(cache, "tri_" + hashlib.sha1(p.tobytes()).hexdigest()[:16] + ".npz")
+        if os.path.exists(key):
+            z = np.load(key)
+            return z["t"], float(z["dt"])
     t0 = time.perf_counter()
     t = np.ascontiguousarray(Delaunay(p).simplices, dtype=np.int32)
-    return t, time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if key:
+        os.makedirs(cache, exist_ok=True)
+        np.savez(key, t=t, dt=dt)
+    return t, dt
 
 
 def oracle_step_fn(workload, h0, dim):
@@ -157,8 +172,9 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
         "memset_zero_region": 4 * (N + 1),
         # t and p read once, keep flags + the kept cells handed to the bar stage written once
         "cull_scatter": 4 * c * T + 8 * d * N + T + 4 * c * Tk,
-        # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends)
-        "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E,
+        # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends) with the
+        # bar pass K3 fused in (positions read once, h written once per bar for gridded fh)
+        "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E + 8 * d * N + hs,
         "adjacency_heavy": 0,
         "bar_pass+scale": 8 * d * N + 4 * E + 8 * N + hs,
         "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + 2 * hs,
@@ -379,6 +395,7 @@ def main():
         names = [nm.raw[i * stride : (i + 1) * stride].split(b"\0")[0].decode() for i in range(n.value)]
     kern_ms = acc / reps
     alg = algorithmic_bytes(N, T, Tk, E, dim)
+    alg = {k: v for k, v in alg.items() if k in names}
     peak, peak_src = measured_peak()
     table = []
     for nme, msv in zip(names, kern_ms):
@@ -433,7 +450,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 5 * K,
+        "gpu_launches": 4 * K,
         "roofline": roofline, "cpu_baseline": cpu,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
     }

@@ -167,8 +167,8 @@ typedef struct DmPlan {
   void *zero_base;   /* [cnt | sync | counters]: ONE memset per iteration */
   size_t zero_bytes;
   int32_t *cnt;
-  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done */
-  int32_t *counters; /* [0]=E unique bars [1]=T' kept cells [2]=spill records [3]=heavy vertices
+  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] heavy blocks done */
+  int32_t *counters; /* [0]=E unique bars [1]=reserved [2]=spill records [3]=heavy vertices
                         [4]=heap cursor (ints) */
   void *bucket;
   int32_t *ovf_v;

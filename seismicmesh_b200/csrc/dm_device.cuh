@@ -49,14 +49,15 @@ __device__ __forceinline__ void load_cell(const int32_t* __restrict__ t, int64_t
 template <int DIM>
 __device__ __forceinline__ void cell_centroid(const double* __restrict__ p, const int (&v)[4], double& c0,
                                               double& c1, double& c2) {
-  double a0, a1, a2, b0, b1, b2;
-  load_pt<DIM>(p, v[0], a0, a1, a2);
+  double q[DIM + 1][3];
+#pragma unroll
+  for (int k = 0; k <= DIM; ++k) load_pt<DIM>(p, v[k], q[k][0], q[k][1], q[k][2]);  // all gathers in flight
+  double a0 = q[0][0], a1 = q[0][1], a2 = q[0][2];
 #pragma unroll
   for (int k = 1; k <= DIM; ++k) {
-    load_pt<DIM>(p, v[k], b0, b1, b2);
-    a0 = a0 + b0;
-    a1 = a1 + b1;
-    a2 = a2 + b2;
+    a0 = a0 + q[k][0];
+    a1 = a1 + q[k][1];
+    a2 = a2 + q[k][2];
   }
   c0 = a0 / (double)(DIM + 1);
   c1 = a1 / (double)(DIM + 1);

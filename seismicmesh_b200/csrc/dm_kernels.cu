@@ -58,7 +58,9 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   const int64_t K = (int64_t)DIM * (DIM + 1) * T;
   const int64_t K1 = K > 0 ? K : 1, T1 = T > 0 ? T : 1;
   const int64_t heap_ints = K1 + 4 * (N + 1);
-  const int64_t nblocks = cdiv(N > 0 ? N : 1, PL_THREADS);
+  // per-block partials: adjacency blocks (AB_THREADS / G vertices each) + one per heavy vertex +
+  // one per block of the heavy kernel (first level of the final sum)
+  const int64_t nblocks = cdiv(N > 0 ? N : 1, AB_THREADS / PCfg<DIM>::G) + (N + 2) + HV_BLOCKS + 8;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* ptr = base ? base + off : nullptr;
@@ -170,28 +172,53 @@ template <int DIM>
 static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
                               int mode, cudaStream_t st) {
   typedef typename PCfg<DIM>::entry_t entry_t;
-  cull_scatter_kernel<DIM, true><<<nblk(pl->T, PL_THREADS), PL_THREADS, 0, st>>>(
-      prog, p, t, pl->T, geps, mode, pl->keep, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
-      static_cast<entry_t*>(pl->ovf_e), pl->counters);
+  static const int agg = getenv("DM_AGG_MODE") ? atoi(getenv("DM_AGG_MODE")) : 2;  // tuning knob (profiling)
+  const unsigned nb = nblk(pl->T, PL_THREADS);
+#define DM_CS(A)                                                                                               \
+  cull_scatter_kernel<DIM, A><<<nb, PL_THREADS, 0, st>>>(prog, p, t, pl->T, geps, mode, pl->keep, pl->cnt, \
+                                                               static_cast<entry_t*>(pl->bucket), pl->ovf_v,   \
+                                                               static_cast<entry_t*>(pl->ovf_e), pl->counters)
+  switch (agg) {
+    case 0: DM_CS(0); break;
+    case 1: DM_CS(1); break;
+    case 3: DM_CS(3); break;
+    default: DM_CS(2); break;
+  }
+#undef DM_CS
+  mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
 
+// bar: -1 rows only (staged path: a separate bar pass follows) ; otherwise f->kind (0 const, 1 grid):
+// the bar pass is fused into the adjacency kernels and the heavy kernel's last block writes the scale
 template <int DIM>
-static int stage_adjacency(const DmPlan* pl, cudaStream_t st) {
+static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const double* p, cudaStream_t st) {
   typedef typename PCfg<DIM>::entry_t entry_t;
   constexpr int VPB = AB_THREADS / PCfg<DIM>::G;
   const int64_t N = pl->N;
+  const unsigned nb = nblk(N, VPB);
   int2* degs = reinterpret_cast<int2*>(pl->degs);
-  adjacency_kernel<DIM><<<nblk(N, VPB), AB_THREADS, 0, st>>>(pl->cnt, static_cast<const entry_t*>(pl->bucket), N, pl->adj,
-                                                             pl->heap, degs, pl->hv, pl->counters);
-  mark("adjacency", st);
-#ifdef DM_DEBUG_HEAVY
-  if (getenv("DM_SKIP_HEAVY")) return (int)cudaGetLastError();
-#endif
-  adjacency_heavy_kernel<DIM><<<HV_BLOCKS, HV_THREADS, 0, st>>>(pl->cnt, static_cast<const entry_t*>(pl->bucket), pl->ovf_v,
-                                                                static_cast<const entry_t*>(pl->ovf_e), N, pl->adj,
-                                                                pl->heap, degs, pl->hv, pl->counters);
-  mark("adjacency_heavy", st);
+  const entry_t* bucket = static_cast<const entry_t*>(pl->bucket);
+  const entry_t* ovf_e = static_cast<const entry_t*>(pl->ovf_e);
+  DmSizeFn fz;
+  memset(&fz, 0, sizeof(fz));
+  const DmSizeFn& ff = f ? *f : fz;
+  const double* pp = p;
+#define DM_ADJ(B)                                                                                                  \
+  adjacency_kernel<DIM, B><<<nb, AB_THREADS, 0, st>>>(pl->cnt, bucket, N, pl->adj, pl->heap, degs, pl->hv,          \
+                                                      pl->counters, ff, pp, pl->hslot, pl->partials);              \
+  mark("adjacency", st);                                                                                           \
+  adjacency_heavy_kernel<DIM, B><<<HV_BLOCKS, HV_THREADS, 0, st>>>(pl->cnt, bucket, pl->ovf_v, ovf_e, N, pl->adj,   \
+                                                                   pl->heap, degs, pl->hv, pl->counters, ff, pp,   \
+                                                                   pl->hslot, pl->partials, (int64_t)nb,           \
+                                                                   pl->sync + 3, pl->scalars);                     \
+  mark("adjacency_heavy", st)
+  switch (bar) {
+    case 0: DM_ADJ(0); break;
+    case 1: DM_ADJ(1); break;
+    default: DM_ADJ(-1); break;
+  }
+#undef DM_ADJ
   return (int)cudaGetLastError();
 }
 
@@ -255,10 +282,10 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (T == 0) return DM_OK;
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
-    cull_scatter_kernel<2, false><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<2, 0><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   else
-    cull_scatter_kernel<3, false><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<3, 0><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   DM_LAUNCH_CHECK();
   return DM_OK;
@@ -372,10 +399,8 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
   mark("memset_zero_region", st);
   if (pl->T == 0) return DM_OK;
   const int mode = !use_keep ? 2 : (prog ? 0 : 1);
-  const int rc = pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t, geps, mode, st)
-                              : stage_cull_scatter<3>(pl, prog, p, t, geps, mode, st);
-  mark("cull_scatter", st);
-  return rc;
+  return pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t, geps, mode, st)
+                      : stage_cull_scatter<3>(pl, prog, p, t, geps, mode, st);
 }
 
 int dm_stage_build_adjacency(const DmPlan* pl, const int32_t* t, int use_keep, void* stream) {
@@ -383,7 +408,7 @@ int dm_stage_build_adjacency(const DmPlan* pl, const int32_t* t, int use_keep, v
   (void)use_keep;  // the kept cells were already scattered to the vertex buckets by stage A
   if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  return pl->dim == 2 ? stage_adjacency<2>(pl, st) : stage_adjacency<3>(pl, st);
+  return pl->dim == 2 ? stage_adjacency<2>(pl, -1, nullptr, nullptr, st) : stage_adjacency<3>(pl, -1, nullptr, nullptr, st);
 }
 
 int dm_stage_bar_index(const DmPlan* pl, void* stream) {
@@ -419,7 +444,8 @@ int dm_bar_midpoints(const DmPlan* pl, const double* p, double* mid, void* strea
   if (!pl || !p || !mid) return DM_ERR_ARG;
   DmSizeFn f;
   memset(&f, 0, sizeof(f));
-  return pl->dim == 2 ? launch_bar_pass<2>(pl, p, f, 3, mid, S(stream)) : launch_bar_pass<3>(pl, p, f, 3, mid, S(stream));
+  cudaStream_t st = S(stream);
+  return pl->dim == 2 ? launch_bar_pass<2>(pl, p, f, 3, mid, st) : launch_bar_pass<3>(pl, p, f, 3, mid, st);
 }
 
 int dm_stage_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn* f, void* stream) {
@@ -431,11 +457,9 @@ int dm_stage_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn* f, void
   return rc;
 }
 
-int dm_stage_vertex_update(const DmPlan* pl, const double* p, double* p_out, const double* const* progs,
-                           int nlevels, const DmSizeFn* f, double L0mult, double delta_t, double deps, double h0,
-                           int64_t nfix, const uint8_t* fixed, double* Ftot, void* stream) {
-  if (!pl || !p || !p_out || p == p_out || nlevels < 0 || nlevels > DM_MAX_LEVELS) return DM_ERR_ARG;
-  if ((nlevels > 0 && !progs) || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
+static int vertex_update_impl(const DmPlan* pl, const double* p, double* p_out, const double* const* progs,
+                              int nlevels, const DmSizeFn* f, double L0mult, double delta_t, double deps, double h0,
+                              int64_t nfix, const uint8_t* fixed, double* Ftot, cudaStream_t st) {
   Levels lv;
   memset(&lv, 0, sizeof(lv));
   lv.n = nlevels;
@@ -443,7 +467,6 @@ int dm_stage_vertex_update(const DmPlan* pl, const double* p, double* p_out, con
     if (!progs[l]) return DM_ERR_ARG;
     lv.prog[l] = progs[l];
   }
-  cudaStream_t st = S(stream);
   const int rc = pl->dim == 2 ? launch_vertex_update<2>(pl, p, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0, nfix,
                                                         fixed, Ftot, st)
                               : launch_vertex_update<3>(pl, p, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0, nfix,
@@ -452,19 +475,29 @@ int dm_stage_vertex_update(const DmPlan* pl, const double* p, double* p_out, con
   return rc;
 }
 
+int dm_stage_vertex_update(const DmPlan* pl, const double* p, double* p_out, const double* const* progs,
+                           int nlevels, const DmSizeFn* f, double L0mult, double delta_t, double deps, double h0,
+                           int64_t nfix, const uint8_t* fixed, double* Ftot, void* stream) {
+  if (!pl || !p || !p_out || p == p_out || nlevels < 0 || nlevels > DM_MAX_LEVELS) return DM_ERR_ARG;
+  if ((nlevels > 0 && !progs) || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  return vertex_update_impl(pl, p, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,
+                            st);
+}
+
 int dm_force_iteration(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,
                        const double* p, const int32_t* t, double* p_out, double geps, double L0mult,
                        double delta_t, double deps, double h0, int64_t nfix, const uint8_t* fixed, double* Ftot,
                        void* stream) {
-  if (!pl || !progs || nlevels < 1 || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
+  if (!pl || !progs || nlevels < 1 || nlevels > DM_MAX_LEVELS || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
+  if (!p || !p_out || p == p_out || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  // A: cull + scatter ; B+C: adjacency rows with the bar pass fused in ; D: vertex update
   int rc = dm_stage_cull_count(pl, progs[0], p, t, geps, 1, stream);
   if (rc) return rc;
-  rc = dm_stage_build_adjacency(pl, t, 1, stream);
+  rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
   if (rc) return rc;
-  rc = dm_stage_bar_pass(pl, p, f, stream);
-  if (rc) return rc;
-  return dm_stage_vertex_update(pl, p, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,
-                                stream);
+  return vertex_update_impl(pl, p, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }
 
 int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,

@@ -34,7 +34,7 @@ constexpr int PL_THREADS = 256;  // cull / bar pass / vertex update
 constexpr int AB_THREADS = 256;  // adjacency: 256 / G vertices per block
 constexpr int HV_THREADS = 256;  // heavy-vertex path: one block per vertex
 constexpr int HV_BLOCKS = 296;   // fixed grid (2 per SM); loops over the heavy list
-constexpr int HV_SMEM = 6144;    // candidates sorted in shared memory up to this many
+constexpr int HV_SMEM = 6144;    // candidates sorted in shared memory up to this many (ints; 24 KB)
 
 template <int DIM>
 struct PCfg;
@@ -88,7 +88,10 @@ __device__ __forceinline__ int2 others_of<2>(const int (&ids)[4], int j) {
   return make_int2(ids[j == 0 ? 1 : 0], ids[j <= 1 ? 2 : 1]);
 }
 
-template <int DIM, bool AGG>
+// AGG: how lanes that claim a slot of the same vertex in the same step share one atomic
+//   0 none ; 1 match.any at every position ; 2 equal-id runs of consecutive lanes (shfl + ballot) ;
+//   3 match.any at position 0 (the apex Qhull groups its facets around), runs elsewhere
+template <int DIM, int AGG>
 __global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
@@ -111,38 +114,54 @@ __global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
       k = keep[c] != 0;
     }
   }
-  if (cnt != nullptr) {
-    const unsigned km = __ballot_sync(FULL, k);
-    if (k) {
+  if (cnt == nullptr) return;
+  // Slot claims of the DIM+1 vertices are independent: issue all the atomics first and only then
+  // wait for them, so a warp pays ONE L2 round trip instead of DIM+1.
+  const unsigned km = __ballot_sync(FULL, k);
+  const unsigned lt = (1u << lane) - 1u;
+  int base[DIM + 1], rank[DIM + 1], leader[DIM + 1];
 #pragma unroll
-      for (int j = 0; j <= DIM; ++j) {
-        const int v = ids[j];
-        int slot;
-        if (AGG) {
-          // all lanes that claim a slot of the same vertex in this step share one atomic
-          const unsigned m = __match_any_sync(km, v);
-          const int leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(cnt + v, __popc(m));
-          base = __shfl_sync(m, base, leader);
-          slot = base + __popc(m & ((1u << lane) - 1u));
-        } else {
-          slot = atomicAdd(cnt + v, 1);
-        }
-        const typename PCfg<DIM>::entry_t e = others_of<DIM>(ids, j);
-        if (slot < CAP) {
-          bucket[(int64_t)v * CAP + slot] = e;
-        } else {  // bucket full: spill (hull / hub vertices)
-          const int o = atomicAdd(counters + 2, 1);
-          ovf_v[o] = v;
-          ovf_e[o] = e;
-        }
+  for (int j = 0; j <= DIM; ++j) {
+    const bool use_match = AGG == 1 || (AGG == 3 && j == 0);
+    const bool use_runs = AGG == 2 || (AGG == 3 && j != 0);
+    base[j] = 0;
+    rank[j] = 0;
+    leader[j] = lane;
+    if (use_match) {
+      if (k) {
+        const unsigned m = __match_any_sync(km, ids[j]);
+        leader[j] = __ffs(m) - 1;
+        rank[j] = __popc(m & lt);
+        if (lane == leader[j]) base[j] = atomicAdd(cnt + ids[j], __popc(m));
       }
+    } else if (use_runs) {
+      const int vj = k ? ids[j] : -1 - lane;  // a culled lane never continues a run
+      const int prev = __shfl_up_sync(FULL, vj, 1);
+      const unsigned heads = __ballot_sync(FULL, lane == 0 || vj != prev);
+      const int start = 31 - __clz(heads & (lt | (1u << lane)));
+      const unsigned above = heads & ~(lt | (1u << lane));
+      const int end = above ? __ffs(above) - 1 : 32;
+      leader[j] = start;
+      rank[j] = lane - start;
+      if (k && lane == start) base[j] = atomicAdd(cnt + ids[j], end - start);
+    } else {
+      if (k) base[j] = atomicAdd(cnt + ids[j], 1);
     }
   }
-  if (counters != nullptr) {
-    const int nk = __syncthreads_count(k);
-    if (threadIdx.x == 0 && nk) atomicAdd(counters + 1, nk);
+#pragma unroll
+  for (int j = 0; j <= DIM; ++j) {
+    int slot = base[j];
+    if (AGG != 0) slot = __shfl_sync(FULL, base[j], leader[j]) + rank[j];
+    if (k) {
+      const typename PCfg<DIM>::entry_t e = others_of<DIM>(ids, j);
+      if (slot < CAP) {
+        bucket[(int64_t)ids[j] * CAP + slot] = e;
+      } else {  // bucket full: spill (hull / hub vertices)
+        const int o = atomicAdd(counters + 2, 1);
+        ovf_v[o] = ids[j];
+        ovf_e[o] = e;
+      }
+    }
   }
 }
 
@@ -157,57 +176,81 @@ __device__ __forceinline__ unsigned hash_slot(int x) {
   return ((unsigned)x * 2654435761u) >> (32 - LOGH);
 }
 
-// One candidate per lane, all 32 lanes in lockstep.  Group-private open-addressing set in shared
+// NC candidates per lane, all 32 lanes in lockstep.  Group-private open-addressing set in shared
 // memory with plain loads / stores: a lane that finds its slot empty writes its key, the warp
 // synchronises, and every lane re-reads the slot: whoever finds its own key there is done (it
 // either won the slot or lost it to an equal key), everyone else moves to the next slot.  Slots
 // only ever go EMPTY -> key, so a key is stored at the first slot of its probe sequence that was
 // empty when it arrived and later equal keys find it before they find an empty slot.
+// The kernel is bound by shared-memory wavefronts (random banks: ~3.5 per warp access) and by
+// issue slots, so the body keeps no per-candidate flag: a finished candidate is parked on the
+// lane's private word behind the table (tab[H + lg], one bank per lane of the warp, so parked
+// accesses never conflict) with its key replaced by the parked word's content, and from then on
+// it "hits" there for free.  Lanes without a candidate are handed a copy of a real key of the same
+// vertex (a duplicate insert is a no-op).
+constexpr int HASH_PARKED = -2;
 template <int NC, int LOGH>
-__device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, const int (&x)[NC], bool act, bool& punt) {
+__device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC], unsigned park, bool& punt) {
   constexpr unsigned HM = (1u << LOGH) - 1u;
   unsigned h[NC];
-  bool pend[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    h[c] = hash_slot<LOGH>(x[c]);
-    pend[c] = act;
-  }
+  for (int c = 0; c < NC; ++c) h[c] = hash_slot<LOGH>(x[c]);
   int steps = 0;
-  while (true) {
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) any = any || pend[c];
-    if (!__any_sync(FULL, any)) break;
+  bool any;
+  do {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
-      if (pend[c] && tab[h[c]] == HASH_EMPTY) tab[h[c]] = x[c];
+      if (tab[h[c]] == HASH_EMPTY) tab[h[c]] = x[c];
     __syncwarp();
+    any = false;
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (pend[c]) {
-        if (tab[h[c]] == x[c])
-          pend[c] = false;
-        else
-          h[c] = (h[c] + 1u) & HM;
-      }
+    for (int c = 0; c < NC; ++c) {
+      const bool hit = tab[h[c]] == x[c];
+      const unsigned nxt = (h[c] + 1u) & HM;
+      any = any | !hit;
+      h[c] = hit ? park : nxt;
+      x[c] = hit ? HASH_PARKED : x[c];
+    }
     __syncwarp();
     if (++steps > HASH_MAXSTEPS) {  // table (nearly) full: give up, the heavy path takes the vertex
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        punt = punt || pend[c];
-        pend[c] = false;
-      }
+      punt = punt | any;
+      any = false;
     }
+  } while (__any_sync(FULL, any));
+}
+
+// L^d and h^d of the bar (a, p[w]); GRID: h is interpolated at the midpoint and stored at `hout`
+template <int DIM, bool GRID>
+__device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __restrict__ pp, double a0, double a1,
+                                          double a2, int w, double* hout, double& sL, double& sH) {
+  double b0, b1, b2, d0, d1, d2;
+  load_pt<DIM>(pp, w, b0, b1, b2);
+  const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
+  double h = f.hconst;
+  if (GRID) {
+    // midpoint p[edges].sum(1)/2 (mesh_generator.py:699)
+    h = size_eval(f, (a0 + b0) / 2, (a1 + b1) / 2, (a2 + b2) / 2);
+    *hout = h;
+  }
+  if (DIM == 2) {
+    sL += L * L;
+    sH += h * h;
+  } else {
+    sL += L * L * L;
+    sH += h * h * h;
   }
 }
 
-template <int DIM>
+// BAR: -1 rows only ; 0 also accumulate sum L^d, sum h^d of the upper bars with constant h ;
+//      1 the same with gridded fh (h stored per upper slot).
+template <int DIM, int BAR>
 __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __restrict__ cnt,
                                                                const typename PCfg<DIM>::entry_t* __restrict__ bucket,
                                                                int64_t N, int32_t* __restrict__ adj,
                                                                int32_t* __restrict__ heap, int2* __restrict__ degs,
-                                                               int32_t* __restrict__ hv, int32_t* __restrict__ counters) {
+                                                               int32_t* __restrict__ hv, int32_t* __restrict__ counters,
+                                                               const DmSizeFn f, const double* __restrict__ pp,
+                                                               double* __restrict__ hslot, double* __restrict__ partials) {
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS, G = PCfg<DIM>::G, LOGH = PCfg<DIM>::LOGH;
   constexpr int H = 1 << LOGH;
   constexpr int VPB = AB_THREADS / G;  // vertices per block
@@ -215,14 +258,18 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
   static_assert(SPL == 8, "compaction below reads two int4 per lane");
   // group stride H + 32/(32/G) ints: the groups of one warp start in different banks, so the
   // broadcast reads of the rank sort (same k in every group) do not conflict
-  constexpr int GS = H + 32 / (32 / G);
+  constexpr int GS = H + G;  // G parking words behind the table / >= 4 ints of padding behind the list;
+                             // G == 32 / (groups per warp), so the groups of a warp start in different banks
+  static_assert(G >= 4 && 32 % G == 0, "group layout");
   static_assert((GS * 4) % 16 == 0, "int4 access");
   __shared__ __align__(16) int32_t s_tab[VPB * GS];
   __shared__ __align__(16) int32_t s_lst[VPB * GS];
-  __shared__ int s_red[33];
+  __shared__ int s_arrived;  // warps that have left their totals (see the end of the kernel)
   const int tid = threadIdx.x, lane = tid & 31;
   const int lg = tid % G, grp = tid / G;
   const int64_t v = (int64_t)blockIdx.x * VPB + grp;
+  if (tid == 0) s_arrived = 0;
+  __syncthreads();  // the only block barrier: at the very start, where no warp has to wait long
   int32_t* tab = s_tab + grp * GS;
   int32_t* lst = s_lst + grp * GS;
 
@@ -231,27 +278,38 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
     int4* t4 = reinterpret_cast<int4*>(tab + lg * SPL);
     t4[0] = make_int4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
     t4[1] = make_int4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
+    tab[H + lg] = HASH_PARKED;  // the lane's parking word (see hash_insert_lockstep)
   }
   int n = v < N ? cnt[v] : 0;
   bool punt = n > CAP;  // overflowed bucket: part of the star lives in the spill list
   if (punt) n = 0;
   __syncwarp();
 
-  // ---- insert every candidate of the bucket: lane lg takes entries lg, lg+G, ...
-  const typename PCfg<DIM>::entry_t* brow = bucket + v * CAP;
-  for (int i = lg; __any_sync(FULL, i < n); i += G) {
-    const bool act = i < n;
-    int x[DIM];
-    if (act) {
-      const typename PCfg<DIM>::entry_t e = brow[i];
-      x[0] = e.x;
-      x[1] = e.y;
-      if (DIM == 3) x[DIM - 1] = reinterpret_cast<const int*>(&e)[DIM - 1];
-    } else {
+  // ---- insert every candidate of the bucket: each round, lane lg takes EPL entries (lg, lg+G, ...).
+  //      The loads of round r+1 are issued before round r is hashed (the bucket comes from DRAM).
+  constexpr int EPL = 2;
+  typedef typename PCfg<DIM>::entry_t entry_t;
+  const entry_t* brow = bucket + v * CAP;
+  const int key0 = n > 0 ? reinterpret_cast<const int*>(brow)[0] : 0;  // filler for idle lanes
+  entry_t cur[EPL], nxt[EPL];
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) x[c] = 0;
+  for (int u = 0; u < EPL; ++u)
+    if (lg + u * G < n) cur[u] = brow[lg + u * G];
+  for (int i = lg; __any_sync(FULL, i < n); i += EPL * G) {
+#pragma unroll
+    for (int u = 0; u < EPL; ++u)
+      if (i + (EPL + u) * G < n) nxt[u] = brow[i + (EPL + u) * G];
+    int x[EPL * DIM];
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) {
+      const bool a = i + u * G < n;
+      const int* ei = reinterpret_cast<const int*>(&cur[u]);
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) x[u * DIM + c] = a ? ei[c] : key0;
     }
-    hash_insert_lockstep<DIM, LOGH>(tab, x, act, punt);
+    hash_insert_lockstep<EPL * DIM, LOGH>(tab, x, (unsigned)(H + lg), punt);
+#pragma unroll
+    for (int u = 0; u < EPL; ++u) cur[u] = nxt[u];
   }
   // group-wide punt flag
   const unsigned gsh = (unsigned)(lane - lg);
@@ -276,7 +334,7 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
     if (lg >= d) inc += o;
   }
   int U = __shfl_sync(FULL, inc, G - 1, G);
-  if (punt) U = 0;
+  if (punt || n == 0) U = 0;  // n == 0: nothing but filler keys went in
   {
     int off = inc - c;
 #pragma unroll
@@ -285,14 +343,27 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
   }
   __syncwarp();
 
-  // ---- rank sort: lst (unsorted, unique) -> tab (ascending)
+  // ---- rank sort: lst (unsorted, unique, padded with +inf to a multiple of 4) -> tab (ascending);
+  //      two elements per lane and four list entries per shared-memory load
+  if (lg < 4) lst[U + lg] = 0x7fffffff;
+  __syncwarp();
   int lo = 0;
-  for (int i = lg; i < U; i += G) {
-    const int x = lst[i];
-    int r = 0;
-    for (int k = 0; k < U; ++k) r += lst[k] < x ? 1 : 0;
-    tab[r] = x;
-    lo += x < (int)v ? 1 : 0;
+  for (int i = lg; i < U; i += 2 * G) {
+    const int x0 = lst[i];
+    const bool two = i + G < U;
+    const int x1 = two ? lst[i + G] : 0x7fffffff;
+    int r0 = 0, r1 = 0;
+    for (int k = 0; k < U; k += 4) {
+      const int4 q = *reinterpret_cast<const int4*>(lst + k);
+      r0 += (q.x < x0 ? 1 : 0) + (q.y < x0 ? 1 : 0) + (q.z < x0 ? 1 : 0) + (q.w < x0 ? 1 : 0);
+      r1 += (q.x < x1 ? 1 : 0) + (q.y < x1 ? 1 : 0) + (q.z < x1 ? 1 : 0) + (q.w < x1 ? 1 : 0);
+    }
+    tab[r0] = x0;
+    lo += x0 < (int)v ? 1 : 0;
+    if (two) {
+      tab[r1] = x1;
+      lo += x1 < (int)v ? 1 : 0;
+    }
   }
 #pragma unroll
   for (int d = G / 2; d > 0; d >>= 1) lo += __shfl_xor_sync(FULL, lo, d, G);
@@ -300,11 +371,13 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
 
   // ---- write the row
   int bars = 0;
+  double sL = 0.0, sH = 0.0;
   if (v < N) {
     if (punt) {
       if (lg == 0) hv[atomicAdd(counters + 3, 1)] = (int32_t)v;
     } else {
       int32_t* row = adj + v * RS;
+      int64_t sbase = v * RS;
       if (U <= RS) {
         // RS ints = G lanes x int4 (3-D: 8 x 16 B = one 128-B line; 2-D: 4 x 16 B)
         static_assert(RS == 4 * G, "one int4 per lane");
@@ -315,16 +388,60 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
         base = __shfl_sync(gmask, base, 0, G);  // group-uniform branch: only this group's lanes are here
         for (int i = lg; i < U; i += G) heap[base + i] = tab[i];
         if (lg == 0) row[0] = base;
+        sbase = N * RS + base;
       }
       if (lg == 0) {
         degs[v] = make_int2(U, lo);
         bars = U - lo;
       }
+      if (BAR >= 0 && U > lo) {  // bar pass over the upper neighbours (mesh_generator.py:696-700)
+        double a0, a1, a2;
+        load_pt<DIM>(pp, v, a0, a1, a2);
+        for (int j = lo + lg; j < U; j += G) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH);
+      }
     }
   }
-  int total;
-  block_exclusive_scan(bars, total, s_red);  // unique bars owned by this block's vertices
-  if (tid == 0 && total) atomicAdd(counters, total);
+  // ---- block totals without a barrier: every warp leaves its (fixed shuffle tree) sums in shared
+  //      memory; the warp that arrives last adds them in warp order and publishes the block's values
+  __shared__ double s_wL[AB_THREADS / 32], s_wH[AB_THREADS / 32];
+  __shared__ int s_wbars[AB_THREADS / 32];
+  {
+    const int wid = tid >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bars += __shfl_down_sync(FULL, bars, d);
+    if (BAR >= 0) {
+      sL = warp_sum(sL);
+      sH = warp_sum(sH);
+    }
+    bool last = false;
+    if (lane == 0) {
+      s_wbars[wid] = bars;
+      if (BAR >= 0) {
+        s_wL[wid] = sL;
+        s_wH[wid] = sH;
+      }
+      __threadfence_block();
+      last = atomicAdd(&s_arrived, 1) == AB_THREADS / 32 - 1;
+    }
+    if (last) {  // lane 0 of the last warp
+      __threadfence_block();
+      int tb = 0;
+      double tL = 0.0, tH = 0.0;
+#pragma unroll
+      for (int w = 0; w < AB_THREADS / 32; ++w) {
+        tb += s_wbars[w];
+        if (BAR >= 0) {
+          tL += s_wL[w];
+          tH += s_wH[w];
+        }
+      }
+      if (tb) atomicAdd(counters, tb);  // unique bars owned by this block's vertices
+      if (BAR >= 0) {
+        partials[2 * (int64_t)blockIdx.x] = tL;
+        partials[2 * (int64_t)blockIdx.x + 1] = tH;
+      }
+    }
+  }
 }
 
 // ---- heavy vertices: one block per vertex -------------------------------------------------------
@@ -349,19 +466,46 @@ __device__ __forceinline__ void block_sort_ascending(PTR a, int n) {
   }
 }
 
-template <int DIM>
+constexpr int HV_RANK = 768;   // up to this many candidates: one-pass rank sort instead of the network
+constexpr int HV_FINAL = 1024;  // heavy vertices whose bar sums are added in vertex order
+
+// BAR as in adjacency_kernel.  With BAR >= 0 the block that finishes last also reduces all the
+// per-block bar sums (adjacency blocks in block order, then the heavy vertices in vertex order)
+// into scalars[0..2]: the scale of mesh_generator.py:700.
+template <int DIM, int BAR>
 __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
     const int32_t* __restrict__ cnt, const typename PCfg<DIM>::entry_t* __restrict__ bucket,
     const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N,
     int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
-    int32_t* __restrict__ counters) {
+    int32_t* __restrict__ counters, const DmSizeFn f, const double* __restrict__ pp, double* __restrict__ hslot,
+    double* partials, int64_t nb_adj, int32_t* done, double* scalars) {
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS;
-  __shared__ int32_t s_val[HV_SMEM];
+  __shared__ __align__(16) int32_t s_val[HV_SMEM];
   __shared__ int s_scan[33];
+  __shared__ double s_dbl[32];
   __shared__ int s_base, s_pos;
+  __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int nheavy = counters[3];
   const int novf = counters[2];
+  const int64_t slice0 = nb_adj + N + 1;  // partials of the slices below live behind the heavy ones
+  if (BAR >= 0) {
+    // first level of the final sum: block b adds the bar sums of a fixed slice of adjacency blocks
+    // (the adjacency kernel has finished), so the last block only has gridDim.x values left
+    const int64_t per = (nb_adj + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * per, i1 = i0 + per < nb_adj ? i0 + per : nb_adj;
+    double tL = 0.0, tH = 0.0;
+    for (int64_t i = i0 + tid; i < i1; i += HV_THREADS) {
+      tL += __ldcg(partials + 2 * i);
+      tH += __ldcg(partials + 2 * i + 1);
+    }
+    const double bl = block_sum(tL, s_dbl);
+    const double bh = block_sum(tH, s_dbl);
+    if (tid == 0) {
+      partials[2 * (slice0 + blockIdx.x)] = bl;
+      partials[2 * (slice0 + blockIdx.x) + 1] = bh;
+    }
+  }
   for (int ih = blockIdx.x; ih < nheavy; ih += gridDim.x) {
     const int v = hv[ih];
     const int nc = cnt[v];
@@ -375,9 +519,6 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
     __syncthreads();
     int32_t* reg = heap + s_base;  // candidates, later the row, live here
     const bool in_smem = n <= HV_SMEM;
-#ifdef DM_DEBUG_HEAVY
-    if (tid == 0) printf("heavy ih=%d v=%d nc=%d nb=%d n=%d base=%d novf=%d nheavy=%d\n", ih, v, nc, nb, n, s_base, novf, nheavy);
-#endif
     // gather the candidates
     for (int i = tid; i < nb; i += HV_THREADS) {
       const typename PCfg<DIM>::entry_t e = bucket[(int64_t)v * CAP + i];
@@ -407,45 +548,152 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
       }
     }
     __syncthreads();
-    if (in_smem)
-      block_sort_ascending(s_val, n);
-    else
-      block_sort_ascending(reg, n);
-#ifdef DM_DEBUG_HEAVY
-    if (tid == 0) printf("heavy ih=%d sorted\n", ih);
-#endif
-    // unique: chunk by chunk; an element's output position never exceeds its input position and
-    // all reads of a chunk complete before its writes, so compaction in place is safe
     int U = 0, lo = 0;
-    for (int c0 = 0; c0 < n; c0 += HV_THREADS) {
-      const int i = c0 + tid;
-      int x = 0;
-      bool first = false;
-      if (i < n) {
-        x = in_smem ? s_val[i] : reg[i];
-        first = i == 0 || (in_smem ? s_val[i - 1] : reg[i - 1]) != x;
+    if (n <= HV_RANK) {
+      // one pass: candidate i is the first of its value if no equal value precedes it, and its
+      // row position is the number of DISTINCT smaller values = #{j : val[j] < val[i], j first}.
+      // Two sweeps over shared memory instead of ~50 barrier-separated network stages.
+      constexpr int PER = HV_RANK / HV_THREADS;
+      bool first[PER];
+      int x[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = tid + u * HV_THREADS;
+        first[u] = i < n;
+        x[u] = i < n ? s_val[i] : 0;
+      }
+      for (int j = 0; j < n; ++j) {
+        const int y = s_val[j];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) first[u] = first[u] && !(y == x[u] && j < tid + u * HV_THREADS);
+      }
+      __syncthreads();
+      // mark duplicates so that the rank sweep counts distinct values only
+      int32_t* s_first = s_val + HV_RANK;  // HV_SMEM >= 2 * HV_RANK
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = tid + u * HV_THREADS;
+        if (i < n) s_first[i] = first[u] ? 1 : 0;
+      }
+      __syncthreads();
+      int r[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) r[u] = 0;
+      for (int j = 0; j < n; ++j) {
+        const int y = s_val[j];
+        const int fj = s_first[j];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) r[u] += (fj && y < x[u]) ? 1 : 0;
+      }
+      int nf = 0, nl = 0;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        if (first[u]) {
+          reg[r[u]] = x[u];
+          ++nf;
+          nl += x[u] < v ? 1 : 0;
+        }
       }
       int tot;
-      const int off = block_exclusive_scan(first ? 1 : 0, tot, s_scan);  // syncs: reads done
-      if (first) reg[U + off] = x;
-      const int nl = __syncthreads_count(first && x < v);
-      U += tot;
-      lo += nl;
+      block_exclusive_scan(nf, tot, s_scan);
+      U = tot;
+      block_exclusive_scan(nl, tot, s_scan);
+      lo = tot;
+    } else {
+      if (in_smem)
+        block_sort_ascending(s_val, n);
+      else
+        block_sort_ascending(reg, n);
+      // unique: chunk by chunk; an element's output position never exceeds its input position and
+      // all reads of a chunk complete before its writes, so compaction in place is safe
+      for (int c0 = 0; c0 < n; c0 += HV_THREADS) {
+        const int i = c0 + tid;
+        int x = 0;
+        bool first = false;
+        if (i < n) {
+          x = in_smem ? s_val[i] : reg[i];
+          first = i == 0 || (in_smem ? s_val[i - 1] : reg[i - 1]) != x;
+        }
+        int tot;
+        const int off = block_exclusive_scan(first ? 1 : 0, tot, s_scan);  // syncs: reads done
+        if (first) reg[U + off] = x;
+        const int nl = __syncthreads_count(first && x < v);
+        U += tot;
+        lo += nl;
+      }
     }
     __syncthreads();
     int32_t* row = adj + (int64_t)v * RS;
+    int64_t sbase = (int64_t)v * RS;
     if (U <= RS) {
       for (int i = tid; i < U; i += HV_THREADS) row[i] = reg[i];
-    } else if (tid == 0) {
-      row[0] = s_base;
+    } else {
+      if (tid == 0) row[0] = s_base;
+      sbase = N * RS + s_base;
     }
     if (tid == 0) {
       degs[v] = make_int2(U, lo);
       atomicAdd(counters, U - lo);
-#ifdef DM_DEBUG_HEAVY
-      printf("heavy ih=%d done U=%d lo=%d\n", ih, U, lo);
-#endif
     }
+    if (BAR >= 0) {
+      double sL = 0.0, sH = 0.0;
+      double a0, a1, a2;
+      load_pt<DIM>(pp, v, a0, a1, a2);
+      for (int j = lo + tid; j < U; j += HV_THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
+      const double bl = block_sum(sL, s_dbl);
+      const double bh = block_sum(sH, s_dbl);
+      if (tid == 0) {
+        partials[2 * (nb_adj + ih)] = bl;
+        partials[2 * (nb_adj + ih) + 1] = bh;
+      }
+    }
+  }
+  if (BAR < 0) return;
+  // ---- the last block to finish reduces everything in a FIXED order
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double tL = 0.0, tH = 0.0;
+  for (int64_t i = tid; i < (int64_t)gridDim.x; i += HV_THREADS) {
+    tL += __ldcg(partials + 2 * (slice0 + i));
+    tH += __ldcg(partials + 2 * (slice0 + i) + 1);
+  }
+  if (nheavy <= HV_FINAL) {
+    // heavy vertices were appended in a run-dependent order: add their sums in vertex order
+    int32_t* s_id = s_val;
+    for (int i = tid; i < nheavy; i += HV_THREADS) s_id[i] = hv[i];
+    __syncthreads();
+    double* s_sorted = reinterpret_cast<double*>(s_val + HV_FINAL);  // 2 * HV_FINAL doubles
+    for (int i = tid; i < nheavy; i += HV_THREADS) {
+      const int x = s_id[i];
+      int r = 0;
+      for (int j = 0; j < nheavy; ++j) r += s_id[j] < x ? 1 : 0;
+      s_sorted[2 * r] = __ldcg(partials + 2 * (nb_adj + i));
+      s_sorted[2 * r + 1] = __ldcg(partials + 2 * (nb_adj + i) + 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < nheavy; i += HV_THREADS) {
+      tL += s_sorted[2 * i];
+      tH += s_sorted[2 * i + 1];
+    }
+  } else {
+    for (int64_t i = tid; i < nheavy; i += HV_THREADS) {
+      tL += __ldcg(partials + 2 * (nb_adj + i));
+      tH += __ldcg(partials + 2 * (nb_adj + i) + 1);
+    }
+  }
+  const double rl = block_sum(tL, s_dbl);
+  const double rh = block_sum(tH, s_dbl);
+  if (tid == 0) {
+    scalars[0] = rl;
+    scalars[1] = rh;
+    const double r = rl / rh;
+    scalars[2] = DIM == 2 ? sqrt(r) : pow(r, 1.0 / 3.0);  // ** (1.0 / dim), mesh_generator.py:700
   }
 }
 
@@ -497,7 +745,7 @@ __device__ __forceinline__ int bar_id_of(const Rows<DIM>& R, const int32_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// C: bar pass.  HMODE 0: constant h ; 1: gridded fh (h stored at the upper directed slot) ;
+// C: bar pass (stand-alone version for the staged path).  HMODE 0: constant h ; 1: gridded fh (h stored at the upper directed slot) ;
 //               2: h per bar id supplied by the caller ; 3: write bar midpoints only
 // ---------------------------------------------------------------------------------------------
 template <int DIM, int HMODE>
