@@ -169,7 +169,8 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
     c, d = dim + 1, dim
     hs = 8 * E if grid_fh else 0
     return {
-        "memset_zero_region": 4 * (N + 1),
+        # zero the per-iteration counters; 3-D: p read once, the padded copy written once
+        "prep(zero+pad)": 4 * (N + 1) + (56 * N if dim == 3 else 0),
         # t and p read once, keep flags + the kept cells handed to the bar stage written once
         "cull_scatter": 4 * c * T + 8 * d * N + T + 4 * c * Tk,
         # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends) with the
@@ -450,7 +451,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 4 * K,
+        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, adjacency_heavy, vertex_update
         "roofline": roofline, "cpu_baseline": cpu,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
     }

@@ -164,12 +164,12 @@ typedef struct DmPlan {
   int32_t dim, _pad0;
   int64_t K;         /* dim*(dim+1)*T : directed (vertex, neighbour) candidates */
   uint8_t *keep;
-  void *zero_base;   /* [cnt | sync | counters]: ONE memset per iteration */
+  void *zero_base;   /* [cnt | sync | counters]: zeroed by stage A's prep kernel */
   size_t zero_bytes;
   int32_t *cnt;
-  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] heavy blocks done */
+  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] heavy blocks done [4] projection blocks done */
   int32_t *counters; /* [0]=E unique bars [1]=reserved [2]=spill records [3]=heavy vertices
-                        [4]=heap cursor (ints) */
+                        [4]=heap cursor (ints) [5]=escaped vertices (stage D) */
   void *bucket;
   int32_t *ovf_v;
   void *ovf_e;
@@ -182,6 +182,8 @@ typedef struct DmPlan {
   double *hbar;
   double *partials;  /* per-block partial sums / maxima */
   double *scalars;   /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp */
+  double *p4;        /* 3-D: (N,4) padded copy of p made by stage A (32-B rows: one 256-bit gather) */
+  int32_t *esc;      /* (N) vertices that left a level set in stage D, projected by its second kernel */
   void *scan_tmp;    /* scratch of the on-demand scans */
   size_t scan_tmp_bytes;
 } DmPlan;

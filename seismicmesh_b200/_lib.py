@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdistmesh_b200.so")
+# DM_LIB_PATH: developer override to time an experimental build of the same C ABI (still CUDA-only)
+LIB_PATH = os.environ.get("DM_LIB_PATH") or os.path.join(_HERE, "libdistmesh_b200.so")
 
 DM_MAX_LEVELS = 8
 DM_SDF_WORDS = 24
@@ -56,6 +57,8 @@ class DmPlan(C.Structure):
         ("hbar", C.c_void_p),
         ("partials", C.c_void_p),
         ("scalars", C.c_void_p),
+        ("p4", C.c_void_p),
+        ("esc", C.c_void_p),
         ("scan_tmp", C.c_void_p),
         ("scan_tmp_bytes", C.c_size_t),
     ]

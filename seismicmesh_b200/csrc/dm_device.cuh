@@ -7,7 +7,17 @@
 
 namespace dm {
 
-template <int DIM>
+// 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): one request per gathered 3-D point
+__device__ __forceinline__ void ldg256(const double* q, double& a, double& b, double& c, double& d) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(q));
+}
+__device__ __forceinline__ void stg256(double* q, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(q), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// PAD: 3-D points come from the plan's padded copy (4 doubles = 32 B per point, 32-B aligned: a
+// gather is ONE 256-bit request touching one sector instead of three 8-B requests over two)
+template <int DIM, bool PAD = false>
 __device__ __forceinline__ void load_pt(const double* __restrict__ p, int64_t i, double& x0, double& x1,
                                         double& x2) {
   if (DIM == 2) {
@@ -15,6 +25,9 @@ __device__ __forceinline__ void load_pt(const double* __restrict__ p, int64_t i,
     x0 = v.x;
     x1 = v.y;
     x2 = 0.0;
+  } else if (PAD) {
+    double w;
+    ldg256(p + 4 * i, x0, x1, x2, w);
   } else {
     const double* q = p + 3 * i;
     x0 = q[0];
@@ -46,12 +59,12 @@ __device__ __forceinline__ void load_cell(const int32_t* __restrict__ t, int64_t
 }
 
 // centroid p[t].sum(1)/(dim+1), vertices added in order (mesh_generator.py:737)
-template <int DIM>
+template <int DIM, bool PAD = false>
 __device__ __forceinline__ void cell_centroid(const double* __restrict__ p, const int (&v)[4], double& c0,
                                               double& c1, double& c2) {
   double q[DIM + 1][3];
 #pragma unroll
-  for (int k = 0; k <= DIM; ++k) load_pt<DIM>(p, v[k], q[k][0], q[k][1], q[k][2]);  // all gathers in flight
+  for (int k = 0; k <= DIM; ++k) load_pt<DIM, PAD>(p, v[k], q[k][0], q[k][1], q[k][2]);  // all gathers in flight
   double a0 = q[0][0], a1 = q[0][1], a2 = q[0][2];
 #pragma unroll
   for (int k = 1; k <= DIM; ++k) {

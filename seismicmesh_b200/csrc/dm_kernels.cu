@@ -87,6 +87,8 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   char* hbar = take((size_t)(K1 / 2 + 1) * 8);
   char* partials = take((size_t)(2 * nblocks) * 8);
   char* scalars = take(8 * 8);
+  char* p4 = take(DIM == 3 ? (size_t)(N + 1) * 32 : 0);
+  char* esc = take((size_t)(N + 1) * 4);
   const size_t scan_bytes = scan_scratch_bytes(N + 1);
   char* scan_tmp = take(scan_bytes);
   if (pl) {
@@ -113,6 +115,8 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
     pl->hbar = reinterpret_cast<double*>(hbar);
     pl->partials = reinterpret_cast<double*>(partials);
     pl->scalars = reinterpret_cast<double*>(scalars);
+    pl->p4 = DIM == 3 ? reinterpret_cast<double*>(p4) : nullptr;
+    pl->esc = reinterpret_cast<int32_t*>(esc);
     pl->scan_tmp = scan_tmp;
     pl->scan_tmp_bytes = scan_bytes;
   }
@@ -149,22 +153,38 @@ int launch_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn& f, int hm
   return (int)cudaGetLastError();
 }
 
+// pad: gather neighbour positions from the plan's padded copy (made by stage A from this same p)
 template <int DIM>
-int launch_vertex_update(const DmPlan* pl, const double* p, double* p_out, const Levels& lv, const DmSizeFn& f,
-                         int hmode, double L0mult, double delta_t, double deps, double h0, int64_t nfix,
-                         const uint8_t* fixed, double* Ftot, cudaStream_t st) {
-  const unsigned nb = nblk(pl->N, PL_THREADS);
-#define DM_VU(H)                                                                                                  \
-  vertex_update_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, p_out, rows_of<DIM>(pl), pl->rowptr, pl->hslot,   \
-                                                          pl->hbar, pl->scalars, pl->N, lv, L0mult, delta_t, deps, \
-                                                          h0, nfix, fixed, Ftot, pl->partials, pl->sync + 2,       \
-                                                          pl->scalars)
-  switch (hmode) {
-    case 0: DM_VU(0); break;
-    case 1: DM_VU(1); break;
-    default: DM_VU(2); break;
+int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_out, const Levels& lv,
+                         const DmSizeFn& f, int hmode, double L0mult, double delta_t, double deps, double h0,
+                         int64_t nfix, const uint8_t* fixed, double* Ftot, cudaStream_t st) {
+  const unsigned nb = nblk(pl->N, VU_THREADS);
+  const double* pg = pad ? pl->p4 : p;
+#define DM_VU(H, P)                                                                                              \
+  vertex_update_kernel<DIM, H, P><<<nb, VU_THREADS, 0, st>>>(f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr,      \
+                                                             pl->hslot, pl->hbar, pl->scalars, pl->N, lv, L0mult, \
+                                                             delta_t, deps, h0, nfix, fixed, Ftot, pl->partials,  \
+                                                             pl->sync + 2, pl->scalars, pl->esc, pl->counters + 5)
+  if (DIM == 3 && pad) {
+    switch (hmode) {
+      case 0: DM_VU(0, true); break;
+      case 1: DM_VU(1, true); break;
+      default: return DM_ERR_ARG;
+    }
+  } else {
+    switch (hmode) {
+      case 0: DM_VU(0, false); break;
+      case 1: DM_VU(1, false); break;
+      default: DM_VU(2, false); break;
+    }
   }
 #undef DM_VU
+  mark("vertex_update+maxdp", st);
+  if (lv.n > 0) {  // Newton projection of the listed (escaped) vertices
+    project_list_kernel<DIM><<<PJ_BLOCKS, PJ_THREADS, 0, st>>>(lv, deps, h0, pl->esc, pl->counters + 5, pl->sync + 4,
+                                                               p_out);
+    mark("project_escaped", st);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -172,19 +192,11 @@ template <int DIM>
 static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
                               int mode, cudaStream_t st) {
   typedef typename PCfg<DIM>::entry_t entry_t;
-  static const int agg = getenv("DM_AGG_MODE") ? atoi(getenv("DM_AGG_MODE")) : 2;  // tuning knob (profiling)
   const unsigned nb = nblk(pl->T, PL_THREADS);
-#define DM_CS(A)                                                                                               \
-  cull_scatter_kernel<DIM, A><<<nb, PL_THREADS, 0, st>>>(prog, p, t, pl->T, geps, mode, pl->keep, pl->cnt, \
-                                                               static_cast<entry_t*>(pl->bucket), pl->ovf_v,   \
-                                                               static_cast<entry_t*>(pl->ovf_e), pl->counters)
-  switch (agg) {
-    case 0: DM_CS(0); break;
-    case 1: DM_CS(1); break;
-    case 3: DM_CS(3); break;
-    default: DM_CS(2); break;
-  }
-#undef DM_CS
+  const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
+  cull_scatter_kernel<DIM, DIM == 3><<<nb, PL_THREADS, 0, st>>>(prog, pc, t, pl->T, geps, mode, pl->keep, pl->cnt,
+                                                                static_cast<entry_t*>(pl->bucket), pl->ovf_v,
+                                                                static_cast<entry_t*>(pl->ovf_e), pl->counters);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
@@ -203,7 +215,7 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   DmSizeFn fz;
   memset(&fz, 0, sizeof(fz));
   const DmSizeFn& ff = f ? *f : fz;
-  const double* pp = p;
+  const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
 #define DM_ADJ(B)                                                                                                  \
   adjacency_kernel<DIM, B><<<nb, AB_THREADS, 0, st>>>(pl->cnt, bucket, N, pl->adj, pl->heap, degs, pl->hv,          \
                                                       pl->counters, ff, pp, pl->hslot, pl->partials);              \
@@ -282,10 +294,10 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (T == 0) return DM_OK;
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
-    cull_scatter_kernel<2, 0><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<2><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   else
-    cull_scatter_kernel<3, 0><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<3><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
   DM_LAUNCH_CHECK();
   return DM_OK;
@@ -395,8 +407,14 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
                         int use_keep, void* stream) {
   if (!pl || (!t && pl->T > 0) || (use_keep && prog && !p)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  DM_CUDA_TRY(cudaMemsetAsync(pl->zero_base, 0, pl->zero_bytes, st));
-  mark("memset_zero_region", st);
+  {  // zero [cnt | sync | counters] and (3-D) refresh the padded point copy, one launch
+    const int64_t zq = (int64_t)(pl->zero_bytes / 16);
+    const bool pad = pl->dim == 3 && p != nullptr;
+    const int64_t n = pad && pl->N > zq ? pl->N : zq;
+    prep_kernel<<<nblk(n, PL_THREADS), PL_THREADS, 0, st>>>(static_cast<int4*>(pl->zero_base), zq, p,
+                                                            pad ? pl->p4 : nullptr, pl->N);
+    mark("prep(zero+pad)", st);
+  }
   if (pl->T == 0) return DM_OK;
   const int mode = !use_keep ? 2 : (prog ? 0 : 1);
   return pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t, geps, mode, st)
@@ -457,7 +475,7 @@ int dm_stage_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn* f, void
   return rc;
 }
 
-static int vertex_update_impl(const DmPlan* pl, const double* p, double* p_out, const double* const* progs,
+static int vertex_update_impl(const DmPlan* pl, const double* p, bool pad, double* p_out, const double* const* progs,
                               int nlevels, const DmSizeFn* f, double L0mult, double delta_t, double deps, double h0,
                               int64_t nfix, const uint8_t* fixed, double* Ftot, cudaStream_t st) {
   Levels lv;
@@ -467,11 +485,10 @@ static int vertex_update_impl(const DmPlan* pl, const double* p, double* p_out, 
     if (!progs[l]) return DM_ERR_ARG;
     lv.prog[l] = progs[l];
   }
-  const int rc = pl->dim == 2 ? launch_vertex_update<2>(pl, p, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0, nfix,
-                                                        fixed, Ftot, st)
-                              : launch_vertex_update<3>(pl, p, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0, nfix,
-                                                        fixed, Ftot, st);
-  mark("vertex_update+maxdp", st);
+  const int rc = pl->dim == 2 ? launch_vertex_update<2>(pl, p, false, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0,
+                                                        nfix, fixed, Ftot, st)
+                              : launch_vertex_update<3>(pl, p, pad, p_out, lv, *f, f->kind, L0mult, delta_t, deps, h0,
+                                                        nfix, fixed, Ftot, st);
   return rc;
 }
 
@@ -481,7 +498,7 @@ int dm_stage_vertex_update(const DmPlan* pl, const double* p, double* p_out, con
   if (!pl || !p || !p_out || p == p_out || nlevels < 0 || nlevels > DM_MAX_LEVELS) return DM_ERR_ARG;
   if ((nlevels > 0 && !progs) || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  return vertex_update_impl(pl, p, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,
+  return vertex_update_impl(pl, p, false, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,
                             st);
 }
 
@@ -497,7 +514,7 @@ int dm_force_iteration(const DmPlan* pl, const double* const* progs, int nlevels
   if (rc) return rc;
   rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
   if (rc) return rc;
-  return vertex_update_impl(pl, p, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
+  return vertex_update_impl(pl, p, true, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }
 
 int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,

@@ -35,6 +35,16 @@ constexpr int AB_THREADS = 256;  // adjacency: 256 / G vertices per block
 constexpr int HV_THREADS = 256;  // heavy-vertex path: one block per vertex
 constexpr int HV_BLOCKS = 296;   // fixed grid (2 per SM); loops over the heavy list
 constexpr int HV_SMEM = 6144;    // candidates sorted in shared memory up to this many (ints; 24 KB)
+// tuning knobs (resident blocks per SM the register allocation is held to)
+#ifndef DM_CS_MINB
+#define DM_CS_MINB 4
+#endif
+#ifndef DM_HASH_MAXSTEPS
+#define DM_HASH_MAXSTEPS 12
+#endif
+#ifndef DM_VU_MINB
+#define DM_VU_MINB 8
+#endif
 
 template <int DIM>
 struct PCfg;
@@ -75,6 +85,20 @@ struct Rows {
 };
 
 // ---------------------------------------------------------------------------------------------
+// prep: zero the per-iteration counters and (3-D) make the padded point copy p4 (N,4)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PL_THREADS) prep_kernel(int4* __restrict__ zero, int64_t zquads,
+                                                         const double* __restrict__ p, double* __restrict__ p4,
+                                                         int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < zquads) zero[i] = make_int4(0, 0, 0, 0);
+  if (p4 != nullptr && i < N) {
+    const double* q = p + 3 * i;
+    stg256(p4 + 4 * i, q[0], q[1], q[2], 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // A: cull + scatter.  mode 0: evaluate fd on the centroid, write keep ; 1: keep given ; 2: all kept
 // ---------------------------------------------------------------------------------------------
 template <int DIM>
@@ -88,11 +112,15 @@ __device__ __forceinline__ int2 others_of<2>(const int (&ids)[4], int j) {
   return make_int2(ids[j == 0 ? 1 : 0], ids[j <= 1 ? 2 : 1]);
 }
 
-// AGG: how lanes that claim a slot of the same vertex in the same step share one atomic
-//   0 none ; 1 match.any at every position ; 2 equal-id runs of consecutive lanes (shfl + ballot) ;
-//   3 match.any at position 0 (the apex Qhull groups its facets around), runs elsewhere
-template <int DIM, int AGG>
-__global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
+// Lanes that claim a slot of the same vertex in the same step share one atomic when they are
+// consecutive (equal-id runs: host Delaunay codes emit cells grouped around vertices).
+// The kernel sits at the L1 data-pipe bound of its access pattern: about one scattered access (a
+// position gather, a slot claim, an entry store: ~33 M of them on the ball h0=0.02 mesh) per SM per
+// cycle; l1tex__data_pipe_lsu_wavefronts is its top ncu metric.  Measured and rejected: claiming the
+// slots before the cull decision is known + prefetching the next cell in a grid-stride loop (the
+// longer live ranges spill and cost more than the overlap gains), more resident blocks, 4-byte entries.
+template <int DIM, bool PAD = false>
+__global__ void __launch_bounds__(PL_THREADS, DM_CS_MINB) cull_scatter_kernel(
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
     typename PCfg<DIM>::entry_t* __restrict__ bucket, int32_t* __restrict__ ovf_v,
@@ -107,7 +135,7 @@ __global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
     k = true;
     if (mode == 0) {
       double c0, c1, c2;
-      cell_centroid<DIM>(p, ids, c0, c1, c2);
+      cell_centroid<DIM, PAD>(p, ids, c0, c1, c2);
       k = sdf_eval(prog, DIM, c0, c1, c2) < -geps;
       keep[c] = k ? 1 : 0;
     } else if (mode == 1) {
@@ -117,41 +145,24 @@ __global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
   if (cnt == nullptr) return;
   // Slot claims of the DIM+1 vertices are independent: issue all the atomics first and only then
   // wait for them, so a warp pays ONE L2 round trip instead of DIM+1.
-  const unsigned km = __ballot_sync(FULL, k);
   const unsigned lt = (1u << lane) - 1u;
   int base[DIM + 1], rank[DIM + 1], leader[DIM + 1];
 #pragma unroll
   for (int j = 0; j <= DIM; ++j) {
-    const bool use_match = AGG == 1 || (AGG == 3 && j == 0);
-    const bool use_runs = AGG == 2 || (AGG == 3 && j != 0);
+    const int vj = k ? ids[j] : -1 - lane;  // a culled lane never continues a run
+    const int prev = __shfl_up_sync(FULL, vj, 1);
+    const unsigned heads = __ballot_sync(FULL, lane == 0 || vj != prev);
+    const int start = 31 - __clz(heads & (lt | (1u << lane)));
+    const unsigned above = heads & ~(lt | (1u << lane));
+    const int end = above ? __ffs(above) - 1 : 32;
+    leader[j] = start;
+    rank[j] = lane - start;
     base[j] = 0;
-    rank[j] = 0;
-    leader[j] = lane;
-    if (use_match) {
-      if (k) {
-        const unsigned m = __match_any_sync(km, ids[j]);
-        leader[j] = __ffs(m) - 1;
-        rank[j] = __popc(m & lt);
-        if (lane == leader[j]) base[j] = atomicAdd(cnt + ids[j], __popc(m));
-      }
-    } else if (use_runs) {
-      const int vj = k ? ids[j] : -1 - lane;  // a culled lane never continues a run
-      const int prev = __shfl_up_sync(FULL, vj, 1);
-      const unsigned heads = __ballot_sync(FULL, lane == 0 || vj != prev);
-      const int start = 31 - __clz(heads & (lt | (1u << lane)));
-      const unsigned above = heads & ~(lt | (1u << lane));
-      const int end = above ? __ffs(above) - 1 : 32;
-      leader[j] = start;
-      rank[j] = lane - start;
-      if (k && lane == start) base[j] = atomicAdd(cnt + ids[j], end - start);
-    } else {
-      if (k) base[j] = atomicAdd(cnt + ids[j], 1);
-    }
+    if (k && lane == start) base[j] = atomicAdd(cnt + ids[j], end - start);
   }
 #pragma unroll
   for (int j = 0; j <= DIM; ++j) {
-    int slot = base[j];
-    if (AGG != 0) slot = __shfl_sync(FULL, base[j], leader[j]) + rank[j];
+    const int slot = __shfl_sync(FULL, base[j], leader[j]) + rank[j];
     if (k) {
       const typename PCfg<DIM>::entry_t e = others_of<DIM>(ids, j);
       if (slot < CAP) {
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(PL_THREADS) cull_scatter_kernel(
 // B: adjacency rows
 // ---------------------------------------------------------------------------------------------
 constexpr int HASH_EMPTY = -1;
-constexpr int HASH_MAXSTEPS = 12;  // probe sequence longer than this -> vertex goes the heavy way
+constexpr int HASH_MAXSTEPS = DM_HASH_MAXSTEPS;  // probe sequence longer than this -> vertex goes the heavy way
 
 template <int LOGH>
 __device__ __forceinline__ unsigned hash_slot(int x) {
@@ -186,15 +197,17 @@ __device__ __forceinline__ unsigned hash_slot(int x) {
 // issue slots, so the body keeps no per-candidate flag: a finished candidate is parked on the
 // lane's private word behind the table (tab[H + lg], one bank per lane of the warp, so parked
 // accesses never conflict) with its key replaced by the parked word's content, and from then on
-// it "hits" there for free.  Lanes without a candidate are handed a copy of a real key of the same
-// vertex (a duplicate insert is a no-op).
+// it "hits" there for free.  A negative key (idle lane) starts parked.
 constexpr int HASH_PARKED = -2;
 template <int NC, int LOGH>
 __device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC], unsigned park, bool& punt) {
   constexpr unsigned HM = (1u << LOGH) - 1u;
   unsigned h[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) h[c] = hash_slot<LOGH>(x[c]);
+  for (int c = 0; c < NC; ++c) {
+    h[c] = x[c] < 0 ? park : hash_slot<LOGH>(x[c]);  // no candidate (idle lane): parked
+    x[c] = x[c] < 0 ? HASH_PARKED : x[c];
+  }
   int steps = 0;
   bool any;
   do {
@@ -224,7 +237,7 @@ template <int DIM, bool GRID>
 __device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __restrict__ pp, double a0, double a1,
                                           double a2, int w, double* hout, double& sL, double& sH) {
   double b0, b1, b2, d0, d1, d2;
-  load_pt<DIM>(pp, w, b0, b1, b2);
+  load_pt<DIM, true>(pp, w, b0, b1, b2);  // pp: the plan's padded point copy
   const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
   double h = f.hconst;
   if (GRID) {
@@ -290,7 +303,6 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
   constexpr int EPL = 2;
   typedef typename PCfg<DIM>::entry_t entry_t;
   const entry_t* brow = bucket + v * CAP;
-  const int key0 = n > 0 ? reinterpret_cast<const int*>(brow)[0] : 0;  // filler for idle lanes
   entry_t cur[EPL], nxt[EPL];
 #pragma unroll
   for (int u = 0; u < EPL; ++u)
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
       const bool a = i + u * G < n;
       const int* ei = reinterpret_cast<const int*>(&cur[u]);
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) x[u * DIM + c] = a ? ei[c] : key0;
+      for (int c = 0; c < DIM; ++c) x[u * DIM + c] = a ? ei[c] : -1;
     }
     hash_insert_lockstep<EPL * DIM, LOGH>(tab, x, (unsigned)(H + lg), punt);
 #pragma unroll
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
     if (lg >= d) inc += o;
   }
   int U = __shfl_sync(FULL, inc, G - 1, G);
-  if (punt || n == 0) U = 0;  // n == 0: nothing but filler keys went in
+  if (punt) U = 0;
   {
     int off = inc - c;
 #pragma unroll
@@ -396,7 +408,7 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
       }
       if (BAR >= 0 && U > lo) {  // bar pass over the upper neighbours (mesh_generator.py:696-700)
         double a0, a1, a2;
-        load_pt<DIM>(pp, v, a0, a1, a2);
+        load_pt<DIM, true>(pp, v, a0, a1, a2);
         for (int j = lo + lg; j < U; j += G) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH);
       }
     }
@@ -559,9 +571,10 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
         const int i = tid + u * HV_THREADS;
-        first[u] = i < n;
         x[u] = i < n ? s_val[i] : 0;
+        first[u] = i < n;
       }
+#pragma unroll 8  // the shared-memory loads of eight steps in flight (latency, not issue, bounds this sweep)
       for (int j = 0; j < n; ++j) {
         const int y = s_val[j];
 #pragma unroll
@@ -579,6 +592,7 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
       int r[PER];
 #pragma unroll
       for (int u = 0; u < PER; ++u) r[u] = 0;
+#pragma unroll 8
       for (int j = 0; j < n; ++j) {
         const int y = s_val[j];
         const int fj = s_first[j];
@@ -638,7 +652,7 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
     if (BAR >= 0) {
       double sL = 0.0, sH = 0.0;
       double a0, a1, a2;
-      load_pt<DIM>(pp, v, a0, a1, a2);
+      load_pt<DIM, true>(pp, v, a0, a1, a2);
       for (int j = lo + tid; j < U; j += HV_THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
       const double bl = block_sum(sL, s_dbl);
       const double bh = block_sum(sH, s_dbl);
@@ -672,6 +686,7 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
     for (int i = tid; i < nheavy; i += HV_THREADS) {
       const int x = s_id[i];
       int r = 0;
+#pragma unroll 8
       for (int j = 0; j < nheavy; ++j) r += s_id[j] < x ? 1 : 0;
       s_sorted[2 * r] = __ldcg(partials + 2 * (nb_adj + i));
       s_sorted[2 * r + 1] = __ldcg(partials + 2 * (nb_adj + i) + 1);
@@ -840,13 +855,51 @@ struct Levels {
   int n;
 };
 
-template <int DIM, int HMODE>
-__global__ void __launch_bounds__(PL_THREADS) vertex_update_kernel(
-    const DmSizeFn f, const double* __restrict__ p, double* __restrict__ p_out, const Rows<DIM> R,
-    const int32_t* __restrict__ rowptr, const double* __restrict__ hslot, const double* __restrict__ hbar,
-    const double* scalars_in, int64_t N, Levels lv, double L0mult, double delta_t, double deps, double h0,
-    int64_t nfix, const uint8_t* __restrict__ fixed, double* __restrict__ Ftot, double* partials, int32_t* done,
-    double* scalars) {
+// One thread per vertex.  The reference accumulates bar by bar (coo_matrix.toarray): row v
+// receives -Fvec of its lower bars (u,v), u ascending, then +Fvec of its upper bars (v,w), w
+// ascending.  The row is sorted, and -(F/L*(p[u]-p[v])) == (F/L)*(p[v]-p[u]) exactly, so one
+// ascending sweep with d = p[v]-p[nbr] reproduces the reference's sum bit for bit.
+// The kernel is latency bound (dependent row load -> position gather -> sqrt -> divide per
+// neighbour), so the row is consumed four neighbours at a time: their gathers and their
+// sqrt / divide chains are independent and in flight together, only the additions into F are
+// serial.  Slots past the end of the row are redirected to the vertex itself (a valid address;
+// their term is discarded).  (A lane-group-per-vertex variant with the ordered sum done through
+// shared memory was measured at 2.4x the time of this one: the serial tail then holds a whole block.)
+constexpr int VU_THREADS = 128;
+
+// The listed vertices (those that left a level set, see vertex_update_kernel) get the reference's
+// sequence of projections, level after level, starting from the updated position in p_out: a vertex
+// that is not listed is one no level would have moved, so the result equals projecting everybody.
+constexpr int PJ_THREADS = 128;
+constexpr int PJ_BLOCKS = 592;
+template <int DIM>
+__global__ void __launch_bounds__(PJ_THREADS) project_list_kernel(const Levels lv, double deps, double h0,
+                                                                  const int32_t* __restrict__ esc,
+                                                                  int32_t* esc_count, int32_t* done,
+                                                                  double* __restrict__ p_out) {
+  const int n = *reinterpret_cast<volatile int32_t*>(esc_count);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = esc[i];
+    double x0, x1, x2;
+    load_pt<DIM>(p_out, v, x0, x1, x2);
+    for (int l = 0; l < lv.n; ++l) sdf_project(lv.prog[l], DIM, deps, h0, l, x0, x1, x2);
+    store_pt<DIM>(p_out, v, x0, x1, x2);
+  }
+  // the last block to finish empties the list, so stage D can run again without stage A
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(done, 1) == (int)gridDim.x - 1) {
+    *esc_count = 0;
+    *done = 0;
+  }
+}
+
+template <int DIM, int HMODE, bool PAD>
+__global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
+    const DmSizeFn f, const double* __restrict__ p, const double* __restrict__ pg, double* __restrict__ p_out,
+    const Rows<DIM> R, const int32_t* __restrict__ rowptr, const double* __restrict__ hslot,
+    const double* __restrict__ hbar, const double* scalars_in, int64_t N, Levels lv, double L0mult, double delta_t,
+    double deps, double h0, int64_t nfix, const uint8_t* __restrict__ fixed, double* __restrict__ Ftot,
+    double* partials, int32_t* done, double* scalars, int32_t* __restrict__ esc, int32_t* __restrict__ esc_count) {
   __shared__ double sm[32];
   __shared__ bool s_last;
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -855,45 +908,49 @@ __global__ void __launch_bounds__(PL_THREADS) vertex_update_kernel(
     const double scale = __ldcg(scalars_in + 2);
     const double k0 = L0mult;
     double a0, a1, a2;
-    load_pt<DIM>(p, v, a0, a1, a2);
+    load_pt<DIM, PAD>(pg, v, a0, a1, a2);
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
     const int2 dg = R.degs[v];
     const int lo = dg.y, m = dg.x;
     const int32_t* row = R.row(v, m);
     const int64_t base = R.slot_base(v, m);
-    // The reference accumulates bar by bar (coo_matrix.toarray): row v receives -Fvec of its
-    // lower bars (u,v), u ascending, then +Fvec of its upper bars (v,w), w ascending.  The row is
-    // sorted, and -(F/L*(p[u]-p[v])) == (F/L)*(p[v]-p[u]) exactly, so one ascending sweep with
-    // d = p[v]-p[nbr] reproduces the reference's sum bit for bit.
-    for (int j0 = 0; j0 < m; j0 += 4) {
+    for (int j0 = 0; j0 < m; j0 += 4) {  // rows are 16-B aligned and padded to a multiple of 4 ints
       const int4 q = *reinterpret_cast<const int4*>(row + j0);
       const int wq[4] = {q.x, q.y, q.z, q.w};
+      double c0[4], c1[4], c2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = j0 + u;
-        if (j >= m) break;
-        const int w = wq[u];
+        const int w = j < m ? wq[u] : (int)v;
         double b0, b1, b2, d0, d1, d2;
-        load_pt<DIM>(p, w, b0, b1, b2);
+        load_pt<DIM, PAD>(pg, w, b0, b1, b2);
         const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
         double h;
         if (HMODE == 0) {
           h = f.hconst;
         } else if (HMODE == 1) {
           if (j >= lo)
-            h = hslot[base + j];
+            h = j < m ? hslot[base + j] : 0.0;
           else  // lower bar: same midpoint bits as its owner computed -> same h bits
             h = size_eval(f, (b0 + a0) / 2, (b1 + a1) / 2, (b2 + a2) / 2);
         } else {
-          const int e = j >= lo ? rowptr[v] + (j - lo) : bar_id_of<DIM>(R, rowptr, w, (int)v);
-          h = hbar[e];
+          h = 0.0;
+          if (j < m) h = hbar[j >= lo ? rowptr[v] + (j - lo) : bar_id_of<DIM>(R, rowptr, w, (int)v)];
         }
         double Fs = h * k0 * scale - L;  // L0 - L  (mesh_generator.py:700-702)
         if (Fs < 0) Fs = 0;
         const double qf = Fs / L;
-        F0 = F0 + qf * d0;
-        F1 = F1 + qf * d1;
-        if (DIM == 3) F2 = F2 + qf * d2;
+        c0[u] = qf * d0;
+        c1[u] = qf * d1;
+        c2[u] = qf * d2;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < m) {
+          F0 = F0 + c0[u];
+          F1 = F1 + c1[u];
+          if (DIM == 3) F2 = F2 + c2[u];
+        }
       }
     }
     if (v < nfix || (fixed != nullptr && fixed[v])) {  // Ftot[ifix] = 0 (mesh_generator.py:499)
@@ -904,10 +961,18 @@ __global__ void __launch_bounds__(PL_THREADS) vertex_update_kernel(
     if (Ftot != nullptr) store_pt<DIM>(Ftot, v, F0, F1, F2);
     f2 = F0 * F0 + F1 * F1;
     if (DIM == 3) f2 = f2 + F2 * F2;
-    // p += delta_t * Ftot (mesh_generator.py:502), then one Newton projection per level (:505-506)
-    double x0 = a0 + delta_t * F0, x1 = a1 + delta_t * F1, x2 = a2 + delta_t * F2;
-    for (int l = 0; l < lv.n; ++l) sdf_project(lv.prog[l], DIM, deps, h0, l, x0, x1, x2);
+    // p += delta_t * Ftot (mesh_generator.py:502).  The Newton projection per level (:505-506) moves
+    // only the few vertices that left a level set; doing it here would leave 1-2 lanes of nearly
+    // every warp walking the finite-difference path while 30 wait, so those vertices are only
+    // LISTED here (fd evaluated once per level, all lanes) and projected by project_list_kernel.
+    const double x0 = a0 + delta_t * F0, x1 = a1 + delta_t * F1, x2 = a2 + delta_t * F2;
     store_pt<DIM>(p_out, v, x0, x1, x2);
+    bool out = false;
+    for (int l = 0; l < lv.n; ++l) {
+      const double d = sdf_eval(lv.prog[l], DIM, x0, x1, x2);
+      out = out || (l == 0 ? (d > 0.0) : (d > 0.0 && d < h0 / 1.5));
+    }
+    if (out) esc[atomicAdd(esc_count, 1)] = (int32_t)v;
   }
   const double bm = block_max(f2, sm);
   if (threadIdx.x == 0) {
@@ -919,11 +984,12 @@ __global__ void __launch_bounds__(PL_THREADS) vertex_update_kernel(
   if (s_last) {
     __threadfence();
     double mx = 0.0;
-    for (int64_t i = threadIdx.x; i < (int64_t)gridDim.x; i += PL_THREADS) mx = fmax(mx, __ldcg(partials + i));
+    for (int64_t i = threadIdx.x; i < (int64_t)gridDim.x; i += VU_THREADS) mx = fmax(mx, __ldcg(partials + i));
     const double r = block_max(mx, sm);
     if (threadIdx.x == 0) {
       scalars[3] = r;
       scalars[4] = delta_t * sqrt(r);  // maxdp, mesh_generator.py:514
+      *done = 0;
     }
   }
 }
