@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- DistMesh force-iteration throughput (vertex-updates/s) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ball|disk] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ball|disk|bp2004|eage] [--impl ours|reference]
 
 A *step* is one pass of the hot path (cull -> unique bars -> forces -> update -> projection ->
 max|dp|, i.e. one iteration of the loop body of SeismicMesh generate_mesh AFTER its Delaunay
@@ -82,13 +82,94 @@ def triangulate(p):
     return t, dt
 
 
-def oracle_step_fn(workload, h0, dim):
+def synth_vp(workload):
+    """Synthetic velocity models of BASELINE.json configs[2] / configs[3]: the
+    named grid shapes and physical extents, layered background + water layer + salt body."""
+    if workload == "bp2004":
+        nz, nx = 1911, 5395
+        bbox = (-12000.0, 0.0, 0.0, 67000.0)
+        z = np.linspace(bbox[0], bbox[1], nz)[:, None]
+        x = np.linspace(bbox[2], bbox[3], nx)[None, :]
+        vp = 1500 + (-z / 12000) * 3000 + 150 * np.sin(x / 3000) * np.cos(z / 1500)
+        vp = np.where(z > -1000 - 300 * np.sin(x / 8000), 1486.0, vp)
+        vp = np.where(((x - 30000) / 9000) ** 2 + ((z + 6000) / 2500) ** 2 < 1, 4790.0, vp)
+        return np.ascontiguousarray(vp), bbox
+    nz, nx, ny = 210, 676, 676
+    bbox = (-4200.0, 0.0, 0.0, 13520.0, 0.0, 13520.0)
+    z = np.linspace(bbox[0], bbox[1], nz)[:, None, None]
+    x = np.linspace(bbox[2], bbox[3], nx)[None, :, None]
+    y = np.linspace(bbox[4], bbox[5], ny)[None, None, :]
+    vp = 1500 + (-z / 4200) * 2800 + 120 * np.sin(x / 2500) * np.cos(y / 2000) + 0 * z
+    r2 = ((x - 6500) / 3000) ** 2 + ((y - 7000) / 2600) ** 2 + ((z + 2300) / 900) ** 2
+    vp = np.where(r2 < 1, 4480.0, vp)
+    return np.ascontiguousarray(vp), bbox
+
+
+def build_workload(workload, h0=None, freq=None, settle=2):
+    """-> dict(p, t, dim, dom, size, h0, spec, fh_grid, delaunay_s, desc).  ball / disk: the reference's
+    lattice inside the SDF (uniform h).  bp2004 / eage: gridded fh from our own
+    get_sizing_function_from_segy on the synthetic velocity model (device gradient limiter), the
+    reference's rejection-sampled initial points, then `settle` real iterations so that the timed
+    (p, t) is a mid-run state (non-degenerate Delaunay), as for the jittered ball."""
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200.engine import SizeSpec
+
+    if workload in ("ball", "disk"):
+        h0 = h0 or (0.02 if workload == "ball" else 0.01)
+        p, dim = make_points(workload, h0)
+        dom = sm.Ball([0.0, 0.0, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 0.0], 1.0)
+        t, dt = triangulate(p)
+        spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)) if dim == 3 else ("disk", dict(x0=[0.0, 0.0], r=1.0))
+        return dict(p=p, t=t, dim=dim, dom=dom, size=SizeSpec(dim, const=h0), h0=h0, spec=spec, fh_grid=None,
+                    delaunay_s=dt, desc=f"{workload}_h0={h0:g}", sizing_s=0.0)
+    import torch
+
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200.engine import ForceLoop, Level
+    from seismicmesh_b200.generation import _initial_points
+
+    vp, bbox = synth_vp(workload)
+    if workload == "bp2004":  # README.md:176-186, benchmarks/benchmark_BP2004.py:31-39
+        hmin, fr = h0 or 75.0, freq or 2.0
+        kw = dict(hmin=hmin, wl=10, freq=fr, dt=0.001, grade=0.15, domain_pad=1e3, pad_style="edge",
+                  nz=vp.shape[0], nx=vp.shape[1])
+        dim = 2
+    else:  # README.md:275-292
+        hmin, fr = h0 or 150.0, freq or 2.0
+        kw = dict(hmin=hmin, wl=5, freq=fr, dt=0.001, grade=0.15, hmax=5e3, domain_pad=250.0,
+                  pad_style="linear_ramp", nz=vp.shape[0], nx=vp.shape[1], ny=vp.shape[2])
+        dim = 3
+    t0 = time.perf_counter()
+    ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, **kw)
+    sizing_s = time.perf_counter() - t0
+    del vp
+    dom = sm.Rectangle(ef.bbox) if dim == 2 else sm.Cube(ef.bbox)
+    size = SizeSpec(dim, interp=ef.interpolant())
+    geps, deps = 0.1 * hmin, np.sqrt(np.finfo(np.double).eps) * hmin
+    level = Level(dom, dim)
+    p = _initial_points(hmin, geps, dim, np.array(ef.bbox).reshape(-1, 2), size, level, np.empty((0, dim)),
+                        dict(r0m_is_h0=False, seed=0))
+    p = np.ascontiguousarray(p)
+    loop = ForceLoop(dim, [level], size, hmin, geps, deps)
+    dt = 0.0
+    for _ in range(settle):
+        t, dt = triangulate(p)
+        p = loop.iterate(D.to_dev(p, torch.float64), D.to_dev(t, torch.int32))[0].cpu().numpy()
+    t, dt = triangulate(p)
+    spec = ("rectangle", dict(bbox=tuple(ef.bbox))) if dim == 2 else ("cube", dict(bbox=tuple(ef.bbox)))
+    g = ef.interpolant()
+    return dict(p=p, t=t, dim=dim, dom=dom, size=size, h0=hmin, spec=spec, fh_grid=(g.grid, g.values),
+                delaunay_s=dt, sizing_s=sizing_s,
+                desc=f"{workload}_shaped_grid{'x'.join(str(n) for n in g.values.shape)}_hmin={hmin:g}_freq={fr:g}")
+
+
+def oracle_step_fn(wl):
     """The reference's loop body (oracle port, + the reference's own native unique_edges from
     oracle/_ref when it was built) as a closure step(p, t) -> p_new."""
     from oracle import distmesh_oracle as orc
     from oracle import ref_harness
 
-    spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)) if workload == "ball" else ("disk", dict(x0=[0.0, 0.0], r=1.0))
+    spec, h0 = wl["spec"], wl["h0"]
     native = None
     if ref_harness.native_available():
         try:
@@ -104,7 +185,11 @@ def oracle_step_fn(workload, h0, dim):
         orc.unique_bars = unique_bars
     geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
     fd = lambda x: orc.sdf(spec, x)  # noqa: E731
-    fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    if wl["fh_grid"] is None:
+        fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    else:
+        axes, grid = wl["fh_grid"]
+        fh = lambda x: orc.interp_grid(list(axes), grid, x)  # noqa: E731
 
     def step(p, t):
         return orc.force_iteration(p, t, [fd], fh, h0, geps, deps)["p"]
@@ -197,18 +282,24 @@ def run_reference(args, rank, world):
         return
     K, W = args.steps, args.warmup
     workload = args.workload
-    base_h0 = 0.02 if workload == "ball" else 0.01
-    # bounded sample: coarsen h0 until (K+W) steps + set-up fit in ~150 s (cost ~ 1/h0^dim)
-    dim = 3 if workload == "ball" else 2
-    est_full = 8.0 if workload == "ball" else 0.12
-    h0 = base_h0
-    for cand in (1.0, 1.25, 1.5, 2.0, 3.0):
-        h0 = base_h0 * cand
-        if (K + W) * est_full / cand**dim + (30.0 if workload == "ball" else 1.0) / cand**dim <= 150.0:
-            break
-    p, dim = make_points(workload, h0)
-    t, tq = triangulate(p)
-    step, kind = oracle_step_fn(workload, h0, dim)
+    if workload in ("ball", "disk"):
+        base_h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
+        # bounded sample: coarsen h0 until (K+W) steps + set-up fit in ~150 s (cost ~ 1/h0^dim)
+        dim = 3 if workload == "ball" else 2
+        est_full = 8.0 if workload == "ball" else 0.12
+        h0 = base_h0
+        for cand in (1.0, 1.25, 1.5, 2.0, 3.0):
+            h0 = base_h0 * cand
+            if (K + W) * est_full / cand**dim + (30.0 if workload == "ball" else 1.0) / cand**dim <= 150.0:
+                break
+        wl = build_workload(workload, h0)
+    else:
+        # gridded workloads need the device for their set-up (sizing function, settling iterations);
+        # the timed loop body below is host-only
+        wl = build_workload(workload, args.h0, args.freq)
+        base_h0 = h0 = wl["h0"]
+    p, t, dim, tq = wl["p"], wl["t"], wl["dim"], wl["delaunay_s"]
+    step, kind = oracle_step_fn(wl)
     for _ in range(W):
         step(p, t)
     t0 = time.perf_counter()
@@ -217,11 +308,11 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     N = len(p)
     val = N * K / dt
-    sample = f"{workload} h0={h0:g} (N={N}, T={len(t)}), {K} steps of the full loop body on 1 core"
+    sample = f"{wl['desc']} (N={N}, T={len(t)}), {K} steps of the full loop body on 1 core"
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"{workload}_h0={base_h0:g}", "sample_h0": h0, "delaunay": "excluded (host, set-up)"},
+        "data": "synthetic", "config": {"workload": wl["desc"] if workload not in ("ball", "disk") else f"{workload}_h0={base_h0:g}", "sample_h0": h0, "delaunay": "excluded (host, set-up)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "detail": kind},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "delaunay_s": tq,
@@ -235,8 +326,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ball", choices=["ball", "disk"])
-    ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing (scale-up runs)")
+    ap.add_argument("--workload", default="ball", choices=["ball", "disk", "bp2004", "eage"])
+    ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing / hmin (scale-up runs)")
+    ap.add_argument("--freq", type=float, default=None, help="bp2004 / eage: override the sizing frequency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
     args = ap.parse_args()
@@ -264,28 +356,32 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     workload = args.workload
-    h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
     K, W = args.steps, args.warmup
 
     # ---- set-up (untimed): points + ONE host Delaunay per rank (weak scaling: one slab per GPU) ----
     layout = None
     if world == 1:
-        p, dim = make_points(workload, h0)
-        dom = sm.Ball([0.0, 0.0, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 0.0], 1.0)
+        wl = build_workload(workload, args.h0, args.freq)
+        p, t, dim, dom, h0, t_delaunay = wl["p"], wl["t"], wl["dim"], wl["dom"], wl["h0"], wl["delaunay_s"]
+        size = wl["size"]
         n_owned = len(p)
     else:
         # weak scaling: a cylinder (3-D) / rectangle (2-D) of `world` slabs along axis 1, each slab
         # with the volume of the N=1 ball / disk; every rank meshes its slab + ghost layers
         from seismicmesh_b200.parallel import make_slab_workload
 
+        if workload not in ("ball", "disk"):
+            raise SystemExit("multi-GPU bench: --workload ball|disk (slab workload)")
+        h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
         p, dim, dom, layout = make_slab_workload(workload, h0, rank, world)
         n_owned = layout.n_owned
-    t, t_delaunay = triangulate(p)
-    if layout is not None:  # cells made only of ghost vertices belong to the neighbours
-        t = np.ascontiguousarray(t[(t < n_owned).any(axis=1)])
+        t, t_delaunay = triangulate(p)
+        t = np.ascontiguousarray(t[(t < n_owned).any(axis=1)])  # cells made only of ghosts belong to the neighbours
+        size = SizeSpec(dim, const=h0)
+        wl = dict(desc=f"{workload}_h0={h0:g}", fh_grid=None, sizing_s=0.0)
     N, T = len(p), len(t)
     geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
-    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+    loop = ForceLoop(dim, [Level(dom, dim)], size, h0, geps, deps)
 
     p_dev = D.to_dev(p, torch.float64)
     t_dev = D.to_dev(t, torch.int32)
@@ -395,7 +491,7 @@ def main():
         acc = cur if acc is None else acc + cur
         names = [nm.raw[i * stride : (i + 1) * stride].split(b"\0")[0].decode() for i in range(n.value)]
     kern_ms = acc / reps
-    alg = algorithmic_bytes(N, T, Tk, E, dim)
+    alg = algorithmic_bytes(N, T, Tk, E, dim, grid_fh=wl["fh_grid"] is not None)
     alg = {k: v for k, v in alg.items() if k in names}
     peak, peak_src = measured_peak()
     table = []
@@ -416,7 +512,7 @@ def main():
     if args.kernel_table:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
         with open(args.kernel_table, "w") as fo:
-            json.dump({"workload": workload, "h0": h0, "N": N, "T": T, "T_kept": Tk, "E": E, "peak_gbs": peak,
+            json.dump({"workload": wl["desc"], "h0": h0, "N": N, "T": T, "T_kept": Tk, "E": E, "peak_gbs": peak,
                        "kernels": table}, fo, indent=1)
     for row in table:
         print("  %-26s %8.4f ms  %5.1f%%  %8.1f GB/s  %5.1f%% of peak" % (
@@ -425,9 +521,8 @@ def main():
     # ---- CPU baseline: the reference's loop body (oracle port) on one host core, same (p, t) ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        step, kind = oracle_step_fn(workload, h0, dim)
-        p0 = make_points(workload, h0, seed=0)[0] if world > 1 else p
-        t0_ = triangulate(p0)[0] if world > 1 else t
+        step, kind = oracle_step_fn(wl)
+        p0, t0_ = p, t
         nrep = 1 if N > 200000 else max(1, int(2e5 // N))
         c0 = time.perf_counter()
         for _ in range(nrep):
@@ -443,7 +538,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{workload}_h0={h0:g}", "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
+        "config": {"workload": wl["desc"], "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
                    "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
                    "parallelism": (f"{world} slabs along axis 1 (owned+ghost per GPU), NCCL P2P halo exchange per step; "
                                    f"halo bytes/step/rank={halo.bytes_per_exchange}") if world > 1 else "single",
@@ -453,7 +548,8 @@ def main():
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
         "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, adjacency_heavy, vertex_update
         "roofline": roofline, "cpu_baseline": cpu,
-        "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "maxdp": maxdp, "wall_s_timed_region": wall,
+        "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "sizing_s": wl["sizing_s"], "maxdp": maxdp,
+        "wall_s_timed_region": wall,
     }
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -254,6 +254,17 @@ int dm_halo_select(const double *p, const int32_t *t, int64_t T, int64_t N, int 
                    const double *boxes_host, int has_below, int has_above, uint8_t *flags,
                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sizing preprocessing: gradient limiting of a gridded size function in place (replaces
+ * _FastHJ.limgrad, sizing/cpp/FastHJ.cpp:63-190, called from _enforce_gradation_sizing,
+ * sizing/mesh_size_function.py:471-496).  f (n0,n1,n2) float64 C order (n2 = 1 in 2-D);
+ * delta = elen*dfdx ; ftol = min(f)*sqrt(1e-9) as in the reference.  Relaxes to the reference's
+ * fixed point (unique up to ftol).  changed_dev: one int32 of device scratch.  Synchronises the
+ * stream every 32 sweeps; *sweeps_host = sweeps run.  DM_ERR_WORKSPACE if max_sweeps did not suffice.
+ * ------------------------------------------------------------------------------------------- */
+int dm_limgrad(double *f, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol,
+               int max_sweeps, int32_t *changed_dev, int *sweeps_host, void *stream);
+
 /* utilities */
 size_t dm_scan_scratch_bytes(int64_t n);
 /* exclusive scan of int32 in[0..n) -> out[0..n], out[n] = total (in == out allowed) */

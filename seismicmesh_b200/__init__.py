@@ -20,7 +20,7 @@ from .geometry import (
     Torus,
     Union,
 )
-from .sizing import GridInterpolant, SizeFunction
+from .sizing import GridInterpolant, SizeFunction, get_sizing_function_from_segy
 
 __version__ = "0.1.0"
 
@@ -42,6 +42,7 @@ __all__ = [
     "generate_mesh",
     "sliver_removal",
     "SizeFunction",
+    "get_sizing_function_from_segy",
     "GridInterpolant",
     "last_run_stats",
 ]

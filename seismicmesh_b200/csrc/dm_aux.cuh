@@ -263,4 +263,33 @@ __global__ void halo_select_kernel(const double* __restrict__ p, const int32_t* 
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// gradient limiting of a gridded size function (sizing/cpp/FastHJ.cpp:63-157, c_limgrad): the
+// reference relaxes node pairs of the 6-edge stencil in a sequential active-set sweep until no
+// pair differs by more than delta (+ ftol).  The operator only ever lowers values and its fixed
+// point is unique (min-plus closure over grid paths), so any relaxation order converges to it:
+// here every node is relaxed against its clamped neighbours in place, one launch per sweep.
+// ---------------------------------------------------------------------------------------------
+__global__ void limgrad_sweep_kernel(double* f, int n0, int n1, int n2, double delta, double ftol,
+                                     int32_t* __restrict__ changed) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k2 = (int)(i % n2), k1 = (int)((i / n2) % n1), k0 = (int)(i / ((int64_t)n2 * n1));
+  const int64_t s1 = n2, s0 = (int64_t)n1 * n2;
+  const double v = __ldcg(f + i);
+  double m = v;
+  if (k2 > 0) m = fmin(m, __ldcg(f + i - 1));
+  if (k2 < n2 - 1) m = fmin(m, __ldcg(f + i + 1));
+  if (k1 > 0) m = fmin(m, __ldcg(f + i - s1));
+  if (k1 < n1 - 1) m = fmin(m, __ldcg(f + i + s1));
+  if (k0 > 0) m = fmin(m, __ldcg(f + i - s0));
+  if (k0 < n0 - 1) m = fmin(m, __ldcg(f + i + s0));
+  const double cand = m + delta;  // FastHJ.cpp:138,147
+  if (v > cand + ftol) {
+    f[i] = cand;
+    *changed = 1;
+  }
+}
+
 }  // namespace dm

@@ -547,6 +547,26 @@ int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, in
   return (int)e;
 }
 
+int dm_limgrad(double* f, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
+               int32_t* changed_dev, int* sweeps_host, void* stream) {
+  if (!f || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;
+  if (n0 > INT32_MAX || n1 > INT32_MAX || n2 > INT32_MAX) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  const int64_t n = n0 * n1 * n2;
+  const int batch = 32;  // sweeps between two looks at the convergence flag
+  int done = 0, flag = 1;
+  while (flag && done < max_sweeps) {
+    DM_CUDA_TRY(cudaMemsetAsync(changed_dev, 0, sizeof(int32_t), st));
+    for (int b = 0; b < batch && done < max_sweeps; ++b, ++done)
+      limgrad_sweep_kernel<<<nblk(n, 256), 256, 0, st>>>(f, (int)n0, (int)n1, (int)n2, delta, ftol, changed_dev);
+    DM_LAUNCH_CHECK();
+    DM_CUDA_TRY(cudaMemcpyAsync(&flag, changed_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DM_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (sweeps_host) *sweeps_host = done;
+  return flag ? DM_ERR_WORKSPACE : DM_OK;  // not converged within max_sweeps
+}
+
 int dm_halo_select(const double* p, const int32_t* t, int64_t T, int64_t N, int dim, const double* boxes,
                    int has_below, int has_above, uint8_t* flags, void* stream) {
   if (!p || !boxes || !flags || T < 0 || N < 0 || bad_dim(dim) || (!t && T > 0)) return DM_ERR_ARG;

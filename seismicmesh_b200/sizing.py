@@ -7,6 +7,7 @@ it is lowered to a device descriptor and evaluated by the CUDA interpolation ker
 exact semantics (float32-rounded axes, linear extrapolation outside the grid).
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -15,7 +16,7 @@ from . import _lib
 from . import device as D
 from ._lib import check, lib
 
-__all__ = ["SizeFunction", "GridInterpolant", "grid_axes"]
+__all__ = ["SizeFunction", "GridInterpolant", "grid_axes", "get_sizing_function_from_segy", "limgrad"]
 
 
 def grid_axes(bbox, shape):
@@ -106,3 +107,163 @@ class SizeFunction:
         if self._interp is not None:
             return self._interp(x)
         return self.cell_size(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# Sizing preprocessing (SURVEY section 8f "next #3"): velocity model -> gridded size function
+# with the reference's interface (sizing/mesh_size_function.py:27-232).  The elementwise steps
+# are host NumPy (one pass each, seconds at most); the gradient limiter -- the reference's only
+# native code on this path (sizing/cpp/FastHJ.cpp) -- runs on the device.
+# ----------------------------------------------------------------------------------------------
+_SIZING_DEFAULTS = {  # mesh_size_function.py:103-126
+    "velocity_data": None, "vp_water": 1500.0, "hmin": 150.0, "hmax": 10000.0, "wl": 0, "freq": 2.0, "grad": 0.0,
+    "grade": 0.0, "stencil_size": 10.0, "space_order": 1, "dt": 0.0, "cr_max": 1.0, "pad_style": "edge",
+    "domain_pad": 0.0, "units": "m-s", "nz": None, "nx": None, "ny": None, "byte_order": "byte_order",
+    "axes_order": (0, 1, 2), "axes_order_sort": "F", "dtype": "float32",
+}
+
+
+def limgrad(cell_size, grade, elen, max_sweeps=None):
+    """Gradient-limit a gridded size function on the device (replaces _FastHJ.limgrad as called by
+    _enforce_gradation_sizing, mesh_size_function.py:471-496): afterwards neighbouring nodes of the
+    2*dim-edge stencil differ by at most ``elen*grade`` (+ the reference's ftol = min*sqrt(1e-9))."""
+    a = np.ascontiguousarray(cell_size, dtype=np.float64)
+    if a.ndim not in (2, 3):
+        raise ValueError("Dimension not supported")
+    shp = a.shape if a.ndim == 3 else (a.shape[0], a.shape[1], 1)
+    D.require_cuda()
+    f = torch.from_numpy(a).to(D.device())
+    flag = torch.zeros(1, dtype=torch.int32, device=f.device)
+    ftol = float(a.min()) * np.sqrt(1e-9)  # FastHJ.cpp:72 (EPS = 1e-9)
+    sweeps = C.c_int(0)
+    cap = int(max_sweeps) if max_sweeps is not None else 4 * int(sum(shp)) + 64
+    check(lib.dm_limgrad(D.ptr(f), shp[0], shp[1], shp[2], float(elen) * float(grade), ftol, cap, D.ptr(flag),
+                         C.byref(sweeps), D.stream_ptr()), "dm_limgrad")
+    limgrad.last_sweeps = sweeps.value
+    return f.cpu().numpy().reshape(a.shape)
+
+
+def _read_bin(filename, nz, nx, ny, byte_order, axes_order, axes_order_sort, dtype):
+    """Binary velocity model -> (z, x, y) array, z flipped (mesh_size_function.py:609-630)."""
+    if (nz is None) or (nx is None) or (ny is None):
+        raise ValueError("Please specify the number of grid points in each dimension (e.g., `nz`, `nx`, `ny`)...")
+    axes = [nz, nx, ny]
+    axes = [axes[o] for o in np.argsort(axes_order)]
+    if byte_order not in ("big", "little"):
+        raise ValueError("Please specify byte_order as either: little or big.")
+    vp = np.fromfile(filename, dtype=np.dtype(dtype).newbyteorder(">" if byte_order == "big" else "<"))
+    vp = vp.reshape(*axes, order=axes_order_sort)
+    return np.flipud(vp.transpose((*axes_order,))), nz, nx, ny
+
+
+def _pad(array, padding, style, extra):  # mesh_size_function.py:575-587
+    if style == "edge":
+        return np.pad(array, padding, "edge")
+    if style == "constant":
+        return np.pad(array, padding, "constant", constant_values=tuple(extra))
+    if style == "linear_ramp":
+        return np.pad(array, padding, "linear_ramp", end_values=tuple(extra))
+    raise ValueError("pad style currently not supported. Try `linear_ramp`, `edge`, or `constant`")
+
+
+def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
+    """Build a mesh-size function from a seismic velocity model: same name, arguments, defaults,
+    errors and step order as the reference (mesh_size_function.py:27-232).  ``velocity_data=`` arrays
+    and binary files are supported; SEG-Y files need ``segyio`` exactly as in the reference."""
+    opts = dict(_SIZING_DEFAULTS)
+    opts.update(kwargs)
+    if comm is not None and getattr(comm, "rank", 0) != 0:
+        return SizeFunction(bbox, lambda p: 1, opts["hmin"])  # the reference computes on rank 0 only (:128,:220)
+    vp, nz, nx, ny = opts["velocity_data"], opts["nz"], opts["nx"], opts["ny"]
+    if vp is None:
+        if str(filename).endswith(".segy"):
+            import segyio  # noqa: F401  (not shipped here; same dependency as the reference, :633-646)
+
+            with segyio.open(filename, ignore_geometry=True) as fh_:
+                nz, nx = len(fh_.samples), len(fh_.trace)
+                vp = np.zeros(shape=(nz, nx))
+                for index, trace in enumerate(fh_.trace):
+                    vp[:, index] = trace
+            vp, ny = np.flipud(vp), 0
+        else:
+            vp, nz, nx, ny = _read_bin(filename, nz, nx, ny, opts["byte_order"], opts["axes_order"],
+                                       opts["axes_order_sort"], opts["dtype"])
+    if opts["units"] == "km-s":
+        vp *= 1000.0
+    elif opts["units"] == "ft-s":
+        vp *= 0.30
+    pos = np.where(vp < 1e-3)  # water positions in shear-velocity data (:148-159)
+    if len(pos) > 0 and any(pos[0]):
+        if opts["vp_water"] is None or opts["vp_water"] < 1300 or opts["vp_water"] > 1800:
+            raise ValueError("vp_water is None or out of bounds. It should be >1300 and <1800 m/s")
+        vp[pos] = opts["vp_water"]
+    if len(bbox) not in (4, 6):
+        raise ValueError("Dimension not supported")
+    dim = len(bbox) // 2
+    if nz is None and opts["velocity_data"] is not None:  # lenient: grid shape of the array handed in
+        nz, nx, ny = (tuple(vp.shape) + (None,))[:3]
+    for key in kwargs:
+        if key not in _SIZING_DEFAULTS:
+            raise ValueError("Option %s with parameter %s not recognized " % (key, kwargs[key]))
+    cell_size = np.full((nz, nx) if dim == 2 else (nz, nx, ny), opts["hmin"], dtype=float)
+    if opts["wl"] > 0 or opts["grad"] > 0:
+        # wavelength sizing (:411-426) and gradient sizing (:429-450)
+        if opts["wl"] < 0:
+            raise ValueError("Parameter `wl` must be set > 0")
+        if opts["freq"] < 0.0:
+            raise ValueError("Parameter `freq` must be set > 0.0")
+        h_wl = 99999 if opts["wl"] == 0.0 else vp / (opts["freq"] * opts["wl"])
+        h_gr = 99999
+        if opts["grad"] < 0:
+            raise ValueError("Parameter grad must be > 0")
+        if opts["grad"] != 0.0:
+            from scipy import ndimage
+
+            st = opts["stencil_size"]
+            window = [st] * vp.ndim if np.isscalar(st) else st
+            win_mean = ndimage.uniform_filter(vp, tuple(window))
+            win_sqr_mean = ndimage.uniform_filter(vp**2, tuple(window))
+            win_var = win_sqr_mean - win_mean**2
+            win_var = np.divide(win_var, np.amax(win_var))
+            win_var -= np.amin(win_var)
+            h_gr = opts["grad"] / (win_var + 0.10)
+        cell_size = np.minimum(h_wl, h_gr)
+    cell_size[cell_size < opts["hmin"]] = opts["hmin"]
+    cell_size[cell_size > opts["hmax"]] = opts["hmax"]
+    # CFL limit (:453-468)
+    cr_max, dt, so = opts["cr_max"], opts["dt"], opts["space_order"]
+    if not ((cr_max == 0.0) or (dt == 0.0) or (so == 0.0)):
+        if cr_max < 0:
+            raise ValueError("Parameter `cr_max` must be > 0.0")
+        if dt < 0:
+            raise ValueError("Parameter `dt` must be > 0.0")
+        if so < 1:
+            raise ValueError("Parameter `space_order` must be >= 1 ")
+        cr_old = (vp * dt) / (dim * cell_size)
+        cr_lim = cr_max / (dim * so)
+        cell_size = np.where(cr_old > cr_lim, (vp * dt) / (dim * cr_lim), cell_size)
+    # gradation (:471-496)
+    grade = opts["grade"]
+    if grade == 0.0:
+        warnings.warn("Mesh size gradient is deactiavted. This may compromise mesh quality")
+    else:
+        if grade < 0:
+            raise ValueError("Parameter `grade` must be > 0.0")
+        if grade > 1.0:
+            warnings.warn("Parameter `grade` is set pretty high (> 1.0)!")
+        cell_size = limgrad(cell_size, grade, (bbox[1] - bbox[0]) / nz)
+    # domain extension (:526-572)
+    pad = opts["domain_pad"]
+    if pad < 0:
+        raise ValueError("Domain extension must be >= 0")
+    if pad > 0:
+        n = vp.shape
+        d = [(bbox[2 * k + 1] - bbox[2 * k]) / n[k] for k in range(dim)]
+        nn = [int(pad / dk) for dk in d]
+        bbox = tuple(v for k in range(dim) for v in ((bbox[2 * k] - pad, bbox[2 * k + 1] + (pad if k > 0 else 0.0))))
+        padding = tuple((nn[k], 0) if k == 0 else (nn[k], nn[k]) for k in range(dim))
+        mx_h, mx_v = np.amax(cell_size), np.amax(vp)
+        cell_size = _pad(cell_size, padding, opts["pad_style"], [mx_h] * 2)
+        vp = _pad(vp, padding, opts["pad_style"], [mx_v] * 2)
+    # gridded interpolant with the reference's float32-linspace axes (:391-408, :514-523)
+    return SizeFunction(tuple(bbox), GridInterpolant(grid_axes(bbox, cell_size.shape), cell_size), opts["hmin"])

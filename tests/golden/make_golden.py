@@ -19,6 +19,8 @@ Everything written here is produced by calling the *unmodified* reference functi
   sliver_3d.npz         : `calc_dihedral_angles`, `_calc_dihedral_angles`,
                           `calc_circumsphere_grad` + the perturbation step
   init_points.npz       : `_generate_initial_points` for Disk / Ball / gridded Rectangle
+  sizing_<case>.npz     : grids built by `get_sizing_function_from_segy` (incl. the native FastHJ
+                          gradient limiter) for the velocity models of tests/golden/synth.py
   e2e.json              : aggregate outcomes of full `generate_mesh` / `sliver_removal` runs
                           (vertex count, cell count, min/mean quality, area) with Qhull as
                           the triangulator.
@@ -138,19 +140,8 @@ def gen_sdf():
         json.dump(specs, f, indent=1)
 
 
-def synth_vp_2d(nz, nx, bbox):
-    z = np.linspace(bbox[0], bbox[1], nz)[:, None]
-    x = np.linspace(bbox[2], bbox[3], nx)[None, :]
-    vp = 1500 + (-z / (bbox[1] - bbox[0]) * 1.0) * 3000 + 150 * np.sin(x / 900.0) * np.cos(z / 400.0)
-    return np.ascontiguousarray(vp)
-
-
-def synth_vp_3d(nz, nx, ny, bbox):
-    z = np.linspace(bbox[0], bbox[1], nz)[:, None, None]
-    x = np.linspace(bbox[2], bbox[3], nx)[None, :, None]
-    y = np.linspace(bbox[4], bbox[5], ny)[None, None, :]
-    vp = 1500 + (-z / (bbox[1] - bbox[0])) * 3000 + 100 * np.sin(x / 700.0) * np.cos(y / 500.0)
-    return np.ascontiguousarray(vp)
+sys.path.insert(0, HERE)
+from synth import sizing_cases, synth_vp_2d, synth_vp_3d  # noqa: E402
 
 
 def _rgi_parts(ef):
@@ -210,6 +201,25 @@ def gen_interp():
         os.path.join(HERE, "r0m_values.npz"), axis0=axes[0], axis1=axes[1], grid=grid, x=xq, h=hq,
         bbox=np.asarray(ef.bbox),
     )
+
+
+def gen_sizing():
+    """sizing_<case>.npz: the gridded size function the REFERENCE's get_sizing_function_from_segy
+    builds (wavelength / gradient sizing, clamps, CFL, FastHJ gradation, domain pad) for the cases of
+    tests/golden/synth.py -- stored as float32 + the exact min/max (grids are smooth; 1e-7 relative
+    rounding is far below the gradation tolerance the tests allow)."""
+    import warnings
+
+    for name, (vp, bbox, kw) in sizing_cases().items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp.copy(), **kw)
+        axes, grid = _rgi_parts(ef)
+        np.savez_compressed(
+            os.path.join(HERE, f"sizing_{name}.npz"), grid=grid.astype(np.float32), gmin=grid.min(), gmax=grid.max(),
+            bbox=np.asarray(ef.bbox), hmin=ef.hmin, checksum=float(grid.sum()),
+        )
+        print("sizing", name, grid.shape, grid.min(), grid.max())
 
 
 def _jittered_mesh(fd_obj, h0, bbox, seed, dim):
@@ -367,4 +377,5 @@ if __name__ == "__main__":
     gen_sliver()
     gen_init()
     gen_e2e()
+    gen_sizing()
     print("golden vectors written to", HERE)

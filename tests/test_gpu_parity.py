@@ -445,3 +445,73 @@ def test_api_errors(sm):
         sm.generate_mesh(lambda x: x, 0.1, bbox=(0, 1, 0, 1))  # ints in bbox
     with pytest.raises(Exception):
         sm.sliver_removal(points=np.zeros((4, 2)), domain=disk, edge_length=0.1)
+
+
+# ------------------------------------------------------------------------------------------------
+# sizing preprocessing: get_sizing_function_from_segy with the CUDA gradient limiter
+# ------------------------------------------------------------------------------------------------
+import sys  # noqa: E402
+
+sys.path.insert(0, GOLDEN)
+from synth import salt_vp_2d, sizing_cases  # noqa: E402
+
+SIZING = sizing_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SIZING))
+def test_sizing_function_matches_reference(sm, name):
+    import warnings
+
+    vp, bbox, kw = SIZING[name]
+    g = load_golden(f"sizing_{name}.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp.copy(), **kw)
+    grid = ef.cell_size.values
+    assert isinstance(ef, sm.SizeFunction) and ef.hmin == g["hmin"]
+    assert grid.shape == g["grid"].shape and np.array_equal(np.asarray(ef.bbox), g["bbox"])
+    assert grid.min() == g["gmin"] and grid.max() == g["gmax"]
+    assert np.abs(grid - g["grid"]).max() <= 6e-8 * g["gmax"]  # golden grid stored as float32
+    assert abs(grid.sum() - g["checksum"]) <= 1e-12 * abs(g["checksum"])
+    # ... and the interpolant is the device one: a node value comes back exactly
+    axes = ef.cell_size.grid
+    idx = tuple(n // 3 for n in grid.shape)
+    x = np.array([[axes[k][idx[k]] for k in range(grid.ndim)]])
+    assert ef.eval(x)[0] == grid[idx]
+
+
+def test_limgrad_kernel_vs_oracle_large(sm):
+    """BP2004-shaped grid (1911 x 5395): the CUDA limiter against the oracle's fixed point through
+    size-independent properties (gradient bound, never raises a value, idempotent) and against the
+    oracle itself on a sub-grid the NumPy sweeps finish in seconds."""
+    from seismicmesh_b200.sizing import limgrad
+
+    bbox = (-12000.0, 0.0, 0.0, 67000.0)
+    vp = salt_vp_2d(1911, 5395, bbox)
+    f0 = np.maximum(vp / 20.0, 75.0)
+    elen, grade = 12000.0 / 1911, 0.15
+    f = limgrad(f0, grade, elen)
+    ftol = f0.min() * np.sqrt(1e-9)
+    assert (f <= f0).all()
+    assert max(np.abs(np.diff(f, axis=0)).max(), np.abs(np.diff(f, axis=1)).max()) <= elen * grade + ftol
+    assert np.array_equal(limgrad(f, grade, elen), f)
+    sub = f0[600:1000, 2000:2600]
+    ref = orc.limgrad(sub, elen * grade, sub.min() * np.sqrt(1e-9))
+    got = limgrad(sub, grade, elen)
+    assert np.abs(got - ref).max() <= 4 * ftol
+
+
+def test_sizing_errors(sm):
+    vp = np.full((10, 12), 2000.0)
+    bbox = (-100.0, 0.0, 0.0, 120.0)
+    with pytest.raises(ValueError, match="not recognized"):
+        sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, nz=10, nx=12, bogus=1)
+    with pytest.raises(ValueError, match="Dimension not supported"):
+        sm.get_sizing_function_from_segy(None, (0.0, 1.0), velocity_data=vp, nz=10, nx=12)
+    with pytest.raises(ValueError, match="Domain extension"):
+        sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, nz=10, nx=12, wl=5, domain_pad=-1.0)
+    with pytest.raises(ValueError, match="pad style"):
+        sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, nz=10, nx=12, wl=5, domain_pad=30.0,
+                                         pad_style="mirror")
+    with pytest.raises(ValueError, match="vp_water"):
+        sm.get_sizing_function_from_segy(None, bbox, velocity_data=np.zeros((10, 12)), nz=10, nx=12, vp_water=900.0)

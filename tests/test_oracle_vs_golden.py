@@ -108,3 +108,48 @@ def test_initial_points():
     p = orc.initial_points(0.2, 0.02, 3, np.array([[-1.0, 1.0]] * 3), lambda x: np.array([0.2] * len(x)),
                            ball, np.empty((0, 3)))
     assert np.array_equal(p, g["ball"])
+
+
+# --------------------------------------------------------------------------------------------
+# sizing preprocessing: the reference's get_sizing_function_from_segy (incl. its native FastHJ
+# gradient limiter) on the velocity models of tests/golden/synth.py
+# --------------------------------------------------------------------------------------------
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from synth import sizing_cases  # noqa: E402
+
+SIZING = sizing_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SIZING))
+def test_sizing_matches_reference(name):
+    vp, bbox, kw = SIZING[name]
+    g = load_golden(f"sizing_{name}.npz")
+    cell, bb = orc.sizing_from_velocity(vp, bbox, **kw)
+    assert cell.shape == g["grid"].shape and np.allclose(bb, g["bbox"], rtol=0, atol=0)
+    assert cell.min() == g["gmin"] and cell.max() == g["gmax"]
+    # the golden grid is stored as float32; its float64 checksum pins the rest
+    assert np.abs(cell - g["grid"]).max() <= 6e-8 * g["gmax"]
+    assert abs(cell.sum() - g["checksum"]) <= 1e-12 * abs(g["checksum"])
+
+
+def test_limgrad_is_a_fixed_point_and_minimal():
+    rng = np.random.default_rng(3)
+    f0 = rng.uniform(50.0, 900.0, (23, 31, 17))
+    delta, ftol = 12.5, 50.0 * np.sqrt(1e-9)
+    f = orc.limgrad(f0, delta, ftol)
+    assert (f <= f0).all()
+    for ax in range(3):
+        assert np.abs(np.diff(f, axis=ax)).max() <= delta + ftol
+    # minimality: a limited value is either untouched or sits exactly delta above a neighbour
+    lowered = f < f0
+    m = np.full_like(f, np.inf)
+    for ax in range(3):
+        lo = [slice(None)] * 3
+        hi = [slice(None)] * 3
+        lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+        m[tuple(hi)] = np.minimum(m[tuple(hi)], f[tuple(lo)])
+        m[tuple(lo)] = np.minimum(m[tuple(lo)], f[tuple(hi)])
+    assert np.abs(f[lowered] - (m[lowered] + delta)).max() <= 2 * ftol
