@@ -15,9 +15,45 @@
     if (e__ != cudaSuccess) return (int)e__;    \
   } while (0)
 
+// Programmatic dependent launch (sm_90+): the six kernels of an iteration form a dependent chain of
+// short launches; each kernel lets its successor be scheduled as soon as all of its own blocks have
+// started and then waits for its predecessor's results, which takes the launch latency and the
+// block ramp-up of kernel k+1 off the critical path.  DM_PDL=0 builds plain stream-ordered launches.
+#ifndef DM_PDL
+#define DM_PDL 1
+#endif
+
 namespace dm {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void pdl_prologue() {
+#if DM_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st,
+                                       Args&&... args) {
+#if DM_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+#else
+  kern<<<grid, block, 0, st>>>(static_cast<KArgs>(args)...);
+  return cudaGetLastError();
+#endif
+}
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -161,10 +161,9 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
   const unsigned nb = nblk(pl->N, VU_THREADS);
   const double* pg = pad ? pl->p4 : p;
 #define DM_VU(H, P)                                                                                              \
-  vertex_update_kernel<DIM, H, P><<<nb, VU_THREADS, 0, st>>>(f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr,      \
-                                                             pl->hslot, pl->hbar, pl->scalars, pl->N, lv, L0mult, \
-                                                             delta_t, deps, h0, nfix, fixed, Ftot, pl->partials,  \
-                                                             pl->sync + 2, pl->scalars, pl->esc, pl->counters + 5)
+  launch_chain(vertex_update_kernel<DIM, H, P>, nb, VU_THREADS, st, f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr, \
+               pl->hslot, pl->hbar, pl->scalars, pl->N, lv, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,          \
+               pl->partials, pl->sync + 2, pl->scalars, pl->esc, pl->counters + 5)
   if (DIM == 3 && pad) {
     switch (hmode) {
       case 0: DM_VU(0, true); break;
@@ -181,8 +180,8 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
 #undef DM_VU
   mark("vertex_update+maxdp", st);
   if (lv.n > 0) {  // Newton projection of the listed (escaped) vertices
-    project_list_kernel<DIM><<<PJ_BLOCKS, PJ_THREADS, 0, st>>>(lv, deps, h0, pl->esc, pl->counters + 5, pl->sync + 4,
-                                                               p_out);
+    launch_chain(project_list_kernel<DIM>, PJ_BLOCKS, PJ_THREADS, st, lv, deps, h0, pl->esc, pl->counters + 5,
+                 pl->sync + 4, p_out);
     mark("project_escaped", st);
   }
   return (int)cudaGetLastError();
@@ -194,9 +193,8 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   typedef typename PCfg<DIM>::entry_t entry_t;
   const unsigned nb = nblk(pl->T, PL_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
-  cull_scatter_kernel<DIM, DIM == 3><<<nb, PL_THREADS, 0, st>>>(prog, pc, t, pl->T, geps, mode, pl->keep, pl->cnt,
-                                                                static_cast<entry_t*>(pl->bucket), pl->ovf_v,
-                                                                static_cast<entry_t*>(pl->ovf_e), pl->counters);
+  launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, PL_THREADS, st, prog, pc, t, pl->T, geps, mode, pl->keep,
+               pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v, static_cast<entry_t*>(pl->ovf_e), pl->counters);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
@@ -217,13 +215,12 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   const DmSizeFn& ff = f ? *f : fz;
   const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
 #define DM_ADJ(B)                                                                                                  \
-  adjacency_kernel<DIM, B><<<nb, AB_THREADS, 0, st>>>(pl->cnt, bucket, N, pl->adj, pl->heap, degs, pl->hv,          \
-                                                      pl->counters, ff, pp, pl->hslot, pl->partials);              \
-  mark("adjacency", st);                                                                                           \
-  adjacency_heavy_kernel<DIM, B><<<HV_BLOCKS, HV_THREADS, 0, st>>>(pl->cnt, bucket, pl->ovf_v, ovf_e, N, pl->adj,   \
-                                                                   pl->heap, degs, pl->hv, pl->counters, ff, pp,   \
-                                                                   pl->hslot, pl->partials, (int64_t)nb,           \
-                                                                   pl->sync + 3, pl->scalars);                     \
+  launch_chain(adjacency_kernel<DIM, B>, nb, AB_THREADS, st, pl->cnt, bucket, N, pl->adj, pl->heap, degs, pl->hv,     \
+               pl->counters, ff, pp, pl->hslot, pl->partials);                                                      \
+  mark("adjacency", st);                                                                                            \
+  launch_chain(adjacency_heavy_kernel<DIM, B>, HV_BLOCKS, HV_THREADS, st, pl->cnt, bucket, pl->ovf_v, ovf_e, N,      \
+               pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, (int64_t)nb,         \
+               pl->sync + 3, pl->scalars);                                                                          \
   mark("adjacency_heavy", st)
   switch (bar) {
     case 0: DM_ADJ(0); break;
@@ -411,6 +408,8 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
     const int64_t zq = (int64_t)(pl->zero_bytes / 16);
     const bool pad = pl->dim == 3 && p != nullptr;
     const int64_t n = pad && pl->N > zq ? pl->N : zq;
+    // head of the chain: a plain stream-ordered launch (whatever precedes it -- a copy, somebody
+    // else's kernel -- completes first); its successors are launched programmatically
     prep_kernel<<<nblk(n, PL_THREADS), PL_THREADS, 0, st>>>(static_cast<int4*>(pl->zero_base), zq, p,
                                                             pad ? pl->p4 : nullptr, pl->N);
     mark("prep(zero+pad)", st);

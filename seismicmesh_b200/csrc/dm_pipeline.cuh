@@ -90,6 +90,7 @@ struct Rows {
 __global__ void __launch_bounds__(PL_THREADS) prep_kernel(int4* __restrict__ zero, int64_t zquads,
                                                          const double* __restrict__ p, double* __restrict__ p4,
                                                          int64_t N) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < zquads) zero[i] = make_int4(0, 0, 0, 0);
   if (p4 != nullptr && i < N) {
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(PL_THREADS, DM_CS_MINB) cull_scatter_kernel(
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
     typename PCfg<DIM>::entry_t* __restrict__ bucket, int32_t* __restrict__ ovf_v,
     typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int32_t* __restrict__ counters) {
+  pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
                                                                int32_t* __restrict__ hv, int32_t* __restrict__ counters,
                                                                const DmSizeFn f, const double* __restrict__ pp,
                                                                double* __restrict__ hslot, double* __restrict__ partials) {
+  pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS, G = PCfg<DIM>::G, LOGH = PCfg<DIM>::LOGH;
   constexpr int H = 1 << LOGH;
   constexpr int VPB = AB_THREADS / G;  // vertices per block
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
     int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
     int32_t* __restrict__ counters, const DmSizeFn f, const double* __restrict__ pp, double* __restrict__ hslot,
     double* partials, int64_t nb_adj, int32_t* done, double* scalars) {
+  pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS;
   __shared__ __align__(16) int32_t s_val[HV_SMEM];
   __shared__ int s_scan[33];
@@ -877,6 +881,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_list_kernel(const Levels l
                                                                   const int32_t* __restrict__ esc,
                                                                   int32_t* esc_count, int32_t* done,
                                                                   double* __restrict__ p_out) {
+  pdl_prologue();
   const int n = *reinterpret_cast<volatile int32_t*>(esc_count);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = esc[i];
@@ -900,6 +905,7 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     const double* __restrict__ hbar, const double* scalars_in, int64_t N, Levels lv, double L0mult, double delta_t,
     double deps, double h0, int64_t nfix, const uint8_t* __restrict__ fixed, double* __restrict__ Ftot,
     double* partials, int32_t* done, double* scalars, int32_t* __restrict__ esc, int32_t* __restrict__ esc_count) {
+  pdl_prologue();
   __shared__ double sm[32];
   __shared__ bool s_last;
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
