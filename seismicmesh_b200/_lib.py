@@ -29,6 +29,7 @@ class DmSizeFn(C.Structure):
         ("axis", C.c_void_p * 3),
         ("grid", C.c_void_p),
         ("hconst", C.c_double),
+        ("cells", C.c_void_p),
     ]
 
 
@@ -73,6 +74,7 @@ _SZ = C.c_size_t
 _SIGNATURES = {
     "dm_sdf_eval": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "dm_size_eval": (_INT, [C.POINTER(DmSizeFn), _P, _I64, _P, _P]),
+    "dm_size_build_cells": (_INT, [C.POINTER(DmSizeFn), _P, _P]),
     "dm_centroids": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "dm_cull_cells": (_INT, [_P, _P, _P, _I64, _INT, _D, _P, _P]),
     "dm_compact_cells": (_INT, [_P, _P, _I64, _INT, _P, _P, _P, _SZ, _P]),

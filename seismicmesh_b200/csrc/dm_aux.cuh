@@ -28,6 +28,20 @@ __global__ void size_eval_kernel(const DmSizeFn f, const double* __restrict__ x,
   out[i] = size_eval(f, x0, x1, x2);
 }
 
+// cell records of a 3-D size grid (DmSizeFn::cells): thread per cell, 64 B written contiguously
+__global__ void size_cells_kernel(const double* __restrict__ grid, int n0, int n1, int n2, double* __restrict__ cells) {
+  const int64_t nc = (int64_t)(n0 - 1) * (n1 - 1) * (n2 - 1);
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int i2 = (int)(c % (n2 - 1)), i1 = (int)((c / (n2 - 1)) % (n1 - 1)), i0 = (int)(c / ((int64_t)(n2 - 1) * (n1 - 1)));
+  const double* g = grid + ((int64_t)i0 * n1 + i1) * n2 + i2;
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = g[((int64_t)(k >> 2) * n1 + ((k >> 1) & 1)) * n2 + (k & 1)];
+  stg256(cells + c * 8, v[0], v[1], v[2], v[3]);
+  stg256(cells + c * 8 + 4, v[4], v[5], v[6], v[7]);
+}
+
 template <int DIM>
 __global__ void centroid_kernel(const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
                                 double* __restrict__ out) {

@@ -273,6 +273,15 @@ int dm_size_eval(const DmSizeFn* f, const double* x, int64_t M, double* out, voi
   return DM_OK;
 }
 
+int dm_size_build_cells(const DmSizeFn* f, double* cells, void* stream) {
+  if (!f || !cells || f->kind != DM_SIZE_GRID || f->dim != 3 || check_size_fn(f, 3)) return DM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(cells) & 63) != 0) return DM_ERR_ARG;
+  const int64_t nc = (int64_t)(f->n[0] - 1) * (f->n[1] - 1) * (f->n[2] - 1);
+  size_cells_kernel<<<nblk(nc, 256), 256, 0, S(stream)>>>(f->grid, f->n[0], f->n[1], f->n[2], cells);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_centroids(const double* p, const int32_t* t, int64_t T, int dim, double* out, void* stream) {
   if (T < 0 || bad_dim(dim)) return DM_ERR_ARG;
   if (T == 0) return DM_OK;

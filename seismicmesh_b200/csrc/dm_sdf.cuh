@@ -23,6 +23,16 @@
 
 namespace dm {
 
+// eight consecutive doubles of a 64-B aligned record: two 256-bit read-only loads on the device
+DM_HD void dm_load8(const double* c, double (&v)[8]) {
+#if defined(__CUDA_ARCH__)
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(c));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(c + 4));
+#else
+  for (int k = 0; k < 8; ++k) v[k] = c[k];
+#endif
+}
+
 DM_HD double dmin(double a, double b) { return a < b ? a : b; }  // std::min(a,b) semantics
 DM_HD double dmax(double a, double b) { return a > b ? a : b; }
 
@@ -271,7 +281,15 @@ DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
   const double a20 = DM_LDG(f.axis[2] + i2), a21 = DM_LDG(f.axis[2] + i2 + 1);
   const double y2 = (x2 - a20) / (a21 - a20);
   const int64_t n1 = f.n[1], n2 = f.n[2];
-  const double* g = f.grid + ((int64_t)i0 * n1 + i1) * n2 + i2;
+  double cv[8];  // corner values in itertools.product order
+  if (f.cells != nullptr) {
+    const double* c = f.cells + (((int64_t)i0 * (n1 - 1) + i1) * (n2 - 1) + i2) * 8;
+    dm_load8(c, cv);
+  } else {
+    const double* g = f.grid + ((int64_t)i0 * n1 + i1) * n2 + i2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cv[k] = DM_LDG(g + ((int64_t)(k >> 2) * n1 + ((k >> 1) & 1)) * n2 + (k & 1));
+  }
   // scipy _rgi._evaluate_linear: corners in itertools.product order, weight ((1*w0)*w1)*w2,
   // value = value + v*weight starting from 0.0
   double out = 0.0;
@@ -283,7 +301,7 @@ DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         const double w = ((1.0 * w0[c0]) * w1[c1]) * w2[c2];
-        out = out + DM_LDG(g + ((int64_t)c0 * n1 + c1) * n2 + c2) * w;
+        out = out + cv[c0 * 4 + c1 * 2 + c2] * w;
       }
   return out;
 }

@@ -97,7 +97,7 @@ class Plan:
         return int(self.counters()[0].item())
 
 
-def size_fn_struct(kind, dim, hconst=0.0, axes=None, grid=None):
+def size_fn_struct(kind, dim, hconst=0.0, axes=None, grid=None, cells=None):
     f = DmSizeFn()
     f.kind = kind
     f.dim = dim
@@ -107,6 +107,7 @@ def size_fn_struct(kind, dim, hconst=0.0, axes=None, grid=None):
             f.n[k] = int(axes[k].numel())
             f.axis[k] = axes[k].data_ptr()
         f.grid = grid.data_ptr()
+        f.cells = cells.data_ptr() if cells is not None else None
     return f
 
 

@@ -94,6 +94,23 @@ def test_size_eval_bit_exact(sm, name):
         assert h[0] == 100 and h[1] == 150  # reference tests/test_2dmesher_r0m_values.py:42-43
 
 
+def test_size_eval_cell_records_same_bits(sm):
+    """3-D grids are also kept as per-cell 64-B corner records (DmSizeFn.cells); lookups through the
+    records and through the plain grid must agree bit for bit (inside, on nodes, extrapolating)."""
+    g = load_golden("interp_3d.npz")
+    axes = [g[k] for k in ("axis0", "axis1", "axis2")]
+    rng = np.random.default_rng(5)
+    lo = np.array([a[0] for a in axes]) - 300.0
+    hi = np.array([a[-1] for a in axes]) + 300.0
+    x = np.vstack([g["x"], rng.uniform(lo, hi, (20000, 3))])
+    a = sm.GridInterpolant(axes, g["grid"], cell_records=True)
+    b = sm.GridInterpolant(axes, g["grid"], cell_records=False)
+    assert a.struct().cells and not b.struct().cells
+    ha, hb = a(x), b(x)
+    assert np.array_equal(ha, hb)
+    assert np.array_equal(ha[: len(g["x"])], g["h"])
+
+
 def test_size_function_accepts_scipy_rgi(sm):
     from scipy.interpolate import RegularGridInterpolator
 
