@@ -261,7 +261,6 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
         # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends) with the
         # bar pass K3 fused in (positions read once, h written once per bar for gridded fh)
         "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E + 8 * d * N + hs,
-        "adjacency_heavy": 0,
         "bar_pass+scale": 8 * d * N + 4 * E + 8 * N + hs,
         "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + 2 * hs,
     }
@@ -546,7 +545,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, adjacency_heavy, vertex_update
+        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
         "roofline": roofline, "cpu_baseline": cpu,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "sizing_s": wl["sizing_s"], "maxdp": maxdp,
         "wall_s_timed_region": wall,

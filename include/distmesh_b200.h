@@ -174,7 +174,8 @@ typedef struct DmPlan {
   void *zero_base;   /* [cnt | sync | counters]: zeroed by stage A's prep kernel */
   size_t zero_bytes;
   int32_t *cnt;
-  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] heavy blocks done [4] projection blocks done */
+  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] bar-sum arrivals (adjacency) [4] projection blocks done */
+  int32_t *gdone;    /* adjacency blocks done, per reduction group of 128 blocks (zeroed with cnt) */
   int32_t *counters; /* [0]=E unique bars [1]=reserved [2]=spill records [3]=heavy vertices
                         [4]=heap cursor (ints) [5]=escaped vertices (stage D) */
   void *bucket;

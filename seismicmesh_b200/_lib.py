@@ -45,6 +45,7 @@ class DmPlan(C.Structure):
         ("zero_bytes", C.c_size_t),
         ("cnt", C.c_void_p),
         ("sync", C.c_void_p),
+        ("gdone", C.c_void_p),
         ("counters", C.c_void_p),
         ("bucket", C.c_void_p),
         ("ovf_v", C.c_void_p),

@@ -60,7 +60,10 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   const int64_t heap_ints = K1 + 4 * (N + 1);
   // per-block partials: adjacency blocks (AB_THREADS / G vertices each) + one per heavy vertex +
   // one per block of the heavy kernel (first level of the final sum)
-  const int64_t nblocks = cdiv(N > 0 ? N : 1, AB_THREADS / PCfg<DIM>::G) + (N + 2) + HV_BLOCKS + 8;
+  // bar sums: one per adjacency block + one per group of RG blocks + one per heavy vertex (dm_pipeline.cuh)
+  const int64_t nbm = cdiv(N > 0 ? N : 1, AB_THREADS / PCfg<DIM>::G);
+  const int64_t ngrp = cdiv(nbm, RG);
+  const int64_t nblocks = nbm + ngrp + (N + 2) + 8;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* ptr = base ? base + off : nullptr;
@@ -73,6 +76,7 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   char* cnt = take((size_t)(N + 1) * 4);
   char* sync = take(8 * 4);
   char* counters = take(8 * 4);
+  char* gdone = take((size_t)(ngrp + 1) * 4);
   const size_t zbytes = off - z0;
   // ----
   char* bucket = take((size_t)(N + 1) * CAP * esz);
@@ -103,6 +107,7 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
     pl->cnt = reinterpret_cast<int32_t*>(cnt);
     pl->sync = reinterpret_cast<int32_t*>(sync);
     pl->counters = reinterpret_cast<int32_t*>(counters);
+    pl->gdone = reinterpret_cast<int32_t*>(gdone);
     pl->bucket = bucket;
     pl->ovf_v = reinterpret_cast<int32_t*>(ovf_v);
     pl->ovf_e = ovf_e;
@@ -194,7 +199,8 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   const unsigned nb = nblk(pl->T, PL_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
   launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, PL_THREADS, st, prog, pc, t, pl->T, geps, mode, pl->keep,
-               pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v, static_cast<entry_t*>(pl->ovf_e), pl->counters);
+               pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v, static_cast<entry_t*>(pl->ovf_e), pl->hv,
+               pl->counters);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
@@ -214,14 +220,11 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   memset(&fz, 0, sizeof(fz));
   const DmSizeFn& ff = f ? *f : fz;
   const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
-#define DM_ADJ(B)                                                                                                  \
-  launch_chain(adjacency_kernel<DIM, B>, nb, AB_THREADS, st, pl->cnt, bucket, N, pl->adj, pl->heap, degs, pl->hv,     \
-               pl->counters, ff, pp, pl->hslot, pl->partials);                                                      \
-  mark("adjacency", st);                                                                                            \
-  launch_chain(adjacency_heavy_kernel<DIM, B>, HV_BLOCKS, HV_THREADS, st, pl->cnt, bucket, pl->ovf_v, ovf_e, N,      \
-               pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, (int64_t)nb,         \
+#define DM_ADJ(B)                                                                                                   \
+  launch_chain(adjacency_kernel<DIM, B>, nb + HV_BLOCKS, AB_THREADS, st, pl->cnt, bucket, pl->ovf_v, ovf_e, N,       \
+               pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone,           \
                pl->sync + 3, pl->scalars);                                                                          \
-  mark("adjacency_heavy", st)
+  mark("adjacency", st)
   switch (bar) {
     case 0: DM_ADJ(0); break;
     case 1: DM_ADJ(1); break;
@@ -301,10 +304,10 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
     cull_scatter_kernel<2><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
-        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   else
     cull_scatter_kernel<3><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
-        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr);
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }

@@ -32,15 +32,18 @@ namespace dm {
 
 constexpr int PL_THREADS = 256;  // cull / bar pass / vertex update
 constexpr int AB_THREADS = 256;  // adjacency: 256 / G vertices per block
-constexpr int HV_THREADS = 256;  // heavy-vertex path: one block per vertex
-constexpr int HV_BLOCKS = 296;   // fixed grid (2 per SM); loops over the heavy list
-constexpr int HV_SMEM = 6144;    // candidates sorted in shared memory up to this many (ints; 24 KB)
+constexpr int HV_BLOCKS = 148;   // heavy-vertex blocks at the head of the adjacency grid; they loop over the heavy list
+constexpr int HV_SMEM = 4608;    // heavy path: candidates sorted in shared memory up to this many ints (the main
+                                 // path's tables + lists: 2 * 32 * 72 in 3-D, 2 * 64 * 36 in 2-D)
 // tuning knobs (resident blocks per SM the register allocation is held to)
 #ifndef DM_CS_MINB
 #define DM_CS_MINB 4
 #endif
 #ifndef DM_HASH_MAXSTEPS
 #define DM_HASH_MAXSTEPS 12
+#endif
+#ifndef DM_AB_MINB
+#define DM_AB_MINB 5
 #endif
 #ifndef DM_VU_MINB
 #define DM_VU_MINB 8
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(PL_THREADS, DM_CS_MINB) cull_scatter_kernel(
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
     typename PCfg<DIM>::entry_t* __restrict__ bucket, int32_t* __restrict__ ovf_v,
-    typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int32_t* __restrict__ counters) {
+    typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int32_t* __restrict__ hv, int32_t* __restrict__ counters) {
   pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,10 +172,11 @@ __global__ void __launch_bounds__(PL_THREADS, DM_CS_MINB) cull_scatter_kernel(
       const typename PCfg<DIM>::entry_t e = others_of<DIM>(ids, j);
       if (slot < CAP) {
         bucket[(int64_t)ids[j] * CAP + slot] = e;
-      } else {  // bucket full: spill (hull / hub vertices)
+      } else {  // bucket full: spill (hull / hub vertices); the first spill lists the vertex as heavy
         const int o = atomicAdd(counters + 2, 1);
         ovf_v[o] = ids[j];
         ovf_e[o] = e;
+        if (slot == CAP) hv[atomicAdd(counters + 3, 1)] = ids[j];
       }
     }
   }
@@ -256,16 +260,306 @@ __device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __res
   }
 }
 
+// ---- heavy vertices: one block per vertex -------------------------------------------------------
+// ascending compare-exchange network (bitonic with the "flip" first step, so every comparator
+// points the same way): positions >= n behave as +inf and never move, hence any n works in place.
+template <typename PTR>
+__device__ __forceinline__ void block_sort_ascending(PTR a, int n) {
+  for (int k = 2; (k >> 1) < n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < n) {
+          const int x = a[i], y = a[l];
+          if (x > y) {
+            a[i] = y;
+            a[l] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr int HV_RANK = 768;  // up to this many candidates: one-pass rank sort instead of the network
+constexpr int RG = 128;       // adjacency blocks per reduction group (second level of the bar sums)
+
+// Where the bar sums of the adjacency kernel live in `partials` (pairs {sum L^d, sum h^d}):
+//   [0, nb)            one per main block            (nb = blocks of VPB vertices)
+//   [nb, nb + ng)      one per group of RG blocks    (ng = ceil(nb / RG))
+//   [nb + ng, ...)     one per heavy vertex, at the RANK of the vertex id among the heavy vertices
+// Every level is added in index order by one warp (lane-strided, fixed shuffle tree), so the scale
+// ((sum L^d)/(sum h^d))^(1/d) (mesh_generator.py:700) is deterministic although blocks finish in any
+// order: the last block of a group adds the group, the last arrival overall adds groups + heavy.
+template <int DIM>
+__device__ __forceinline__ void final_scale(const double* partials, int64_t nb, int ng, int nheavy, double* scalars) {
+  const int lane = threadIdx.x & 31;
+  __threadfence();
+  double tL = 0.0, tH = 0.0;
+  for (int g = lane; g < ng; g += 32) {
+    tL += __ldcg(partials + 2 * (nb + g));
+    tH += __ldcg(partials + 2 * (nb + g) + 1);
+  }
+  tL = warp_sum(tL);
+  tH = warp_sum(tH);
+  double hL = 0.0, hH = 0.0;
+  for (int i = lane; i < nheavy; i += 32) {
+    hL += __ldcg(partials + 2 * (nb + ng + i));
+    hH += __ldcg(partials + 2 * (nb + ng + i) + 1);
+  }
+  hL = warp_sum(hL);
+  hH = warp_sum(hH);
+  if (lane == 0) {
+    const double rl = tL + hL, rh = tH + hH;
+    scalars[0] = rl;
+    scalars[1] = rh;
+    const double r = rl / rh;
+    scalars[2] = DIM == 2 ? sqrt(r) : pow(r, 1.0 / 3.0);  // ** (1.0 / dim), mesh_generator.py:700
+  }
+}
+
+// A vertex whose bucket overflowed (hull / hub vertices; listed by stage A): the whole block gathers
+// its star from the bucket and the spill list, sorts + de-duplicates it and writes the row.
+template <int DIM, int BAR>
+__device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t* s_val, int* s_scan, double* s_dbl,
+                                             int* s_base, int* s_pos, const int32_t* __restrict__ cnt,
+                                             const typename PCfg<DIM>::entry_t* __restrict__ bucket,
+                                             const int32_t* __restrict__ ovf_v,
+                                             const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N,
+                                             int32_t* __restrict__ adj, int32_t* __restrict__ heap,
+                                             int2* __restrict__ degs, const int32_t* __restrict__ hv,
+                                             int32_t* __restrict__ counters, const DmSizeFn& f,
+                                             const double* __restrict__ pp, double* __restrict__ hslot,
+                                             double* hpart) {
+  constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS;
+  const int tid = threadIdx.x;
+  const int v = hv[ih];
+  const int nc = cnt[v];
+  const int nb = nc < CAP ? nc : CAP;  // entries in the bucket; the other nc - nb were spilled
+  const int n = DIM * nc;              // candidates
+  __syncthreads();
+  if (tid == 0) {
+    *s_base = atomicAdd(counters + 4, (int)round4(n));
+    *s_pos = 0;
+  }
+  __syncthreads();
+  int32_t* reg = heap + *s_base;  // candidates, later the row, live here
+  const bool in_smem = n <= HV_SMEM;
+  for (int i = tid; i < nb; i += AB_THREADS) {
+    const typename PCfg<DIM>::entry_t e = bucket[(int64_t)v * CAP + i];
+    const int* ei = reinterpret_cast<const int*>(&e);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      if (in_smem)
+        s_val[i * DIM + c] = ei[c];
+      else
+        reg[i * DIM + c] = ei[c];
+    }
+  }
+  for (int k = tid; k < novf; k += AB_THREADS) {
+    if (ovf_v[k] == v) {
+      const int i = nb + atomicAdd(s_pos, 1);
+      const typename PCfg<DIM>::entry_t e = ovf_e[k];
+      const int* ei = reinterpret_cast<const int*>(&e);
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) {
+        if (in_smem)
+          s_val[i * DIM + c] = ei[c];
+        else
+          reg[i * DIM + c] = ei[c];
+      }
+    }
+  }
+  // rank of v among the heavy vertices: where its bar sums go (see final_scale)
+  int vrank = 0;
+  for (int j0 = 0; j0 < nheavy; j0 += AB_THREADS) {
+    const int j = j0 + tid;
+    vrank += __syncthreads_count(j < nheavy && hv[j] < v);
+  }
+  __syncthreads();
+  int U = 0, lo = 0;
+  if (n <= HV_RANK) {
+    // one pass: candidate i is the first of its value if no equal value precedes it, and its
+    // row position is the number of DISTINCT smaller values = #{j : val[j] < val[i], j first}.
+    constexpr int PER = HV_RANK / AB_THREADS;
+    bool first[PER];
+    int x[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = tid + u * AB_THREADS;
+      first[u] = i < n;
+      x[u] = i < n ? s_val[i] : 0;
+    }
+#pragma unroll 8  // the shared-memory loads of eight steps in flight (latency, not issue, bounds this sweep)
+    for (int j = 0; j < n; ++j) {
+      const int y = s_val[j];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) first[u] = first[u] && !(y == x[u] && j < tid + u * AB_THREADS);
+    }
+    __syncthreads();
+    int32_t* s_first = s_val + HV_RANK;  // HV_SMEM >= 2 * HV_RANK
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = tid + u * AB_THREADS;
+      if (i < n) s_first[i] = first[u] ? 1 : 0;
+    }
+    __syncthreads();
+    int r[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) r[u] = 0;
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) {
+      const int y = s_val[j];
+      const int fj = s_first[j];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) r[u] += (fj && y < x[u]) ? 1 : 0;
+    }
+    int nf = 0, nl = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      if (first[u]) {
+        reg[r[u]] = x[u];
+        ++nf;
+        nl += x[u] < v ? 1 : 0;
+      }
+    }
+    int tot;
+    block_exclusive_scan(nf, tot, s_scan);
+    U = tot;
+    block_exclusive_scan(nl, tot, s_scan);
+    lo = tot;
+  } else {
+    if (in_smem)
+      block_sort_ascending(s_val, n);
+    else
+      block_sort_ascending(reg, n);
+    // unique: chunk by chunk; an element's output position never exceeds its input position and
+    // all reads of a chunk complete before its writes, so compaction in place is safe
+    for (int c0 = 0; c0 < n; c0 += AB_THREADS) {
+      const int i = c0 + tid;
+      int x = 0;
+      bool first = false;
+      if (i < n) {
+        x = in_smem ? s_val[i] : reg[i];
+        first = i == 0 || (in_smem ? s_val[i - 1] : reg[i - 1]) != x;
+      }
+      int tot;
+      const int off = block_exclusive_scan(first ? 1 : 0, tot, s_scan);  // syncs: reads done
+      if (first) reg[U + off] = x;
+      const int nl = __syncthreads_count(first && x < v);
+      U += tot;
+      lo += nl;
+    }
+  }
+  __syncthreads();
+  int32_t* row = adj + (int64_t)v * RS;
+  int64_t sbase = (int64_t)v * RS;
+  if (U <= RS) {
+    for (int i = tid; i < U; i += AB_THREADS) row[i] = reg[i];
+  } else {
+    if (tid == 0) row[0] = *s_base;
+    sbase = N * RS + *s_base;
+  }
+  if (tid == 0) {
+    degs[v] = make_int2(U, lo);
+    atomicAdd(counters, U - lo);
+  }
+  if (BAR >= 0) {
+    double sL = 0.0, sH = 0.0;
+    double a0, a1, a2;
+    load_pt<DIM, true>(pp, v, a0, a1, a2);
+    for (int j = lo + tid; j < U; j += AB_THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
+    const double bl = block_sum(sL, s_dbl);
+    const double bh = block_sum(sH, s_dbl);
+    if (tid == 0) {
+      hpart[2 * vrank] = bl;
+      hpart[2 * vrank + 1] = bh;
+    }
+  }
+}
+
+// A neighbour set that does not fit the group table (more than ~H distinct ids within CAP cells:
+// not a manifold star, but legal input): the group selects the ids in ascending order straight from
+// its bucket, minimum by minimum, into the heap, then writes the row and does its bar pass.  Called
+// by the whole warp; groups with punt == false only take part in the shuffles.
+struct RowSums {
+  int bars;
+  double sL, sH;
+};
+template <int DIM, int BAR>
+__device__ __noinline__ RowSums select_row(bool punt, int n, int v,
+                                           const typename PCfg<DIM>::entry_t* __restrict__ brow, int64_t N,
+                                           int32_t* __restrict__ adj, int32_t* __restrict__ heap,
+                                           int2* __restrict__ degs, int32_t* __restrict__ counters,
+                                           const DmSizeFn& f, const double* __restrict__ pp,
+                                           double* __restrict__ hslot) {
+  constexpr int RS = PCfg<DIM>::RS, G = PCfg<DIM>::G;
+  RowSums out;
+  out.bars = 0;
+  out.sL = 0.0;
+  out.sH = 0.0;
+  typedef typename PCfg<DIM>::entry_t entry_t;
+  const int lg = threadIdx.x % G;
+  int base = 0;
+  if (punt && lg == 0) base = atomicAdd(counters + 4, (int)round4(DIM * n));
+  base = __shfl_sync(FULL, base, 0, G);
+  const int* bi = reinterpret_cast<const int*>(brow);
+  constexpr int EW = sizeof(entry_t) / 4;  // ints per entry (DIM ids + padding)
+  int last = -1, Up = 0, lop = 0;
+  for (;;) {
+    int m = 0x7fffffff;
+    if (punt)
+      for (int i = lg; i < DIM * n; i += G) {
+        const int x = bi[(i / DIM) * EW + i % DIM];
+        if (x > last && x < m) m = x;
+      }
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(FULL, m, d, G));
+    const bool more = punt && m != 0x7fffffff;
+    if (!__any_sync(FULL, more)) break;
+    if (more) {
+      if (lg == 0) heap[base + Up] = m;
+      ++Up;
+      lop += m < v ? 1 : 0;
+      last = m;
+    }
+  }
+  __syncwarp();
+  if (!punt) return out;
+  const int32_t* srt = heap + base;
+  int32_t* row = adj + (int64_t)v * RS;
+  int64_t sbase = (int64_t)v * RS;
+  if (Up <= RS) {
+    if (4 * lg < Up) reinterpret_cast<int4*>(row)[lg] = reinterpret_cast<const int4*>(srt)[lg];
+  } else {
+    if (lg == 0) row[0] = base;
+    sbase = N * RS + base;
+  }
+  if (lg == 0) {
+    degs[v] = make_int2(Up, lop);
+    out.bars = Up - lop;
+  }
+  if (BAR >= 0 && Up > lop) {
+    double a0, a1, a2;
+    load_pt<DIM, true>(pp, v, a0, a1, a2);
+    for (int j = lop + lg; j < Up; j += G)
+      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, out.sL, out.sH);
+  }
+  return out;
+}
+
 // BAR: -1 rows only ; 0 also accumulate sum L^d, sum h^d of the upper bars with constant h ;
 //      1 the same with gridded fh (h stored per upper slot).
+// Grid = HV_BLOCKS heavy-vertex blocks (they start first and run beside the main blocks; the heavy
+// list is complete when the kernel starts) + one main block per VPB vertices.
 template <int DIM, int BAR>
-__global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __restrict__ cnt,
-                                                               const typename PCfg<DIM>::entry_t* __restrict__ bucket,
-                                                               int64_t N, int32_t* __restrict__ adj,
-                                                               int32_t* __restrict__ heap, int2* __restrict__ degs,
-                                                               int32_t* __restrict__ hv, int32_t* __restrict__ counters,
-                                                               const DmSizeFn f, const double* __restrict__ pp,
-                                                               double* __restrict__ hslot, double* __restrict__ partials) {
+__global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
+    const int32_t* __restrict__ cnt, const typename PCfg<DIM>::entry_t* __restrict__ bucket,
+    const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N,
+    int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
+    int32_t* __restrict__ counters, const __grid_constant__ DmSizeFn f, const double* __restrict__ pp,
+    double* __restrict__ hslot, double* partials, int32_t* gdone, int32_t* total_done, double* scalars) {
   pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS, G = PCfg<DIM>::G, LOGH = PCfg<DIM>::LOGH;
   constexpr int H = 1 << LOGH;
@@ -278,12 +572,39 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
                              // G == 32 / (groups per warp), so the groups of a warp start in different banks
   static_assert(G >= 4 && 32 % G == 0, "group layout");
   static_assert((GS * 4) % 16 == 0, "int4 access");
-  __shared__ __align__(16) int32_t s_tab[VPB * GS];
-  __shared__ __align__(16) int32_t s_lst[VPB * GS];
+  static_assert(2 * VPB * GS <= HV_SMEM && HV_SMEM >= 2 * HV_RANK, "shared buffer");
+  __shared__ __align__(16) int32_t s_raw[HV_SMEM];  // main: tables | lists ; heavy block: candidates
+  __shared__ int s_scan[33];
+  __shared__ double s_dbl[32];
+  __shared__ int s_base, s_pos;
   __shared__ int s_arrived;  // warps that have left their totals (see the end of the kernel)
+  __shared__ bool s_fin;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t nbm = (int64_t)gridDim.x - HV_BLOCKS;  // main blocks
+  const int ng = (int)((nbm + RG - 1) / RG);
+
+  if (blockIdx.x < HV_BLOCKS) {  // ---------------- heavy-vertex block
+    const int nheavy = counters[3], novf = counters[2];
+    for (int ih = blockIdx.x; ih < nheavy; ih += HV_BLOCKS)
+      heavy_vertex<DIM, BAR>(ih, nheavy, novf, s_raw, s_scan, s_dbl, &s_base, &s_pos, cnt, bucket, ovf_v, ovf_e, N, adj,
+                             heap, degs, hv, counters, f, pp, hslot, partials + 2 * (nbm + ng));
+    if (BAR < 0) return;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      s_fin = atomicAdd(total_done, 1) == ng + HV_BLOCKS - 1;
+    }
+    __syncthreads();
+    if (s_fin && tid < 32) final_scale<DIM>(partials, nbm, ng, nheavy, scalars);
+    return;
+  }
+
+  // ---------------- main block
+  const int64_t bidx = (int64_t)blockIdx.x - HV_BLOCKS;
+  int32_t* s_tab = s_raw;
+  int32_t* s_lst = s_raw + VPB * GS;
   const int lg = tid % G, grp = tid / G;
-  const int64_t v = (int64_t)blockIdx.x * VPB + grp;
+  const int64_t v = bidx * VPB + grp;
   if (tid == 0) s_arrived = 0;
   __syncthreads();  // the only block barrier: at the very start, where no warp has to wait long
   int32_t* tab = s_tab + grp * GS;
@@ -297,8 +618,9 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
     tab[H + lg] = HASH_PARKED;  // the lane's parking word (see hash_insert_lockstep)
   }
   int n = v < N ? cnt[v] : 0;
-  bool punt = n > CAP;  // overflowed bucket: part of the star lives in the spill list
-  if (punt) n = 0;
+  const bool heavy = n > CAP;  // overflowed bucket: a heavy-vertex block builds this row
+  if (heavy) n = 0;
+  bool punt = false;
   __syncwarp();
 
   // ---- insert every candidate of the bucket: each round, lane lg takes EPL entries (lg, lg+G, ...).
@@ -387,58 +709,58 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
   // ---- write the row
   int bars = 0;
   double sL = 0.0, sH = 0.0;
-  if (v < N) {
-    if (punt) {
-      if (lg == 0) hv[atomicAdd(counters + 3, 1)] = (int32_t)v;
-    } else {
-      int32_t* row = adj + v * RS;
-      int64_t sbase = v * RS;
-      if (U <= RS) {
-        // RS ints = G lanes x int4 (3-D: 8 x 16 B = one 128-B line; 2-D: 4 x 16 B)
-        static_assert(RS == 4 * G, "one int4 per lane");
-        if (4 * lg < U) reinterpret_cast<int4*>(row)[lg] = reinterpret_cast<const int4*>(tab)[lg];
-      } else {  // rare: more than RS neighbours but still within the group hash
-        int base = 0;
-        if (lg == 0) base = atomicAdd(counters + 4, (int)round4(U));
-        base = __shfl_sync(gmask, base, 0, G);  // group-uniform branch: only this group's lanes are here
-        for (int i = lg; i < U; i += G) heap[base + i] = tab[i];
-        if (lg == 0) row[0] = base;
-        sbase = N * RS + base;
-      }
-      if (lg == 0) {
-        degs[v] = make_int2(U, lo);
-        bars = U - lo;
-      }
-      if (BAR >= 0 && U > lo) {  // bar pass over the upper neighbours (mesh_generator.py:696-700)
-        double a0, a1, a2;
-        load_pt<DIM, true>(pp, v, a0, a1, a2);
-        for (int j = lo + lg; j < U; j += G) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH);
-      }
+  if (v < N && !heavy && !punt) {
+    int32_t* row = adj + v * RS;
+    int64_t sbase = v * RS;
+    if (U <= RS) {
+      // RS ints = G lanes x int4 (3-D: 8 x 16 B = one 128-B line; 2-D: 4 x 16 B)
+      static_assert(RS == 4 * G, "one int4 per lane");
+      if (4 * lg < U) reinterpret_cast<int4*>(row)[lg] = reinterpret_cast<const int4*>(tab)[lg];
+    } else {  // rare: more than RS neighbours but still within the group hash
+      int base = 0;
+      if (lg == 0) base = atomicAdd(counters + 4, (int)round4(U));
+      base = __shfl_sync(gmask, base, 0, G);  // group-uniform branch: only this group's lanes are here
+      for (int i = lg; i < U; i += G) heap[base + i] = tab[i];
+      if (lg == 0) row[0] = base;
+      sbase = N * RS + base;
     }
+    if (lg == 0) {
+      degs[v] = make_int2(U, lo);
+      bars = U - lo;
+    }
+    if (BAR >= 0 && U > lo) {  // bar pass over the upper neighbours (mesh_generator.py:696-700)
+      double a0, a1, a2;
+      load_pt<DIM, true>(pp, v, a0, a1, a2);
+      for (int j = lo + lg; j < U; j += G) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH);
+    }
+  }
+  // ---- a neighbour set that does not fit the group table: rare, out of line.  Warp-uniform branch.
+  if (__any_sync(FULL, punt)) {
+    const RowSums rs = select_row<DIM, BAR>(punt, n, (int)v, brow, N, adj, heap, degs, counters, f, pp, hslot);
+    bars += rs.bars;
+    sL += rs.sL;
+    sH += rs.sH;
   }
   // ---- block totals without a barrier: every warp leaves its (fixed shuffle tree) sums in shared
   //      memory; the warp that arrives last adds them in warp order and publishes the block's values
   __shared__ double s_wL[AB_THREADS / 32], s_wH[AB_THREADS / 32];
   __shared__ int s_wbars[AB_THREADS / 32];
-  {
-    const int wid = tid >> 5;
+  const int wid = tid >> 5;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bars += __shfl_down_sync(FULL, bars, d);
+  for (int d = 16; d > 0; d >>= 1) bars += __shfl_down_sync(FULL, bars, d);
+  if (BAR >= 0) {
+    sL = warp_sum(sL);
+    sH = warp_sum(sH);
+  }
+  int lead = 0;  // lane 0: 1 = this warp closes its reduction group
+  if (lane == 0) {
+    s_wbars[wid] = bars;
     if (BAR >= 0) {
-      sL = warp_sum(sL);
-      sH = warp_sum(sH);
+      s_wL[wid] = sL;
+      s_wH[wid] = sH;
     }
-    bool last = false;
-    if (lane == 0) {
-      s_wbars[wid] = bars;
-      if (BAR >= 0) {
-        s_wL[wid] = sL;
-        s_wH[wid] = sH;
-      }
-      __threadfence_block();
-      last = atomicAdd(&s_arrived, 1) == AB_THREADS / 32 - 1;
-    }
-    if (last) {  // lane 0 of the last warp
+    __threadfence_block();
+    if (atomicAdd(&s_arrived, 1) == AB_THREADS / 32 - 1) {  // the block's last warp
       __threadfence_block();
       int tb = 0;
       double tL = 0.0, tH = 0.0;
@@ -452,267 +774,37 @@ __global__ void __launch_bounds__(AB_THREADS) adjacency_kernel(const int32_t* __
       }
       if (tb) atomicAdd(counters, tb);  // unique bars owned by this block's vertices
       if (BAR >= 0) {
-        partials[2 * (int64_t)blockIdx.x] = tL;
-        partials[2 * (int64_t)blockIdx.x + 1] = tH;
-      }
-    }
-  }
-}
-
-// ---- heavy vertices: one block per vertex -------------------------------------------------------
-// ascending compare-exchange network (bitonic with the "flip" first step, so every comparator
-// points the same way): positions >= n behave as +inf and never move, hence any n works in place.
-template <typename PTR>
-__device__ __forceinline__ void block_sort_ascending(PTR a, int n) {
-  for (int k = 2; (k >> 1) < n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
-        if (l > i && l < n) {
-          const int x = a[i], y = a[l];
-          if (x > y) {
-            a[i] = y;
-            a[l] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-constexpr int HV_RANK = 768;   // up to this many candidates: one-pass rank sort instead of the network
-constexpr int HV_FINAL = 1024;  // heavy vertices whose bar sums are added in vertex order
-
-// BAR as in adjacency_kernel.  With BAR >= 0 the block that finishes last also reduces all the
-// per-block bar sums (adjacency blocks in block order, then the heavy vertices in vertex order)
-// into scalars[0..2]: the scale of mesh_generator.py:700.
-template <int DIM, int BAR>
-__global__ void __launch_bounds__(HV_THREADS) adjacency_heavy_kernel(
-    const int32_t* __restrict__ cnt, const typename PCfg<DIM>::entry_t* __restrict__ bucket,
-    const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N,
-    int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
-    int32_t* __restrict__ counters, const DmSizeFn f, const double* __restrict__ pp, double* __restrict__ hslot,
-    double* partials, int64_t nb_adj, int32_t* done, double* scalars) {
-  pdl_prologue();
-  constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS;
-  __shared__ __align__(16) int32_t s_val[HV_SMEM];
-  __shared__ int s_scan[33];
-  __shared__ double s_dbl[32];
-  __shared__ int s_base, s_pos;
-  __shared__ bool s_last;
-  const int tid = threadIdx.x;
-  const int nheavy = counters[3];
-  const int novf = counters[2];
-  const int64_t slice0 = nb_adj + N + 1;  // partials of the slices below live behind the heavy ones
-  if (BAR >= 0) {
-    // first level of the final sum: block b adds the bar sums of a fixed slice of adjacency blocks
-    // (the adjacency kernel has finished), so the last block only has gridDim.x values left
-    const int64_t per = (nb_adj + gridDim.x - 1) / gridDim.x;
-    const int64_t i0 = (int64_t)blockIdx.x * per, i1 = i0 + per < nb_adj ? i0 + per : nb_adj;
-    double tL = 0.0, tH = 0.0;
-    for (int64_t i = i0 + tid; i < i1; i += HV_THREADS) {
-      tL += __ldcg(partials + 2 * i);
-      tH += __ldcg(partials + 2 * i + 1);
-    }
-    const double bl = block_sum(tL, s_dbl);
-    const double bh = block_sum(tH, s_dbl);
-    if (tid == 0) {
-      partials[2 * (slice0 + blockIdx.x)] = bl;
-      partials[2 * (slice0 + blockIdx.x) + 1] = bh;
-    }
-  }
-  for (int ih = blockIdx.x; ih < nheavy; ih += gridDim.x) {
-    const int v = hv[ih];
-    const int nc = cnt[v];
-    const int nb = nc < CAP ? nc : CAP;  // entries in the bucket; the other nc - nb were spilled
-    const int n = DIM * nc;              // candidates
-    __syncthreads();
-    if (tid == 0) {
-      s_base = atomicAdd(counters + 4, (int)round4(n));
-      s_pos = 0;
-    }
-    __syncthreads();
-    int32_t* reg = heap + s_base;  // candidates, later the row, live here
-    const bool in_smem = n <= HV_SMEM;
-    // gather the candidates
-    for (int i = tid; i < nb; i += HV_THREADS) {
-      const typename PCfg<DIM>::entry_t e = bucket[(int64_t)v * CAP + i];
-      const int* ei = reinterpret_cast<const int*>(&e);
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) {
-        if (in_smem)
-          s_val[i * DIM + c] = ei[c];
-        else
-          reg[i * DIM + c] = ei[c];
-      }
-    }
-    if (nc > CAP) {
-      for (int k = tid; k < novf; k += HV_THREADS) {
-        if (ovf_v[k] == v) {
-          const int i = nb + atomicAdd(&s_pos, 1);
-          const typename PCfg<DIM>::entry_t e = ovf_e[k];
-          const int* ei = reinterpret_cast<const int*>(&e);
-#pragma unroll
-          for (int c = 0; c < DIM; ++c) {
-            if (in_smem)
-              s_val[i * DIM + c] = ei[c];
-            else
-              reg[i * DIM + c] = ei[c];
-          }
-        }
-      }
-    }
-    __syncthreads();
-    int U = 0, lo = 0;
-    if (n <= HV_RANK) {
-      // one pass: candidate i is the first of its value if no equal value precedes it, and its
-      // row position is the number of DISTINCT smaller values = #{j : val[j] < val[i], j first}.
-      // Two sweeps over shared memory instead of ~50 barrier-separated network stages.
-      constexpr int PER = HV_RANK / HV_THREADS;
-      bool first[PER];
-      int x[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const int i = tid + u * HV_THREADS;
-        x[u] = i < n ? s_val[i] : 0;
-        first[u] = i < n;
-      }
-#pragma unroll 8  // the shared-memory loads of eight steps in flight (latency, not issue, bounds this sweep)
-      for (int j = 0; j < n; ++j) {
-        const int y = s_val[j];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) first[u] = first[u] && !(y == x[u] && j < tid + u * HV_THREADS);
-      }
-      __syncthreads();
-      // mark duplicates so that the rank sweep counts distinct values only
-      int32_t* s_first = s_val + HV_RANK;  // HV_SMEM >= 2 * HV_RANK
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const int i = tid + u * HV_THREADS;
-        if (i < n) s_first[i] = first[u] ? 1 : 0;
-      }
-      __syncthreads();
-      int r[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) r[u] = 0;
-#pragma unroll 8
-      for (int j = 0; j < n; ++j) {
-        const int y = s_val[j];
-        const int fj = s_first[j];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) r[u] += (fj && y < x[u]) ? 1 : 0;
-      }
-      int nf = 0, nl = 0;
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        if (first[u]) {
-          reg[r[u]] = x[u];
-          ++nf;
-          nl += x[u] < v ? 1 : 0;
-        }
-      }
-      int tot;
-      block_exclusive_scan(nf, tot, s_scan);
-      U = tot;
-      block_exclusive_scan(nl, tot, s_scan);
-      lo = tot;
-    } else {
-      if (in_smem)
-        block_sort_ascending(s_val, n);
-      else
-        block_sort_ascending(reg, n);
-      // unique: chunk by chunk; an element's output position never exceeds its input position and
-      // all reads of a chunk complete before its writes, so compaction in place is safe
-      for (int c0 = 0; c0 < n; c0 += HV_THREADS) {
-        const int i = c0 + tid;
-        int x = 0;
-        bool first = false;
-        if (i < n) {
-          x = in_smem ? s_val[i] : reg[i];
-          first = i == 0 || (in_smem ? s_val[i - 1] : reg[i - 1]) != x;
-        }
-        int tot;
-        const int off = block_exclusive_scan(first ? 1 : 0, tot, s_scan);  // syncs: reads done
-        if (first) reg[U + off] = x;
-        const int nl = __syncthreads_count(first && x < v);
-        U += tot;
-        lo += nl;
-      }
-    }
-    __syncthreads();
-    int32_t* row = adj + (int64_t)v * RS;
-    int64_t sbase = (int64_t)v * RS;
-    if (U <= RS) {
-      for (int i = tid; i < U; i += HV_THREADS) row[i] = reg[i];
-    } else {
-      if (tid == 0) row[0] = s_base;
-      sbase = N * RS + s_base;
-    }
-    if (tid == 0) {
-      degs[v] = make_int2(U, lo);
-      atomicAdd(counters, U - lo);
-    }
-    if (BAR >= 0) {
-      double sL = 0.0, sH = 0.0;
-      double a0, a1, a2;
-      load_pt<DIM, true>(pp, v, a0, a1, a2);
-      for (int j = lo + tid; j < U; j += HV_THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
-      const double bl = block_sum(sL, s_dbl);
-      const double bh = block_sum(sH, s_dbl);
-      if (tid == 0) {
-        partials[2 * (nb_adj + ih)] = bl;
-        partials[2 * (nb_adj + ih) + 1] = bh;
+        partials[2 * bidx] = tL;
+        partials[2 * bidx + 1] = tH;
+        __threadfence();
+        const int64_t g = bidx / RG;
+        const int gsize = (int)(nbm - g * RG < RG ? nbm - g * RG : RG);
+        lead = atomicAdd(gdone + g, 1) == gsize - 1 ? 1 : 0;
       }
     }
   }
   if (BAR < 0) return;
-  // ---- the last block to finish reduces everything in a FIXED order
-  __syncthreads();
-  if (tid == 0) {
+  if (!__shfl_sync(FULL, lead, 0)) return;
+  // ---- this warp saw the last block of its group finish: add the group's block sums in block order
+  {
     __threadfence();
-    s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double tL = 0.0, tH = 0.0;
-  for (int64_t i = tid; i < (int64_t)gridDim.x; i += HV_THREADS) {
-    tL += __ldcg(partials + 2 * (slice0 + i));
-    tH += __ldcg(partials + 2 * (slice0 + i) + 1);
-  }
-  if (nheavy <= HV_FINAL) {
-    // heavy vertices were appended in a run-dependent order: add their sums in vertex order
-    int32_t* s_id = s_val;
-    for (int i = tid; i < nheavy; i += HV_THREADS) s_id[i] = hv[i];
-    __syncthreads();
-    double* s_sorted = reinterpret_cast<double*>(s_val + HV_FINAL);  // 2 * HV_FINAL doubles
-    for (int i = tid; i < nheavy; i += HV_THREADS) {
-      const int x = s_id[i];
-      int r = 0;
-#pragma unroll 8
-      for (int j = 0; j < nheavy; ++j) r += s_id[j] < x ? 1 : 0;
-      s_sorted[2 * r] = __ldcg(partials + 2 * (nb_adj + i));
-      s_sorted[2 * r + 1] = __ldcg(partials + 2 * (nb_adj + i) + 1);
+    const int64_t g = bidx / RG;
+    const int gsize = (int)(nbm - g * RG < RG ? nbm - g * RG : RG);
+    double tL = 0.0, tH = 0.0;
+    for (int i = lane; i < gsize; i += 32) {
+      tL += __ldcg(partials + 2 * (g * RG + i));
+      tH += __ldcg(partials + 2 * (g * RG + i) + 1);
     }
-    __syncthreads();
-    for (int i = tid; i < nheavy; i += HV_THREADS) {
-      tL += s_sorted[2 * i];
-      tH += s_sorted[2 * i + 1];
+    tL = warp_sum(tL);
+    tH = warp_sum(tH);
+    int fin = 0;
+    if (lane == 0) {
+      partials[2 * (nbm + g)] = tL;
+      partials[2 * (nbm + g) + 1] = tH;
+      __threadfence();
+      fin = atomicAdd(total_done, 1) == ng + HV_BLOCKS - 1 ? 1 : 0;
     }
-  } else {
-    for (int64_t i = tid; i < nheavy; i += HV_THREADS) {
-      tL += __ldcg(partials + 2 * (nb_adj + i));
-      tH += __ldcg(partials + 2 * (nb_adj + i) + 1);
-    }
-  }
-  const double rl = block_sum(tL, s_dbl);
-  const double rh = block_sum(tH, s_dbl);
-  if (tid == 0) {
-    scalars[0] = rl;
-    scalars[1] = rh;
-    const double r = rl / rh;
-    scalars[2] = DIM == 2 ? sqrt(r) : pow(r, 1.0 / 3.0);  // ** (1.0 / dim), mesh_generator.py:700
+    if (__shfl_sync(FULL, fin, 0)) final_scale<DIM>(partials, nbm, ng, counters[3], scalars);
   }
 }
 

@@ -176,6 +176,27 @@ def test_unique_bars_edge_cases(sm):
     assert np.array_equal(unique_bars(t, N=n), orc.unique_bars(t))
 
 
+@pytest.mark.parametrize("dim,cells", [(3, 40), (3, 48), (2, 14), (2, 16), (3, 49), (3, 300), (2, 17), (2, 900)])
+def test_unique_bars_non_manifold_star(sm, dim, cells):
+    """A vertex whose incident cells share nothing but itself: far more distinct neighbours than a
+    manifold star of that many cells (3-D: 3 per cell instead of ~1/2).  Up to the bucket capacity
+    (48 / 16 cells) the neighbour set overflows the lane-group hash table and takes the in-group
+    selection path; beyond it the heavy-vertex blocks.  Plus ordinary cells around it."""
+    from seismicmesh_b200.engine import unique_bars
+
+    k = dim  # other vertices per cell
+    hub = 7
+    others = np.arange(cells * k, dtype=np.int32).reshape(cells, k) + 100
+    t = np.column_stack([np.full(cells, hub, dtype=np.int32), others]).astype(np.int32)
+    rng = np.random.default_rng(cells)
+    N = int(t.max()) + 50
+    filler = np.sort(rng.choice(np.arange(N, dtype=np.int32), size=(200, dim + 1)), axis=1)
+    filler = filler[(np.diff(filler, axis=1) > 0).all(axis=1)]
+    t = np.ascontiguousarray(np.vstack([t[: cells // 2], filler, t[cells // 2:]]), dtype=np.int32)
+    rng.shuffle(t, axis=0)
+    assert np.array_equal(unique_bars(t, N=N), orc.unique_bars(t))
+
+
 def test_compact_cells_preserves_order(sm):
     from seismicmesh_b200.engine import compact_cells
 
