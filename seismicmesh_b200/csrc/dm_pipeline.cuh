@@ -6,25 +6,28 @@
 // layout is therefore chosen to minimise scattered accesses per cell and to make every per-vertex
 // structure one aligned 128-B line (or a few), read / written by a lane group in one wavefront:
 //
+//   0  prep              zero the per-iteration counters; 3-D: padded point copy p4 (one 256-bit gather per point)
 //   A  cull_scatter      one thread per cell: centroid + fused SDF program -> keep flag; each kept
 //                        cell appends its OTHER vertex ids to the fixed-capacity bucket of each of
-//                        its vertices.  Slots are claimed with warp-aggregated atomics
-//                        (match.any: host Delaunay codes emit cells grouped around vertices, so a
-//                        warp's 128 claims collapse to ~50 atomics); a full bucket spills to a
-//                        global overflow list.
+//                        its vertices.  Slots are claimed with warp-aggregated atomics (one per run
+//                        of equal ids in consecutive lanes: host Delaunay codes emit cells grouped
+//                        around vertices); a full bucket spills to a global overflow list and lists
+//                        its vertex as heavy.
 //   B  adjacency         one lane group (8 lanes in 3-D, 4 in 2-D) per vertex: coalesced read of
 //                        the bucket, de-duplication in a group-private shared-memory hash (plain
 //                        LDS/STS, write-then-verify, no shared atomics), rank sort, ONE 128-B
 //                        store of the sorted neighbour row.  Row = [lower neighbours ascending |
 //                        upper neighbours ascending]; the upper parts of all rows, in vertex
 //                        order, ARE the reference's sorted unique bar list (unique_edges,
-//                        geometry/cpp/fast_geometry.cpp:30-77).
-//      adjacency_heavy   vertices whose bucket overflowed or whose neighbour set does not fit the
-//                        group hash (hull / hub vertices): one block per vertex, sort + unique.
-//   C  bar_pass          L, fh(midpoint), sum L^d, sum h^d over unique bars, fixed-order reduction,
-//                        scale = ((sum L^d)/(sum h^d))^(1/d)   (last block finishes the reduction)
+//                        geometry/cpp/fast_geometry.cpp:30-77).  Fused in: the bar pass over the
+//                        row's upper bars (L, fh(midpoint), sum L^d, sum h^d) and the fixed-order
+//                        reduction to scale = ((sum L^d)/(sum h^d))^(1/d).  The first HV_BLOCKS
+//                        blocks of the grid build the rows of the heavy vertices (bucket spilled:
+//                        hull / hub vertices), one block per vertex, beside the main blocks.
+//   C  bar_pass          stand-alone bar pass of the staged path (opaque fh)
 //   D  vertex_update     per-vertex gather of bar forces in the reference's COO accumulation order,
-//                        pfix, p += dt*F, Newton projection per level, max|F| (last block reduces)
+//                        pfix, p += dt*F, max|F| (last block reduces); vertices that left a level
+//                        set are listed and get their Newton projection from project_list_kernel
 #pragma once
 #include "dm_device.cuh"
 
@@ -203,17 +206,15 @@ __device__ __forceinline__ unsigned hash_slot(int x) {
 // issue slots, so the body keeps no per-candidate flag: a finished candidate is parked on the
 // lane's private word behind the table (tab[H + lg], one bank per lane of the warp, so parked
 // accesses never conflict) with its key replaced by the parked word's content, and from then on
-// it "hits" there for free.  A negative key (idle lane) starts parked.
+// it "hits" there for free.  Lanes without a candidate are handed a copy of a real key of the same
+// vertex (a duplicate insert is a no-op).
 constexpr int HASH_PARKED = -2;
 template <int NC, int LOGH>
 __device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC], unsigned park, bool& punt) {
   constexpr unsigned HM = (1u << LOGH) - 1u;
   unsigned h[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    h[c] = x[c] < 0 ? park : hash_slot<LOGH>(x[c]);  // no candidate (idle lane): parked
-    x[c] = x[c] < 0 ? HASH_PARKED : x[c];
-  }
+  for (int c = 0; c < NC; ++c) h[c] = hash_slot<LOGH>(x[c]);
   int steps = 0;
   bool any;
   do {
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
   constexpr int EPL = 2;
   typedef typename PCfg<DIM>::entry_t entry_t;
   const entry_t* brow = bucket + v * CAP;
+  const int key0 = n > 0 ? reinterpret_cast<const int*>(brow)[0] : 0;  // filler for idle lanes
   entry_t cur[EPL], nxt[EPL];
 #pragma unroll
   for (int u = 0; u < EPL; ++u)
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
       const bool a = i + u * G < n;
       const int* ei = reinterpret_cast<const int*>(&cur[u]);
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) x[u * DIM + c] = a ? ei[c] : -1;
+      for (int c = 0; c < DIM; ++c) x[u * DIM + c] = a ? ei[c] : key0;
     }
     hash_insert_lockstep<EPL * DIM, LOGH>(tab, x, (unsigned)(H + lg), punt);
 #pragma unroll
@@ -671,7 +673,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     if (lg >= d) inc += o;
   }
   int U = __shfl_sync(FULL, inc, G - 1, G);
-  if (punt) U = 0;
+  if (punt || n == 0) U = 0;  // n == 0: nothing but filler keys went in
   {
     int off = inc - c;
 #pragma unroll
