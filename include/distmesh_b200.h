@@ -174,7 +174,7 @@ typedef struct DmPlan {
   void *zero_base;   /* [cnt | sync | counters]: zeroed by stage A's prep kernel */
   size_t zero_bytes;
   int32_t *cnt;
-  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] bar-sum arrivals (adjacency) [4] projection blocks done */
+  int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] bar-sum arrivals (adjacency) [4] projection blocks done [5] displacement blocks done */
   int32_t *gdone;    /* adjacency blocks done, per reduction group of 128 blocks (zeroed with cnt) */
   int32_t *counters; /* [0]=E unique bars [1]=reserved [2]=spill records [3]=heavy vertices
                         [4]=heap cursor (ints) [5]=escaped vertices (stage D) */
@@ -189,7 +189,7 @@ typedef struct DmPlan {
   double *hslot;
   double *hbar;
   double *partials;  /* per-block partial sums / maxima */
-  double *scalars;   /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp */
+  double *scalars;   /* [0]=sum L^d [1]=sum h^d [2]=scale [3]=max|F|^2 [4]=maxdp [5]=max displacement (ttol test) */
   double *p4;        /* 3-D: (N,4) padded copy of p made by stage A (32-B rows: one 256-bit gather) */
   int32_t *esc;      /* (N) vertices that left a level set in stage D, projected by its second kernel */
   void *scan_tmp;    /* scratch of the on-demand scans */
@@ -241,6 +241,19 @@ int dm_force_iteration(const DmPlan *plan_host, const double *const *progs_host,
                        const DmSizeFn *fh_host, const double *p, const int32_t *t, double *p_out,
                        double geps, double L0mult, double delta_t, double deps, double h0,
                        int64_t nfix, const uint8_t *fixed, double *Ftot, void *stream);
+
+/* C+D only, on the rows left by the last dm_force_iteration (or stage B) of this plan: one force
+ * iteration WITHOUT retriangulation (the cell list is unchanged, only p moved).  This is the step
+ * DistMesh takes while the `ttol` displacement test does not fire (Persson & Strang; north_star
+ * item 5); the reference itself retriangulates every iteration (mesh_generator.py:460-470), so the
+ * host driver uses it only when the caller opts in (generate_mesh(..., ttol=...)). */
+int dm_force_iteration_reuse(const DmPlan *plan_host, const double *const *progs_host, int nlevels,
+                             const DmSizeFn *fh_host, const double *p, double *p_out, double L0mult,
+                             double delta_t, double deps, double h0, int64_t nfix,
+                             const uint8_t *fixed, double *Ftot, void *stream);
+/* the `ttol` test: plan->scalars[5] = max_v |p[v] - p_ref[v]|_2 (p_ref = positions at the last
+ * retriangulation). */
+int dm_stage_displacement(const DmPlan *plan_host, const double *p, const double *p_ref, void *stream);
 
 /* dm_force_iteration with a CUDA event recorded after every kernel (measurement only, used by
  * bench.py for the per-kernel roofline table; synchronises the stream).  ms_host[i] and the

@@ -102,6 +102,11 @@ _SIGNATURES = {
         _INT,
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _P, _D, _D, _D, _D, _D, _I64, _P, _P, _P],
     ),
+    "dm_force_iteration_reuse": (
+        _INT,
+        [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _D, _D, _D, _D, _I64, _P, _P, _P],
+    ),
+    "dm_stage_displacement": (_INT, [C.POINTER(DmPlan), _P, _P, _P]),
     "dm_force_iteration_profiled": (
         _INT,
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _P, _D, _D, _D, _D, _D, _I64, _P, _P,

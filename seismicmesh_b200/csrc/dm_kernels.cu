@@ -528,6 +528,32 @@ int dm_force_iteration(const DmPlan* pl, const double* const* progs, int nlevels
   return vertex_update_impl(pl, p, true, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }
 
+int dm_force_iteration_reuse(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,
+                             const double* p, double* p_out, double L0mult, double delta_t, double deps, double h0,
+                             int64_t nfix, const uint8_t* fixed, double* Ftot, void* stream) {
+  if (!pl || !progs || nlevels < 1 || nlevels > DM_MAX_LEVELS || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
+  if (!p || !p_out || p == p_out || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  // C + D on the rows of the last dm_force_iteration / stage B: the cell list has not changed
+  int rc = pl->dim == 2 ? launch_bar_pass<2>(pl, p, *f, f->kind, nullptr, st)
+                        : launch_bar_pass<3>(pl, p, *f, f->kind, nullptr, st);
+  mark("bar_pass+scale", st);
+  if (rc) return rc;
+  return vertex_update_impl(pl, p, false, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
+}
+
+int dm_stage_displacement(const DmPlan* pl, const double* p, const double* p_ref, void* stream) {
+  if (!pl || !p || !p_ref) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  const unsigned nb = nblk(pl->N, PL_THREADS);
+  if (pl->dim == 2)
+    displacement_kernel<2><<<nb, PL_THREADS, 0, st>>>(p, p_ref, pl->N, pl->partials, pl->sync + 5, pl->scalars);
+  else
+    displacement_kernel<3><<<nb, PL_THREADS, 0, st>>>(p, p_ref, pl->N, pl->partials, pl->sync + 5, pl->scalars);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,
                                 const double* p, const int32_t* t, double* p_out, double geps, double L0mult,
                                 double delta_t, double deps, double h0, int64_t nfix, const uint8_t* fixed,

@@ -941,6 +941,7 @@ __global__ void __launch_bounds__(PL_THREADS) bar_pass_kernel(const DmSizeFn f, 
       scalars[1] = rh;
       const double r = rl / rh;
       scalars[2] = DIM == 2 ? sqrt(r) : pow(r, 1.0 / 3.0);  // ** (1.0 / dim), mesh_generator.py:700
+      *done = 0;  // self-resetting: the stage can run again without stage A (row re-use)
     }
   }
 }
@@ -1089,6 +1090,44 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     if (threadIdx.x == 0) {
       scalars[3] = r;
       scalars[4] = delta_t * sqrt(r);  // maxdp, mesh_generator.py:514
+      *done = 0;
+    }
+  }
+}
+
+// max_v |p[v] - p_ref[v]|_2 -> scalars[5]: the displacement since the last retriangulation (the
+// `ttol` test of DistMesh, Persson & Strang; north_star (5)).  Last block reduces; self-resetting.
+template <int DIM>
+__global__ void __launch_bounds__(PL_THREADS) displacement_kernel(const double* __restrict__ p,
+                                                                 const double* __restrict__ p_ref, int64_t N,
+                                                                 double* partials, int32_t* done, double* scalars) {
+  pdl_prologue();
+  __shared__ double sm[32];
+  __shared__ bool s_last;
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (v < N) {
+    double a0, a1, a2, b0, b1, b2;
+    load_pt<DIM>(p, v, a0, a1, a2);
+    load_pt<DIM>(p_ref, v, b0, b1, b2);
+    const double e0 = a0 - b0, e1 = a1 - b1, e2 = a2 - b2;
+    d2 = e0 * e0 + e1 * e1;
+    if (DIM == 3) d2 = d2 + e2 * e2;
+  }
+  const double bm = block_max(d2, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bm;
+    __threadfence();
+    s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < (int64_t)gridDim.x; i += PL_THREADS) mx = fmax(mx, __ldcg(partials + i));
+    const double r = block_max(mx, sm);
+    if (threadIdx.x == 0) {
+      scalars[5] = sqrt(r);
       *done = 0;
     }
   }

@@ -191,6 +191,31 @@ class ForceLoop:
                     self.host_seconds += time.perf_counter() - t0
         return p_out, Ftot
 
+    def iterate_reuse(self, p, p_out=None, want_forces=False):
+        """One force iteration WITHOUT retriangulation: stages C + D on the neighbour rows left by the
+        last :meth:`iterate` (same cell list, moved points).  Opt-in (`ttol`); lowered fd / fh only."""
+        if not self.all_lowered or self.plan is None or self.plan.N != p.shape[0]:
+            raise RuntimeError("iterate_reuse needs a previous iterate() on the same vertices and lowered fd / fh")
+        pl = self.plan
+        if p_out is None:
+            p_out = torch.empty_like(p)
+        Ftot = torch.empty_like(p) if want_forces else None
+        f = self.size.struct()
+        progs = D.prog_array(self._progs)
+        check(
+            lib.dm_force_iteration_reuse(
+                C.byref(pl.c), progs, len(self._progs), C.byref(f), D.ptr(p), D.ptr(p_out), self.L0mult, self.delta_t,
+                self.deps, self.h0, self.nfix, D.ptr(self.fixed_mask), D.ptr(Ftot), D.stream_ptr(),
+            ),
+            "dm_force_iteration_reuse",
+        )
+        return p_out, Ftot
+
+    def displacement(self, p, p_ref):
+        """max_v |p[v] - p_ref[v]| on the device (the DistMesh `ttol` test); returns a float."""
+        check(lib.dm_stage_displacement(C.byref(self.plan.c), D.ptr(p), D.ptr(p_ref), D.stream_ptr()), "displacement")
+        return float(self.plan.scalars()[5].item())
+
     def maxdp(self):
         return float(self.plan.scalars()[4].item())
 

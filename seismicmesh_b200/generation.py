@@ -32,7 +32,10 @@ _ALLOWED = {
     "gamma", "preserve", "mesh_improvement", "r0m_is_h0",
 }
 # API extensions of this implementation (documented in DESIGN.md): none are needed for parity.
-_EXTENSIONS = {"triangulator"}
+# `ttol`: opt-in DistMesh displacement test (Persson & Strang): retriangulate only when some vertex has
+# moved more than ttol*h0 since the last Delaunay; iterations in between re-use the neighbour rows
+# and never leave the device.  Default None = the reference's behaviour (retriangulate every iteration).
+_EXTENSIONS = {"triangulator", "ttol"}
 
 
 def _parse_kwargs(kwargs):
@@ -202,7 +205,7 @@ def generate_mesh(domain, edge_length, comm=None, **kwargs):  # noqa: C901
     gen_opts = {
         "verbose": 1, "max_iter": 50, "seed": 0, "perform_checks": False, "pfix": None, "axis": 1,
         "points": None, "delta_t": 0.30, "geps_mult": 0.1, "subdomains": None, "mesh_improvement": True,
-        "r0m_is_h0": False, "triangulator": None,
+        "r0m_is_h0": False, "triangulator": None, "ttol": None,
     }
     gen_opts.update(kwargs)
     _parse_kwargs(kwargs)
@@ -271,24 +274,46 @@ def generate_mesh(domain, edge_length, comm=None, **kwargs):  # noqa: C901
     loop.nfix = nfix_dev
     loop.fixed_mask = None if fixed_mask is None else D.to_dev(fixed_mask, torch.uint8)
 
+    ttol = gen_opts["ttol"]
+    if ttol is not None:
+        if ttol < 0:
+            raise ValueError("`ttol` must be >= 0")
+        if not loop.all_lowered:
+            warnings.warn("`ttol` needs lowered `domain` / `edge_length` (no opaque callables); retriangulating every iteration")
+            ttol = None
     stats = dict(delaunay=0.0, h2d=0.0, device=0.0, d2h=0.0, termination=0.0, iterations=0, nverts=N,
-                 triangulator=tri.name)
+                 triangulator=tri.name, triangulations=0)
     p_dev = D.to_dev(p, torch.float64)
     p_host = p
+    host_current = True  # p_host mirrors p_dev
+    p_tri = None         # positions at the last retriangulation (ttol test)
+    t_dev = None
+    disp = float("inf")
     count = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     while True:
         start = time.time()
-        t0 = time.perf_counter()
-        t_host = tri.triangulate(p_host)
-        t1 = time.perf_counter()
-        t_dev = D.to_dev(t_host, torch.int32)
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        stats["delaunay"] += t1 - t0
-        stats["h2d"] += t2 - t1
+        last = count == (max_iter - 1)
+        retri = last or ttol is None or p_tri is None or disp > ttol * h0
+        if retri:
+            if not host_current:
+                t3 = time.perf_counter()
+                p_host = p_dev.cpu().numpy()
+                host_current = True
+                stats["d2h"] += time.perf_counter() - t3
+            t0 = time.perf_counter()
+            t_host = tri.triangulate(p_host)
+            t1 = time.perf_counter()
+            t_dev = D.to_dev(t_host, torch.int32)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            stats["delaunay"] += t1 - t0
+            stats["h2d"] += t2 - t1
+            stats["triangulations"] += 1
+            if ttol is not None:
+                p_tri = p_dev.clone()
 
-        if count == (max_iter - 1):
+        if last:
             print_msg1("Termination reached...maximum number of iterations reached.")
             tt = time.perf_counter()
             t_kept = loop.kept_cells(p_dev, t_dev).cpu().numpy()
@@ -305,19 +330,26 @@ def generate_mesh(domain, edge_length, comm=None, **kwargs):  # noqa: C901
             break
 
         ev0.record()
-        p_new, _ = loop.iterate(p_dev, t_dev)
+        if retri:
+            p_new, _ = loop.iterate(p_dev, t_dev)
+        else:
+            p_new, _ = loop.iterate_reuse(p_dev)
         ev1.record()
         torch.cuda.synchronize()
         stats["device"] += ev0.elapsed_time(ev1) * 1e-3
         t3 = time.perf_counter()
         p_dev = p_new
-        p_host = p_dev.cpu().numpy()
+        if ttol is None:
+            p_host = p_dev.cpu().numpy()
+        else:  # positions stay on the device until the next retriangulation
+            host_current = False
+            disp = loop.displacement(p_dev, p_tri)
         maxdp = loop.maxdp()
         stats["d2h"] += time.perf_counter() - t3
         stats["iterations"] += 1
         print_msg2(
             "Iteration #%d, max movement is %f, there are %d vertices and %d cells"
-            % (count + 1, maxdp, len(p_host), _kept_count(loop) if gen_opts["verbose"] > 1 else 0)
+            % (count + 1, maxdp, N, _kept_count(loop) if gen_opts["verbose"] > 1 else 0)
         )
         assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
         count += 1

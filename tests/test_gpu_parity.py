@@ -404,6 +404,37 @@ def test_full_size_iteration_vs_oracle(sm, dim, h0):
     assert dom.eval(p_new.cpu().numpy()).max() < 0.05 * h0
 
 
+@pytest.mark.parametrize("dim,h0,grid", [(2, 0.02, False), (3, 0.08, False), (3, 0.1, True)])
+def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
+    """The opt-in `ttol` path: an iteration that re-uses the neighbour rows (no retriangulation) must
+    equal a full iteration on the same cell list (only the order of the global bar sums differs),
+    can be repeated, and the displacement test is the exact max |p - p_ref|."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dom = sm.Disk([0.0, 0.0], 1.0) if dim == 2 else sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _lattice_mesh(sm, dom, h0, dim)
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    if grid:  # a smooth gridded size function over the bounding box
+        ax = [np.linspace(-1.2, 1.2, 25)] * 3
+        X = np.meshgrid(*ax, indexing="ij")
+        vals = h0 * (1.0 + 0.5 * np.sqrt(X[0] ** 2 + X[1] ** 2 + X[2] ** 2))
+        size = SizeSpec(dim, interp=sm.GridInterpolant(ax, vals))
+    else:
+        size = SizeSpec(dim, const=h0)
+    loop = ForceLoop(dim, [Level(dom, dim)], size, h0, geps, deps)
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    p1 = loop.iterate(pd, td)[0].clone()
+    full, Ff = loop.iterate(p1, td, want_forces=True)
+    full, Ff = full.clone(), Ff.clone()
+    again, Fr = loop.iterate_reuse(p1, want_forces=True)  # rows (and kept cells) of that same iteration
+    assert relerr(Fr.cpu().numpy(), Ff.cpu().numpy()) < TOL
+    assert relerr(again.cpu().numpy(), full.cpu().numpy()) < PTOL
+    twice = loop.iterate_reuse(p1)[0]  # self-resetting counters: the stage can run again
+    assert np.array_equal(twice.cpu().numpy(), again.cpu().numpy())
+    d = loop.displacement(again, pd)
+    assert d == np.sqrt(((again.cpu().numpy() - p) ** 2).sum(1)).max()
+
+
 # ------------------------------------------------------------------------------------------------
 # end to end through the public API
 # ------------------------------------------------------------------------------------------------
@@ -424,6 +455,25 @@ def test_generate_mesh_disk_matches_reference(sm):
     assert q.min() >= ref["min_q"] * 0.99 or q.min() > 0.6
     assert abs(meshutil.simp_vol(p, t).sum() - ref["area"]) < 0.01 * ref["area"]
     assert sm.last_run_stats["iterations"] == 24  # max_iter=K means K-1 force iterations
+
+
+def test_generate_mesh_ttol_opt_in(sm):
+    """`ttol` (extension, off by default): same vertices, fewer Delaunay calls, same mesh quality."""
+    from seismicmesh_b200 import meshutil
+
+    dom = sm.Disk([0.0, 0.0], 1.0)
+    p0, t0 = sm.generate_mesh(dom, 0.05, max_iter=40, verbose=0)
+    base = dict(sm.last_run_stats)
+    p1, t1 = sm.generate_mesh(dom, 0.05, max_iter=40, verbose=0, ttol=0.1)
+    lazy = dict(sm.last_run_stats)
+    assert base["triangulations"] == 40 and lazy["iterations"] == 39
+    assert lazy["triangulations"] < base["triangulations"]
+    assert len(p1) == len(p0)
+    q0, q1 = meshutil.simp_qual(p0, t0), meshutil.simp_qual(p1, t1)
+    assert abs(q1.mean() - q0.mean()) <= 0.01 * q0.mean() and q1.min() > 0.55
+    assert abs(meshutil.simp_vol(p1, t1).sum() - np.pi) < 0.01 * np.pi
+    with pytest.raises(ValueError, match="ttol"):
+        sm.generate_mesh(dom, 0.05, max_iter=3, verbose=0, ttol=-1.0)
 
 
 def test_generate_mesh_gridded_rectangle(sm):
