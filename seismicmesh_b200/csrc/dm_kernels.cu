@@ -58,8 +58,6 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   const int64_t K = (int64_t)DIM * (DIM + 1) * T;
   const int64_t K1 = K > 0 ? K : 1, T1 = T > 0 ? T : 1;
   const int64_t heap_ints = K1 + 4 * (N + 1);
-  // per-block partials: adjacency blocks (AB_THREADS / G vertices each) + one per heavy vertex +
-  // one per block of the heavy kernel (first level of the final sum)
   // bar sums: one per adjacency block + one per group of RG blocks + one per heavy vertex (dm_pipeline.cuh)
   const int64_t nbm = cdiv(N > 0 ? N : 1, AB_THREADS / PCfg<DIM>::G);
   const int64_t ngrp = cdiv(nbm, RG);
@@ -71,7 +69,7 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
     return ptr;
   };
   char* keep = take((size_t)T1);
-  // ---- zero region (contiguous): cnt | sync | counters : ONE memset per iteration
+  // ---- zero region (contiguous): cnt | sync | counters | gdone : zeroed by the prep kernel of stage A
   const size_t z0 = off;
   char* cnt = take((size_t)(N + 1) * 4);
   char* sync = take(8 * 4);
@@ -206,7 +204,7 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
 }
 
 // bar: -1 rows only (staged path: a separate bar pass follows) ; otherwise f->kind (0 const, 1 grid):
-// the bar pass is fused into the adjacency kernels and the heavy kernel's last block writes the scale
+// the bar pass and the reduction to the scale are fused into the adjacency kernel
 template <int DIM>
 static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const double* p, cudaStream_t st) {
   typedef typename PCfg<DIM>::entry_t entry_t;

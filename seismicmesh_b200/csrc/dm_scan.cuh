@@ -1,7 +1,7 @@
 // Single-pass exclusive scan of int32 (decoupled look-back, one launch).
 //
 // Scratch: `desc` = one 64-bit descriptor per 2048-element tile, `ticket` = one int.  Both must be
-// ZERO on entry (the force iteration folds that into its single per-iteration memset).
+// ZERO on entry (exclusive_scan below zeroes them itself).
 // Descriptor word: bits 63..62 = status (0 invalid, 1 tile aggregate, 2 inclusive prefix),
 // low 32 bits = value.  Tiles are handed out through the ticket so that a tile's predecessors
 // are always already running -> the look-back spin cannot deadlock.
