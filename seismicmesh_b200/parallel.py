@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["slab_bounds", "slab_partition", "RingHalo", "SlabLayout"]
+__all__ = ["slab_bounds", "slab_partition", "RingHalo", "SlabLayout", "TorchComm", "generate_mesh_parallel"]
 
 
 def slab_bounds(lo, hi, world):
@@ -161,3 +161,239 @@ def allreduce_force_scale(sum_L, sum_h, group=None):
     buf = torch.stack([sum_L, sum_h])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf[0], buf[1]
+
+
+# ----------------------------------------------------------------------------------------------
+# generate_mesh on several GPUs: the reference's parallel algorithm (mesh_generator.py:430-530,
+# 715-731, 808-880; migration/migration.py:72-183) with one process per GPU over torch.distributed.
+# ----------------------------------------------------------------------------------------------
+class TorchComm:
+    """What to pass as ``comm=`` : the mpi4py-like (rank, size) view of a torch.distributed group."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+
+def _comm_device(dev):
+    """Tensors that travel live on the GPU under NCCL and on the host under gloo (CPU tests)."""
+    return dev if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _exchange_ghosts(below, above, rank, size, dim, cdev, group=None):
+    """Send `below` / `above` (host arrays (k,dim)) to rank-1 / rank+1, return what arrives as
+    (from_above, from_below) -- the message pattern of migration.exchange (migration.py:148-183):
+    counts first, then ONE grouped send/recv of the coordinates."""
+    nb = torch.tensor([len(below)], dtype=torch.int64, device=cdev)
+    na = torch.tensor([len(above)], dtype=torch.int64, device=cdev)
+    rb = torch.zeros(1, dtype=torch.int64, device=cdev)
+    ra = torch.zeros(1, dtype=torch.int64, device=cdev)
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, nb, rank - 1, group), dist.P2POp(dist.irecv, rb, rank - 1, group)]
+    if rank < size - 1:
+        ops += [dist.P2POp(dist.isend, na, rank + 1, group), dist.P2POp(dist.irecv, ra, rank + 1, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    sb = torch.from_numpy(np.ascontiguousarray(below, dtype=np.float64)).to(cdev)
+    sa = torch.from_numpy(np.ascontiguousarray(above, dtype=np.float64)).to(cdev)
+    gb = torch.empty((int(rb.item()), dim), dtype=torch.float64, device=cdev)
+    ga = torch.empty((int(ra.item()), dim), dtype=torch.float64, device=cdev)
+    ops = []
+    if rank > 0:
+        if sb.numel():
+            ops.append(dist.P2POp(dist.isend, sb, rank - 1, group))
+        if gb.numel():
+            ops.append(dist.P2POp(dist.irecv, gb, rank - 1, group))
+    if rank < size - 1:
+        if sa.numel():
+            ops.append(dist.P2POp(dist.isend, sa, rank + 1, group))
+        if ga.numel():
+            ops.append(dist.P2POp(dist.irecv, ga, rank + 1, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return ga.cpu().numpy(), gb.cpu().numpy()
+
+
+def _gather_points(points, rank, size, dim, cdev, group=None):
+    """Owned vertices of every rank -> one array on rank 0, in rank order (None elsewhere)."""
+    counts = torch.zeros(size, dtype=torch.int64, device=cdev)
+    counts[rank] = len(points)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    counts = counts.cpu().numpy()
+    if rank != 0:
+        dist.send(torch.from_numpy(np.ascontiguousarray(points)).to(cdev), 0, group=group)
+        return None
+    parts = [points]
+    for r in range(1, size):
+        pr = torch.empty((int(counts[r]), dim), dtype=torch.float64, device=cdev)
+        dist.recv(pr, r, group=group)
+        parts.append(pr.cpu().numpy())
+    return np.ascontiguousarray(np.vstack(parts))
+
+
+def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
+    """generate_mesh over `comm.size` ranks, one GPU each: every rank owns the vertices created in
+    its slab of the bounding box (equal-width slabs along ``axis``, generation/utils.py:28-44); per
+    iteration it triangulates its vertices, exports those whose incident-cell circumballs reach a
+    neighbour's (5*h0-padded) extent (`dm_halo_select`, replacing cpputils.where_to2/3), receives its
+    neighbours' exports as ghosts, retriangulates owned+ghosts, drops the cells that lie entirely
+    outside its extent, runs the force iteration on the device and keeps the owned rows.  At
+    `max_iter` rank 0 gathers the owned vertices, triangulates them once and cleans up; the other ranks
+    return (True, True) (mesh_generator.py:460-527, migration.py:72-183).
+    The mesh-size grid is replicated on every GPU instead of being resampled per slab
+    (migration.localize_sizing_function), so parallel and serial runs see the same fh."""
+    import ctypes as C
+    import time
+
+    from . import device as D
+    from . import generation as G
+    from . import geometry
+    from ._lib import check, lib
+    from .engine import ForceLoop, Level
+    from .triangulator import get_triangulator
+
+    rank, size_ = int(comm.rank), int(comm.size)
+    group = getattr(comm, "group", None)
+    if not dist.is_initialized() or dist.get_world_size(group) != size_:
+        raise RuntimeError("generate_mesh(comm=...) with comm.size > 1 needs torch.distributed initialised with that many ranks")
+    gen_opts = {
+        "verbose": 1, "max_iter": 50, "seed": 0, "perform_checks": False, "pfix": None, "axis": 1,
+        "points": None, "delta_t": 0.30, "geps_mult": 0.1, "subdomains": None, "mesh_improvement": True,
+        "r0m_is_h0": False, "triangulator": None, "ttol": None,
+    }
+    gen_opts.update(kwargs)
+    G._parse_kwargs(kwargs)
+    if gen_opts["points"] is not None:
+        raise NotImplementedError("user-defined initial points are not supported in parallel here")
+    print_msg1, print_msg2 = G._printers(gen_opts)
+    if rank != 0:
+        print_msg1 = print_msg2 = lambda msg: None  # noqa: E731
+
+    dom, bbox0, _ = G._unpack_domain(domain, gen_opts)
+    payload, bbox1, hmin = G._unpack_sizing(edge_length)
+    bbox = bbox0 if bbox1 is None else G._minmax(bbox0, bbox1)
+    if not isinstance(bbox, tuple):
+        raise ValueError("`bbox` must be a tuple")
+    dim = int(len(bbox) / 2)
+    if bbox0 != bbox1 and bbox1 is not None:
+        dom = geometry.Rectangle(bbox) if dim == 2 else geometry.Cube(bbox)
+    bbox_arr = np.array(bbox, dtype=float).reshape(-1, 2)
+    h0 = hmin if hmin is not None else gen_opts["h0"]
+    if h0 < 0:
+        raise ValueError("`h0` must be > 0")
+    if gen_opts["max_iter"] < 0:
+        raise ValueError("`max_iter` must be > 0")
+    max_iter, axis = gen_opts["max_iter"], gen_opts["axis"]
+    geps = gen_opts["geps_mult"] * h0
+    deps = np.sqrt(np.finfo(np.double).eps) * h0
+    level0 = Level(dom, dim)
+    size = G._size_spec(payload, dim)
+    levels = [level0]
+    if gen_opts["subdomains"] is not None:
+        for sub in gen_opts["subdomains"]:
+            levels.append(Level(G._unpack_domain(sub, gen_opts)[0], dim))
+    dev = D.device()
+    cdev = _comm_device(dev)
+
+    # ---- initial points of this rank's slab (make_init_points + rejection, :808-852) ----
+    lb = bbox_arr.copy()
+    lims = np.linspace(lb[axis, 0], lb[axis, 1], size_ + 1)
+    lb[axis, :] = lims[rank : rank + 2]
+    if rank != 0:  # "starting point must be lasts + h0"
+        prev = lims[rank - 1 : rank + 1]
+        lb[axis, 0] = prev[0] + (int(np.ceil((prev[1] + h0 - prev[0]) / h0)) - 1) * h0 + h0
+    p = G._staggered_grid(h0, dim, lb)
+    p = p[level0.eval_host(p) < geps]
+    r0 = size.eval_host(p)
+    r0m = float(r0.min()) if len(r0) else np.inf
+    if gen_opts["r0m_is_h0"]:
+        r0m = 1.1 * h0 if 1.1 * h0 < r0m else h0
+    t_r0m = torch.tensor([r0m], dtype=torch.float64, device=cdev)
+    dist.all_reduce(t_r0m, op=dist.ReduceOp.MIN, group=group)  # "decimation occurs uniformly across ranks"
+    r0m = float(t_r0m.item())
+    np.random.seed(gen_opts["seed"])
+    p = np.ascontiguousarray(p[np.random.rand(p.shape[0]) < r0m**dim / r0**dim])
+    assert len(p) > 0, "No vertices to mesh with!"
+    # extents of every rank: AABB of its points, padded by 5*h0 along the axis (_form_extents, :867-877)
+    ext = torch.zeros((size_, 2 * dim), dtype=torch.float64, device=cdev)
+    mine = np.concatenate([p.min(0), p.max(0)])
+    mine[axis] -= 5 * h0
+    mine[axis + dim] += 5 * h0
+    ext[rank] = torch.from_numpy(mine).to(cdev)
+    dist.all_reduce(ext, op=dist.ReduceOp.SUM, group=group)
+    extents = ext.cpu().numpy()
+    print_msg1("Commencing mesh generation with %d vertices on rank %d." % (len(p), rank))
+
+    tri = get_triangulator(gen_opts["triangulator"], dim)
+    loop = ForceLoop(dim, levels, size, h0, geps, deps, delta_t=gen_opts["delta_t"], nfix=0)
+    boxes = np.zeros((2, 2 * dim))
+    if rank > 0:
+        boxes[0] = extents[rank - 1]
+    if rank < size_ - 1:
+        boxes[1] = extents[rank + 1]
+    boxes_c = (C.c_double * (4 * dim))(*boxes.ravel())
+    stats = dict(delaunay=0.0, device=0.0, exchange=0.0, iterations=0, nverts=len(p), triangulator=tri.name)
+    count = 0
+    while True:
+        start = time.time()
+        n_own = len(p)
+        t0 = time.perf_counter()
+        t_own = tri.triangulate(p)
+        stats["delaunay"] += time.perf_counter() - t0
+        # ---- ghosts: export the vertices whose cells' circumballs reach a neighbour (enqueue + exchange)
+        t1 = time.perf_counter()
+        pd = D.to_dev(p, torch.float64)
+        td = D.to_dev(t_own, torch.int32)
+        flags = torch.zeros((n_own + 3) // 4 * 4, dtype=torch.uint8, device=dev)
+        check(lib.dm_halo_select(D.ptr(pd), D.ptr(td), td.shape[0], n_own, dim, boxes_c, int(rank > 0),
+                                 int(rank < size_ - 1), D.ptr(flags), D.stream_ptr()), "dm_halo_select")
+        fl = flags[:n_own].cpu().numpy()
+        from_above, from_below = _exchange_ghosts(p[(fl & 1) != 0], p[(fl & 2) != 0], rank, size_, dim, cdev, group)
+        stats["exchange"] += time.perf_counter() - t1
+        ghosts = [g for g in (from_above, from_below) if len(g)]
+        p_loc = np.ascontiguousarray(np.vstack([p] + ghosts)) if ghosts else p
+        t0 = time.perf_counter()
+        t_loc = tri.triangulate(p_loc) if ghosts else t_own
+        stats["delaunay"] += time.perf_counter() - t0
+        # cells with all their vertices outside this rank's extent belong to somebody else
+        # (geometry.remove_external_entities, geometry/utils.py:57-94)
+        e = extents[rank]
+        outside = ((p_loc < e[:dim]) | (p_loc > e[dim:])).any(axis=1)
+        t_loc = np.ascontiguousarray(t_loc[~outside[t_loc].all(axis=1)])
+        pd = D.to_dev(p_loc, torch.float64)
+        td = D.to_dev(t_loc, torch.int32)
+
+        if count == (max_iter - 1):
+            # The reference gathers the local meshes (ghost copies included) and de-duplicates them on
+            # rank 0 (migration.aggregate + fix_mesh); here rank 0 gathers the OWNED vertices and
+            # triangulates them once: the same vertex set, and a conforming mesh by construction.
+            print_msg1("Termination reached...maximum number of iterations reached.")
+            gp = _gather_points(p, rank, size_, dim, cdev, group)
+            G.last_run_stats.clear()
+            G.last_run_stats.update(stats)
+            if rank != 0:
+                return True, True
+            gt = tri.triangulate(gp)
+            t_kept = loop.kept_cells(D.to_dev(gp, torch.float64), D.to_dev(gt, torch.int32)).cpu().numpy()
+            p_out, t_out = G._termination(gp, t_kept, gen_opts, dim, verbose=gen_opts["verbose"])
+            p_out = G._level_set_newton(p_out, t_out, level0, deps, dim)
+            fin = ForceLoop(dim, [level0], size, h0, h0 * 0.001, deps)
+            t_out = fin.kept_cells(D.to_dev(p_out, torch.float64), D.to_dev(t_out, torch.int32)).cpu().numpy().astype(t_out.dtype)
+            return p_out, t_out
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        p_new, _ = loop.iterate(pd, td)
+        ev1.record()
+        p = np.ascontiguousarray(p_new[:n_own].cpu().numpy())  # "delete ghost points"
+        stats["device"] += ev0.elapsed_time(ev1) * 1e-3
+        stats["iterations"] += 1
+        maxdp = loop.maxdp()
+        print_msg2("Iteration #%d, max movement is %f, there are %d vertices and %d cells" % (count + 1, maxdp, len(p_loc), len(t_loc)))
+        if rank == 0:
+            assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
+        count += 1
+        print_msg2("     Elapsed wall-clock time %f : " % (time.time() - start))

@@ -640,3 +640,57 @@ def test_sizing_errors(sm):
                                          pad_style="mirror")
     with pytest.raises(ValueError, match="vp_water"):
         sm.get_sizing_function_from_segy(None, bbox, velocity_data=np.zeros((10, 12)), nz=10, nx=12, vp_water=900.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# generate_mesh on several ranks (one process per rank; on the single-GPU test box both ranks share
+# cuda:0 and talk over gloo -- the device work and the message pattern are those of the NCCL run)
+# ------------------------------------------------------------------------------------------------
+def _par_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import seismicmesh_b200 as sm
+        from seismicmesh_b200.parallel import TorchComm
+
+        torch.cuda.set_device(0)
+        out = sm.generate_mesh(sm.Rectangle((0.0, 1.0, 0.0, 2.0)), 0.04, comm=TorchComm(), max_iter=30, verbose=0)
+        if rank == 0:
+            q.put((out[0], out[1], dict(sm.last_run_stats)))
+        else:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_generate_mesh_parallel_matches_serial(sm, world):
+    import socket
+
+    import torch.multiprocessing as mp
+    from seismicmesh_b200 import meshutil
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_par_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(60)
+    root = [r for r in res if len(r) == 3][0]
+    assert sum(1 for r in res if len(r) == 2 and r[0] is True and r[1] is True) == world - 1  # non-root ranks
+    p, t, stats = root
+    ps, ts = sm.generate_mesh(sm.Rectangle((0.0, 1.0, 0.0, 2.0)), 0.04, max_iter=30, verbose=0)
+    assert abs(len(p) - len(ps)) <= 0.03 * len(ps)
+    assert abs(meshutil.simp_vol(p, t).sum() - 2.0) < 0.01 * 2.0  # reference test_2dmesher_par: area within 1%
+    q_par, q_ser = meshutil.simp_qual(p, t), meshutil.simp_qual(ps, ts)
+    assert q_par.min() > 0.5 and abs(q_par.mean() - q_ser.mean()) < 0.02
+    assert stats["iterations"] == 29 and stats["exchange"] > 0.0

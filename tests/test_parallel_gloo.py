@@ -85,3 +85,53 @@ def test_slab_partition_is_consistent():
         assert np.array_equal(hi.owned[hi.export_below], lo.ghost_above)
         assert np.all(pg[hi.ghost_below, 1] >= faces[r + 1] - 0.25)
         assert np.all(pg[lo.ghost_above, 1] < faces[r + 1] + 0.25)
+
+
+# ---- variable-size ghost exchange + gather used by generate_mesh_parallel (host message pattern) ----
+def _ghost_worker(rank, world, port, q):
+    from seismicmesh_b200.parallel import _exchange_ghosts, _gather_points
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dim = 3
+        cdev = torch.device("cpu")
+        mk = lambda tag, n: np.full((n, dim), 100.0 * rank + tag) + np.arange(n)[:, None]  # noqa: E731
+        below = mk(1, 0 if rank == 0 else rank + 1)          # rank r sends r+1 rows down ...
+        above = mk(2, 0 if rank == world - 1 else 2 * rank)  # ... and 2r rows up (rank 0: an empty message)
+        fa, fb = _exchange_ghosts(below, above, rank, world, dim, cdev)
+        ok = True
+        if rank < world - 1:  # from above: rank+1's "below" list
+            ok &= fa.shape == (rank + 2, dim) and np.array_equal(fa, np.full((rank + 2, dim), 100.0 * (rank + 1) + 1) + np.arange(rank + 2)[:, None])
+        else:
+            ok &= len(fa) == 0
+        if rank > 0:  # from below: rank-1's "above" list
+            n = 2 * (rank - 1)
+            ok &= fb.shape == (n, dim) and np.array_equal(fb, np.full((n, dim), 100.0 * (rank - 1) + 2) + np.arange(n)[:, None])
+        else:
+            ok &= len(fb) == 0
+        g = _gather_points(mk(3, rank + 2), rank, world, dim, cdev)
+        if rank == 0:
+            exp = np.vstack([np.full((r + 2, dim), 100.0 * r + 3) + np.arange(r + 2)[:, None] for r in range(world)])
+            ok &= np.array_equal(g, exp)
+        else:
+            ok &= g is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ghost_exchange_and_gather_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ghost_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(ok for _, ok in res)
