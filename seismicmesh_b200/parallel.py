@@ -224,14 +224,14 @@ def _gather_points(points, rank, size, dim, cdev, group=None):
     dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     counts = counts.cpu().numpy()
     if rank != 0:
-        dist.send(torch.from_numpy(np.ascontiguousarray(points)).to(cdev), 0, group=group)
+        buf = torch.from_numpy(np.ascontiguousarray(points)).to(cdev)
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, buf, 0, group)]):
+            w.wait()
         return None
-    parts = [points]
-    for r in range(1, size):
-        pr = torch.empty((int(counts[r]), dim), dtype=torch.float64, device=cdev)
-        dist.recv(pr, r, group=group)
-        parts.append(pr.cpu().numpy())
-    return np.ascontiguousarray(np.vstack(parts))
+    bufs = [torch.empty((int(counts[r]), dim), dtype=torch.float64, device=cdev) for r in range(1, size)]
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, b, r + 1, group) for r, b in enumerate(bufs)]):
+        w.wait()
+    return np.ascontiguousarray(np.vstack([points] + [b.cpu().numpy() for b in bufs]))
 
 
 def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
