@@ -121,7 +121,7 @@ def build_workload(workload, h0=None, freq=None, settle=2):
         t, dt = triangulate(p)
         spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)) if dim == 3 else ("disk", dict(x0=[0.0, 0.0], r=1.0))
         return dict(p=p, t=t, dim=dim, dom=dom, size=SizeSpec(dim, const=h0), h0=h0, spec=spec, fh_grid=None,
-                    delaunay_s=dt, desc=f"{workload}_h0={h0:g}", sizing_s=0.0)
+                    delaunay_s=dt, desc=f"{workload}_h0={h0:g}", sizing_s=0.0, edge=h0)
     import torch
 
     from seismicmesh_b200 import device as D
@@ -159,7 +159,7 @@ def build_workload(workload, h0=None, freq=None, settle=2):
     spec = ("rectangle", dict(bbox=tuple(ef.bbox))) if dim == 2 else ("cube", dict(bbox=tuple(ef.bbox)))
     g = ef.interpolant()
     return dict(p=p, t=t, dim=dim, dom=dom, size=size, h0=hmin, spec=spec, fh_grid=(g.grid, g.values),
-                delaunay_s=dt, sizing_s=sizing_s,
+                delaunay_s=dt, sizing_s=sizing_s, edge=ef,
                 desc=f"{workload}_shaped_grid{'x'.join(str(n) for n in g.values.shape)}_hmin={hmin:g}_freq={fr:g}")
 
 
@@ -339,6 +339,9 @@ def main():
     ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing / hmin (scale-up runs)")
     ap.add_argument("--freq", type=float, default=None, help="bp2004 / eage: override the sizing frequency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--time-to-mesh", type=int, default=0, metavar="ITERS",
+                    help="also run generate_mesh(max_iter=ITERS) end to end (host Delaunay included) and report "
+                         "time-to-mesh, with the reference's retriangulate-every-iteration and with ttol=0.1")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -588,6 +591,22 @@ def main():
             perr = float(np.abs(out_pin.numpy() - ref_p).max())
             cpu["max_abs_dp_vs_oracle"] = perr
 
+    ttm = None
+    if args.time_to_mesh > 0 and world == 1:
+        from seismicmesh_b200 import meshutil
+
+        edge = wl["edge"]
+        ttm = {}
+        for name, kw in (("reference_semantics", {}), ("ttol_0.1", {"ttol": 0.1})):
+            c0 = time.perf_counter()
+            pm, tm = sm.generate_mesh(dom, edge, max_iter=args.time_to_mesh, verbose=0, **kw)
+            wall_m = time.perf_counter() - c0
+            st_ = dict(sm.last_run_stats)
+            qm = meshutil.simp_qual(pm, tm)
+            ttm[name] = {"wall_s": wall_m, "delaunay_s": st_["delaunay"], "device_s": st_["device"],
+                         "triangulations": st_["triangulations"], "vertices": int(len(pm)), "cells": int(len(tm)),
+                         "mean_quality": float(qm.mean()), "min_quality": float(qm.min())}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -601,7 +620,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
         "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
-        "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse, "sliver_pass": sliver,
+        "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse, "sliver_pass": sliver, "time_to_mesh": ttm,
         "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "sizing_s": wl["sizing_s"], "maxdp": maxdp,
         "wall_s_timed_region": wall,
     }
