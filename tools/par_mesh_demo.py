@@ -20,10 +20,21 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 comm = TorchComm()
-h0 = float(sys.argv[1]) if len(sys.argv) > 1 else 0.06
-dom = sm.Cube((0.0, 1.0, 0.0, 2.0, 0.0, 1.0))
+arg = sys.argv[1] if len(sys.argv) > 1 else "0.06"
+if arg == "eage":  # BASELINE.json configs[4]: the EAGE-shaped sizing grid, slab-decomposed (grid replicated per GPU)
+    from bench import synth_vp
+
+    vp, bbox = synth_vp("eage")
+    edge = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, hmin=150.0, wl=5, freq=2.0, dt=0.001,
+                                            grade=0.15, hmax=5e3, domain_pad=250.0, pad_style="linear_ramp",
+                                            nz=vp.shape[0], nx=vp.shape[1], ny=vp.shape[2])
+    del vp
+    dom = sm.Cube(edge.bbox)
+else:
+    edge = float(arg)
+    dom = sm.Cube((0.0, 1.0, 0.0, 2.0, 0.0, 1.0))
 t0 = time.perf_counter()
-out = sm.generate_mesh(dom, h0, comm=comm, max_iter=25, verbose=0)
+out = sm.generate_mesh(dom, edge, comm=comm, max_iter=25, verbose=0)
 dt = time.perf_counter() - t0
 if comm.rank == 0:
     p, t = out
