@@ -441,6 +441,49 @@ def test_full_size_ball_properties(sm):
     assert np.array_equal(p2.cpu().numpy(), p1) and np.array_equal(F2.cpu().numpy(), F1)
 
 
+@pytest.mark.parametrize("dim,grid", [(2, False), (2, True), (3, False), (3, True)])
+def test_hub_vertex_full_iteration_vs_oracle(sm, dim, grid):
+    """A hub: one centre point joined to every point of a shell around it (hundreds of incident
+    cells, a neighbour row far longer than the fixed 128-B row) inside an ordinary point cloud.
+    Exercises the heavy-vertex blocks, heap rows in the bar pass and in the vertex update, with
+    constant and gridded fh, against the oracle."""
+    from scipy.spatial import Delaunay
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    rng = np.random.default_rng(7 + dim)
+    n_shell = 150 if dim == 2 else 400
+    u = rng.normal(size=(n_shell, dim))
+    shell = 0.45 * u / np.linalg.norm(u, axis=1)[:, None]
+    outer = rng.uniform(-1.0, 1.0, (2500, dim))
+    outer = outer[np.linalg.norm(outer, axis=1) > 0.5]
+    p = np.ascontiguousarray(np.vstack([np.zeros((1, dim)), shell, outer]))
+    t = Delaunay(p).simplices.astype(np.int32)
+    assert (t == 0).any(axis=1).sum() > 100  # the hub really has a large star
+    h0 = 0.08
+    dom = sm.Rectangle((-1.0, 1.0, -1.0, 1.0)) if dim == 2 else sm.Cube((-1.0, 1.0, -1.0, 1.0, -1.0, 1.0))
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    if grid:
+        ax = [np.linspace(-1.3, 1.3, 31)] * dim
+        X = np.meshgrid(*ax, indexing="ij")
+        vals = h0 * (1.0 + 0.8 * np.sqrt(sum(x**2 for x in X)))
+        interp = sm.GridInterpolant(ax, vals)
+        size = SizeSpec(dim, interp=interp)
+        fh = lambda x: orc.interp_grid(list(interp.grid), interp.values, x)  # noqa: E731
+    else:
+        size = SizeSpec(dim, const=h0)
+        fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    loop = ForceLoop(dim, [Level(dom, dim)], size, h0, geps, deps)
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    p_new, F = loop.iterate(pd, td, want_forces=True)
+    spec = dom.spec()
+    ref = orc.force_iteration(p, t, [lambda x: orc.sdf(spec, x)], fh, h0, geps, deps)
+    assert np.array_equal(loop.bars().cpu().numpy(), ref["bars"])
+    assert relerr(F.cpu().numpy(), ref["Ftot"]) < TOL
+    assert relerr(p_new.cpu().numpy(), ref["p"]) < PTOL
+    again, Fr = loop.iterate_reuse(pd, want_forces=True)  # same positions, rows re-used
+    assert relerr(Fr.cpu().numpy(), ref["Ftot"]) < TOL and relerr(again.cpu().numpy(), ref["p"]) < PTOL
+
+
 @pytest.mark.parametrize("dim,h0,grid", [(2, 0.02, False), (3, 0.08, False), (3, 0.1, True)])
 def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
     """The opt-in `ttol` path: an iteration that re-uses the neighbour rows (no retriangulation) must
