@@ -57,6 +57,15 @@ static inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, un
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// arrival counter with release / acquire ordering at device scope: what the arriving thread wrote
+// before is visible to whoever sees its increment, and the thread that sees the last arrival may read
+// what the others wrote -- a lighter fence than __threadfence() (fence.sc) around a relaxed atomic
+__device__ __forceinline__ int arrive_acq_rel(int32_t* counter) {
+  int old;
+  asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+  return old;
+}
+
 __device__ __forceinline__ int warp_inclusive_scan(int v) {
   const int lane = threadIdx.x & 31;
 #pragma unroll

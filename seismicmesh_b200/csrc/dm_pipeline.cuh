@@ -296,7 +296,6 @@ constexpr int RG = 128;       // adjacency blocks per reduction group (second le
 template <int DIM>
 __device__ __forceinline__ void final_scale(const double* partials, int64_t nb, int ng, int nheavy, double* scalars) {
   const int lane = threadIdx.x & 31;
-  __threadfence();
   double tL = 0.0, tH = 0.0;
   for (int g = lane; g < ng; g += 32) {
     tL += __ldcg(partials + 2 * (nb + g));
@@ -591,10 +590,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
                              heap, degs, hv, counters, f, pp, hslot, partials + 2 * (nbm + ng));
     if (BAR < 0) return;
     __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      s_fin = atomicAdd(total_done, 1) == ng + HV_BLOCKS - 1;
-    }
+    if (tid == 0) s_fin = arrive_acq_rel(total_done) == ng + HV_BLOCKS - 1;
     __syncthreads();
     if (s_fin && tid < 32) final_scale<DIM>(partials, nbm, ng, nheavy, scalars);
     return;
@@ -778,10 +774,9 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
       if (BAR >= 0) {
         partials[2 * bidx] = tL;
         partials[2 * bidx + 1] = tH;
-        __threadfence();
         const int64_t g = bidx / RG;
         const int gsize = (int)(nbm - g * RG < RG ? nbm - g * RG : RG);
-        lead = atomicAdd(gdone + g, 1) == gsize - 1 ? 1 : 0;
+        lead = arrive_acq_rel(gdone + g) == gsize - 1 ? 1 : 0;
       }
     }
   }
@@ -789,7 +784,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
   if (!__shfl_sync(FULL, lead, 0)) return;
   // ---- this warp saw the last block of its group finish: add the group's block sums in block order
   {
-    __threadfence();
+    __syncwarp();  // lane 0's acquire orders the other lanes' reads as well
     const int64_t g = bidx / RG;
     const int gsize = (int)(nbm - g * RG < RG ? nbm - g * RG : RG);
     double tL = 0.0, tH = 0.0;
@@ -803,10 +798,12 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     if (lane == 0) {
       partials[2 * (nbm + g)] = tL;
       partials[2 * (nbm + g) + 1] = tH;
-      __threadfence();
-      fin = atomicAdd(total_done, 1) == ng + HV_BLOCKS - 1 ? 1 : 0;
+      fin = arrive_acq_rel(total_done) == ng + HV_BLOCKS - 1 ? 1 : 0;
     }
-    if (__shfl_sync(FULL, fin, 0)) final_scale<DIM>(partials, nbm, ng, counters[3], scalars);
+    if (__shfl_sync(FULL, fin, 0)) {
+      __syncwarp();
+      final_scale<DIM>(partials, nbm, ng, counters[3], scalars);
+    }
   }
 }
 
