@@ -243,13 +243,15 @@ DM_HD bool sdf_project(const double* __restrict__ prog, int dim, double deps, do
 // find_indices: largest i with axis[i] <= x, clamped to [0, n-2]  (== clip(searchsorted(right)-1))
 // ---------------------------------------------------------------------------------------------
 DM_HD int grid_find(const double* __restrict__ ax, int n, double x) {
-  // uniform-spacing guess, then fix up against the ACTUAL (float32-rounded) axis
+  // uniform-spacing guess, then fix up against the ACTUAL (float32-rounded) axis.  The guess only
+  // has to land within a node or two, so it is computed in float32 (a handful of instructions
+  // instead of a float64 division); the loops below make the result exact whatever the guess.
   const double a0 = DM_LDG(ax), a1 = DM_LDG(ax + n - 1);
-  double g = (x - a0) / (a1 - a0) * (double)(n - 1);
+  const float g = (float)(x - a0) / (float)(a1 - a0) * (float)(n - 1);
   int i;
-  if (!(g > 0.0))
+  if (!(g > 0.0f))
     i = 0;
-  else if (g >= (double)(n - 2))
+  else if (g >= (float)(n - 2))
     i = n - 2;
   else
     i = (int)g;
