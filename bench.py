@@ -502,10 +502,12 @@ def main():
     if world == 1 and dim == 3:
         lo_b, hi_b = 10.0 * np.pi / 180, np.pi
 
+        fl = torch.empty(T, dtype=torch.uint8, device=p_dev.device)
+        prog0 = loop._progs[0]
+
         def sliver_pass():
-            tk = loop.kept_cells(p_dev, t_dev)  # one host sync inside (kept-cell count)
-            fl = torch.empty(tk.shape[0], dtype=torch.uint8, device=p_dev.device)
-            check(lib.dm_dihedral(D.ptr(p_dev), D.ptr(tk), tk.shape[0], lo_b, hi_b, None, D.ptr(fl), D.stream_ptr()), "dihedral")
+            check(lib.dm_sliver_flags(D.ptr(prog0), D.ptr(p_dev), D.ptr(t_dev), T, geps, lo_b, hi_b, None, D.ptr(fl),
+                                      D.stream_ptr()), "sliver_flags")
             return fl
 
         for _ in range(2):
@@ -520,7 +522,7 @@ def main():
         barrier()
         s_ms = float(sum(a.elapsed_time(b) for a, b in ev4)) / K
         sliver = {"ms_per_pass": s_ms, "cells_per_s": T * 1e3 / s_ms, "slivers_flagged": int(fl.sum().item()),
-                  "what": "cull + compaction + dihedral-angle bound test of one sliver_removal pass (includes one host sync)"}
+                  "what": "cull + dihedral-angle bound test of one sliver_removal pass (one fused kernel)"}
         loop.iterate(p_dev, t_dev, p_out=p_out)
 
     if rank != 0:

@@ -127,6 +127,12 @@ size_t dm_compact_scratch_bytes(int64_t T);
 int dm_dihedral(const double *p, const int32_t *t, int64_t T, double min_dh, double max_dh,
                 double *angles, uint8_t *flags, void *stream);
 
+/* one sliver_removal pass in one kernel (mesh_generator.py:204-243): keep[c] = fd(centroid) < -geps
+ * (may be NULL), flags[c] = kept AND some dihedral angle < min_dh or > max_dh.  Cell ids are those of
+ * the uncompacted list t (the order of flagged cells equals the reference's after its cull). */
+int dm_sliver_flags(const double *prog, const double *p, const int32_t *t, int64_t T, double geps,
+                    double min_dh, double max_dh, uint8_t *keep, uint8_t *flags, void *stream);
+
 /* gradient of the circumsphere radius wrt vertex 0 of the listed tets (replaces
  * _fast_geometry.calc_circumsphere_grad, fast_geometry.cpp:580-703).  ele (S) int32 cell ids
  * (NULL = all T cells, S=T) -> grad (S,3). */

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dm_compact_cells": (_INT, [_P, _P, _I64, _INT, _P, _P, _P, _SZ, _P]),
     "dm_compact_scratch_bytes": (_SZ, [_I64]),
     "dm_dihedral": (_INT, [_P, _P, _I64, _D, _D, _P, _P, _P]),
+    "dm_sliver_flags": (_INT, [_P, _P, _P, _I64, _D, _D, _D, _P, _P, _P]),
     "dm_circumsphere_grad": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "dm_sliver_perturb": (_INT, [_P, _I64, _P, _P, _I64, _D, _P, _P, _P]),
     "dm_level_set_newton": (_INT, [_P, _P, _P, _I64, _INT, _D, _P]),

@@ -133,6 +133,41 @@ __global__ void dihedral_kernel(const double* __restrict__ p, const int32_t* __r
   if (flags != nullptr) flags[c] = bad ? 1 : 0;
 }
 
+// One sliver_removal pass in one kernel: keep test of the cell (fd(centroid) < -geps,
+// mesh_generator.py:734-738) + dihedral bound test of the kept cells (:532-540); flags[c] = 1 for a
+// kept cell with an angle out of bounds.  Cell ids stay those of the UNcompacted list: the order of
+// the flagged cells is the order the reference sees after its order-preserving cull.
+__global__ void sliver_flags_kernel(const double* __restrict__ prog, const double* __restrict__ p,
+                                    const int32_t* __restrict__ t, int64_t T, double geps, double min_dh,
+                                    double max_dh, uint8_t* __restrict__ keep, uint8_t* __restrict__ flags) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int v[4];
+  load_cell<3>(t, c, v);
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
+  // centroid p[t].sum(1)/4, vertices added in order (mesh_generator.py:737)
+  double c0 = P[0][0], c1 = P[0][1], c2 = P[0][2];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    c0 = c0 + P[k][0];
+    c1 = c1 + P[k][1];
+    c2 = c2 + P[k][2];
+  }
+  const bool kept = sdf_eval(prog, 3, c0 / 4.0, c1 / 4.0, c2 / 4.0) < -geps;
+  bool bad = false;
+  if (kept) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double a = dihedral_angle(P, i);
+      bad = bad || (a < min_dh) || (a > max_dh);
+    }
+  }
+  if (keep != nullptr) keep[c] = kept ? 1 : 0;
+  flags[c] = bad ? 1 : 0;
+}
+
 __global__ void circumsphere_grad_kernel(const double* __restrict__ p, const int32_t* __restrict__ t,
                                          const int32_t* __restrict__ ele, int64_t S_, double* __restrict__ grad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -343,6 +343,16 @@ int dm_dihedral(const double* p, const int32_t* t, int64_t T, double min_dh, dou
   return DM_OK;
 }
 
+int dm_sliver_flags(const double* prog, const double* p, const int32_t* t, int64_t T, double geps, double min_dh,
+                    double max_dh, uint8_t* keep, uint8_t* flags, void* stream) {
+  if (!prog || T < 0) return DM_ERR_ARG;
+  if (T == 0) return DM_OK;
+  if (!p || !t || !flags) return DM_ERR_ARG;
+  sliver_flags_kernel<<<nblk(T, 128), 128, 0, S(stream)>>>(prog, p, t, T, geps, min_dh, max_dh, keep, flags);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_circumsphere_grad(const double* p, const int32_t* t, const int32_t* ele, int64_t S_, double* grad,
                          void* stream) {
   if (S_ < 0) return DM_ERR_ARG;

@@ -429,22 +429,36 @@ def sliver_removal(points, domain, edge_length, comm=None, **kwargs):  # noqa: C
         t_host = tri.triangulate(p_host)
         stats["delaunay"] += time.perf_counter() - t0
         t_dev = D.to_dev(t_host, torch.int32)
-        t_kept = loop.kept_cells(p_dev, t_dev)
-        T = t_kept.shape[0]
-        flags = torch.empty(T, dtype=torch.uint8, device=p_dev.device)
-        check(lib.dm_dihedral(D.ptr(p_dev), D.ptr(t_kept), T, min_dh_bound, max_dh_bound, None, D.ptr(flags), st()), "dihedral")
-        ele_nums = np.nonzero(flags.cpu().numpy())[0].astype(np.int32)
+        if level0.lowered:
+            # cull + dihedral bound test in ONE kernel on the uncompacted cell list; the kept cells are
+            # only compacted when the loop ends (fix_mesh below)
+            t_kept = None
+            t_use = t_dev
+            T = t_dev.shape[0]
+            flags = torch.empty(T, dtype=torch.uint8, device=p_dev.device)
+            check(lib.dm_sliver_flags(D.ptr(level0.prog), D.ptr(p_dev), D.ptr(t_dev), T, geps, min_dh_bound, max_dh_bound,
+                                      None, D.ptr(flags), st()), "sliver_flags")
+            ele_nums = torch.nonzero(flags).flatten().to(torch.int32).cpu().numpy()
+        else:
+            t_kept = loop.kept_cells(p_dev, t_dev)
+            t_use = t_kept
+            T = t_kept.shape[0]
+            flags = torch.empty(T, dtype=torch.uint8, device=p_dev.device)
+            check(lib.dm_dihedral(D.ptr(p_dev), D.ptr(t_kept), T, min_dh_bound, max_dh_bound, None, D.ptr(flags), st()), "dihedral")
+            ele_nums = np.nonzero(flags.cpu().numpy())[0].astype(np.int32)
 
         if count == (max_iter - 1):
             print_msg1(
                 "FAILURE: Termination...maximum number of iterations reached. Try increasing max_iter when generating the mesh",
             )
-            p_host, t_out, _ = meshutil.fix_mesh(p_host, t_kept.cpu().numpy(), dim=dim, delete_unused=True)
+            t_fin = t_kept if t_kept is not None else loop.kept_cells(p_dev, t_dev)
+            p_host, t_out, _ = meshutil.fix_mesh(p_host, t_fin.cpu().numpy(), dim=dim, delete_unused=True)
             break
         print_msg1(f"On rank: {rank}. There are {len(ele_nums)} slivers...")
         if len(ele_nums) == 0:
             print_msg1(f"Termination reached in {count} iterations...no slivers detected!")
-            p_host, t_out, _ = meshutil.fix_mesh(p_host, t_kept.cpu().numpy(), dim=dim, delete_unused=True)
+            t_fin = t_kept if t_kept is not None else loop.kept_cells(p_dev, t_dev)
+            p_host, t_out, _ = meshutil.fix_mesh(p_host, t_fin.cpu().numpy(), dim=dim, delete_unused=True)
             break
 
         num_bad = len(ele_nums)
@@ -457,11 +471,12 @@ def sliver_removal(points, domain, edge_length, comm=None, **kwargs):  # noqa: C
         ele_dev = D.to_dev(ele_nums, torch.int32)
         delta = torch.empty((num_bad, 3), dtype=torch.float64, device=p_dev.device)
         check(
-            lib.dm_sliver_perturb(D.ptr(p_dev), N, D.ptr(t_kept), D.ptr(ele_dev), num_bad, step * h0, D.ptr(winner), D.ptr(delta), st()),
+            lib.dm_sliver_perturb(D.ptr(p_dev), N, D.ptr(t_use), D.ptr(ele_dev), num_bad, step * h0, D.ptr(winner), D.ptr(delta), st()),
             "sliver_perturb",
         )
         if sliver_opts["preserve"]:
-            ph = _level_set_newton(p_dev.cpu().numpy(), t_kept.cpu().numpy(), level0, deps, dim)
+            t_fin = t_kept if t_kept is not None else loop.kept_cells(p_dev, t_dev)
+            ph = _level_set_newton(p_dev.cpu().numpy(), t_fin.cpu().numpy(), level0, deps, dim)
             p_dev = D.to_dev(ph, torch.float64)
         p_host = p_dev.cpu().numpy()
         count += 1

@@ -347,6 +347,34 @@ def test_sliver_kernels(sm):
     assert relerr(q.cpu().numpy(), g["p_new"]) < TOL
 
 
+def test_sliver_flags_fused_pass(sm):
+    """dm_sliver_flags (cull + dihedral bound test in one kernel, uncompacted ids) against the
+    two-step path and the oracle: same kept cells, same slivers in the same order."""
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+    from seismicmesh_b200.geometry import lower
+
+    dom = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    h0 = 0.12
+    p, t = _lattice_mesh(sm, dom, h0, 3, seed=3)
+    geps, lo, hi = 0.1 * h0, 10.0 * np.pi / 180, np.pi
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    T = len(t)
+    keep = torch.empty(T, dtype=torch.uint8, device="cuda")
+    flags = torch.empty(T, dtype=torch.uint8, device="cuda")
+    prog = lower(dom)
+    check(lib.dm_sliver_flags(D.ptr(prog), D.ptr(pd), D.ptr(td), T, geps, lo, hi, D.ptr(keep), D.ptr(flags), D.stream_ptr()), "sliver_flags")
+    keep_h, flags_h = keep.cpu().numpy().astype(bool), flags.cpu().numpy().astype(bool)
+    ref_keep = orc.cull_mask(p, t, lambda x: orc.sdf(dom.spec(), x), geps)
+    assert np.array_equal(keep_h, ref_keep)
+    ref_ele = orc.sliver_cells(p, t[ref_keep], lo, hi)  # ids in the compacted list, as the reference sees them
+    assert len(ref_ele) > 0
+    assert np.array_equal(np.nonzero(flags_h)[0], np.nonzero(ref_keep)[0][ref_ele])
+    # end to end: the public sliver_removal (which uses the fused pass) still removes every sliver
+    pts, cells = sm.sliver_removal(points=p, domain=dom, edge_length=h0, verbose=0, max_iter=60)
+    assert len(orc.sliver_cells(pts, cells, lo, hi)) == 0
+
+
 def test_level_set_newton_kernel(sm):
     from seismicmesh_b200 import device as D
     from seismicmesh_b200._lib import check, lib
