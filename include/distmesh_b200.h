@@ -162,7 +162,8 @@ int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64
  *   bucket   (N*CAP)        per vertex: the OTHER vertex ids of each incident kept cell
  *                           (3-D: CAP=48 entries of 4 ints; 2-D: CAP=16 entries of 2 ints)
  *   ovf_v/e  ((dim+1)*T)    spill records (vertex, entry) of buckets that overflowed
- *   hv       (N)            vertices handled by the heavy path (spilled / very high degree)
+ *   hv       (N)            vertices whose bucket spilled (hull / hub vertices): listed by stage A, their rows
+ *                           are built one block per vertex by the first blocks of stage B's grid
  *   adj      (N*RS)         sorted unique neighbour ids of vertex v at adj[v*RS ...] (RS = 32 ints
  *                           in 3-D = one 128-B line, 16 in 2-D); degs[v] = {deg, nlow}: the first
  *                           nlow are < v.  deg > RS: the row lives in `heap` at offset adj[v*RS].
@@ -171,13 +172,15 @@ int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64
  *   rowptr   (N+1)          bar ids = exclusive scan of deg-nlow (built on demand)
  *   hslot    (N*RS + heap)  gridded fh at the midpoint of bar (v,w), stored at its upper slot
  *   hbar     (K/2)          fh per bar id, for DM_SIZE_EXTERNAL
+ *   p4       (N*4)          3-D: padded copy of p (32-B rows) refreshed by stage A
+ *   esc      (N)            vertices that left a level set in stage D (projected by its second kernel)
  * ------------------------------------------------------------------------------------------- */
 typedef struct DmPlan {
   int64_t N, T;      /* vertices, cells handed over by the host Delaunay */
   int32_t dim, _pad0;
   int64_t K;         /* dim*(dim+1)*T : directed (vertex, neighbour) candidates */
   uint8_t *keep;
-  void *zero_base;   /* [cnt | sync | counters]: zeroed by stage A's prep kernel */
+  void *zero_base;   /* [cnt | sync | counters | gdone]: zeroed by stage A's prep kernel */
   size_t zero_bytes;
   int32_t *cnt;
   int32_t *sync;     /* [1] bar-pass blocks done [2] update blocks done [3] bar-sum arrivals (adjacency) [4] projection blocks done [5] displacement blocks done */
