@@ -400,11 +400,26 @@ def main():
     p_out = torch.empty_like(p_dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=p_dev.device)  # > 126 MB L2
 
-    halo = None
+    halo, halo_kind = None, None
     if world > 1:
-        from seismicmesh_b200.parallel import RingHalo
+        from seismicmesh_b200.parallel import PeerHalo, RingHalo
 
-        halo = RingHalo(layout, dim, p_dev.device, rank=rank, world=world)
+        ring = RingHalo(layout, dim, p_dev.device, rank=rank, world=world)
+        halo, halo_kind = ring, "NCCL P2P send/recv (RingHalo)"
+        if os.environ.get("DM_HALO", "p2p") == "p2p":
+            try:  # NVLink peer-memory push with our own kernel; checked once against the NCCL exchange
+                peer = PeerHalo(layout, dim, p_dev.device, rank=rank, world=world)
+                a, b = p_dev.clone(), p_dev.clone()
+                a[n_owned:] = float("nan")
+                b[n_owned:] = float("nan")
+                ring.exchange(a)
+                peer.exchange(b)
+                peer.exchange(b)  # both slots
+                torch.cuda.synchronize()
+                assert torch.equal(a, b), "PeerHalo and RingHalo disagree"
+                halo, halo_kind = peer, "NVLink peer-memory push, dm_halo_push + symmetric-memory signals (PeerHalo)"
+            except Exception as exc:  # no peer access / symmetric memory on this box: keep NCCL
+                halo_kind += f" [peer-memory path unavailable: {type(exc).__name__}: {exc}]"
 
     def one_step():
         loop.iterate(p_dev, t_dev, p_out=p_out)
@@ -615,7 +630,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["desc"], "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
                    "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
-                   "parallelism": (f"{world} slabs along axis 1 (owned+ghost per GPU), NCCL P2P halo exchange per step; "
+                   "parallelism": (f"{world} slabs along axis 1 (owned+ghost per GPU), halo exchange per step: {halo_kind}; "
                                    f"halo bytes/step/rank={halo.bytes_per_exchange}") if world > 1 else "single",
                    "N_owned_total": N_all},
         "clocks": clocks,

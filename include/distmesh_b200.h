@@ -284,6 +284,13 @@ int dm_halo_select(const double *p, const int32_t *t, int64_t T, int64_t N, int 
                    const double *boxes_host, int has_below, int has_above, uint8_t *flags,
                    void *stream);
 
+/* ghost push over peer memory: dst_peer[i] = p[idx[i]] for i < n, where dst_peer points into a
+ * NEIGHBOUR GPU's ghost buffer (a peer-mapped / symmetric-memory address; NVLink stores).  One kernel
+ * instead of pack + ncclSend/ncclRecv (+ unpack) for migration.exchange (migration.py:148-183); the
+ * caller orders it with the peer through its own signal (parallel.PeerHalo). */
+int dm_halo_push(const double *p, const int32_t *idx, int64_t n, int dim, double *dst_peer,
+                 void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing: gradient limiting of a gridded size function in place (replaces
  * _FastHJ.limgrad, sizing/cpp/FastHJ.cpp:63-190, called from _enforce_gradation_sizing,

@@ -114,6 +114,7 @@ _SIGNATURES = {
          C.POINTER(C.c_float), C.c_char_p, _INT, _INT, C.POINTER(_INT)],
     ),
     "dm_limgrad": (_INT, [_P, _I64, _I64, _I64, _D, _D, _INT, _P, C.POINTER(_INT), _P]),
+    "dm_halo_push": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "dm_halo_select": (_INT, [_P, _P, _I64, _I64, _INT, C.POINTER(_D), _INT, _INT, _P, _P]),
     "dm_scan_scratch_bytes": (_SZ, [_I64]),
     "dm_exclusive_scan_i32": (_INT, [_P, _P, _I64, _P, _SZ, _P]),

@@ -341,4 +341,20 @@ __global__ void limgrad_sweep_kernel(double* f, int n0, int n1, int n2, double d
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// halo push: the rows of p listed in idx go straight into a neighbour GPU's ghost buffer through
+// its peer mapping (NVLink stores; dst is a device pointer into the PEER's memory).  Replaces
+// pack + ncclSend/ncclRecv for the per-iteration ghost exchange (migration.exchange,
+// migration/migration.py:148-183).
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void halo_push_kernel(const double* __restrict__ p, const int32_t* __restrict__ idx, int64_t n,
+                                 double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x0, x1, x2;
+  load_pt<DIM>(p, idx[i], x0, x1, x2);
+  store_pt<DIM>(dst, i, x0, x1, x2);
+}
+
 }  // namespace dm

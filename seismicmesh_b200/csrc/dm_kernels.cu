@@ -612,6 +612,18 @@ int dm_limgrad(double* f, int64_t n0, int64_t n1, int64_t n2, double delta, doub
   return flag ? DM_ERR_WORKSPACE : DM_OK;  // not converged within max_sweeps
 }
 
+int dm_halo_push(const double* p, const int32_t* idx, int64_t n, int dim, double* dst_peer, void* stream) {
+  if (n < 0 || bad_dim(dim)) return DM_ERR_ARG;
+  if (n == 0) return DM_OK;
+  if (!p || !idx || !dst_peer) return DM_ERR_ARG;
+  if (dim == 2)
+    halo_push_kernel<2><<<nblk(n, 256), 256, 0, S(stream)>>>(p, idx, n, dst_peer);
+  else
+    halo_push_kernel<3><<<nblk(n, 256), 256, 0, S(stream)>>>(p, idx, n, dst_peer);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_halo_select(const double* p, const int32_t* t, int64_t T, int64_t N, int dim, const double* boxes,
                    int has_below, int has_above, uint8_t* flags, void* stream) {
   if (!p || !boxes || !flags || T < 0 || N < 0 || bad_dim(dim) || (!t && T > 0)) return DM_ERR_ARG;
