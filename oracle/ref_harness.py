@@ -53,6 +53,15 @@ def load_native():
     return importlib.import_module("_fast_geometry")
 
 
+def load_native_fasthj():
+    """Import the reference's own compiled `_FastHJ` (oracle/_ref): the gradient limiter."""
+    if not native_available() or not any(f.startswith("_FastHJ") for f in os.listdir(REF_NATIVE)):
+        raise ImportError("oracle/_ref/_FastHJ*.so missing: run `make -C oracle`")
+    if REF_NATIVE not in sys.path:
+        sys.path.insert(0, REF_NATIVE)
+    return importlib.import_module("_FastHJ")
+
+
 class _FakeComm:
     rank = 0
     size = 1

@@ -153,3 +153,22 @@ def test_limgrad_is_a_fixed_point_and_minimal():
         m[tuple(hi)] = np.minimum(m[tuple(hi)], f[tuple(lo)])
         m[tuple(lo)] = np.minimum(m[tuple(lo)], f[tuple(hi)])
     assert np.abs(f[lowered] - (m[lowered] + delta)).max() <= 2 * ftol
+
+
+@pytest.mark.parametrize("shape", [(40, 55, 1), (17, 23, 12)])
+def test_limgrad_oracle_vs_reference_native(shape):
+    """The reference's own compiled FastHJ limiter (oracle/_ref, built from its sources) against the
+    oracle's fixed-point restatement on a rough random field."""
+    from oracle import ref_harness
+
+    try:
+        hj = ref_harness.load_native_fasthj()
+    except ImportError:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(shape[0])
+    f0 = rng.uniform(40.0, 1500.0, shape)
+    elen, grade = 12.5, 0.2
+    # the reference flattens in Fortran order and passes dims (sz0, sz1, sz2) (mesh_size_function.py:486-494)
+    out = np.asarray(hj.limgrad([*shape], elen, grade, 10000, f0.flatten("F"))).reshape(shape, order="F")
+    mine = orc.limgrad(f0, elen * grade, f0.min() * np.sqrt(1e-9))
+    assert np.abs(mine - out).max() <= 4 * f0.min() * np.sqrt(1e-9)
