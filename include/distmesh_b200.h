@@ -214,6 +214,14 @@ int dm_plan_init(DmPlan *plan_host, int64_t N, int64_t T, int dim, void *ws, siz
  * use_keep == 0: every cell is kept (plain _get_edges(t) semantics, mesh_generator.py:680-688). */
 int dm_stage_cull_count(const DmPlan *plan_host, const double *prog, const double *p,
                         const int32_t *t, double geps, int use_keep, void *stream);
+/* Stage A in pieces, for callers that stream the cell list in: dm_stage_prep (zero the counters, pad
+ * the points) once, then dm_stage_cull_chunk on cells [cell0, cell0+ncells) as they arrive (t_chunk
+ * points at the first of them; cells are independent, so chunks may be processed in any order), then
+ * dm_force_iteration_tail (stages B-D).  dm_stage_cull_count == prep + one chunk with all cells. */
+int dm_stage_prep(const DmPlan *plan_host, const double *p, void *stream);
+int dm_stage_cull_chunk(const DmPlan *plan_host, const double *prog, const double *p,
+                        const int32_t *t_chunk, int64_t cell0, int64_t ncells, double geps,
+                        int use_keep, void *stream);
 /* stage B: sorted unique neighbour rows (replaces _fast_geometry.unique_edges,
  * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs).  `t` and `use_keep` are unused since
  * stage A already scattered the kept cells (kept for call compatibility). */
@@ -250,6 +258,12 @@ int dm_force_iteration(const DmPlan *plan_host, const double *const *progs_host,
                        const DmSizeFn *fh_host, const double *p, const int32_t *t, double *p_out,
                        double geps, double L0mult, double delta_t, double deps, double h0,
                        int64_t nfix, const uint8_t *fixed, double *Ftot, void *stream);
+
+/* B+C+D after stage A has been run (in one piece or in chunks). */
+int dm_force_iteration_tail(const DmPlan *plan_host, const double *const *progs_host, int nlevels,
+                            const DmSizeFn *fh_host, const double *p, double *p_out, double L0mult,
+                            double delta_t, double deps, double h0, int64_t nfix,
+                            const uint8_t *fixed, double *Ftot, void *stream);
 
 /* C+D only, on the rows left by the last dm_force_iteration (or stage B) of this plan: one force
  * iteration WITHOUT retriangulation (the cell list is unchanged, only p moved).  This is the step

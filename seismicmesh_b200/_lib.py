@@ -87,6 +87,12 @@ _SIGNATURES = {
     "dm_level_set_newton": (_INT, [_P, _P, _P, _I64, _INT, _D, _P]),
     "dm_plan_bytes": (_SZ, [_I64, _I64, _INT]),
     "dm_plan_init": (_INT, [C.POINTER(DmPlan), _I64, _I64, _INT, _P, _SZ]),
+    "dm_stage_prep": (_INT, [C.POINTER(DmPlan), _P, _P]),
+    "dm_stage_cull_chunk": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _I64, _I64, _D, _INT, _P]),
+    "dm_force_iteration_tail": (
+        _INT,
+        [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _D, _D, _D, _D, _I64, _P, _P, _P],
+    ),
     "dm_stage_cull_count": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _D, _INT, _P]),
     "dm_stage_build_adjacency": (_INT, [C.POINTER(DmPlan), _P, _INT, _P]),
     "dm_stage_bar_index": (_INT, [C.POINTER(DmPlan), _P]),

@@ -192,13 +192,15 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
 
 template <int DIM>
 static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
-                              int mode, cudaStream_t st) {
+                              int mode, cudaStream_t st, int64_t cell0 = 0, int64_t ncells = -1) {
   typedef typename PCfg<DIM>::entry_t entry_t;
-  const unsigned nb = nblk(pl->T, PL_THREADS);
+  if (ncells < 0) ncells = pl->T;
+  // cells [cell0, cell0 + ncells): t points at the first of them
+  const unsigned nb = nblk(ncells, PL_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
-  launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, PL_THREADS, st, prog, pc, t, pl->T, geps, mode, pl->keep,
-               pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v, static_cast<entry_t*>(pl->ovf_e), pl->hv,
-               pl->counters);
+  launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, PL_THREADS, st, prog, pc, t, ncells, geps, mode,
+               pl->keep + cell0, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
+               static_cast<entry_t*>(pl->ovf_e), pl->hv, pl->counters);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
@@ -420,11 +422,10 @@ int dm_plan_init(DmPlan* plan, int64_t N, int64_t T, int dim, void* ws, size_t w
   return DM_OK;
 }
 
-int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
-                        int use_keep, void* stream) {
-  if (!pl || (!t && pl->T > 0) || (use_keep && prog && !p)) return DM_ERR_ARG;
+int dm_stage_prep(const DmPlan* pl, const double* p, void* stream) {
+  if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  {  // zero [cnt | sync | counters] and (3-D) refresh the padded point copy, one launch
+  {  // zero [cnt | sync | counters | gdone] and (3-D) refresh the padded point copy, one launch
     const int64_t zq = (int64_t)(pl->zero_bytes / 16);
     const bool pad = pl->dim == 3 && p != nullptr;
     const int64_t n = pad && pl->N > zq ? pl->N : zq;
@@ -434,10 +435,27 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
                                                             pad ? pl->p4 : nullptr, pl->N);
     mark("prep(zero+pad)", st);
   }
-  if (pl->T == 0) return DM_OK;
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
+int dm_stage_cull_chunk(const DmPlan* pl, const double* prog, const double* p, const int32_t* t_chunk, int64_t cell0,
+                        int64_t ncells, double geps, int use_keep, void* stream) {
+  if (!pl || cell0 < 0 || ncells < 0 || cell0 + ncells > pl->T || (!t_chunk && ncells > 0)) return DM_ERR_ARG;
+  if (use_keep && prog && !p) return DM_ERR_ARG;
+  if (ncells == 0) return DM_OK;
   const int mode = !use_keep ? 2 : (prog ? 0 : 1);
-  return pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t, geps, mode, st)
-                      : stage_cull_scatter<3>(pl, prog, p, t, geps, mode, st);
+  cudaStream_t st = S(stream);
+  return pl->dim == 2 ? stage_cull_scatter<2>(pl, prog, p, t_chunk, geps, mode, st, cell0, ncells)
+                      : stage_cull_scatter<3>(pl, prog, p, t_chunk, geps, mode, st, cell0, ncells);
+}
+
+int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
+                        int use_keep, void* stream) {
+  if (!pl || (!t && pl->T > 0) || (use_keep && prog && !p)) return DM_ERR_ARG;
+  const int rc = dm_stage_prep(pl, p, stream);
+  if (rc) return rc;
+  return dm_stage_cull_chunk(pl, prog, p, t, 0, pl->T, geps, use_keep, stream);
 }
 
 int dm_stage_build_adjacency(const DmPlan* pl, const int32_t* t, int use_keep, void* stream) {
@@ -528,10 +546,20 @@ int dm_force_iteration(const DmPlan* pl, const double* const* progs, int nlevels
   if (!pl || !progs || nlevels < 1 || nlevels > DM_MAX_LEVELS || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
   if (!p || !p_out || p == p_out || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
+  (void)st;
   // A: cull + scatter ; B+C: adjacency rows with the bar pass fused in ; D: vertex update
-  int rc = dm_stage_cull_count(pl, progs[0], p, t, geps, 1, stream);
+  const int rc = dm_stage_cull_count(pl, progs[0], p, t, geps, 1, stream);
   if (rc) return rc;
-  rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
+  return dm_force_iteration_tail(pl, progs, nlevels, f, p, p_out, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, stream);
+}
+
+int dm_force_iteration_tail(const DmPlan* pl, const double* const* progs, int nlevels, const DmSizeFn* f,
+                            const double* p, double* p_out, double L0mult, double delta_t, double deps, double h0,
+                            int64_t nfix, const uint8_t* fixed, double* Ftot, void* stream) {
+  if (!pl || !progs || nlevels < 1 || nlevels > DM_MAX_LEVELS || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
+  if (!p || !p_out || p == p_out || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
+  cudaStream_t st = S(stream);
+  const int rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
   if (rc) return rc;
   return vertex_update_impl(pl, p, true, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }

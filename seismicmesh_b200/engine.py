@@ -191,6 +191,60 @@ class ForceLoop:
                     self.host_seconds += time.perf_counter() - t0
         return p_out, Ftot
 
+    def iterate_host(self, p_pin, t_pin, out_pin, chunks=4):
+        """One force iteration with HOST buffers in and out (pinned torch CPU tensors: p (N,dim) f64,
+        t (T,dim+1) i32, out (N,dim) f64): what a driver whose Delaunay lives on the host does every
+        iteration.  The cell list is uploaded in `chunks` pieces on a copy stream and stage A runs on
+        each piece as it lands, so the cull + scatter hides behind the PCIe transfer; stages B-D
+        follow, then the new positions go back.  Returns the device tensor of the new positions."""
+        if not self.all_lowered:
+            raise RuntimeError("iterate_host needs lowered fd / fh")
+        N, T = p_pin.shape[0], t_pin.shape[0]
+        pl = self.ensure_plan(N, T)
+        dev = D.device()
+        hb = getattr(self, "_host_bufs", None)
+        if hb is None or hb[0].shape[0] != N or hb[1].shape[0] < T:
+            hb = (torch.empty((N, self.dim), dtype=torch.float64, device=dev),
+                  torch.empty((max(T, 1), self.dim + 1), dtype=torch.int32, device=dev),
+                  torch.empty((N, self.dim), dtype=torch.float64, device=dev), torch.cuda.Stream(device=dev))
+            self._host_bufs = hb
+        p_dev, t_dev, p_out, cs = hb
+        ms = torch.cuda.current_stream()
+        st = D.stream_ptr()
+        cs.wait_stream(ms)  # the previous call's kernels are done with p_dev / t_dev
+        nch = max(1, min(int(chunks), T)) if T > 0 else 0
+        bounds = [T * k // nch for k in range(nch + 1)] if nch else [0]
+        evs = []
+        with torch.cuda.stream(cs):
+            p_dev.copy_(p_pin, non_blocking=True)
+            ev_p = torch.cuda.Event()
+            ev_p.record(cs)
+            for k in range(nch):
+                a, b = bounds[k], bounds[k + 1]
+                t_dev[a:b].copy_(t_pin[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(cs)
+                evs.append(e)
+        ms.wait_event(ev_p)
+        check(lib.dm_stage_prep(C.byref(pl.c), D.ptr(p_dev), st), "dm_stage_prep")
+        prog0 = D.ptr(self._progs[0])
+        for k in range(nch):
+            a, b = bounds[k], bounds[k + 1]
+            ms.wait_event(evs[k])
+            check(lib.dm_stage_cull_chunk(C.byref(pl.c), prog0, D.ptr(p_dev), C.c_void_p(t_dev.data_ptr() + 4 * (self.dim + 1) * a),
+                                          a, b - a, self.geps, 1, st), "dm_stage_cull_chunk")
+        f = self.size.struct()
+        progs = D.prog_array(self._progs)
+        check(
+            lib.dm_force_iteration_tail(
+                C.byref(pl.c), progs, len(self._progs), C.byref(f), D.ptr(p_dev), D.ptr(p_out), self.L0mult, self.delta_t,
+                self.deps, self.h0, self.nfix, D.ptr(self.fixed_mask), None, st,
+            ),
+            "dm_force_iteration_tail",
+        )
+        out_pin.copy_(p_out, non_blocking=True)
+        return p_out
+
     def iterate_reuse(self, p, p_out=None, want_forces=False):
         """One force iteration WITHOUT retriangulation: stages C + D on the neighbour rows left by the
         last :meth:`iterate` (same cell list, moved points).  Opt-in (`ttol`); lowered fd / fh only."""

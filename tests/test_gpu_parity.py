@@ -469,6 +469,27 @@ def test_full_size_ball_properties(sm):
     assert np.array_equal(p2.cpu().numpy(), p1) and np.array_equal(F2.cpu().numpy(), F1)
 
 
+@pytest.mark.parametrize("dim,h0,chunks", [(2, 0.02, 1), (2, 0.02, 5), (3, 0.07, 4), (3, 0.07, 64)])
+def test_iterate_host_chunked_upload_same_bits(sm, dim, h0, chunks):
+    """Host buffers in / out with the cell list uploaded in chunks and stage A run per chunk: the
+    result must not depend on the chunking (same bits as the one-piece device-resident call)."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dom = sm.Disk([0.0, 0.0], 1.0) if dim == 2 else sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _lattice_mesh(sm, dom, h0, dim)
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+    ref = loop.iterate(dev(p, torch.float64), dev(t, torch.int32))[0].cpu().numpy()
+    bars_ref = loop.bars().cpu().numpy()
+    p_pin, t_pin = torch.from_numpy(p).pin_memory(), torch.from_numpy(t).pin_memory()
+    out_pin = torch.empty_like(p_pin).pin_memory()
+    for _ in range(2):  # twice: the persistent staging buffers are re-used
+        loop.iterate_host(p_pin, t_pin, out_pin, chunks=chunks)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_pin.numpy(), ref)
+    assert np.array_equal(loop.bars().cpu().numpy(), bars_ref)
+
+
 @pytest.mark.parametrize("dim,grid", [(2, False), (2, True), (3, False), (3, True)])
 def test_hub_vertex_full_iteration_vs_oracle(sm, dim, grid):
     """A hub: one centre point joined to every point of a shell around it (hundreds of incident
