@@ -191,7 +191,7 @@ class ForceLoop:
                     self.host_seconds += time.perf_counter() - t0
         return p_out, Ftot
 
-    def iterate_host(self, p_pin, t_pin, out_pin, chunks=4):
+    def iterate_host(self, p_pin, t_pin, out_pin, chunks=8):
         """One force iteration with HOST buffers in and out (pinned torch CPU tensors: p (N,dim) f64,
         t (T,dim+1) i32, out (N,dim) f64): what a driver whose Delaunay lives on the host does every
         iteration.  The cell list is uploaded in `chunks` pieces on a copy stream and stage A runs on
