@@ -196,9 +196,9 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   typedef typename PCfg<DIM>::entry_t entry_t;
   if (ncells < 0) ncells = pl->T;
   // cells [cell0, cell0 + ncells): t points at the first of them
-  const unsigned nb = nblk(ncells, PL_THREADS);
+  const unsigned nb = nblk(ncells, DM_CS_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
-  launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, PL_THREADS, st, prog, pc, t, ncells, geps, mode,
+  launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, DM_CS_THREADS, st, prog, pc, t, ncells, geps, mode,
                pl->keep + cell0, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
                static_cast<entry_t*>(pl->ovf_e), pl->hv, pl->counters);
   mark("cull_scatter", st);

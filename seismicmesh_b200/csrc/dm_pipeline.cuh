@@ -40,7 +40,13 @@ constexpr int HV_SMEM = 4608;    // heavy path: candidates sorted in shared memo
                                  // path's tables + lists: 2 * 32 * 72 in 3-D, 2 * 64 * 36 in 2-D)
 // tuning knobs (resident blocks per SM the register allocation is held to)
 #ifndef DM_CS_MINB
-#define DM_CS_MINB 4
+#define DM_CS_MINB 8
+#endif
+#ifndef DM_CS_THREADS
+#define DM_CS_THREADS 128
+#endif
+#ifndef DM_VU_THREADS
+#define DM_VU_THREADS 128
 #endif
 #ifndef DM_HASH_MAXSTEPS
 #define DM_HASH_MAXSTEPS 12
@@ -127,7 +133,7 @@ __device__ __forceinline__ int2 others_of<2>(const int (&ids)[4], int j) {
 // slots before the cull decision is known + prefetching the next cell in a grid-stride loop (the
 // longer live ranges spill and cost more than the overlap gains), more resident blocks, 4-byte entries.
 template <int DIM, bool PAD = false>
-__global__ void __launch_bounds__(PL_THREADS, DM_CS_MINB) cull_scatter_kernel(
+__global__ void __launch_bounds__(DM_CS_THREADS, DM_CS_MINB) cull_scatter_kernel(
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
     typename PCfg<DIM>::entry_t* __restrict__ bucket, int32_t* __restrict__ ovf_v,
@@ -961,7 +967,7 @@ struct Levels {
 // serial.  Slots past the end of the row are redirected to the vertex itself (a valid address;
 // their term is discarded).  (A lane-group-per-vertex variant with the ordered sum done through
 // shared memory was measured at 2.4x the time of this one: the serial tail then holds a whole block.)
-constexpr int VU_THREADS = 128;
+constexpr int VU_THREADS = DM_VU_THREADS;
 
 // The listed vertices (those that left a level set, see vertex_update_kernel) get the reference's
 // sequence of projections, level after level, starting from the updated position in p_out: a vertex
