@@ -303,10 +303,10 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (T == 0) return DM_OK;
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
-    cull_scatter_kernel<2><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<2><<<nblk(T, DM_CS_THREADS), DM_CS_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   else
-    cull_scatter_kernel<3><<<nblk(T, PL_THREADS), PL_THREADS, 0, S(stream)>>>(
+    cull_scatter_kernel<3><<<nblk(T, DM_CS_THREADS), DM_CS_THREADS, 0, S(stream)>>>(
         prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   DM_LAUNCH_CHECK();
   return DM_OK;
