@@ -219,14 +219,6 @@ def make_slab_workload(workload, h0, rank, world, halo_layers=5, seed=0):
     return np.ascontiguousarray(p[layout.local_ids]), dim, dom, layout
 
 
-def allreduce_force_scale(sum_L, sum_h, group=None):
-    """Optional: global (sum L^d, sum h^d) so that every slab uses the single-GPU force scale
-    (the reference uses rank-local sums, mesh_generator.py:700)."""
-    buf = torch.stack([sum_L, sum_h])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf[0], buf[1]
-
-
 # ----------------------------------------------------------------------------------------------
 # generate_mesh on several GPUs: the reference's parallel algorithm (mesh_generator.py:430-530,
 # 715-731, 808-880; migration/migration.py:72-183) with one process per GPU over torch.distributed.
