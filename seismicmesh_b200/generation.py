@@ -5,7 +5,6 @@ projection, convergence monitor; dihedral test and sliver perturbation) runs in 
 device-resident arrays.  Delaunay retriangulation stays on the host (``triangulator.py``) and its
 time is reported separately in ``last_run_stats``.
 """
-import ctypes as C
 import math
 import time
 import warnings
@@ -16,7 +15,7 @@ import torch
 from . import device as D
 from . import geometry, meshutil
 from ._lib import check, lib
-from .engine import ForceLoop, Level, SizeSpec, compact_cells
+from .engine import ForceLoop, Level, SizeSpec
 from .sizing import SizeFunction
 from .triangulator import get_triangulator
 
