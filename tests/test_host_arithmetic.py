@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 from conftest import load_golden, load_sdf_specs, np_ptr, relerr
 
+from oracle import distmesh_oracle as orc
 from seismicmesh_b200 import _lib, geometry
 
 SPECS = load_sdf_specs()
@@ -70,6 +71,40 @@ def test_interp_arithmetic_bit_exact(hostsim, name):
     out = np.empty(len(x))
     hostsim.hs_size_eval(C.byref(f), np_ptr(x), C.c_long(len(x)), np_ptr(out))
     assert np.array_equal(out, g["h"])
+
+
+@pytest.mark.parametrize("dim,n,seed", [(2, 5395, 0), (2, 3, 1), (3, 676, 2), (3, 2, 3)])
+def test_interp_index_search_any_axis(hostsim, dim, n, seed):
+    """grid_find guesses the cell index in float32 and fixes it up against the real axis: the result
+    must be SciPy's for long float32-rounded axes (BP2004 / EAGE lengths), tiny ones, points on nodes,
+    between nodes one ulp either side, and far outside (linear extrapolation)."""
+    from scipy.interpolate import RegularGridInterpolator
+
+    rng = np.random.default_rng(seed)
+    lo = rng.uniform(-13000.0, -10.0, dim)
+    hi = lo + rng.uniform(50.0, 80000.0, dim)
+    shape = [n, max(2, n // 3)] + ([max(2, n // 7)] if dim == 3 else [])
+    axes = [np.linspace(lo[k], hi[k], shape[k], dtype=np.float32).astype(np.float64) for k in range(dim)]
+    grid = np.ascontiguousarray(rng.uniform(20.0, 900.0, shape))
+    pts = [rng.uniform(lo - 0.3 * (hi - lo), hi + 0.3 * (hi - lo), (4000, dim))]
+    nodes = np.stack([a[rng.integers(0, len(a), 2000)] for a in axes], axis=1)
+    pts += [nodes, np.nextafter(nodes, np.inf), np.nextafter(nodes, -np.inf)]
+    pts.append(np.array([[a[0] for a in axes], [a[-1] for a in axes], [a[0] - 1e9 for a in axes], [a[-1] + 1e9 for a in axes]]))
+    x = np.ascontiguousarray(np.vstack(pts))
+    f = _lib.DmSizeFn()
+    f.kind, f.dim = _lib.SIZE_GRID, dim
+    for k, a in enumerate(axes):
+        f.n[k] = len(a)
+        f.axis[k] = a.ctypes.data
+    f.grid = grid.ctypes.data
+    out = np.empty(len(x))
+    hostsim.hs_size_eval(C.byref(f), np_ptr(x), C.c_long(len(x)), np_ptr(out))
+    ref = RegularGridInterpolator(tuple(axes), grid, bounds_error=False, fill_value=None)(x)
+    if dim == 2:
+        assert np.array_equal(out, ref)  # SciPy's compiled 2-D path: same accumulation order, bit exact
+    else:
+        assert np.array_equal(out, orc.interp_grid(axes, grid, x))  # the oracle restates SciPy's N-D path
+        assert np.allclose(out, ref, rtol=1e-13, atol=0)
 
 
 def test_projection_arithmetic(hostsim):
