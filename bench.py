@@ -59,10 +59,17 @@ def make_points(workload, h0, seed=0, shift=0.0):
     return np.ascontiguousarray(p), dim
 
 
+def delaunay_backend(dim):
+    from seismicmesh_b200.triangulator import get_triangulator
+
+    return get_triangulator(None, dim).name
+
+
 def triangulate(p):
-    """Host Delaunay (Qhull).  DM_BENCH_CACHE=<dir> re-uses the cells of an identical point set
-    between runs of one profiling session (the set-up is untimed either way)."""
-    from scipy.spatial import Delaunay
+    """Host Delaunay with the package's default triangulator (2-D: native sweep-hull, 3-D: Qhull).
+    DM_BENCH_CACHE=<dir> re-uses the cells of an identical point set between runs of one profiling
+    session (the set-up is untimed either way)."""
+    from seismicmesh_b200.triangulator import get_triangulator
 
     cache = os.environ.get("DM_BENCH_CACHE")
     key = None
@@ -74,7 +81,7 @@ def triangulate(p):
             z = np.load(key)
             return z["t"], float(z["dt"])
     t0 = time.perf_counter()
-    t = np.ascontiguousarray(Delaunay(p).simplices, dtype=np.int32)
+    t = get_triangulator(None, p.shape[1]).triangulate(p)
     dt = time.perf_counter() - t0
     if key:
         os.makedirs(cache, exist_ok=True)
@@ -640,7 +647,7 @@ def main():
                 "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
         "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
         "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse, "sliver_pass": sliver, "time_to_mesh": ttm,
-        "delaunay_s": t_delaunay, "delaunay_backend": "qhull (scipy)", "sizing_s": wl["sizing_s"], "maxdp": maxdp,
+        "delaunay_s": t_delaunay, "delaunay_backend": delaunay_backend(dim), "sizing_s": wl["sizing_s"], "maxdp": maxdp,
         "wall_s_timed_region": wall,
     }
     print(json.dumps(out), flush=True)

@@ -1,0 +1,63 @@
+/*
+ * distmesh_host.h -- C ABI of libdistmesh_host.so: the HOST side of the retriangulation step.
+ *
+ * BASELINE.json north_star keeps the Delaunay retriangulation of every DistMesh iteration on the
+ * host.  The reference does it with CGAL behind two pybind11 classes
+ * (SeismicMesh/generation/cpp/delaunay_class.cpp:33-117, delaunay_class3.cpp): the Python loop
+ * hands the coordinates over as a Python list (`dt.insert(p.ravel().tolist())`,
+ * mesh_generator.py:466), CGAL spatially re-sorts them, and `get_finite_vertices` /
+ * `get_finite_cells` copy a RENUMBERED vertex array and the cells back (:480-481).
+ *
+ * This library replaces that with a stateless triangulator on raw buffers that keeps the caller's
+ * vertex numbering, so device-resident coordinates never have to be
+ * permuted: `points` can be the pinned staging buffer the device loop downloads into, `cells`
+ * the pinned buffer it uploads from.
+ *
+ *   - every pointer is a HOST pointer; float64 row-major coordinates, int32 row-major cells;
+ *   - no global state, re-entrant; the only allocation is internal scratch freed before return;
+ *   - results are exact Delaunay triangulations: the orientation / in-circle predicates run a
+ *     floating-point filter and fall back to exact expansion arithmetic, so co-circular and
+ *     collinear inputs (the initial lattice, boundary vertices projected onto straight edges) are
+ *     handled without tolerances; for points in general position the cell SET equals the one any
+ *     other correct Delaunay code (CGAL, Qhull) returns.
+ */
+#ifndef DISTMESH_HOST_H
+#define DISTMESH_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMH_OK 0
+#define DMH_ERR_ARG (-1)      /* null pointer / negative size */
+#define DMH_ERR_CAPACITY (-2) /* `cells` too small (see dmh_delaunay2d_max_cells) */
+
+/* "distmesh_host <version>" */
+const char* dmh_version(void);
+
+/* Upper bound of the number of triangles of a 2-D Delaunay triangulation of N points (2N - 5,
+ * at least 1): the capacity to give `cells`. */
+int64_t dmh_delaunay2d_max_cells(int64_t N);
+
+/* Delaunay triangulation of `points` (N,2).  Replaces DelaunayTriangulation.insert +
+ * get_finite_cells (generation/cpp/delaunay_class.cpp:45-62, 99-117) with the vertex ids = input
+ * rows.  Writes *T_out counter-clockwise triangles to `cells` (capacity `cap` rows) and the number
+ * of input rows that are in no triangle to *skipped_out (exact duplicates of an earlier row; all
+ * rows when the input is collinear or has fewer than 3 distinct points, in which case *T_out = 0).
+ * Sweep-hull construction (points inserted by distance from a seed circumcentre, advancing convex
+ * front, Lawson flips), O(N log N). */
+int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                   int64_t* skipped_out);
+
+/* The two exact predicates, exported for the tests.
+ * orient2d > 0: a, b, c counter-clockwise; incircle > 0: d strictly inside the circle through the
+ * counter-clockwise a, b, c.  Only the SIGN is meaningful (exact, including 0). */
+double dmh_orient2d(const double* a, const double* b, const double* c);
+double dmh_incircle(const double* a, const double* b, const double* c, const double* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,443 @@
+// Host Delaunay triangulator behind include/distmesh_host.h (2-D).
+//
+// The reference retriangulates with CGAL on every DistMesh iteration
+// (SeismicMesh/generation/cpp/delaunay_class.cpp:45-117 behind mesh_generator.py:466-481); this is
+// the from-scratch replacement on raw buffers that keeps the caller's vertex numbering.
+//
+// Construction: sweep-hull.  A seed triangle near the centre of the bounding box is chosen (the
+// point closest to the centre, its nearest neighbour, and the third point giving the smallest
+// circumcircle); all other points are inserted in order of distance from the seed circumcentre.
+// Every new point lies outside the convex hull of the points inserted so far, so it is connected
+// to the hull edges it can see (the hull is a doubly linked list; the first visible edge is found
+// through a hash of the hull vertices by pseudo-angle around the centre), and the Delaunay
+// property is restored by Lawson flips on a half-edge structure (cell 3*t+k holds vertex k of
+// triangle t; half[e] is the opposite half-edge or -1 on the hull).
+//
+// Exactness: orient2d / incircle evaluate a filtered floating-point determinant and fall back to
+// exact arithmetic on floating-point expansions (error-free two_sum / two_prod, sums of
+// non-overlapping components) when the filter cannot certify the sign, so ties are recognised as
+// ties: flips terminate on co-circular lattices and collinear boundary vertices stay on the hull.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off (the error-free transformations must not be
+// contracted or re-associated; never -ffast-math).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+#include "distmesh_host.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// exact arithmetic on expansions
+// ---------------------------------------------------------------------------------------------
+inline void two_sum(double a, double b, double& x, double& y) {
+  x = a + b;
+  const double bv = x - a;
+  const double av = x - bv;
+  y = (a - av) + (b - bv);
+}
+inline void two_prod(double a, double b, double& x, double& y) {
+  x = a * b;
+  y = std::fma(a, b, -x);  // exact residual of the product
+}
+
+// A value held as a sum of doubles, non-overlapping and of increasing magnitude (zeros allowed).
+struct Expansion {
+  std::vector<double> c;
+  // this += b
+  void grow(double b) {
+    double q = b;
+    for (double& ci : c) {
+      double s, r;
+      two_sum(q, ci, s, r);
+      ci = r;
+      q = s;
+    }
+    c.push_back(q);
+  }
+  void add(const Expansion& o) {
+    for (double v : o.c) grow(v);
+  }
+  // this *= b
+  void scale(double b) {
+    if (c.empty()) return;
+    std::vector<double> h;
+    h.reserve(2 * c.size());
+    double q, lo;
+    two_prod(c[0], b, q, lo);
+    h.push_back(lo);
+    for (size_t i = 1; i < c.size(); ++i) {
+      double t, tl, s, r;
+      two_prod(c[i], b, t, tl);
+      two_sum(q, tl, s, r);
+      h.push_back(r);
+      two_sum(t, s, q, r);
+      h.push_back(r);
+    }
+    h.push_back(q);
+    c.swap(h);
+  }
+  // the most significant non-zero component carries the sign
+  double sign() const {
+    for (size_t i = c.size(); i-- > 0;)
+      if (c[i] != 0.0) return c[i];
+    return 0.0;
+  }
+};
+
+// sum += s * f0 * f1 [* f2 * f3]
+inline void add_product(Expansion& sum, double s, double f0, double f1) {
+  Expansion e;
+  e.c.push_back(s * f0);  // s = +-1: exact
+  e.scale(f1);
+  sum.add(e);
+}
+inline void add_product(Expansion& sum, double s, double f0, double f1, double f2, double f3) {
+  Expansion e;
+  e.c.push_back(s * f0);
+  e.scale(f1);
+  e.scale(f2);
+  e.scale(f3);
+  sum.add(e);
+}
+
+constexpr double EPS = 1.1102230246251565e-16;  // 2^-53
+constexpr double CCW_BOUND = (3.0 + 16.0 * EPS) * EPS;
+constexpr double ICC_BOUND = (10.0 + 96.0 * EPS) * EPS;
+
+double orient2d_exact(const double* a, const double* b, const double* c) {
+  // (ax-cx)(by-cy) - (ay-cy)(bx-cx), multiplied out: no subtraction of inputs is rounded
+  Expansion s;
+  add_product(s, +1.0, a[0], b[1]);
+  add_product(s, -1.0, a[0], c[1]);
+  add_product(s, -1.0, c[0], b[1]);
+  add_product(s, -1.0, a[1], b[0]);
+  add_product(s, +1.0, a[1], c[0]);
+  add_product(s, +1.0, c[1], b[0]);
+  return s.sign();
+}
+
+inline double orient2d(const double* a, const double* b, const double* c) {
+  const double dl = (a[0] - c[0]) * (b[1] - c[1]);
+  const double dr = (a[1] - c[1]) * (b[0] - c[0]);
+  const double det = dl - dr;
+  double sum;
+  if (dl > 0.0) {
+    if (dr <= 0.0) return det;
+    sum = dl + dr;
+  } else if (dl < 0.0) {
+    if (dr >= 0.0) return det;
+    sum = -dl - dr;
+  } else {
+    return det;
+  }
+  const double bound = CCW_BOUND * sum;
+  if (det >= bound || -det >= bound) return det;
+  return orient2d_exact(a, b, c);
+}
+
+// 3x3 minor | p q r | over the columns (x, y, x^2 + y^2), multiplied out, added with sign s
+void add_minor(Expansion& sum, double s, const double* p, const double* q, const double* r) {
+  for (int k = 0; k < 2; ++k) {  // the lifted coordinate is x*x + y*y: one pass per square
+    add_product(sum, +s, p[0], q[1], r[k], r[k]);
+    add_product(sum, -s, p[0], r[1], q[k], q[k]);
+    add_product(sum, -s, p[1], q[0], r[k], r[k]);
+    add_product(sum, +s, p[1], r[0], q[k], q[k]);
+    add_product(sum, +s, q[0], r[1], p[k], p[k]);
+    add_product(sum, -s, q[1], r[0], p[k], p[k]);
+  }
+}
+
+double incircle_exact(const double* a, const double* b, const double* c, const double* d) {
+  // | x y x^2+y^2 1 | over the rows a, b, c, d, expanded along the column of ones
+  Expansion s;
+  add_minor(s, -1.0, b, c, d);
+  add_minor(s, +1.0, a, c, d);
+  add_minor(s, -1.0, a, b, d);
+  add_minor(s, +1.0, a, b, c);
+  return s.sign();
+}
+
+inline double incircle(const double* a, const double* b, const double* c, const double* d) {
+  const double adx = a[0] - d[0], ady = a[1] - d[1];
+  const double bdx = b[0] - d[0], bdy = b[1] - d[1];
+  const double cdx = c[0] - d[0], cdy = c[1] - d[1];
+  const double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy;
+  const double alift = adx * adx + ady * ady;
+  const double cdxady = cdx * ady, adxcdy = adx * cdy;
+  const double blift = bdx * bdx + bdy * bdy;
+  const double adxbdy = adx * bdy, bdxady = bdx * ady;
+  const double clift = cdx * cdx + cdy * cdy;
+  const double det = alift * (bdxcdy - cdxbdy) + blift * (cdxady - adxcdy) + clift * (adxbdy - bdxady);
+  const double permanent = (std::fabs(bdxcdy) + std::fabs(cdxbdy)) * alift +
+                           (std::fabs(cdxady) + std::fabs(adxcdy)) * blift +
+                           (std::fabs(adxbdy) + std::fabs(bdxady)) * clift;
+  const double bound = ICC_BOUND * permanent;
+  if (det > bound || -det > bound) return det;
+  return incircle_exact(a, b, c, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sweep-hull
+// ---------------------------------------------------------------------------------------------
+struct SweepHull {
+  const double* P;
+  int64_t n;
+  std::vector<int32_t> tri, half;
+  int64_t len = 0;  // half-edges in use (3 per triangle)
+  std::vector<int32_t> hprev, hnext, htri, hhash, stack;
+  int64_t hsize = 0;
+  double cx = 0.0, cy = 0.0;
+  int32_t hstart = 0;
+
+  const double* pt(int64_t i) const { return P + 2 * i; }
+
+  int64_t key(double x, double y) const {
+    const double dx = x - cx, dy = y - cy;
+    const double den = std::fabs(dx) + std::fabs(dy);
+    const double p = den > 0.0 ? dx / den : 0.0;
+    const double a = (dy > 0.0 ? 3.0 - p : 1.0 + p) / 4.0;  // monotone in the angle, in [0, 1]
+    int64_t k = (int64_t)std::floor(a * (double)hsize);
+    if (k < 0) k = 0;
+    return k % hsize;
+  }
+  void link(int32_t a, int32_t b) {
+    half[a] = b;
+    if (b != -1) half[b] = a;
+  }
+  int32_t add_triangle(int32_t i0, int32_t i1, int32_t i2, int32_t a, int32_t b, int32_t c) {
+    const int32_t t = (int32_t)len;
+    tri[t] = i0;
+    tri[t + 1] = i1;
+    tri[t + 2] = i2;
+    link(t, a);
+    link(t + 1, b);
+    link(t + 2, c);
+    len += 3;
+    return t;
+  }
+  // Restore the Delaunay property around half-edge a (and, transitively, around the edges a flip
+  // exposes).  Returns the half-edge that now leaves the newest point along the hull side.
+  int32_t legalize(int32_t a) {
+    stack.clear();
+    int32_t ar = 0;
+    for (;;) {
+      const int32_t b = half[a];
+      const int32_t a0 = a - a % 3;
+      ar = a0 + (a + 2) % 3;
+      if (b == -1) {  // hull edge
+        if (stack.empty()) break;
+        a = stack.back();
+        stack.pop_back();
+        continue;
+      }
+      const int32_t b0 = b - b % 3;
+      const int32_t al = a0 + (a + 1) % 3;
+      const int32_t bl = b0 + (b + 2) % 3;
+      const int32_t p0 = tri[ar], pr = tri[a], pl = tri[al], p1 = tri[bl];
+      if (incircle(pt(p0), pt(pr), pt(pl), pt(p1)) > 0.0) {  // p1 strictly inside: flip the edge
+        tri[a] = p1;
+        tri[b] = p0;
+        const int32_t hbl = half[bl];
+        if (hbl == -1) {  // the flipped edge moved a hull half-edge: repoint the hull vertex at it
+          int32_t e = hstart;
+          do {
+            if (htri[e] == bl) {
+              htri[e] = a;
+              break;
+            }
+            e = hprev[e];
+          } while (e != hstart);
+        }
+        link(a, hbl);
+        link(b, half[ar]);
+        link(ar, bl);
+        stack.push_back(b0 + (b + 1) % 3);
+      } else {
+        if (stack.empty()) break;
+        a = stack.back();
+        stack.pop_back();
+      }
+    }
+    return ar;
+  }
+
+  // returns the number of input rows left out of the triangulation
+  int64_t run() {
+    if (n < 3) return n;
+    double minx = std::numeric_limits<double>::infinity(), miny = minx, maxx = -minx, maxy = -minx;
+    for (int64_t i = 0; i < n; ++i) {
+      minx = std::min(minx, P[2 * i]);
+      maxx = std::max(maxx, P[2 * i]);
+      miny = std::min(miny, P[2 * i + 1]);
+      maxy = std::max(maxy, P[2 * i + 1]);
+    }
+    const double mx = 0.5 * (minx + maxx), my = 0.5 * (miny + maxy);
+    auto d2 = [&](int64_t i, double x, double y) {
+      const double dx = P[2 * i] - x, dy = P[2 * i + 1] - y;
+      return dx * dx + dy * dy;
+    };
+    const double inf = std::numeric_limits<double>::infinity();
+    // seed: the point closest to the centre, its nearest distinct neighbour, smallest circumcircle
+    int64_t i0 = 0, i1 = -1, i2 = -1;
+    double best = inf;
+    for (int64_t i = 0; i < n; ++i) {
+      const double d = d2(i, mx, my);
+      if (d < best) best = d, i0 = i;
+    }
+    best = inf;
+    for (int64_t i = 0; i < n; ++i) {
+      const double d = d2(i, P[2 * i0], P[2 * i0 + 1]);
+      if (d > 0.0 && d < best) best = d, i1 = i;
+    }
+    if (i1 < 0) return n;  // all rows coincide
+    double rbest = inf, ccx = 0.0, ccy = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (i == i0 || i == i1) continue;
+      const double dx = P[2 * i1] - P[2 * i0], dy = P[2 * i1 + 1] - P[2 * i0 + 1];
+      const double ex = P[2 * i] - P[2 * i0], ey = P[2 * i + 1] - P[2 * i0 + 1];
+      const double bl = dx * dx + dy * dy, cl = ex * ex + ey * ey;
+      const double den = dx * ey - dy * ex;
+      if (den == 0.0 || cl == 0.0) continue;
+      const double s = 0.5 / den;
+      const double x = (ey * bl - dy * cl) * s, y = (dx * cl - ex * bl) * s;
+      const double r = x * x + y * y;
+      if (r < rbest && orient2d(pt(i0), pt(i1), pt(i)) != 0.0) rbest = r, i2 = i, ccx = x, ccy = y;
+    }
+    if (i2 < 0) return n;  // collinear input: no triangle
+    if (orient2d(pt(i0), pt(i1), pt(i2)) < 0.0) std::swap(i1, i2);  // seed counter-clockwise
+    cx = P[2 * i0] + ccx;
+    cy = P[2 * i0 + 1] + ccy;
+
+    // insertion order: distance from the seed circumcentre; ties by coordinates, so that exact
+    // duplicates are neighbours in the order
+    std::vector<double> dist(n);
+    std::vector<int32_t> ids(n);
+    for (int64_t i = 0; i < n; ++i) dist[i] = d2(i, cx, cy), ids[i] = (int32_t)i;
+    std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
+      if (dist[a] != dist[b]) return dist[a] < dist[b];
+      if (P[2 * a] != P[2 * b]) return P[2 * a] < P[2 * b];
+      if (P[2 * a + 1] != P[2 * b + 1]) return P[2 * a + 1] < P[2 * b + 1];
+      return a < b;
+    });
+
+    const int64_t maxt = std::max<int64_t>(2 * n - 5, 1);
+    tri.assign(3 * maxt, 0);
+    half.assign(3 * maxt, -1);
+    hsize = (int64_t)std::ceil(std::sqrt((double)n));
+    hprev.assign(n, 0);
+    hnext.assign(n, 0);
+    htri.assign(n, 0);
+    hhash.assign(hsize, -1);
+    stack.reserve(512);
+
+    hstart = (int32_t)i0;
+    hnext[i0] = hprev[i2] = (int32_t)i1;
+    hnext[i1] = hprev[i0] = (int32_t)i2;
+    hnext[i2] = hprev[i1] = (int32_t)i0;
+    htri[i0] = 0;
+    htri[i1] = 1;
+    htri[i2] = 2;
+    hhash[key(P[2 * i0], P[2 * i0 + 1])] = (int32_t)i0;
+    hhash[key(P[2 * i1], P[2 * i1 + 1])] = (int32_t)i1;
+    hhash[key(P[2 * i2], P[2 * i2 + 1])] = (int32_t)i2;
+    add_triangle((int32_t)i0, (int32_t)i1, (int32_t)i2, -1, -1, -1);
+
+    int64_t skipped = 0;
+    double xp = 0.0, yp = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+      const int32_t i = ids[k];
+      const double x = P[2 * i], y = P[2 * i + 1];
+      if (k > 0 && x == xp && y == yp) {  // exact duplicate of the previous row in the order
+        ++skipped;
+        continue;
+      }
+      xp = x;
+      yp = y;
+      if (i == i0 || i == i1 || i == i2) continue;
+
+      // a hull vertex near the direction of the new point, then forward to the first visible edge
+      int32_t start = 0;
+      const int64_t kk = key(x, y);
+      for (int64_t j = 0; j < hsize; ++j) {
+        start = hhash[(kk + j) % hsize];
+        if (start != -1 && start != hnext[start]) break;
+      }
+      start = hprev[start];
+      int32_t e = start, q;
+      while (q = hnext[e], orient2d(pt(i), pt(e), pt(q)) >= 0.0) {
+        e = q;
+        if (e == start) {
+          e = -1;
+          break;
+        }
+      }
+      if (e == -1) {  // sees no hull edge: not outside the hull (distance ties lost to rounding)
+        ++skipped;
+        continue;
+      }
+      int32_t t = add_triangle(e, i, hnext[e], -1, -1, htri[e]);
+      htri[i] = legalize(t + 2);
+      htri[e] = t;
+      // forward along the hull while the edges are visible
+      int32_t nx = hnext[e];
+      while (q = hnext[nx], orient2d(pt(i), pt(nx), pt(q)) < 0.0) {
+        t = add_triangle(nx, i, q, htri[i], -1, htri[nx]);
+        htri[i] = legalize(t + 2);
+        hnext[nx] = nx;  // removed from the hull
+        nx = q;
+      }
+      // backward, if the first visible edge was the one the search started from
+      if (e == start) {
+        while (q = hprev[e], orient2d(pt(i), pt(q), pt(e)) < 0.0) {
+          t = add_triangle(q, i, e, -1, htri[e], htri[q]);
+          legalize(t + 2);
+          htri[q] = t;
+          hnext[e] = e;  // removed from the hull
+          e = q;
+        }
+      }
+      hstart = hprev[i] = e;
+      hnext[e] = hprev[nx] = i;
+      hnext[i] = nx;
+      hhash[key(x, y)] = i;
+      hhash[key(P[2 * e], P[2 * e + 1])] = e;
+    }
+    return skipped;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* dmh_version(void) { return "distmesh_host 0.1"; }
+
+int64_t dmh_delaunay2d_max_cells(int64_t N) { return N < 3 ? 1 : 2 * N - 5; }
+
+int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                   int64_t* skipped_out) {
+  if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
+      N > (int64_t)std::numeric_limits<int32_t>::max() / 6)
+    return DMH_ERR_ARG;
+  SweepHull s;
+  s.P = points;
+  s.n = N;
+  const int64_t skipped = s.run();
+  const int64_t T = s.len / 3;
+  *T_out = T;
+  if (skipped_out != nullptr) *skipped_out = skipped;
+  if (T > cap) return DMH_ERR_CAPACITY;
+  std::copy(s.tri.begin(), s.tri.begin() + 3 * T, cells);
+  return DMH_OK;
+}
+
+double dmh_orient2d(const double* a, const double* b, const double* c) { return orient2d(a, b, c); }
+double dmh_incircle(const double* a, const double* b, const double* c, const double* d) {
+  return incircle(a, b, c, d);
+}
+
+}  // extern "C"
