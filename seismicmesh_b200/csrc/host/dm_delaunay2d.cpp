@@ -189,6 +189,8 @@ struct SweepHull {
   std::vector<int32_t> tri, half;
   int64_t len = 0;  // half-edges in use (3 per triangle)
   std::vector<int32_t> hprev, hnext, htri, hhash, stack;
+  std::vector<int32_t> ids;    // rank in the insertion order -> input row
+  std::vector<double> sorted;  // coordinates in insertion order
   int64_t hsize = 0;
   double cx = 0.0, cy = 0.0;
   int32_t hstart = 0;
@@ -282,7 +284,7 @@ struct SweepHull {
     };
     const double inf = std::numeric_limits<double>::infinity();
     // seed: the point closest to the centre, its nearest distinct neighbour, smallest circumcircle
-    int64_t i0 = 0, i1 = -1, i2 = -1;
+    int64_t i0 = 0, i1 = -1, i2 = -1, r0 = 0, r1 = 0, r2 = 0;
     double best = inf;
     for (int64_t i = 0; i < n; ++i) {
       const double d = d2(i, mx, my);
@@ -313,16 +315,35 @@ struct SweepHull {
     cy = P[2 * i0 + 1] + ccy;
 
     // insertion order: distance from the seed circumcentre; ties by coordinates, so that exact
-    // duplicates are neighbours in the order
-    std::vector<double> dist(n);
-    std::vector<int32_t> ids(n);
-    for (int64_t i = 0; i < n; ++i) dist[i] = d2(i, cx, cy), ids[i] = (int32_t)i;
-    std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
-      if (dist[a] != dist[b]) return dist[a] < dist[b];
-      if (P[2 * a] != P[2 * b]) return P[2 * a] < P[2 * b];
-      if (P[2 * a + 1] != P[2 * b + 1]) return P[2 * a + 1] < P[2 * b + 1];
-      return a < b;
+    // duplicates are neighbours in the order.  From here on the points are addressed by their RANK
+    // in this order (coordinates copied in that order: a new point, the hull vertices around it and
+    // the triangles it touches were all written recently), and `ids` maps ranks back to input rows.
+    struct Item {
+      double d, x, y;
+      int32_t id;
+    };
+    std::vector<Item> items(n);
+    for (int64_t i = 0; i < n; ++i) items[i] = Item{d2(i, cx, cy), P[2 * i], P[2 * i + 1], (int32_t)i};
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+      if (a.d != b.d) return a.d < b.d;
+      if (a.x != b.x) return a.x < b.x;
+      if (a.y != b.y) return a.y < b.y;
+      return a.id < b.id;
     });
+    ids.resize(n);
+    sorted.resize(2 * n);
+    for (int64_t k = 0; k < n; ++k) {
+      ids[k] = items[k].id;
+      sorted[2 * k] = items[k].x;
+      sorted[2 * k + 1] = items[k].y;
+      if (items[k].id == i0) r0 = k;
+      if (items[k].id == i1) r1 = k;
+      if (items[k].id == i2) r2 = k;
+    }
+    items.clear();
+    items.shrink_to_fit();
+    P = sorted.data();
+    i0 = r0, i1 = r1, i2 = r2;
 
     const int64_t maxt = std::max<int64_t>(2 * n - 5, 1);
     tri.assign(3 * maxt, 0);
@@ -349,7 +370,7 @@ struct SweepHull {
     int64_t skipped = 0;
     double xp = 0.0, yp = 0.0;
     for (int64_t k = 0; k < n; ++k) {
-      const int32_t i = ids[k];
+      const int32_t i = (int32_t)k;
       const double x = P[2 * i], y = P[2 * i + 1];
       if (k > 0 && x == xp && y == yp) {  // exact duplicate of the previous row in the order
         ++skipped;
@@ -431,7 +452,7 @@ int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap,
   *T_out = T;
   if (skipped_out != nullptr) *skipped_out = skipped;
   if (T > cap) return DMH_ERR_CAPACITY;
-  std::copy(s.tri.begin(), s.tri.begin() + 3 * T, cells);
+  for (int64_t j = 0; j < 3 * T; ++j) cells[j] = s.ids[s.tri[j]];
   return DMH_OK;
 }
 
