@@ -44,64 +44,99 @@ inline void two_prod(double a, double b, double& x, double& y) {
   y = std::fma(a, b, -x);  // exact residual of the product
 }
 
-// A value held as a sum of doubles, non-overlapping and of increasing magnitude (zeros allowed).
-struct Expansion {
-  std::vector<double> c;
-  // this += b
-  void grow(double b) {
-    double q = b;
-    for (double& ci : c) {
-      double s, r;
-      two_sum(q, ci, s, r);
-      ci = r;
-      q = s;
-    }
-    c.push_back(q);
-  }
-  void add(const Expansion& o) {
-    for (double v : o.c) grow(v);
-  }
-  // this *= b
-  void scale(double b) {
-    if (c.empty()) return;
-    std::vector<double> h;
-    h.reserve(2 * c.size());
-    double q, lo;
-    two_prod(c[0], b, q, lo);
-    h.push_back(lo);
-    for (size_t i = 1; i < c.size(); ++i) {
-      double t, tl, s, r;
-      two_prod(c[i], b, t, tl);
-      two_sum(q, tl, s, r);
-      h.push_back(r);
-      two_sum(t, s, q, r);
-      h.push_back(r);
-    }
-    h.push_back(q);
-    c.swap(h);
-  }
-  // the most significant non-zero component carries the sign
-  double sign() const {
-    for (size_t i = c.size(); i-- > 0;)
-      if (c[i] != 0.0) return c[i];
-    return 0.0;
-  }
+inline void two_diff(double a, double b, double& x, double& y) {
+  x = a - b;
+  const double bv = a - x;
+  const double av = x + bv;
+  y = (a - av) + (bv - b);
+}
+
+// A value held exactly as a sum of doubles: non-overlapping components of increasing magnitude,
+// zeros eliminated (a zero value is the single component 0.0).  Because zeros are dropped, the cost
+// of every operation follows the number of components that are actually needed: differences of
+// nearby coordinates are exact in one double, and the whole determinant then stays a few dozen
+// components long.
+template <int CAP>
+struct Ex {
+  double c[CAP];
+  int n;
 };
 
-// sum += s * f0 * f1 [* f2 * f3]
-inline void add_product(Expansion& sum, double s, double f0, double f1) {
-  Expansion e;
-  e.c.push_back(s * f0);  // s = +-1: exact
-  e.scale(f1);
-  sum.add(e);
+// h = e + f (linear-time merge by magnitude, then one carry sweep); h must not alias e or f
+inline int ex_sum(const double* e, int en, const double* f, int fn, double* h) {
+  int ei = 0, fi = 0, hn = 0;
+  auto take = [&]() {  // the next component in order of increasing magnitude
+    if (fi >= fn || (ei < en && std::fabs(e[ei]) <= std::fabs(f[fi]))) return e[ei++];
+    return f[fi++];
+  };
+  double q = take();
+  while (ei < en || fi < fn) {
+    double s, r;
+    two_sum(q, take(), s, r);
+    q = s;
+    if (r != 0.0) h[hn++] = r;
+  }
+  if (q != 0.0 || hn == 0) h[hn++] = q;
+  return hn;
 }
-inline void add_product(Expansion& sum, double s, double f0, double f1, double f2, double f3) {
-  Expansion e;
-  e.c.push_back(s * f0);
-  e.scale(f1);
-  e.scale(f2);
-  e.scale(f3);
-  sum.add(e);
+
+// h = e * b; h holds up to 2 * en components and must not alias e
+inline int ex_scale(const double* e, int en, double b, double* h) {
+  int hn = 0;
+  double q, lo;
+  two_prod(e[0], b, q, lo);
+  if (lo != 0.0) h[hn++] = lo;
+  for (int i = 1; i < en; ++i) {
+    double t, tl, s, r;
+    two_prod(e[i], b, t, tl);
+    two_sum(q, tl, s, r);
+    if (r != 0.0) h[hn++] = r;
+    two_sum(t, s, q, r);
+    if (r != 0.0) h[hn++] = r;
+  }
+  if (q != 0.0 || hn == 0) h[hn++] = q;
+  return hn;
+}
+
+template <int A, int B, int R>
+inline void ex_add(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
+  static_assert(R >= A + B, "capacity");
+  r.n = ex_sum(x.c, x.n, y.c, y.n, r.c);
+}
+template <int A, int B, int R>
+inline void ex_sub(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
+  static_assert(R >= A + B, "capacity");
+  Ex<B> m;
+  for (int i = 0; i < y.n; ++i) m.c[i] = -y.c[i];
+  r.n = ex_sum(x.c, x.n, m.c, y.n, r.c);
+}
+// r = x * y: the partial products x * y_i are added up one by one
+template <int A, int B, int R>
+inline void ex_mul(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
+  static_assert(R >= 2 * A * B, "capacity");
+  Ex<R> acc;
+  Ex<2 * A> part;
+  r.n = ex_scale(x.c, x.n, y.c[0], r.c);
+  for (int i = 1; i < y.n; ++i) {
+    part.n = ex_scale(x.c, x.n, y.c[i], part.c);
+    acc.n = ex_sum(r.c, r.n, part.c, part.n, acc.c);
+    for (int k = 0; k < acc.n; ++k) r.c[k] = acc.c[k];
+    r.n = acc.n;
+  }
+}
+template <int CAP>
+inline double ex_sign(const Ex<CAP>& x) {
+  return x.c[x.n - 1];  // the most significant component carries the sign
+}
+// a - b, exactly
+inline Ex<2> ex_diff(double a, double b) {
+  Ex<2> r;
+  double hi, lo;
+  two_diff(a, b, hi, lo);
+  r.n = 0;
+  if (lo != 0.0) r.c[r.n++] = lo;
+  if (hi != 0.0 || r.n == 0) r.c[r.n++] = hi;
+  return r;
 }
 
 constexpr double EPS = 1.1102230246251565e-16;  // 2^-53
@@ -109,15 +144,15 @@ constexpr double CCW_BOUND = (3.0 + 16.0 * EPS) * EPS;
 constexpr double ICC_BOUND = (10.0 + 96.0 * EPS) * EPS;
 
 double orient2d_exact(const double* a, const double* b, const double* c) {
-  // (ax-cx)(by-cy) - (ay-cy)(bx-cx), multiplied out: no subtraction of inputs is rounded
-  Expansion s;
-  add_product(s, +1.0, a[0], b[1]);
-  add_product(s, -1.0, a[0], c[1]);
-  add_product(s, -1.0, c[0], b[1]);
-  add_product(s, -1.0, a[1], b[0]);
-  add_product(s, +1.0, a[1], c[0]);
-  add_product(s, +1.0, c[1], b[0]);
-  return s.sign();
+  // (ax-cx)(by-cy) - (ay-cy)(bx-cx) with every difference and product carried exactly
+  const Ex<2> acx = ex_diff(a[0], c[0]), acy = ex_diff(a[1], c[1]);
+  const Ex<2> bcx = ex_diff(b[0], c[0]), bcy = ex_diff(b[1], c[1]);
+  Ex<8> l, r;
+  ex_mul(acx, bcy, l);
+  ex_mul(acy, bcx, r);
+  Ex<16> det;
+  ex_sub(l, r, det);
+  return ex_sign(det);
 }
 
 inline double orient2d(const double* a, const double* b, const double* c) {
@@ -139,26 +174,37 @@ inline double orient2d(const double* a, const double* b, const double* c) {
   return orient2d_exact(a, b, c);
 }
 
-// 3x3 minor | p q r | over the columns (x, y, x^2 + y^2), multiplied out, added with sign s
-void add_minor(Expansion& sum, double s, const double* p, const double* q, const double* r) {
-  for (int k = 0; k < 2; ++k) {  // the lifted coordinate is x*x + y*y: one pass per square
-    add_product(sum, +s, p[0], q[1], r[k], r[k]);
-    add_product(sum, -s, p[0], r[1], q[k], q[k]);
-    add_product(sum, -s, p[1], q[0], r[k], r[k]);
-    add_product(sum, +s, p[1], r[0], q[k], q[k]);
-    add_product(sum, +s, q[0], r[1], p[k], p[k]);
-    add_product(sum, -s, q[1], r[0], p[k], p[k]);
-  }
+// One term of the in-circle determinant: ((px-dx)^2 + (py-dy)^2) * ((qx-dx)(ry-dy) - (rx-dx)(qy-dy))
+struct Rel {
+  Ex<2> x, y;
+};
+void incircle_term(const Rel& p, const Rel& q, const Rel& r, Ex<512>& out) {
+  Ex<8> xx, yy, qr, rq;
+  ex_mul(p.x, p.x, xx);
+  ex_mul(p.y, p.y, yy);
+  Ex<16> lift, cross;
+  ex_add(xx, yy, lift);
+  ex_mul(q.x, r.y, qr);
+  ex_mul(r.x, q.y, rq);
+  ex_sub(qr, rq, cross);
+  ex_mul(lift, cross, out);
 }
 
 double incircle_exact(const double* a, const double* b, const double* c, const double* d) {
-  // | x y x^2+y^2 1 | over the rows a, b, c, d, expanded along the column of ones
-  Expansion s;
-  add_minor(s, -1.0, b, c, d);
-  add_minor(s, +1.0, a, c, d);
-  add_minor(s, -1.0, a, b, d);
-  add_minor(s, +1.0, a, b, c);
-  return s.sign();
+  // | a-d ; b-d ; c-d | over the columns (x, y, x^2 + y^2): the differences are carried exactly as
+  // two-component values, so this is the exact sign of the untranslated 4 x 4 determinant
+  const Rel ra{ex_diff(a[0], d[0]), ex_diff(a[1], d[1])};
+  const Rel rb{ex_diff(b[0], d[0]), ex_diff(b[1], d[1])};
+  const Rel rc{ex_diff(c[0], d[0]), ex_diff(c[1], d[1])};
+  static thread_local Ex<512> ta, tb, tc;
+  static thread_local Ex<1024> tab;
+  static thread_local Ex<1536> det;
+  incircle_term(ra, rb, rc, ta);
+  incircle_term(rb, rc, ra, tb);
+  incircle_term(rc, ra, rb, tc);
+  ex_add(ta, tb, tab);
+  ex_add(tab, tc, det);
+  return ex_sign(det);
 }
 
 inline double incircle(const double* a, const double* b, const double* c, const double* d) {
