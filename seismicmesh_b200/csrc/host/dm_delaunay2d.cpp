@@ -290,16 +290,9 @@ struct SweepHull {
         tri[a] = p1;
         tri[b] = p0;
         const int32_t hbl = half[bl];
-        if (hbl == -1) {  // the flipped edge moved a hull half-edge: repoint the hull vertex at it
-          int32_t e = hstart;
-          do {
-            if (htri[e] == bl) {
-              htri[e] = a;
-              break;
-            }
-            e = hprev[e];
-          } while (e != hstart);
-        }
+        // the flip moves the hull half-edge bl (if it is one) to a: repoint its hull vertex, which
+        // is the vertex the half-edge starts from (htri[v] always starts at v)
+        if (hbl == -1 && htri[p1] == bl) htri[p1] = a;
         link(a, hbl);
         link(b, half[ar]);
         link(ar, bl);
