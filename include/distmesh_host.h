@@ -43,13 +43,16 @@ int64_t dmh_delaunay2d_max_cells(int64_t N);
 
 /* Delaunay triangulation of `points` (N,2).  Replaces DelaunayTriangulation.insert +
  * get_finite_cells (generation/cpp/delaunay_class.cpp:45-62, 99-117) with the vertex ids = input
- * rows.  Writes *T_out counter-clockwise triangles to `cells` (capacity `cap` rows) and the number
- * of input rows that are in no triangle to *skipped_out (exact duplicates of an earlier row; all
- * rows when the input is collinear or has fewer than 3 distinct points, in which case *T_out = 0).
+ * rows.  Writes *T_out counter-clockwise triangles to `cells` (capacity `cap` rows).  Input rows
+ * that are in no triangle are counted in *duplicates_out (exact duplicates of an earlier row, which
+ * keeps the cells; CGAL and Qhull leave those out as well) and *lost_out (everything else: all rows
+ * when the input is collinear or has fewer than 3 distinct points, in which case *T_out = 0; a row
+ * whose insertion-order tie was lost to rounding -- callers should retriangulate such an input with
+ * another code).  Either pointer may be NULL.
  * Sweep-hull construction (points inserted by distance from a seed circumcentre, advancing convex
  * front, Lawson flips), O(N log N). */
 int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
-                   int64_t* skipped_out);
+                   int64_t* duplicates_out, int64_t* lost_out);
 
 /* The two exact predicates, exported for the tests.
  * orient2d > 0: a, b, c counter-clockwise; incircle > 0: d strictly inside the circle through the

@@ -10,7 +10,7 @@ _P, _I64 = C.c_void_p, C.c_int64
 _SIGNATURES = {
     "dmh_version": (C.c_char_p, []),
     "dmh_delaunay2d_max_cells": (_I64, [_I64]),
-    "dmh_delaunay2d": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "dmh_delaunay2d": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "dmh_orient2d": (C.c_double, [_P, _P, _P]),
     "dmh_incircle": (C.c_double, [_P, _P, _P, _P]),
 }

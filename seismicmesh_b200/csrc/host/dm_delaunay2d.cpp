@@ -306,9 +306,14 @@ struct SweepHull {
     return ar;
   }
 
-  // returns the number of input rows left out of the triangulation
-  int64_t run() {
-    if (n < 3) return n;
+  int64_t dups = 0;  // rows left out as exact duplicates of an earlier row
+  int64_t lost = 0;  // rows left out for any other reason (degenerate input, no visible hull edge)
+
+  void run() {
+    if (n < 3) {
+      lost = n;
+      return;
+    }
     double minx = std::numeric_limits<double>::infinity(), miny = minx, maxx = -minx, maxy = -minx;
     for (int64_t i = 0; i < n; ++i) {
       minx = std::min(minx, P[2 * i]);
@@ -334,7 +339,11 @@ struct SweepHull {
       const double d = d2(i, P[2 * i0], P[2 * i0 + 1]);
       if (d > 0.0 && d < best) best = d, i1 = i;
     }
-    if (i1 < 0) return n;  // all rows coincide
+    if (i1 < 0) {  // all rows coincide
+      dups = n - 1;
+      lost = 1;
+      return;
+    }
     double rbest = inf, ccx = 0.0, ccy = 0.0;
     for (int64_t i = 0; i < n; ++i) {
       if (i == i0 || i == i1) continue;
@@ -348,7 +357,10 @@ struct SweepHull {
       const double r = x * x + y * y;
       if (r < rbest && orient2d(pt(i0), pt(i1), pt(i)) != 0.0) rbest = r, i2 = i, ccx = x, ccy = y;
     }
-    if (i2 < 0) return n;  // collinear input: no triangle
+    if (i2 < 0) {  // collinear input: no triangle
+      lost = n;
+      return;
+    }
     if (orient2d(pt(i0), pt(i1), pt(i2)) < 0.0) std::swap(i1, i2);  // seed counter-clockwise
     cx = P[2 * i0] + ccx;
     cy = P[2 * i0 + 1] + ccy;
@@ -387,7 +399,15 @@ struct SweepHull {
     const int64_t maxt = std::max<int64_t>(2 * n - 5, 1);
     tri.assign(3 * maxt, 0);
     half.assign(3 * maxt, -1);
-    hsize = (int64_t)std::ceil(std::sqrt((double)n));
+    // Angular hash of the hull vertices.  The front has O(sqrt(n)) vertices, but on an elongated
+    // domain the part of it that still advances is squeezed into a narrow range of angles, so the
+    // resolution grows with the aspect ratio of the bounding box (a coarse hash lands far from the
+    // visible edge and the search below walks the hull: 10 steps per point on the BP2004 shape).
+    {
+      const double w = maxx - minx, h = maxy - miny;
+      const double aspect = (w > 0.0 && h > 0.0) ? std::min(64.0, std::max(w / h, h / w)) : 1.0;
+      hsize = std::min<int64_t>(std::max<int64_t>(n, 16), (int64_t)std::ceil(2.0 * aspect * std::sqrt((double)n)));
+    }
     hprev.assign(n, 0);
     hnext.assign(n, 0);
     htri.assign(n, 0);
@@ -406,13 +426,12 @@ struct SweepHull {
     hhash[key(P[2 * i2], P[2 * i2 + 1])] = (int32_t)i2;
     add_triangle((int32_t)i0, (int32_t)i1, (int32_t)i2, -1, -1, -1);
 
-    int64_t skipped = 0;
     double xp = 0.0, yp = 0.0;
     for (int64_t k = 0; k < n; ++k) {
       const int32_t i = (int32_t)k;
       const double x = P[2 * i], y = P[2 * i + 1];
       if (k > 0 && x == xp && y == yp) {  // exact duplicate of the previous row in the order
-        ++skipped;
+        ++dups;
         continue;
       }
       xp = x;
@@ -436,7 +455,7 @@ struct SweepHull {
         }
       }
       if (e == -1) {  // sees no hull edge: not outside the hull (distance ties lost to rounding)
-        ++skipped;
+        ++lost;
         continue;
       }
       int32_t t = add_triangle(e, i, hnext[e], -1, -1, htri[e]);
@@ -466,7 +485,6 @@ struct SweepHull {
       hhash[key(x, y)] = i;
       hhash[key(P[2 * e], P[2 * e + 1])] = e;
     }
-    return skipped;
   }
 };
 
@@ -479,17 +497,18 @@ const char* dmh_version(void) { return "distmesh_host 0.1"; }
 int64_t dmh_delaunay2d_max_cells(int64_t N) { return N < 3 ? 1 : 2 * N - 5; }
 
 int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
-                   int64_t* skipped_out) {
+                   int64_t* duplicates_out, int64_t* lost_out) {
   if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
       N > (int64_t)std::numeric_limits<int32_t>::max() / 6)
     return DMH_ERR_ARG;
   SweepHull s;
   s.P = points;
   s.n = N;
-  const int64_t skipped = s.run();
+  s.run();
   const int64_t T = s.len / 3;
   *T_out = T;
-  if (skipped_out != nullptr) *skipped_out = skipped;
+  if (duplicates_out != nullptr) *duplicates_out = s.dups;
+  if (lost_out != nullptr) *lost_out = s.lost;
   if (T > cap) return DMH_ERR_CAPACITY;
   for (int64_t j = 0; j < 3 * T; ++j) cells[j] = s.ids[s.tri[j]];
   return DMH_OK;

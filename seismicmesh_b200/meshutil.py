@@ -48,7 +48,38 @@ def simp_qual(p, t):
 
 
 def _unique_rows(a, return_index=False, return_inverse=False, return_counts=False):
-    return np.unique(a, axis=0, return_index=return_index, return_inverse=return_inverse, return_counts=return_counts)
+    """`np.unique(a, axis=0, ...)` (rows in lexicographic order, index of the first occurrence,
+    inverse, counts) without NumPy's structured-dtype sort, which dominates the termination step:
+    integer rows are packed into one int64 key per row when they fit, everything else goes through
+    a stable lexsort."""
+    a = np.ascontiguousarray(a)
+    n, m = a.shape
+    if n == 0:
+        return np.unique(a, axis=0, return_index=return_index, return_inverse=return_inverse, return_counts=return_counts)
+    bits = 63 // m
+    if a.dtype.kind in "iu" and a.min() >= 0 and int(a.max()) < (1 << bits):
+        key = a[:, 0].astype(np.int64)
+        for j in range(1, m):
+            key = (key << bits) | a[:, j].astype(np.int64)
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        first = np.concatenate(([True], ks[1:] != ks[:-1]))
+    else:
+        order = np.lexsort(a.T[::-1])  # stable; last key is the primary one
+        srt = a[order]
+        first = np.concatenate(([True], (srt[1:] != srt[:-1]).any(axis=1)))
+    idx = order[first]
+    out = [a[idx]]
+    if return_index:
+        out.append(idx)
+    if return_inverse:
+        inv = np.empty(n, dtype=np.intp)
+        inv[order] = np.cumsum(first) - 1
+        out.append(inv)
+    if return_counts:
+        pos = np.flatnonzero(first)
+        out.append(np.diff(np.concatenate((pos, [n]))))
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def fix_mesh(p, t, ptol=2e-13, dim=2, delete_unused=False, fix_orientation=True):

@@ -49,16 +49,16 @@ class SweepHullTriangulator:
         n = len(p)
         cap = self._lib.dmh_delaunay2d_max_cells(n)
         cells = np.empty((cap, 3), dtype=np.int32)
-        T, skipped = C.c_int64(0), C.c_int64(0)
-        rc = self._lib.dmh_delaunay2d(p.ctypes.data, n, cells.ctypes.data, cap, C.byref(T), C.byref(skipped))
+        T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        rc = self._lib.dmh_delaunay2d(p.ctypes.data, n, cells.ctypes.data, cap, C.byref(T), C.byref(dups), C.byref(lost))
         if rc != 0:
             raise RuntimeError(f"dmh_delaunay2d failed with code {rc}")
-        if skipped.value and T.value:
-            # Rows in no triangle are exact duplicates of an earlier row (Qhull leaves those out as
-            # well).  Anything else (an insertion-order tie lost to rounding) is handed to Qhull.
-            if skipped.value != n - len(np.unique(p, axis=0)):
-                self.qhull_retries += 1
-                return QhullTriangulator(2).triangulate(p)
+        if lost.value and T.value:
+            # A row left out although it is no exact duplicate (an insertion-order tie lost to
+            # rounding; never seen so far): hand this input to Qhull.  Exact duplicates are left out
+            # by every Delaunay code (`dups`, e.g. a lattice point that coincides with a fixed corner).
+            self.qhull_retries += 1
+            return QhullTriangulator(2).triangulate(p)
         return np.ascontiguousarray(cells[: T.value])
 
 

@@ -138,3 +138,20 @@ def test_program_depth_guard():
     with pytest.raises(geometry.SDFProgramError):
         deep.program()
     assert geometry.lower(lambda x: x) is None
+
+
+def test_unique_rows_matches_numpy():
+    """meshutil._unique_rows (packed-key / lexsort) == np.unique(axis=0) incl. index, inverse, counts."""
+    from seismicmesh_b200.meshutil import _unique_rows
+
+    rng = np.random.default_rng(0)
+    cases = [rng.integers(0, 50, (2000, 2)), rng.integers(0, 30, (3000, 3)).astype(np.int32), rng.integers(-5, 5, (500, 2)),
+             np.round(rng.random((3000, 2)) * 20) / 20, rng.integers(0, 2**40, (100, 3)), np.zeros((0, 2), int),
+             rng.integers(0, 9, (1, 3)), rng.integers(0, 2**30, (400, 4))]
+    for a in cases:
+        got = _unique_rows(a, return_index=True, return_inverse=True, return_counts=True)
+        exp = np.unique(a, axis=0, return_index=True, return_inverse=True, return_counts=True)
+        for x, y in zip(got, exp):
+            assert np.array_equal(np.asarray(x).ravel(), np.asarray(y).ravel())
+        assert got[0].dtype == exp[0].dtype and got[0].shape == exp[0].shape
+        assert np.array_equal(_unique_rows(a), exp[0])

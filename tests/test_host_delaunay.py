@@ -198,11 +198,19 @@ def test_empty_collinear_and_coincident_inputs(hl, tri):
     # C ABI error codes: capacity too small, null output
     p = np.random.default_rng(0).random((50, 2))
     out = np.empty((4, 3), np.int32)
-    T, S = C.c_int64(), C.c_int64()
-    assert hl.dmh_delaunay2d(p.ctypes.data, 50, out.ctypes.data, 4, C.byref(T), C.byref(S)) == -2
+    T, dups, lost = C.c_int64(), C.c_int64(), C.c_int64()
+    assert hl.dmh_delaunay2d(p.ctypes.data, 50, out.ctypes.data, 4, C.byref(T), C.byref(dups), C.byref(lost)) == -2
     assert T.value > 4  # the required size is reported
-    assert hl.dmh_delaunay2d(p.ctypes.data, 50, None, 4, C.byref(T), C.byref(S)) == -1
-    assert hl.dmh_delaunay2d(p.ctypes.data, -1, out.ctypes.data, 4, C.byref(T), C.byref(S)) == -1
+    assert hl.dmh_delaunay2d(p.ctypes.data, 50, None, 4, C.byref(T), None, None) == -1
+    assert hl.dmh_delaunay2d(p.ctypes.data, -1, out.ctypes.data, 4, C.byref(T), None, None) == -1
+    # the two reasons a row can be left out are reported separately
+    d = np.r_[p, p[:7]]
+    big = np.empty((hl.dmh_delaunay2d_max_cells(57), 3), np.int32)
+    assert hl.dmh_delaunay2d(d.ctypes.data, 57, big.ctypes.data, len(big), C.byref(T), C.byref(dups), C.byref(lost)) == 0
+    assert (dups.value, lost.value) == (7, 0)
+    line = np.ascontiguousarray(np.c_[np.arange(10.0), np.arange(10.0)])
+    assert hl.dmh_delaunay2d(line.ctypes.data, 10, big.ctypes.data, len(big), C.byref(T), C.byref(dups), C.byref(lost)) == 0
+    assert (T.value, dups.value, lost.value) == (0, 0, 10)
 
 
 def test_get_triangulator_defaults():
