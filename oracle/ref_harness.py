@@ -11,6 +11,8 @@ stand-ins for what is missing:
   ``ruge_stuben_solver`` so ``laplacian2_fixed_point`` still solves its linear system)
 * ``_delaunay_class(3)``    -> ``scipy.spatial.Delaunay`` (Qhull) behind the reference's
   ``insert/move/get_finite_vertices/get_finite_cells`` interface.  Vertex order is kept.
+* ``segyio``                -> a plain struct-based SEG-Y trace decoder (``_SegyFile``), so the reference's
+  own tests on ``tests/testing.segy`` can be replayed
 * ``_fast_geometry``/``_FastHJ`` -> the reference's OWN C++ sources compiled by
   ``oracle/Makefile`` into ``oracle/_ref`` (not copied).
 
@@ -111,6 +113,45 @@ class _DT3(_DT):
     dim = 3
 
 
+class _SegyFile:
+    """Stand-in for ``segyio.open(filename, ignore_geometry=True)`` as the reference uses it
+    (sizing/mesh_size_function.py:633-646: ``len(f.samples)``, ``len(f.trace)``, iteration over
+    ``f.trace``).  A deliberately plain, value-by-value decoder (struct), independent of the product's
+    vectorised reader, for IBM-float (format 1) and IEEE-float (format 5) files."""
+
+    def __init__(self, filename):
+        import struct
+
+        with open(filename, "rb") as f:
+            raw = f.read()
+        ns = struct.unpack(">H", raw[3220:3222])[0]
+        fmt = struct.unpack(">H", raw[3224:3226])[0]
+        if fmt not in (1, 5):
+            raise NotImplementedError(f"SEG-Y format code {fmt}")
+        stride = 240 + 4 * ns
+        ntr = (len(raw) - 3600) // stride
+
+        def ibm(w):
+            sign = -1.0 if w >> 31 else 1.0
+            return sign * ((w & 0xFFFFFF) / float(1 << 24)) * 16.0 ** (((w >> 24) & 0x7F) - 64)
+
+        self.samples = list(range(ns))
+        self.trace = []
+        for k in range(ntr):
+            off = 3600 + k * stride + 240
+            if fmt == 1:
+                words = struct.unpack(f">{ns}I", raw[off:off + 4 * ns])
+                self.trace.append(np.array([ibm(w) for w in words], dtype=np.float32))
+            else:
+                self.trace.append(np.array(struct.unpack(f">{ns}f", raw[off:off + 4 * ns]), dtype=np.float32))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _unique_rows_np2(A, return_index=False, return_inverse=False):
     A = np.require(A, requirements="C")
     assert A.ndim == 2
@@ -161,8 +202,11 @@ def load_reference():
 
     pyamg.ruge_stuben_solver = lambda A: _LU(A)
     sys.modules.setdefault("pyamg", pyamg)
-    for name in ("_cpputils", "segyio", "h5py"):
+    for name in ("_cpputils", "h5py"):
         sys.modules.setdefault(name, types.ModuleType(name))
+    segyio = types.ModuleType("segyio")
+    segyio.open = lambda filename, ignore_geometry=True: _SegyFile(filename)
+    sys.modules.setdefault("segyio", segyio)
     dl = types.ModuleType("_delaunay")
 
     def _not_available(*a, **k):

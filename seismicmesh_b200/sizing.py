@@ -178,10 +178,62 @@ def _pad(array, padding, style, extra):  # mesh_size_function.py:575-587
     raise ValueError("pad style currently not supported. Try `linear_ramp`, `edge`, or `constant`")
 
 
+_SEGY_FORMATS = {  # data sample format code (binary header bytes 3225-3226) -> big-endian dtype
+    2: ">i4", 3: ">i2", 5: ">f4", 6: ">f8", 8: "i1", 9: ">i8", 10: ">u4", 11: ">u2", 12: ">u8", 16: "u1",
+}
+
+
+def _ibm32_to_float64(u):
+    """IBM System/360 single precision (SEG-Y format code 1): sign, 7-bit excess-64 exponent of 16,
+    24-bit fraction.  Every such value is exactly representable in float64."""
+    u = u.astype(np.uint32)
+    frac = (u & np.uint32(0x00FFFFFF)).astype(np.float64)
+    expo = ((u >> np.uint32(24)) & np.uint32(0x7F)).astype(np.int64) - 64
+    val = np.ldexp(frac, (4 * expo - 24).astype(np.int32))
+    return np.where((u >> np.uint32(31)) != 0, -val, val)
+
+
+def _read_segy(filename):
+    """Velocity model from a SEG-Y file: what the reference gets out of ``segyio`` with
+    ``ignore_geometry=True`` (sizing/mesh_size_function.py:633-646: one column per trace, samples
+    down the column, then flipped so that row 0 is the deepest sample), read here with NumPy.
+    Layout (SEG-Y rev 1): 3200-byte textual header, 400-byte binary header (samples per trace at
+    bytes 3221-3222, format code at 3225-3226, extended textual headers at 3505-3506), then
+    240-byte trace header + samples per trace, all traces the same length."""
+    raw = np.fromfile(filename, dtype=np.uint8)
+    if raw.size < 3600:
+        raise ValueError(f"{filename}: not a SEG-Y file (shorter than its 3600-byte headers)")
+    hdr = raw[3200:3600]
+
+    def u16(off):
+        return int(hdr[off]) << 8 | int(hdr[off + 1])
+
+    ns, fmt = u16(20), u16(24)
+    next_ = u16(304)
+    ext = 0 if next_ >= 0x8000 else next_  # -1 = variable number of extended headers: not supported
+    if fmt != 1 and fmt not in _SEGY_FORMATS:
+        raise ValueError(f"{filename}: unsupported SEG-Y data sample format code {fmt}")
+    width = 4 if fmt == 1 else np.dtype(_SEGY_FORMATS[fmt]).itemsize
+    start = 3600 + 3200 * ext
+    stride = 240 + ns * width
+    if ns == 0 or (raw.size - start) % stride != 0 or raw.size <= start:
+        raise ValueError(f"{filename}: size does not match {ns} samples per trace of {width} bytes")
+    ntr = (raw.size - start) // stride
+    body = raw[start:].reshape(ntr, stride)[:, 240:]
+    if fmt == 1:
+        traces = _ibm32_to_float64(np.ascontiguousarray(body).view(">u4"))
+    else:
+        traces = np.ascontiguousarray(body).view(_SEGY_FORMATS[fmt]).astype(np.float64)
+    vp = np.ascontiguousarray(traces.T)  # (nz, nx): vp[:, index] = trace
+    if np.amin(vp) < 1000.0:
+        warnings.warn("Velocity appear to be in km/s. Maybe pass `units` km-s key pair?")
+    return np.flipud(vp), int(ns), int(ntr), 0
+
+
 def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     """Build a mesh-size function from a seismic velocity model: same name, arguments, defaults,
     errors and step order as the reference (mesh_size_function.py:27-232).  ``velocity_data=`` arrays
-    and binary files are supported; SEG-Y files need ``segyio`` exactly as in the reference."""
+    binary files and SEG-Y files (own reader, no ``segyio``) are supported."""
     opts = dict(_SIZING_DEFAULTS)
     opts.update(kwargs)
     if comm is not None and getattr(comm, "rank", 0) != 0:
@@ -189,14 +241,7 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     vp, nz, nx, ny = opts["velocity_data"], opts["nz"], opts["nx"], opts["ny"]
     if vp is None:
         if str(filename).endswith(".segy"):
-            import segyio  # noqa: F401  (not shipped here; same dependency as the reference, :633-646)
-
-            with segyio.open(filename, ignore_geometry=True) as fh_:
-                nz, nx = len(fh_.samples), len(fh_.trace)
-                vp = np.zeros(shape=(nz, nx))
-                for index, trace in enumerate(fh_.trace):
-                    vp[:, index] = trace
-            vp, ny = np.flipud(vp), 0
+            vp, nz, nx, ny = _read_segy(filename)
         else:
             vp, nz, nx, ny = _read_bin(filename, nz, nx, ny, opts["byte_order"], opts["axes_order"],
                                        opts["axes_order_sort"], opts["dtype"])

@@ -370,7 +370,36 @@ def gen_e2e():
     print(json.dumps(res, indent=1))
 
 
+def gen_segy():
+    """segy_testing.npz / segy_tests.json: the velocity model of the reference's own SEG-Y fixture
+    (tests/testing.segy, decoded value by value by the harness's segyio stand-in) and the outcome of
+    the reference's tests that mesh it (tests/test_2dmesher_domain_extension.py:16-62 with the
+    answers it asserts to +-100; tests/test_2dmesher.py:16-46), replayed with the unmodified reference."""
+    fname = os.path.join(ref_harness.REF_ROOT, "tests", "testing.segy")
+    with ref_harness._SegyFile(fname) as f:
+        vp = np.zeros((len(f.samples), len(f.trace)))
+        for k, tr in enumerate(f.trace):
+            vp[:, k] = tr
+    np.savez(os.path.join(HERE, "segy_testing.npz"), vp=np.flipud(vp), traces=vp)
+    bbox = (-10e3, 0.0, 0.0, 10e3)
+    res = {"bbox": bbox, "domain_extension": {}}
+    for style, answer in (("linear_ramp", [9428, 18525]), ("edge", [9724, 19078]), ("constant", [9428, 18525])):
+        ef = sm.get_sizing_function_from_segy(fname, bbox=bbox, grade=0.005, grad=50.0, stencil_size=100, wl=5, freq=5.0,
+                                              hmin=100, hmax=10e6, pad_style=style, domain_pad=1e3)
+        p, t = sm.generate_mesh(sm.Rectangle(bbox), ef, h0=100, perform_checks=True, verbose=0)
+        res["domain_extension"][style] = {"asserted_by_reference_test": answer, "reference_run_here": [len(p), len(t)]}
+    ef = sm.get_sizing_function_from_segy(fname, bbox=bbox, grade=0.005, grad=50.0, wl=5, freq=5.0, hmin=100, hmax=10e6)
+    p, t = sm.generate_mesh(sm.Rectangle(bbox), ef, h0=100, perform_checks=True, verbose=0)
+    res["test_2dmesher"] = {"reference_run_here": [len(p), len(t)]}
+    with open(os.path.join(HERE, "segy_tests.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
+    if "segy" in sys.argv[1:]:
+        gen_segy()
+        sys.exit(0)
     gen_sdf()
     gen_interp()
     gen_loop()
@@ -378,4 +407,5 @@ if __name__ == "__main__":
     gen_init()
     gen_e2e()
     gen_sizing()
+    gen_segy()
     print("golden vectors written to", HERE)

@@ -697,6 +697,33 @@ def test_sizing_function_matches_reference(sm, name):
     assert ef.eval(x)[0] == grid[idx]
 
 
+@pytest.mark.parametrize("style", ["linear_ramp", "edge", "constant"])
+def test_reference_segy_domain_extension_answers(sm, tmp_path, style):
+    """The reference's own end-to-end test on its SEG-Y fixture
+    (tests/test_2dmesher_domain_extension.py:16-62): read the file, build the sizing function with a
+    padded domain, mesh the rectangle, and land within +-100 of the vertex / cell counts THE
+    REFERENCE'S TEST ASSERTS.  The fixture's velocity model is committed decoded
+    (tests/golden/segy_testing.npz) and written back to a SEG-Y file here, so the whole path
+    (own SEG-Y reader -> sizing -> device loop -> termination) runs through a file name."""
+    import warnings
+
+    from segy_util import write_segy
+
+    with open(os.path.join(GOLDEN, "segy_tests.json")) as f:
+        ref = json.load(f)
+    fname = str(tmp_path / "testing.segy")
+    write_segy(fname, load_golden("segy_testing.npz")["traces"], fmt=1)
+    bbox = (-10e3, 0.0, 0.0, 10e3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ef = sm.get_sizing_function_from_segy(fname, bbox=bbox, grade=0.005, grad=50.0, stencil_size=100, wl=5,
+                                              freq=5.0, hmin=100, hmax=10e6, pad_style=style, domain_pad=1e3)
+    p, t = sm.generate_mesh(sm.Rectangle(bbox), ef, h0=100, perform_checks=True, verbose=0)
+    case = ref["domain_extension"][style]
+    assert np.allclose([len(p), len(t)], case["asserted_by_reference_test"], atol=100)  # the reference's own bar
+    assert np.allclose([len(p), len(t)], case["reference_run_here"], atol=100)  # and the unmodified reference run here
+
+
 def test_limgrad_kernel_vs_oracle_large(sm):
     """BP2004-shaped grid (1911 x 5395): the CUDA limiter against the oracle's fixed point through
     size-independent properties (gradient bound, never raises a value, idempotent) and against the
