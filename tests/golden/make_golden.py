@@ -370,6 +370,50 @@ def gen_e2e():
     print(json.dumps(res, indent=1))
 
 
+def gen_meshutil():
+    """meshutil_2d.npz / meshutil_3d.npz: the reference's mesh utilities used at termination
+    (geometry/utils.py: simp_vol :175, fix_mesh :204, simp_qual :252, get_boundary_edges :310,
+    get_boundary_vertices :364, get_boundary_entities :385, get_boundary_facets :421,
+    delete_boundary_entities :440, laplacian2_fixed_point :494) on small jittered meshes."""
+    gu = sm.geometry.utils
+    out = {}
+    p, t = _jittered_mesh(sm.Disk([0.0, 0.0], 1.0), 0.12, (-1.0, 1.0, -1.0, 1.0), 5, 2)
+    t = mg._remove_triangles_outside(p, t, sm.Disk([0.0, 0.0], 1.0).eval, 0.012)
+    out["p"], out["t"] = p, t.astype(np.int64)
+    out["vol"], out["qual"] = gu.simp_vol(p, t), gu.simp_qual(p, t)
+    out["bedges"] = gu.get_boundary_edges(t)
+    out["bverts"] = gu.get_boundary_vertices(t)
+    out["bents"] = gu.get_boundary_entities(p, t)
+    # a dirty mesh: duplicated vertices (cells re-pointed at the copies), a duplicated cell, an unused vertex
+    pd = np.vstack((p, p[:7], [[5.0, 5.0]]))
+    td = t.copy()
+    td[::3][td[::3] < 7] += len(p)
+    td = np.vstack((td, td[:4, [1, 2, 0]]))
+    out["dirty_p"], out["dirty_t"] = pd, td.astype(np.int64)
+    fp, ft, fj = gu.fix_mesh(pd.copy(), td.copy(), delete_unused=True)
+    out["fix_p"], out["fix_t"] = fp, ft
+    fp2, ft2, _ = gu.fix_mesh(pd.copy(), td.copy(), delete_unused=False)
+    out["fix2_p"], out["fix2_t"] = fp2, ft2
+    dp, dt_ = gu.delete_boundary_entities(p.copy(), t.copy(), dim=2, min_qual=0.55, verbose=0)
+    out["del_p"], out["del_t"] = dp, dt_
+    lp, _ = gu.laplacian2_fixed_point(p.copy(), t.copy())
+    out["lap_p"] = lp
+    np.savez(os.path.join(HERE, "meshutil_2d.npz"), **out)
+    out = {}
+    ball = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _jittered_mesh(ball, 0.3, (-1.0, 1.0, -1.0, 1.0, -1.0, 1.0), 6, 3)
+    t = mg._remove_triangles_outside(p, t, ball.eval, 0.03)
+    out["p"], out["t"] = p, t.astype(np.int64)
+    out["vol"], out["qual"] = gu.simp_vol(p, t), gu.simp_qual(p, t)
+    out["bfacets"] = gu.get_boundary_facets(t)
+    out["bverts"] = gu.get_boundary_vertices(t, dim=3)
+    out["bents"] = gu.get_boundary_entities(p, t, dim=3)
+    dp, dt_ = gu.delete_boundary_entities(p.copy(), t.copy(), dim=3, min_qual=0.2, verbose=0)
+    out["del_p"], out["del_t"] = dp, dt_
+    np.savez(os.path.join(HERE, "meshutil_3d.npz"), **out)
+    print("meshutil goldens:", {k: np.asarray(v).shape for k, v in out.items()})
+
+
 def gen_segy():
     """segy_testing.npz / segy_tests.json: the velocity model of the reference's own SEG-Y fixture
     (tests/testing.segy, decoded value by value by the harness's segyio stand-in) and the outcome of
@@ -397,8 +441,11 @@ def gen_segy():
 
 
 if __name__ == "__main__":
-    if "segy" in sys.argv[1:]:
-        gen_segy()
+    if "segy" in sys.argv[1:] or "meshutil" in sys.argv[1:]:
+        if "segy" in sys.argv[1:]:
+            gen_segy()
+        if "meshutil" in sys.argv[1:]:
+            gen_meshutil()
         sys.exit(0)
     gen_sdf()
     gen_interp()
@@ -408,4 +455,5 @@ if __name__ == "__main__":
     gen_e2e()
     gen_sizing()
     gen_segy()
+    gen_meshutil()
     print("golden vectors written to", HERE)
