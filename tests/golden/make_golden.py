@@ -414,6 +414,49 @@ def gen_meshutil():
     print("meshutil goldens:", {k: np.asarray(v).shape for k, v in out.items()})
 
 
+def gen_reference_tests():
+    """reference_tests.json: the reference's own known-answer tests on this path, replayed with the
+    unmodified reference (Qhull behind its CGAL interface), next to the answers those tests assert:
+    tests/test_2dmesher_SDF.py, test_immersion.py, test_smooth_sets.py, test_pfix.py, test_verbose.py."""
+    import contextlib
+    import io
+
+    res = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        disk = sm.geometry.Disk([0.0, 0.0], 1)
+        p, c = sm.generate_mesh(bbox=(-1.0, 1.0, -1.0, 1.0), domain=disk, h0=0.2,
+                                edge_length=lambda x: 0.2 - disk.eval(x) * 0.15, max_iter=100)
+        res["test_2dmesher_SDF"] = {"asserted": {"counts": [63, 93], "atol": 10, "area": 3.14, "area_atol": 0.2},
+                                    "reference_run_here": [len(p), len(c), float(sm.geometry.simp_vol(p, c).sum())]}
+        runs = []
+        for radius in [0.25, 0.30, 0.35]:
+            disk0 = sm.Disk([0.5, 0.5], radius)
+            p, c = sm.generate_mesh(domain=sm.Rectangle((0.0, 1.0, 0.0, 1.0)), h0=0.05, subdomains=[disk0],
+                                    edge_length=lambda x, d=disk0: 0.05 * np.abs(d.eval(x)) + 0.05)
+            sd = disk0.eval(p[c].sum(1) / 3)
+            runs.append([radius, len(p), len(c), float(np.sum(sm.geometry.simp_vol(p, c[sd < 0])))])
+        res["test_immersion"] = {"asserted": "immersed area == pi r^2 to rtol 1e-2", "reference_run_here": runs}
+        dom = sm.Difference([sm.Ball((0.0, 0.0, 0.5), 0.85), sm.Cube((-0.5, 0.5, -0.5, 0.5, -0.5, 0.5))], smoothness=0.20)
+        p, c = sm.generate_mesh(domain=dom, edge_length=0.10)
+        p, c = sm.sliver_removal(points=p, domain=dom, edge_length=0.10)
+        res["test_smooth_diff"] = {"asserted": {"cells": 9004, "atol": 100}, "reference_run_here": [len(p), len(c)]}
+        bbox = (0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        pf = np.vstack((np.linspace((0.0, 0.0, 0.0), (1.0, 0.0, 1.0), int(np.sqrt(2) / 0.05)), sm.geometry.corners(bbox)))
+        p, c = sm.generate_mesh(domain=sm.Cube(bbox), edge_length=0.05, pfix=pf)
+        res["test_pfix"] = {"asserted": "every fixed point is a mesh vertex (squared distance isclose 0)",
+                            "reference_run_here": [len(p), len(c), max(float(((p - q) ** 2).sum(1).min()) for q in pf)]}
+    sizes = []
+    for v in (0, 1, 2):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            sm.generate_mesh(domain=sm.Rectangle((0.0, 1.0, 0.0, 1.0)), edge_length=0.1, verbose=v)
+        sizes.append(len(buf.getvalue().encode()))
+    res["test_verbose"] = {"asserted": {"stdout_bytes": [0, 192, 6014]}, "reference_run_here": sizes}
+    with open(os.path.join(HERE, "reference_tests.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res))
+
+
 def gen_segy():
     """segy_testing.npz / segy_tests.json: the velocity model of the reference's own SEG-Y fixture
     (tests/testing.segy, decoded value by value by the harness's segyio stand-in) and the outcome of
@@ -441,6 +484,9 @@ def gen_segy():
 
 
 if __name__ == "__main__":
+    if "reftests" in sys.argv[1:]:
+        gen_reference_tests()
+        sys.exit(0)
     if "segy" in sys.argv[1:] or "meshutil" in sys.argv[1:]:
         if "segy" in sys.argv[1:]:
             gen_segy()
@@ -456,4 +502,5 @@ if __name__ == "__main__":
     gen_sizing()
     gen_segy()
     gen_meshutil()
+    gen_reference_tests()
     print("golden vectors written to", HERE)

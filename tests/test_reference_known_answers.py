@@ -1,0 +1,106 @@
+"""The reference's own known-answer tests for generate_mesh / sliver_removal, replayed through
+seismicmesh_b200 with the tolerances THOSE TESTS assert (reference tests/test_2dmesher_SDF.py,
+test_immersion.py, test_smooth_sets.py, test_pfix.py, test_verbose.py).  tests/golden/
+reference_tests.json records, next to each asserted answer, what the unmodified reference gives when
+replayed in the build container with Qhull behind its CGAL interface (make_golden.py `reftests`).
+All GPU: the loop body runs on the device."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sm():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import seismicmesh_b200
+
+    return seismicmesh_b200
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with open(os.path.join(GOLDEN, "reference_tests.json")) as f:
+        return json.load(f)
+
+
+def test_2dmesher_SDF(sm, ref):
+    """Unit disk with a callable edge length (reference tests/test_2dmesher_SDF.py:8-30)."""
+    from seismicmesh_b200 import meshutil
+
+    hmin = 0.2
+    disk = sm.Disk([0.0, 0.0], 1)
+
+    def EF(p):
+        return hmin - disk.eval(p) * 0.15
+
+    points, cells = sm.generate_mesh(bbox=(-1.0, 1.0, -1.0, 1.0), domain=disk, h0=hmin, edge_length=EF, max_iter=100,
+                                     verbose=0)
+    a = ref["test_2dmesher_SDF"]["asserted"]
+    assert np.allclose([len(points), len(cells)], a["counts"], atol=a["atol"])
+    assert np.allclose(meshutil.simp_vol(points, cells).sum(), a["area"], atol=hmin)
+
+
+def test_immersion(sm, ref):
+    """A disk immersed in a square through `subdomains` (reference tests/test_immersion.py:11-33): the
+    cells inside the disk add up to its area within 1 %."""
+    from seismicmesh_b200 import meshutil
+
+    hmin = 0.05
+    for radius in [0.25, 0.30, 0.35]:
+        box0 = sm.Rectangle((0.0, 1.0, 0.0, 1.0))
+        disk0 = sm.Disk([0.5, 0.5], radius)
+
+        def fh(p):
+            return 0.05 * np.abs(disk0.eval(p)) + hmin
+
+        points, cells = sm.generate_mesh(domain=box0, edge_length=fh, h0=hmin, subdomains=[disk0], verbose=0)
+        sd = disk0.eval(points[cells].sum(1) / 3)
+        subdomain_vol = np.sum(meshutil.simp_vol(points, cells[sd < 0]))
+        assert np.isclose(subdomain_vol, np.pi * radius**2, rtol=1e-2)
+
+
+def test_smooth_diff(sm, ref):
+    """Smooth difference of a ball and a cube, generate_mesh + sliver_removal
+    (reference tests/test_smooth_sets.py:8-23): 9004 cells +- 100."""
+    cube1 = sm.Cube((-0.5, 0.5, -0.5, 0.5, -0.5, 0.5))
+    ball1 = sm.Ball((0.0, 0.0, 0.5), 0.85)
+    domain = sm.Difference([ball1, cube1], smoothness=0.20)
+    points, cells = sm.generate_mesh(domain=domain, edge_length=0.10, verbose=0)
+    points, cells = sm.sliver_removal(points=points, domain=domain, edge_length=0.10, verbose=0)
+    a = ref["test_smooth_diff"]["asserted"]
+    assert np.abs(cells.shape[0] - a["cells"]) < a["atol"]
+
+
+def test_pfix(sm, ref):
+    """Fixed points along a diagonal of the unit cube plus its corners (reference tests/test_pfix.py:8-27):
+    every one of them is a vertex of the final mesh."""
+    hmin = 0.05
+    bbox = (0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    pfix = np.linspace((0.0, 0.0, 0.0), (1.0, 0.0, 1.0), int(np.sqrt(2) / hmin))
+    pfix = np.vstack((pfix, sm.geometry.corners(bbox)))
+    points, cells = sm.generate_mesh(domain=sm.Cube(bbox), edge_length=hmin, pfix=pfix, verbose=0)
+    for p in pfix:
+        deltas = points - p
+        assert np.isclose(np.min(np.einsum("ij,ij->i", deltas, deltas)), 0.0)
+    n_ref = ref["test_pfix"]["reference_run_here"][0]
+    assert abs(len(points) - n_ref) <= 0.01 * n_ref
+
+
+def test_verbose(sm, ref):
+    """stdout size per verbosity level (reference tests/test_verbose.py:9-24): 0, 192 and 6014 bytes."""
+    square = sm.Rectangle((0.0, 1.0, 0.0, 1.0))
+    for verbosity, correct_size in zip([0, 1, 2], ref["test_verbose"]["asserted"]["stdout_bytes"]):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            sm.generate_mesh(domain=square, edge_length=0.1, verbose=verbosity)
+        assert len(buf.getvalue().encode()) == correct_size, buf.getvalue()
