@@ -1,5 +1,5 @@
 /*
- * distmesh_host.h -- C ABI of libdistmesh_host.so: the HOST side of the retriangulation step.
+ * distmesh_host.h -- C ABI of libdistmesh_host.so: the HOST side of the retriangulation step (2-D and 3-D).
  *
  * BASELINE.json north_star keeps the Delaunay retriangulation of every DistMesh iteration on the
  * host.  The reference does it with CGAL behind two pybind11 classes
@@ -54,7 +54,29 @@ int64_t dmh_delaunay2d_max_cells(int64_t N);
 int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
                    int64_t* duplicates_out, int64_t* lost_out);
 
-/* The two exact predicates, exported for the tests.
+/* Capacity to give `cells` of dmh_delaunay3d for N points: 8 N + 64 tetrahedra, generous for mesh-like
+ * point sets (about 6.7 N); a pathological input can need more, see DMH_ERR_CAPACITY below. */
+int64_t dmh_delaunay3d_max_cells(int64_t N);
+
+/* Delaunay triangulation of `points` (N,3).  Replaces DelaunayTriangulation3.insert +
+ * get_finite_cells (generation/cpp/delaunay_class3.cpp) with the vertex ids = input rows.  Writes
+ * *T_out positively oriented tetrahedra (orient3d of the four rows > 0) to `cells`; with
+ * DMH_ERR_CAPACITY nothing is written and *T_out is the capacity that is needed.  *duplicates_out
+ * counts rows left out as exact duplicates of another row (ONE copy is in the cells, not necessarily
+ * the first), *lost_out rows left out for any other reason: all N when there are not four affinely
+ * independent points (then *T_out = 0), non-zero also when an internal consistency check failed --
+ * callers should retriangulate such an input with another code.  Incremental Bowyer-Watson in a
+ * biased randomised insertion order (Morton curve within a round), ghost tetrahedra on the hull. */
+int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                   int64_t* duplicates_out, int64_t* lost_out);
+
+/* The exact predicates, exported for the tests.
+ * orient3d > 0: (a, b, c, d) positively oriented (the orientation of every cell dmh_delaunay3d
+ * returns); insphere > 0: e strictly inside the sphere through a positively oriented (a, b, c, d). */
+double dmh_orient3d(const double* a, const double* b, const double* c, const double* d);
+double dmh_insphere(const double* a, const double* b, const double* c, const double* d, const double* e);
+
+/* The two 2-D predicates.
  * orient2d > 0: a, b, c counter-clockwise; incircle > 0: d strictly inside the circle through the
  * counter-clockwise a, b, c.  Only the SIGN is meaningful (exact, including 0). */
 double dmh_orient2d(const double* a, const double* b, const double* c);

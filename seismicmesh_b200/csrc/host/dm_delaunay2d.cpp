@@ -27,117 +27,11 @@
 #include <vector>
 
 #include "distmesh_host.h"
+#include "dm_exact.h"
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------
-// exact arithmetic on expansions
-// ---------------------------------------------------------------------------------------------
-inline void two_sum(double a, double b, double& x, double& y) {
-  x = a + b;
-  const double bv = x - a;
-  const double av = x - bv;
-  y = (a - av) + (b - bv);
-}
-inline void two_prod(double a, double b, double& x, double& y) {
-  x = a * b;
-  y = std::fma(a, b, -x);  // exact residual of the product
-}
-
-inline void two_diff(double a, double b, double& x, double& y) {
-  x = a - b;
-  const double bv = a - x;
-  const double av = x + bv;
-  y = (a - av) + (bv - b);
-}
-
-// A value held exactly as a sum of doubles: non-overlapping components of increasing magnitude,
-// zeros eliminated (a zero value is the single component 0.0).  Because zeros are dropped, the cost
-// of every operation follows the number of components that are actually needed: differences of
-// nearby coordinates are exact in one double, and the whole determinant then stays a few dozen
-// components long.
-template <int CAP>
-struct Ex {
-  double c[CAP];
-  int n;
-};
-
-// h = e + f (linear-time merge by magnitude, then one carry sweep); h must not alias e or f
-inline int ex_sum(const double* e, int en, const double* f, int fn, double* h) {
-  int ei = 0, fi = 0, hn = 0;
-  auto take = [&]() {  // the next component in order of increasing magnitude
-    if (fi >= fn || (ei < en && std::fabs(e[ei]) <= std::fabs(f[fi]))) return e[ei++];
-    return f[fi++];
-  };
-  double q = take();
-  while (ei < en || fi < fn) {
-    double s, r;
-    two_sum(q, take(), s, r);
-    q = s;
-    if (r != 0.0) h[hn++] = r;
-  }
-  if (q != 0.0 || hn == 0) h[hn++] = q;
-  return hn;
-}
-
-// h = e * b; h holds up to 2 * en components and must not alias e
-inline int ex_scale(const double* e, int en, double b, double* h) {
-  int hn = 0;
-  double q, lo;
-  two_prod(e[0], b, q, lo);
-  if (lo != 0.0) h[hn++] = lo;
-  for (int i = 1; i < en; ++i) {
-    double t, tl, s, r;
-    two_prod(e[i], b, t, tl);
-    two_sum(q, tl, s, r);
-    if (r != 0.0) h[hn++] = r;
-    two_sum(t, s, q, r);
-    if (r != 0.0) h[hn++] = r;
-  }
-  if (q != 0.0 || hn == 0) h[hn++] = q;
-  return hn;
-}
-
-template <int A, int B, int R>
-inline void ex_add(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
-  static_assert(R >= A + B, "capacity");
-  r.n = ex_sum(x.c, x.n, y.c, y.n, r.c);
-}
-template <int A, int B, int R>
-inline void ex_sub(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
-  static_assert(R >= A + B, "capacity");
-  Ex<B> m;
-  for (int i = 0; i < y.n; ++i) m.c[i] = -y.c[i];
-  r.n = ex_sum(x.c, x.n, m.c, y.n, r.c);
-}
-// r = x * y: the partial products x * y_i are added up one by one
-template <int A, int B, int R>
-inline void ex_mul(const Ex<A>& x, const Ex<B>& y, Ex<R>& r) {
-  static_assert(R >= 2 * A * B, "capacity");
-  Ex<R> acc;
-  Ex<2 * A> part;
-  r.n = ex_scale(x.c, x.n, y.c[0], r.c);
-  for (int i = 1; i < y.n; ++i) {
-    part.n = ex_scale(x.c, x.n, y.c[i], part.c);
-    acc.n = ex_sum(r.c, r.n, part.c, part.n, acc.c);
-    for (int k = 0; k < acc.n; ++k) r.c[k] = acc.c[k];
-    r.n = acc.n;
-  }
-}
-template <int CAP>
-inline double ex_sign(const Ex<CAP>& x) {
-  return x.c[x.n - 1];  // the most significant component carries the sign
-}
-// a - b, exactly
-inline Ex<2> ex_diff(double a, double b) {
-  Ex<2> r;
-  double hi, lo;
-  two_diff(a, b, hi, lo);
-  r.n = 0;
-  if (lo != 0.0) r.c[r.n++] = lo;
-  if (hi != 0.0 || r.n == 0) r.c[r.n++] = hi;
-  return r;
-}
+using namespace dmx;
 
 constexpr double EPS = 1.1102230246251565e-16;  // 2^-53
 constexpr double CCW_BOUND = (3.0 + 16.0 * EPS) * EPS;

@@ -4,10 +4,12 @@
 The reference wraps CGAL's ``Delaunay_triangulation_2/3`` (generation/cpp/delaunay_class*.cpp) and
 renumbers the vertices on every call; here the triangulator sits behind one small interface that
 keeps the input vertex order, so device-resident coordinates never have to be permuted or
-re-uploaded.  CGAL is not installed in this image.  In 2-D the backend is our own exact sweep-hull
-triangulator on raw buffers (``libdistmesh_host.so``, include/distmesh_host.h: ~9x faster than Qhull);
-in 3-D it is Qhull through ``scipy.spatial.Delaunay``.  Any correct Delaunay code returns the same
-cell set for points in general position; tie-breaking on co-circular points differs, see DESIGN.md.
+re-uploaded.  CGAL is not installed in this image.  The backends are our own exact triangulators on
+raw buffers (``libdistmesh_host.so``, include/distmesh_host.h): sweep-hull in 2-D (~10x faster than
+Qhull), incremental Bowyer-Watson in 3-D (~5x); Qhull through ``scipy.spatial.Delaunay`` stays
+available (``triangulator="qhull"``) and takes over a call the native code reports as not clean.  Any
+correct Delaunay code returns the same cell set for points in general position; tie-breaking on
+co-circular / co-spherical points differs, see DESIGN.md.
 """
 import ctypes as C
 
@@ -62,13 +64,53 @@ class SweepHullTriangulator:
         return np.ascontiguousarray(cells[: T.value])
 
 
+class BowyerWatsonTriangulator:
+    """3-D Delaunay by ``dmh_delaunay3d`` (exact predicates, vertex ids = input rows)."""
+
+    name = "bowyer-watson (libdistmesh_host)"
+
+    def __init__(self, dim):
+        if dim != 3:
+            raise ValueError("BowyerWatsonTriangulator is 3-D; the 2-D native triangulator is SweepHullTriangulator")
+        from ._hostlib import lib
+
+        self.dim = dim
+        self._lib = lib()
+        self.qhull_retries = 0
+
+    def triangulate(self, points):
+        """points (N,3) float64 host array -> cells (T,4) int32, positively oriented, ids = input rows."""
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise ValueError("points must be (N, 3)")
+        n = len(p)
+        cap = self._lib.dmh_delaunay3d_max_cells(n)
+        T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        for _ in range(2):
+            cells = np.empty((cap, 4), dtype=np.int32)
+            rc = self._lib.dmh_delaunay3d(p.ctypes.data, n, cells.ctypes.data, cap, C.byref(T), C.byref(dups), C.byref(lost))
+            if rc != -2:  # DMH_ERR_CAPACITY: *T_out holds the size that is needed
+                break
+            cap = T.value
+        if rc != 0:
+            raise RuntimeError(f"dmh_delaunay3d failed with code {rc}")
+        if lost.value and n >= 4:
+            # not a clean triangulation of every distinct row (input without four affinely independent
+            # points, or a failed internal check): hand this input to Qhull, which raises on the former
+            self.qhull_retries += 1
+            return QhullTriangulator(3).triangulate(p)
+        return np.ascontiguousarray(cells[: T.value])
+
+
 def get_triangulator(spec, dim):
-    if spec is None:
-        return SweepHullTriangulator(dim) if dim == 2 else QhullTriangulator(dim)
+    if spec is None or spec == "native":
+        return SweepHullTriangulator(dim) if dim == 2 else BowyerWatsonTriangulator(dim)
     if spec == "qhull":
         return QhullTriangulator(dim)
-    if spec in ("native", "sweephull"):
+    if spec == "sweephull":
         return SweepHullTriangulator(dim)
+    if spec == "bowyer-watson":
+        return BowyerWatsonTriangulator(dim)
     if hasattr(spec, "triangulate"):
         return spec
     raise ValueError(f"unknown triangulator {spec!r}")

@@ -24,9 +24,10 @@ def hl():
 
     from seismicmesh_b200 import _hostlib
 
-    src = os.path.join(ROOT, "seismicmesh_b200", "csrc", "host", "dm_delaunay2d.cpp")
-    if not os.path.exists(_hostlib.LIB_PATH) or os.path.getmtime(_hostlib.LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["bash", os.path.join(os.path.dirname(src), "build.sh")])
+    host = os.path.join(ROOT, "seismicmesh_b200", "csrc", "host")
+    newest = max(os.path.getmtime(os.path.join(host, f)) for f in os.listdir(host))
+    if not os.path.exists(_hostlib.LIB_PATH) or os.path.getmtime(_hostlib.LIB_PATH) < newest:
+        subprocess.check_call(["bash", os.path.join(host, "build.sh")])
 
     return _hostlib.lib()
 
@@ -217,10 +218,16 @@ def test_get_triangulator_defaults():
     from seismicmesh_b200.triangulator import QhullTriangulator, SweepHullTriangulator, get_triangulator
 
     assert isinstance(get_triangulator(None, 2), SweepHullTriangulator)
-    assert isinstance(get_triangulator(None, 3), QhullTriangulator)
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    assert isinstance(get_triangulator(None, 3), BowyerWatsonTriangulator)
     assert isinstance(get_triangulator("qhull", 2), QhullTriangulator)
+    assert isinstance(get_triangulator("qhull", 3), QhullTriangulator)
     assert isinstance(get_triangulator("native", 2), SweepHullTriangulator)
+    assert isinstance(get_triangulator("native", 3), BowyerWatsonTriangulator)
     with pytest.raises(ValueError):
-        get_triangulator("native", 3)
+        get_triangulator("sweephull", 3)
+    with pytest.raises(ValueError):
+        get_triangulator("bowyer-watson", 2)
     with pytest.raises(ValueError):
         get_triangulator("cgal", 2)

@@ -1,0 +1,195 @@
+"""Host 3-D Delaunay triangulator (dmh_delaunay3d in libdistmesh_host.so) -- the retriangulation step
+north_star keeps on the host (reference: CGAL behind generation/cpp/delaunay_class3.cpp).
+
+Checked on the CPU: exact predicates against rational arithmetic, the cell set against Qhull on points
+in general position (random and DistMesh iterates), and orientation / partition / empty-circumsphere
+properties on the degenerate inputs DistMesh produces (cubic and the reference's staggered lattice,
+vertices on a sphere and on the faces of a cube, duplicates, coplanar input)."""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from test_host_delaunay import hl  # noqa: F401  (fixture: builds / loads libdistmesh_host.so)
+
+
+@pytest.fixture(scope="module")
+def tri(hl):  # noqa: F811
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    return BowyerWatsonTriangulator(3)
+
+
+def _canon(t):
+    t = np.sort(np.asarray(t, dtype=np.int64), axis=1)
+    return t[np.lexsort(t.T[::-1])]
+
+
+def _sgn(x):
+    return (x > 0) - (x < 0)
+
+
+def _det(m):
+    if len(m) == 1:
+        return m[0][0]
+    return sum((-1) ** j * m[0][j] * _det([r[:j] + r[j + 1:] for r in m[1:]]) for j in range(len(m)))
+
+
+def _ptrs(*pts):
+    keep = [np.ascontiguousarray(x, dtype=np.float64) for x in pts]
+    return keep, [x.ctypes.data for x in keep]
+
+
+def _check_triangulation(hl, p, t, n_used=None):  # noqa: F811
+    """positively oriented, non-degenerate, manifold, fills the convex hull, empty circumspheres."""
+    from scipy.spatial import ConvexHull
+
+    a = p[t]
+    vol = np.einsum("ij,ij->i", np.cross(a[:, 1] - a[:, 0], a[:, 2] - a[:, 0]), a[:, 3] - a[:, 0]) / 6
+    # every cell is positively oriented by the EXACT predicate (a sliver of four nearly coplanar hull
+    # vertices may have a volume of 1e-19 that rounds to anything in floating point)
+    for tt in t:
+        keep, q = _ptrs(*p[tt])
+        assert hl.dmh_orient3d(*q) > 0
+    assert (np.sign(vol[np.abs(vol) > 1e-15 * np.abs(vol).max()]) == np.sign(vol[np.argmax(np.abs(vol))])).all()
+    hull = ConvexHull(p).volume
+    assert abs(abs(vol.sum()) - hull) <= 1e-9 * hull
+    assert np.unique(t).size == (len(p) if n_used is None else n_used)
+    faces = {}
+    for ti, tt in enumerate(t.tolist()):
+        for k in range(4):
+            faces.setdefault(tuple(sorted(tt[:k] + tt[k + 1:])), []).append((ti, tt[k]))
+    for lst in faces.values():
+        assert len(lst) <= 2
+        if len(lst) == 2:
+            (t1, _), (_, w2) = lst
+            keep, q = _ptrs(*[p[x] for x in t[t1]], p[w2])
+            assert hl.dmh_insphere(*q) <= 0  # the opposite vertex is not strictly inside
+
+
+def test_predicates_are_exact(hl):  # noqa: F811
+    rng = np.random.default_rng(1)
+
+    def o3(a, b, c, d):
+        q = [[Fraction(float(v)) for v in x] for x in (a, b, c, d)]
+        return _sgn(_det([[q[i][k] - q[3][k] for k in range(3)] for i in range(3)]))
+
+    def isph(a, b, c, d, e):
+        q = [[Fraction(float(v)) for v in x] for x in (a, b, c, d, e)]
+        rows = []
+        for i in range(4):
+            r = [q[i][k] - q[4][k] for k in range(3)]
+            rows.append(r + [sum(v * v for v in r)])
+        return _sgn(_det(rows))
+
+    # convention: for a positively oriented tetrahedron the centroid is inside (insphere > 0)
+    tet = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    keep, q = _ptrs(*tet)
+    if hl.dmh_orient3d(*q) < 0:
+        tet = tet[[1, 0, 2, 3]]
+    keep, q = _ptrs(*tet, tet.mean(0))
+    assert hl.dmh_orient3d(*q[:4]) > 0 and hl.dmh_insphere(*q) > 0
+    zeros = 0
+    for trial in range(800):
+        kind = trial % 4
+        if kind == 0:
+            pts = rng.random((5, 3))
+        elif kind == 1:  # lattice points far from the origin: exact ties
+            pts = rng.integers(0, 4, (5, 3)).astype(float) * 0.25 + rng.integers(0, 2) * 100
+        elif kind == 2:  # on a sphere up to rounding
+            v = rng.normal(size=(5, 3))
+            pts = rng.random(3) + 0.5 * v / np.linalg.norm(v, axis=1)[:, None]
+        else:  # four points in a plane up to rounding
+            o, u, w = rng.random(3), rng.random(3), rng.random(3)
+            pts = np.array([o + s * u + t * w for s, t in rng.random((5, 2))])
+            pts[4] = rng.random(3)
+        keep, q = _ptrs(*pts)
+        e1, e2 = o3(*pts[:4]), isph(*pts)
+        assert _sgn(hl.dmh_orient3d(*q[:4])) == e1
+        assert _sgn(hl.dmh_insphere(*q)) == e2  # the same determinant: its sign means 'inside' when e1 > 0
+        zeros += (e1 == 0) + (e2 == 0)
+    assert zeros > 40
+
+
+@pytest.mark.parametrize("n,seed", [(4, 0), (5, 1), (20, 2), (200, 3), (5000, 4), (40000, 5)])
+def test_same_cells_as_qhull_in_general_position(tri, n, seed):
+    from scipy.spatial import Delaunay
+
+    p = np.random.default_rng(seed).random((n, 3)) * [3.0, 1.0, 0.5] - [1.0, 0.5, 0.0]
+    t = tri.triangulate(p)
+    assert t.dtype == np.int32 and t.flags.c_contiguous and t.shape[1] == 4
+    assert np.array_equal(_canon(t), _canon(Delaunay(p).simplices))
+    assert tri.qhull_retries == 0
+
+
+def test_distmesh_iterates(hl, tri):  # noqa: F811
+    """Ball, h0 = 0.15, oracle force iterations.  From the reference's own initial points the interior
+    stays a lattice (balanced forces), i.e. co-spherical: the triangulation must be a valid Delaunay
+    one (ties may be broken differently from Qhull).  From jittered initial points everything is in
+    general position and the cells must EQUAL Qhull's, iteration after iteration."""
+    from scipy.spatial import Delaunay
+
+    from oracle import distmesh_oracle as orc
+
+    h0 = 0.15
+    spec = ("ball", {"x0": [0.0, 0.0, 0.0], "r": 1.0})
+    fd = lambda x: orc.sdf(spec, x)  # noqa: E731
+    fh = lambda x: np.full(len(x), h0)  # noqa: E731
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(float).eps) * h0
+    p0 = orc.initial_points(h0, geps, 3, np.array([[-1.0, 1.0]] * 3), fh, fd, np.empty((0, 3)))
+    p = p0.copy()
+    for it in range(3):
+        t = tri.triangulate(p)
+        _check_triangulation(hl, p, t)
+        p = orc.force_iteration(p, t, [fd], fh, h0, geps, deps)["p"]
+    p = p0 + np.random.default_rng(0).uniform(-0.1 * h0, 0.1 * h0, p0.shape)
+    for it in range(4):
+        t = tri.triangulate(p)
+        assert np.array_equal(_canon(t), _canon(Delaunay(p).simplices))
+        p = orc.force_iteration(p, t, [fd], fh, h0, geps, deps)["p"]
+    assert tri.qhull_retries == 0
+
+
+def test_degenerate_inputs(hl, tri):  # noqa: F811
+    rng = np.random.default_rng(7)
+    g = np.stack(np.meshgrid(np.arange(7.0), np.arange(8.0), np.arange(9.0), indexing="ij"), -1).reshape(-1, 3) * 0.1
+    t = tri.triangulate(g)  # cubic lattice: every cube is co-spherical
+    assert len(t) >= 5 * 6 * 7 * 8
+    _check_triangulation(hl, g, t)
+    from seismicmesh_b200.generation import _staggered_grid
+
+    s = np.ascontiguousarray(_staggered_grid(0.25, 3, np.array([[-1.0, 1.0]] * 3)))  # generation/utils.py:15-25
+    _check_triangulation(hl, s, tri.triangulate(s))
+    b = rng.normal(size=(1500, 3))  # ball: vertices exactly on the sphere (up to rounding) + interior
+    b /= np.linalg.norm(b, axis=1)[:, None]
+    b[:900] *= rng.random((900, 1)) ** (1 / 3)
+    _check_triangulation(hl, b, tri.triangulate(b))
+    c = rng.random((1500, 3))  # cube: vertices exactly on the faces
+    for k in range(3):
+        c[100 * (2 * k): 100 * (2 * k + 1), k] = 0.0
+        c[100 * (2 * k + 1): 100 * (2 * k + 2), k] = 1.0
+    _check_triangulation(hl, c, tri.triangulate(c))
+    d = rng.random((300, 3))  # exact duplicates: one copy of each is in the cells
+    d2 = np.r_[d, d[:25]]
+    t = tri.triangulate(d2)
+    t = np.where(t >= 300, t - 300, t)
+    _check_triangulation(hl, d, t)
+    assert tri.qhull_retries == 0
+
+
+def test_degenerate_and_error_paths(hl):  # noqa: F811
+    T, dups, lost = C.c_int64(), C.c_int64(), C.c_int64()
+    out = np.empty((64, 4), np.int32)
+    flat = np.ascontiguousarray(np.c_[np.random.default_rng(0).random((30, 2)), np.zeros(30)])
+    assert hl.dmh_delaunay3d(flat.ctypes.data, 30, out.ctypes.data, 64, C.byref(T), C.byref(dups), C.byref(lost)) == 0
+    assert (T.value, lost.value) == (0, 30)  # coplanar input: no cell, every row reported
+    assert hl.dmh_delaunay3d(flat.ctypes.data, 3, out.ctypes.data, 64, C.byref(T), None, None) == 0 and T.value == 0
+    p = np.random.default_rng(1).random((100, 3))
+    assert hl.dmh_delaunay3d(p.ctypes.data, 100, out.ctypes.data, 64, C.byref(T), None, None) == -2
+    assert T.value > 64  # the size that is needed
+    assert hl.dmh_delaunay3d(p.ctypes.data, 100, None, 64, C.byref(T), None, None) == -1
+    bad = p.copy()
+    bad[5, 1] = np.nan
+    big = np.empty((hl.dmh_delaunay3d_max_cells(100), 4), np.int32)
+    assert hl.dmh_delaunay3d(bad.ctypes.data, 100, big.ctypes.data, len(big), C.byref(T), None, None) == -1
