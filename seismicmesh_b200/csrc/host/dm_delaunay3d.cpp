@@ -38,7 +38,63 @@ constexpr double ISP_BOUND = (16.0 + 224.0 * EPS) * EPS;
 
 inline XV xd(double a, double b) { return XV(ex_diff(a, b)); }
 
+// ---- tie path for exactly representable differences (the common case: nearby points whose
+//      coordinate differences need no tail): everything on the stack, sizes known at compile time
+inline Ex<2> prod2(double a, double b) {
+  Ex<2> r;
+  double hi, lo;
+  two_prod(a, b, hi, lo);
+  r.n = 0;
+  if (lo != 0.0) r.c[r.n++] = lo;
+  if (hi != 0.0 || r.n == 0) r.c[r.n++] = hi;
+  return r;
+}
+template <int A>
+inline Ex<2 * A> scaled(const Ex<A>& x, double b) {
+  Ex<2 * A> r;
+  r.n = ex_scale(x.c, x.n, b, r.c);
+  return r;
+}
+// u*v - w*z
+inline Ex<4> cross2(double u, double v, double w, double z) {
+  Ex<4> r;
+  ex_sub(prod2(u, v), prod2(w, z), r);
+  return r;
+}
+// x*p + s*y*q + z*r with s = +-1 (the 3 x 3 minors)
+inline Ex<24> minor3(double x, const Ex<4>& p, double sy, const Ex<4>& q, double z, const Ex<4>& r) {
+  Ex<16> t;
+  ex_add(scaled(p, x), scaled(q, sy), t);
+  Ex<24> out;
+  ex_add(t, scaled(r, z), out);
+  return out;
+}
+inline Ex<6> lift3(double x, double y, double z) {
+  Ex<4> t;
+  ex_add(prod2(x, x), prod2(y, y), t);
+  Ex<6> out;
+  ex_add(t, prod2(z, z), out);
+  return out;
+}
+
+inline bool exact_diff(double a, double b, double& d) {
+  double lo;
+  two_diff(a, b, d, lo);
+  return lo == 0.0;
+}
+
 double orient3d_exact(const double* a, const double* b, const double* c, const double* d) {
+  {
+    double v[9];
+    bool ok = true;
+    for (int k = 0; k < 3; ++k)
+      ok = ok & exact_diff(a[k], d[k], v[k]) & exact_diff(b[k], d[k], v[3 + k]) & exact_diff(c[k], d[k], v[6 + k]);
+    if (ok) {
+      const double adx = v[0], ady = v[1], adz = v[2], bdx = v[3], bdy = v[4], bdz = v[5], cdx = v[6], cdy = v[7], cdz = v[8];
+      const Ex<24> det = minor3(adz, cross2(bdx, cdy, cdx, bdy), bdz, cross2(cdx, ady, adx, cdy), cdz, cross2(adx, bdy, bdx, ady));
+      return ex_sign(det);
+    }
+  }
   const XV adx = xd(a[0], d[0]), ady = xd(a[1], d[1]), adz = xd(a[2], d[2]);
   const XV bdx = xd(b[0], d[0]), bdy = xd(b[1], d[1]), bdz = xd(b[2], d[2]);
   const XV cdx = xd(c[0], d[0]), cdy = xd(c[1], d[1]), cdz = xd(c[2], d[2]);
@@ -66,6 +122,32 @@ inline double orient3d(const double* a, const double* b, const double* c, const 
 }
 
 double insphere_exact(const double* a, const double* b, const double* c, const double* d, const double* e) {
+  {
+    double v[12];
+    bool ok = true;
+    for (int k = 0; k < 3; ++k)
+      ok = ok & exact_diff(a[k], e[k], v[k]) & exact_diff(b[k], e[k], v[3 + k]) & exact_diff(c[k], e[k], v[6 + k]) &
+           exact_diff(d[k], e[k], v[9 + k]);
+    if (ok) {
+      const double aex = v[0], aey = v[1], aez = v[2], bex = v[3], bey = v[4], bez = v[5];
+      const double cex = v[6], cey = v[7], cez = v[8], dex = v[9], dey = v[10], dez = v[11];
+      const Ex<4> ab = cross2(aex, bey, bex, aey), bc = cross2(bex, cey, cex, bey), cd = cross2(cex, dey, dex, cey);
+      const Ex<4> da = cross2(dex, aey, aex, dey), ac = cross2(aex, cey, cex, aey), bd = cross2(bex, dey, dex, bey);
+      const Ex<24> abc = minor3(aez, bc, -bez, ac, cez, ab), bcd = minor3(bez, cd, -cez, bd, dez, bc);
+      const Ex<24> cda = minor3(cez, da, dez, ac, aez, cd), dab = minor3(dez, ab, aez, bd, bez, da);
+      static thread_local Ex<288> t1, t2, t3, t4;
+      static thread_local Ex<576> s1, s2;
+      static thread_local Ex<1152> det;
+      ex_mul(abc, lift3(dex, dey, dez), t1);
+      ex_mul(dab, lift3(cex, cey, cez), t2);
+      ex_mul(cda, lift3(bex, bey, bez), t3);
+      ex_mul(bcd, lift3(aex, aey, aez), t4);
+      ex_sub(t1, t2, s1);
+      ex_sub(t3, t4, s2);
+      ex_add(s1, s2, det);
+      return ex_sign(det);
+    }
+  }
   const XV aex = xd(a[0], e[0]), aey = xd(a[1], e[1]), aez = xd(a[2], e[2]);
   const XV bex = xd(b[0], e[0]), bey = xd(b[1], e[1]), bez = xd(b[2], e[2]);
   const XV cex = xd(c[0], e[0]), cey = xd(c[1], e[1]), cez = xd(c[2], e[2]);
