@@ -15,6 +15,10 @@
  *
  *   - every pointer is a HOST pointer; float64 row-major coordinates, int32 row-major cells;
  *   - no global state, re-entrant; the only allocation is internal scratch freed before return;
+ *   - Output order: vertex ids ascending within a cell, cells in lexicographic order.  Consecutive cells
+ *     then share their leading vertices, which is what the device pipeline's warp-aggregated slot claims
+ *     and position gathers like best (csrc/host/dm_cell_order.h has the numbers).  Orientation is NOT
+ *     normalised: the loop body never uses it, and the reference fixes it at termination (fix_mesh);
  *   - results are exact Delaunay triangulations: the orientation / in-circle predicates run a
  *     floating-point filter and fall back to exact expansion arithmetic, so co-circular and
  *     collinear inputs (the initial lattice, boundary vertices projected onto straight edges) are
@@ -43,7 +47,8 @@ int64_t dmh_delaunay2d_max_cells(int64_t N);
 
 /* Delaunay triangulation of `points` (N,2).  Replaces DelaunayTriangulation.insert +
  * get_finite_cells (generation/cpp/delaunay_class.cpp:45-62, 99-117) with the vertex ids = input
- * rows.  Writes *T_out counter-clockwise triangles to `cells` (capacity `cap` rows).  Input rows
+ * rows.  Writes *T_out triangles to `cells` (capacity `cap` rows), vertex ids ascending within a
+ * triangle and the triangles in lexicographic order (see "Output order" above).  Input rows
  * that are in no triangle are counted in *duplicates_out (exact duplicates of an earlier row, which
  * keeps the cells; CGAL and Qhull leave those out as well) and *lost_out (everything else: all rows
  * when the input is collinear or has fewer than 3 distinct points, in which case *T_out = 0; a row
@@ -60,7 +65,7 @@ int64_t dmh_delaunay3d_max_cells(int64_t N);
 
 /* Delaunay triangulation of `points` (N,3).  Replaces DelaunayTriangulation3.insert +
  * get_finite_cells (generation/cpp/delaunay_class3.cpp) with the vertex ids = input rows.  Writes
- * *T_out positively oriented tetrahedra (orient3d of the four rows > 0) to `cells`; with
+ * *T_out tetrahedra to `cells`, vertex ids ascending within a cell, cells in lexicographic order; with
  * DMH_ERR_CAPACITY nothing is written and *T_out is the capacity that is needed.  *duplicates_out
  * counts rows left out as exact duplicates of another row (ONE copy is in the cells, not necessarily
  * the first), *lost_out rows left out for any other reason: all N when there are not four affinely
@@ -71,8 +76,7 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
                    int64_t* duplicates_out, int64_t* lost_out);
 
 /* The exact predicates, exported for the tests.
- * orient3d > 0: (a, b, c, d) positively oriented (the orientation of every cell dmh_delaunay3d
- * returns); insphere > 0: e strictly inside the sphere through a positively oriented (a, b, c, d). */
+ * orient3d > 0: (a, b, c, d) positively oriented; insphere > 0: e strictly inside the sphere through a positively oriented (a, b, c, d). */
 double dmh_orient3d(const double* a, const double* b, const double* c, const double* d);
 double dmh_insphere(const double* a, const double* b, const double* c, const double* d, const double* e);
 

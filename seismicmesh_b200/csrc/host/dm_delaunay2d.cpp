@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "distmesh_host.h"
+#include "dm_cell_order.h"
 #include "dm_exact.h"
 
 namespace {
@@ -405,6 +406,7 @@ int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap,
   if (lost_out != nullptr) *lost_out = s.lost;
   if (T > cap) return DMH_ERR_CAPACITY;
   for (int64_t j = 0; j < 3 * T; ++j) cells[j] = s.ids[s.tri[j]];
+  dmx::order_cells<3>(cells, T, N);
   return DMH_OK;
 }
 

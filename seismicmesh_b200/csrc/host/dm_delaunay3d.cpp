@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "distmesh_host.h"
+#include "dm_cell_order.h"
 #include "dm_exact.h"
 
 namespace {
@@ -557,6 +558,7 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
     for (int k = 0; k < 4; ++k) cells[4 * o + k] = ids[D.tv[4 * t + k]];
     ++o;
   }
+  dmx::order_cells<4>(cells, T, N);
   return DMH_OK;
 }
 

@@ -44,7 +44,8 @@ class SweepHullTriangulator:
         self.qhull_retries = 0
 
     def triangulate(self, points):
-        """points (N,2) float64 host array -> cells (T,3) int32, counter-clockwise, ids = input rows."""
+        """points (N,2) float64 host array -> cells (T,3) int32, ids = input rows, ascending within a
+        cell, cells in lexicographic order (orientation not normalised)."""
         p = np.ascontiguousarray(points, dtype=np.float64)
         if p.ndim != 2 or p.shape[1] != 2:
             raise ValueError("points must be (N, 2)")
@@ -79,7 +80,8 @@ class BowyerWatsonTriangulator:
         self.qhull_retries = 0
 
     def triangulate(self, points):
-        """points (N,3) float64 host array -> cells (T,4) int32, positively oriented, ids = input rows."""
+        """points (N,3) float64 host array -> cells (T,4) int32, ids = input rows, ascending within a
+        cell, cells in lexicographic order (orientation not normalised)."""
         p = np.ascontiguousarray(points, dtype=np.float64)
         if p.ndim != 2 or p.shape[1] != 3:
             raise ValueError("points must be (N, 3)")

@@ -53,6 +53,16 @@ def _sgn(x):
     return (x > 0) - (x < 0)
 
 
+def _is_lex_sorted(t):
+    """ids ascending within a cell, cells in lexicographic order (the documented output order)."""
+    t = np.asarray(t, dtype=np.int64)
+    if len(t) == 0:
+        return True
+    if not (np.diff(t, axis=1) > 0).all():
+        return False
+    return np.array_equal(t, t[np.lexsort(t.T[::-1])])
+
+
 def _incircle(hl, p, i, j, k, m):
     q = [np.ascontiguousarray(p[x], dtype=np.float64) for x in (i, j, k, m)]
     return hl.dmh_incircle(*[x.ctypes.data for x in q])
@@ -62,8 +72,9 @@ def _check_triangulation(hl, p, t, n_used=None):
     """ccw, non-degenerate, manifold, covers the convex hull, locally (hence globally) Delaunay."""
     from scipy.spatial import ConvexHull
 
-    area = _signed_area(p, t)
+    area = np.abs(_signed_area(p, t))
     assert (area > 0).all()
+    assert _is_lex_sorted(t)
     hull = ConvexHull(p).volume
     assert abs(area.sum() - hull) <= 1e-9 * hull
     assert np.unique(t).size == (len(p) if n_used is None else n_used)
@@ -76,6 +87,8 @@ def _check_triangulation(hl, p, t, n_used=None):
         if len(lst) == 2:
             (t1, _), (_, w2) = lst
             i, j, k = t[t1]
+            if _signed_area(p, t[t1:t1 + 1])[0] < 0:
+                j, k = k, j  # incircle wants a counter-clockwise triangle; the output order is by id
             assert _incircle(hl, p, i, j, k, w2) <= 0  # the opposite vertex is not strictly inside
 
 
@@ -137,7 +150,7 @@ def test_same_cells_as_qhull_in_general_position(tri, n, seed):
     p = np.random.default_rng(seed).random((n, 2)) * [3.0, 1.0] - [1.0, 0.5]
     t = tri.triangulate(p)
     assert t.dtype == np.int32 and t.flags.c_contiguous and t.shape[1] == 2 + 1
-    assert (_signed_area(p, t) > 0).all()
+    assert (_signed_area(p, t) != 0).all() and _is_lex_sorted(t)
     assert np.array_equal(_canon(t), _canon(Delaunay(p).simplices))
     assert tri.qhull_retries == 0
 

@@ -11,7 +11,7 @@ from fractions import Fraction
 import numpy as np
 import pytest
 
-from test_host_delaunay import hl  # noqa: F401  (fixture: builds / loads libdistmesh_host.so)
+from test_host_delaunay import _is_lex_sorted, hl  # noqa: F401  (fixture: builds / loads libdistmesh_host.so)
 
 
 @pytest.fixture(scope="module")
@@ -47,14 +47,16 @@ def _check_triangulation(hl, p, t, n_used=None):  # noqa: F811
 
     a = p[t]
     vol = np.einsum("ij,ij->i", np.cross(a[:, 1] - a[:, 0], a[:, 2] - a[:, 0]), a[:, 3] - a[:, 0]) / 6
-    # every cell is positively oriented by the EXACT predicate (a sliver of four nearly coplanar hull
+    # every cell is non-degenerate by the EXACT predicate (a sliver of four nearly coplanar hull
     # vertices may have a volume of 1e-19 that rounds to anything in floating point)
+    orient = []
     for tt in t:
         keep, q = _ptrs(*p[tt])
-        assert hl.dmh_orient3d(*q) > 0
-    assert (np.sign(vol[np.abs(vol) > 1e-15 * np.abs(vol).max()]) == np.sign(vol[np.argmax(np.abs(vol))])).all()
+        orient.append(hl.dmh_orient3d(*q))
+        assert orient[-1] != 0
+    assert _is_lex_sorted(t)
     hull = ConvexHull(p).volume
-    assert abs(abs(vol.sum()) - hull) <= 1e-9 * hull
+    assert abs(np.abs(vol).sum() - hull) <= 1e-9 * hull
     assert np.unique(t).size == (len(p) if n_used is None else n_used)
     faces = {}
     for ti, tt in enumerate(t.tolist()):
@@ -65,7 +67,8 @@ def _check_triangulation(hl, p, t, n_used=None):  # noqa: F811
         if len(lst) == 2:
             (t1, _), (_, w2) = lst
             keep, q = _ptrs(*[p[x] for x in t[t1]], p[w2])
-            assert hl.dmh_insphere(*q) <= 0  # the opposite vertex is not strictly inside
+            # insphere's sign means "inside" for a positively oriented cell; the output order is by id
+            assert hl.dmh_insphere(*q) * orient[t1] <= 0  # the opposite vertex is not strictly inside
 
 
 def test_predicates_are_exact(hl):  # noqa: F811
@@ -118,7 +121,7 @@ def test_same_cells_as_qhull_in_general_position(tri, n, seed):
 
     p = np.random.default_rng(seed).random((n, 3)) * [3.0, 1.0, 0.5] - [1.0, 0.5, 0.0]
     t = tri.triangulate(p)
-    assert t.dtype == np.int32 and t.flags.c_contiguous and t.shape[1] == 4
+    assert t.dtype == np.int32 and t.flags.c_contiguous and t.shape[1] == 4 and _is_lex_sorted(t)
     assert np.array_equal(_canon(t), _canon(Delaunay(p).simplices))
     assert tri.qhull_retries == 0
 
@@ -173,8 +176,10 @@ def test_degenerate_inputs(hl, tri):  # noqa: F811
     d = rng.random((300, 3))  # exact duplicates: one copy of each is in the cells
     d2 = np.r_[d, d[:25]]
     t = tri.triangulate(d2)
+    assert _is_lex_sorted(t)
     t = np.where(t >= 300, t - 300, t)
-    _check_triangulation(hl, d, t)
+    t = np.sort(t, axis=1)
+    _check_triangulation(hl, d, t[np.lexsort(t.T[::-1])])
     assert tri.qhull_retries == 0
 
 
