@@ -201,6 +201,36 @@ def test_degenerate_inputs(hl, tri):
     assert tri.qhull_retries == 0
 
 
+def test_random_degenerate_stress_2d(hl, tri):
+    """Massively degenerate random inputs (tiny integer lattices full of duplicates, all points on a
+    circle, half of them on a line): every distinct point used, hull filled, no circumcircle contains
+    a vertex (exact predicates), without Qhull."""
+    rng = np.random.default_rng(321)
+    done = 0
+    for trial in range(120):
+        kind, n = trial % 4, int(rng.integers(3, 150))
+        if kind == 0:
+            p = rng.integers(0, 5, (n, 2)).astype(float)
+        elif kind == 1:
+            p = rng.integers(0, 9, (n, 2)).astype(float) * 0.1 - 3.0
+        elif kind == 2:
+            th = rng.random(n) * 6.283
+            p = np.c_[np.cos(th), np.sin(th)]
+        else:
+            p = rng.random((n, 2))
+            p[: n // 2, 1] = 0.25
+        p = np.ascontiguousarray(p)
+        t = tri.triangulate(p)
+        if len(t) == 0:
+            continue
+        _, first, inv = np.unique(p, axis=0, return_index=True, return_inverse=True)
+        tm = np.sort(first[np.asarray(inv).ravel()][t], axis=1)
+        tm = tm[np.lexsort(tm.T[::-1])].astype(np.int32)
+        _check_triangulation(hl, p, tm, n_used=len(np.unique(p, axis=0)))
+        done += 1
+    assert done >= 100 and tri.qhull_retries == 0
+
+
 def test_empty_collinear_and_coincident_inputs(hl, tri):
     assert tri.triangulate(np.zeros((0, 2))).shape == (0, 3)
     assert tri.triangulate(np.array([[0.0, 0.0], [1.0, 0.0]])).shape == (0, 3)

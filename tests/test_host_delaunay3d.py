@@ -198,3 +198,40 @@ def test_degenerate_and_error_paths(hl):  # noqa: F811
     bad[5, 1] = np.nan
     big = np.empty((hl.dmh_delaunay3d_max_cells(100), 4), np.int32)
     assert hl.dmh_delaunay3d(bad.ctypes.data, 100, big.ctypes.data, len(big), C.byref(T), None, None) == -1
+
+
+def _first_occurrence_cells(p, t):
+    """duplicate rows -> their first occurrence, ids ascending, cells lex-sorted"""
+    _, first, inv = np.unique(p, axis=0, return_index=True, return_inverse=True)
+    tm = np.sort(first[np.asarray(inv).ravel()][t], axis=1)
+    return tm[np.lexsort(tm.T[::-1])].astype(np.int32)
+
+
+def test_random_degenerate_stress_3d(hl, tri):  # noqa: F811
+    """Massively degenerate random inputs: tiny integer lattices full of duplicates, all points on a
+    sphere, half of them in a plane, a collinear bunch.  Every distinct point must be used, the cells
+    must fill the hull, and no circumball may contain a vertex (exact predicates), without Qhull."""
+    rng = np.random.default_rng(123)
+    done = 0
+    for trial in range(100):
+        kind, n = trial % 5, int(rng.integers(5, 100))
+        if kind == 0:
+            p = rng.integers(0, 4, (n, 3)).astype(float)
+        elif kind == 1:
+            p = rng.integers(0, 7, (n, 3)).astype(float) * 0.1 + 5.0
+        elif kind == 2:
+            v = rng.normal(size=(n, 3))
+            p = v / np.linalg.norm(v, axis=1)[:, None]
+        elif kind == 3:
+            p = rng.random((n, 3))
+            p[: n // 2, 2] = 0.5
+        else:
+            p = rng.random((n, 3))
+            p[: n // 3] = p[0] + np.outer(rng.random(n // 3), p[1] - p[0])
+        p = np.ascontiguousarray(p)
+        t = tri.triangulate(p)
+        if len(t) == 0:
+            continue  # no four affinely independent points: Qhull raised, the wrapper has no cells
+        _check_triangulation(hl, p, _first_occurrence_cells(p, t), n_used=len(np.unique(p, axis=0)))
+        done += 1
+    assert done >= 90 and tri.qhull_retries == 0
