@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define DMH_OK 0
-#define DMH_ERR_ARG (-1)      /* null pointer / negative size */
+#define DMH_ERR_ARG (-1)      /* null pointer / negative size / a coordinate that is not finite */
 #define DMH_ERR_CAPACITY (-2) /* `cells` too small (see dmh_delaunay2d_max_cells) */
 
 /* "distmesh_host <version>" */

@@ -396,6 +396,8 @@ int dmh_delaunay2d(const double* points, int64_t N, int32_t* cells, int64_t cap,
   if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
       N > (int64_t)std::numeric_limits<int32_t>::max() / 6)
     return DMH_ERR_ARG;
+  for (int64_t i = 0; i < 2 * N; ++i)
+    if (!(points[i] == points[i]) || std::fabs(points[i]) == std::numeric_limits<double>::infinity()) return DMH_ERR_ARG;
   SweepHull s;
   s.P = points;
   s.n = N;

@@ -247,6 +247,10 @@ def test_empty_collinear_and_coincident_inputs(hl, tri):
     assert T.value > 4  # the required size is reported
     assert hl.dmh_delaunay2d(p.ctypes.data, 50, None, 4, C.byref(T), None, None) == -1
     assert hl.dmh_delaunay2d(p.ctypes.data, -1, out.ctypes.data, 4, C.byref(T), None, None) == -1
+    bad = p.copy()
+    bad[3, 0] = np.inf
+    big0 = np.empty((hl.dmh_delaunay2d_max_cells(50), 3), np.int32)
+    assert hl.dmh_delaunay2d(bad.ctypes.data, 50, big0.ctypes.data, len(big0), C.byref(T), None, None) == -1
     # the two reasons a row can be left out are reported separately
     d = np.r_[p, p[:7]]
     big = np.empty((hl.dmh_delaunay2d_max_cells(57), 3), np.int32)
