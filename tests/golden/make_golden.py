@@ -24,6 +24,17 @@ Everything written here is produced by calling the *unmodified* reference functi
   e2e.json              : aggregate outcomes of full `generate_mesh` / `sliver_removal` runs
                           (vertex count, cell count, min/mean quality, area) with Qhull as
                           the triangulator.
+  segy_testing.npz,
+  segy_tests.json       : the velocity model of the reference's SEG-Y fixture (tests/testing.segy,
+                          decoded by the harness's segyio stand-in) and the outcome of the reference
+                          tests that mesh it, next to the answers those tests assert  [`segy`]
+  meshutil_{2d,3d}.npz  : geometry/utils.py at termination: simp_vol, simp_qual, boundary edges /
+                          facets / vertices / entities, fix_mesh, delete_boundary_entities,
+                          laplacian2_fixed_point  [`meshutil`]
+  reference_tests.json  : the reference's known-answer tests (2dmesher_SDF, immersion, smooth_sets,
+                          pfix, verbose) replayed, next to the answers they assert  [`reftests`]
+
+`python tests/golden/make_golden.py segy|meshutil|reftests` regenerates only those.
 """
 import json
 import os
