@@ -19,9 +19,19 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="ball")
 ap.add_argument("--h0", type=float, default=0.02)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--triangulator", default=None, choices=[None, "native", "qhull"],
+                help="whose cells (and cell ORDER: stage A is sensitive to it) to feed; default: the package's")
+ap.add_argument("--shuffle", action="store_true", help="feed the cells in random order (worst case for stage A)")
 a = ap.parse_args()
 p, dim = make_points(a.workload, a.h0)
-t, _ = triangulate(p)
+if a.triangulator is None:
+    t, _ = triangulate(p)
+else:
+    from seismicmesh_b200.triangulator import get_triangulator  # noqa: E402
+
+    t = get_triangulator(a.triangulator, dim).triangulate(p)
+if a.shuffle:
+    t = np.ascontiguousarray(t[np.random.default_rng(0).permutation(len(t))])
 dom = sm.Ball([0.0, 0.0, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 0.0], 1.0)
 loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=a.h0), a.h0, 0.1 * a.h0, 1e-8 * a.h0)
 pd, td = D.to_dev(p, torch.float64), D.to_dev(t, torch.int32)
@@ -39,4 +49,4 @@ for r in range(a.reps + 3):
     torch.cuda.synchronize()
     if r >= 3:
         ms.append(e0.elapsed_time(e1))
-print(f"stage A ({os.environ.get('DM_LIB_PATH', 'default')}): mean {np.mean(ms):.4f} ms  min {np.min(ms):.4f} ms")
+print(f"stage A ({os.environ.get('DM_LIB_PATH', 'default')}, cells: {a.triangulator or 'package default'}{', shuffled' if a.shuffle else ''}): mean {np.mean(ms):.4f} ms  min {np.min(ms):.4f} ms")
