@@ -59,10 +59,13 @@ def make_points(workload, h0, seed=0, shift=0.0):
     return np.ascontiguousarray(p), dim
 
 
+TRIANGULATOR = None  # --triangulator: None = the package default (native), "qhull", "native"
+
+
 def delaunay_backend(dim):
     from seismicmesh_b200.triangulator import get_triangulator
 
-    return get_triangulator(None, dim).name
+    return get_triangulator(TRIANGULATOR, dim).name
 
 
 def triangulate(p):
@@ -76,12 +79,12 @@ def triangulate(p):
     if cache:
         import hashlib
 
-        key = os.path.join(cache, "tri_" + hashlib.sha1(p.tobytes()).hexdigest()[:16] + ".npz")
+        key = os.path.join(cache, f"tri_{TRIANGULATOR or 'default'}_" + hashlib.sha1(p.tobytes()).hexdigest()[:16] + ".npz")
         if os.path.exists(key):
             z = np.load(key)
             return z["t"], float(z["dt"])
     t0 = time.perf_counter()
-    t = get_triangulator(None, p.shape[1]).triangulate(p)
+    t = get_triangulator(TRIANGULATOR, p.shape[1]).triangulate(p)
     dt = time.perf_counter() - t0
     if key:
         os.makedirs(cache, exist_ok=True)
@@ -346,11 +349,16 @@ def main():
     ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing / hmin (scale-up runs)")
     ap.add_argument("--freq", type=float, default=None, help="bp2004 / eage: override the sizing frequency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--triangulator", default=None, choices=["native", "qhull"],
+                    help="host Delaunay of the set-up (untimed); it also decides the ORDER of the cell list the device "
+                         "step is fed, which stage A is sensitive to.  Default: the package's (native)")
     ap.add_argument("--time-to-mesh", type=int, default=0, metavar="ITERS",
                     help="also run generate_mesh(max_iter=ITERS) end to end (host Delaunay included) and report "
                          "time-to-mesh, with the reference's retriangulate-every-iteration and with ttol=0.1")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
     args = ap.parse_args()
+    global TRIANGULATOR
+    TRIANGULATOR = args.triangulator
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
