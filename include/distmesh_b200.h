@@ -145,6 +145,14 @@ int dm_circumsphere_grad(const double *p, const int32_t *t, const int32_t *ele, 
 int dm_sliver_perturb(double *p, int64_t N, const int32_t *t, const int32_t *ele, int64_t S,
                       double step_h0, int32_t *winner, double *delta, void *stream);
 
+/* Column order of the tetrahedra handed to the sliver loop.  The reference moves "vertex 0 of every
+ * sliver" (mesh_generator.py:234,245-274) and takes whatever vertex order CGAL's cells have
+ * (generation/cpp/delaunay_class3.cpp get_finite_cells); here the triangulation stage decides it:
+ * key (N) = fd at the vertices; column 0 becomes, among the vertices with key < thresh (well inside
+ * the domain), the one picked by (sum of the cell's ids) mod (their count), and the vertex with the
+ * smallest key when there is none.  Even permutation of the columns, in place; t (T,4). */
+int dm_cells_lead_interior(const double *key, int32_t *t, int64_t T, double thresh, void *stream);
+
 /* 5 damped Newton steps onto the zero level set for the listed vertices (replaces
  * _improve_level_set_newton, mesh_generator.py:741-759).  p updated in place. */
 int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64_t nb, int dim,
@@ -223,9 +231,8 @@ int dm_stage_cull_chunk(const DmPlan *plan_host, const double *prog, const doubl
                         const int32_t *t_chunk, int64_t cell0, int64_t ncells, double geps,
                         int use_keep, void *stream);
 /* stage B: sorted unique neighbour rows (replaces _fast_geometry.unique_edges,
- * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs).  `t` and `use_keep` are unused since
- * stage A already scattered the kept cells (kept for call compatibility). */
-int dm_stage_build_adjacency(const DmPlan *plan_host, const int32_t *t, int use_keep, void *stream);
+ * fast_geometry.cpp:30-77, bit-exact: see dm_bars_pairs) from the kept cells stage A scattered. */
+int dm_stage_build_adjacency(const DmPlan *plan_host, void *stream);
 /* bar ids (rowptr) for dm_bars_pairs / dm_bar_midpoints / DM_SIZE_EXTERNAL. */
 int dm_stage_bar_index(const DmPlan *plan_host, void *stream);
 /* (E,2) int32 pairs in the reference's order (needs dm_stage_bar_index). */

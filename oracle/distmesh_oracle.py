@@ -564,3 +564,21 @@ def sizing_from_velocity(vp, bbox, hmin=150.0, hmax=10000.0, wl=0, freq=2.0, gra
         else:
             raise ValueError("pad style currently not supported. Try `linear_ramp`, `edge`, or `constant`")
     return cell, tuple(bbox)
+
+
+def cells_lead_interior(t, key, thresh):
+    """Column order of the tetrahedra handed to the sliver loop (restates dm_cells_lead_interior,
+    include/distmesh_b200.h; not a reference function: the reference moves `t[ele, 0]`,
+    mesh_generator.py:234,245-274, with whatever order CGAL's get_finite_cells has).  Column 0 becomes,
+    among the vertices with key < thresh, the one picked by (sum of the ids) mod (their count), and the
+    vertex with the smallest key when there is none; applied as an even permutation."""
+    t = np.asarray(t)
+    kk = np.asarray(key)[t]
+    ok = kk < thresh
+    cnt = ok.sum(axis=1)
+    pick = np.where(cnt > 0, t.astype(np.int64).sum(axis=1) % np.maximum(cnt, 1), 0)
+    cs = np.cumsum(ok, axis=1)
+    sel = np.argmax((cs == (pick[:, None] + 1)) & ok, axis=1)
+    sel = np.where(cnt > 0, sel, np.argmin(kk, axis=1))
+    even = np.array([[0, 1, 2, 3], [1, 2, 0, 3], [2, 0, 1, 3], [3, 1, 0, 2]])
+    return np.ascontiguousarray(np.take_along_axis(t, even[sel], axis=1))

@@ -5,7 +5,7 @@ Drop-in for that path only: ``generate_mesh``, ``sliver_removal``, the SDF primi
 combinators, and ``SizeFunction``.  Importing this package loads ``libdistmesh_b200.so``; there
 is no CPU fallback.
 """
-from . import geometry, sizing
+from . import decomp, geometry, migration, sizing
 from .generation import generate_mesh, last_run_stats, sliver_removal
 from .geometry import (
     Ball,
@@ -20,7 +20,7 @@ from .geometry import (
     Torus,
     Union,
 )
-from .sizing import GridInterpolant, SizeFunction, get_sizing_function_from_segy
+from .sizing import GridInterpolant, SizeFunction, get_sizing_function_from_segy, read_velocity_model
 
 __version__ = "0.1.0"
 
@@ -28,6 +28,9 @@ __all__ = [
     "__version__",
     "geometry",
     "sizing",
+    "decomp",
+    "migration",
+    "read_velocity_model",
     "Rectangle",
     "Cube",
     "Cylinder",

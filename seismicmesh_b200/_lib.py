@@ -84,6 +84,7 @@ _SIGNATURES = {
     "dm_sliver_flags": (_INT, [_P, _P, _P, _I64, _D, _D, _D, _P, _P, _P]),
     "dm_circumsphere_grad": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "dm_sliver_perturb": (_INT, [_P, _I64, _P, _P, _I64, _D, _P, _P, _P]),
+    "dm_cells_lead_interior": (_INT, [_P, _P, _I64, _D, _P]),
     "dm_level_set_newton": (_INT, [_P, _P, _P, _I64, _INT, _D, _P]),
     "dm_plan_bytes": (_SZ, [_I64, _I64, _INT]),
     "dm_plan_init": (_INT, [C.POINTER(DmPlan), _I64, _I64, _INT, _P, _SZ]),
@@ -94,7 +95,7 @@ _SIGNATURES = {
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _D, _D, _D, _D, _I64, _P, _P, _P],
     ),
     "dm_stage_cull_count": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _D, _INT, _P]),
-    "dm_stage_build_adjacency": (_INT, [C.POINTER(DmPlan), _P, _INT, _P]),
+    "dm_stage_build_adjacency": (_INT, [C.POINTER(DmPlan), _P]),
     "dm_stage_bar_index": (_INT, [C.POINTER(DmPlan), _P]),
     "dm_bars_pairs": (_INT, [C.POINTER(DmPlan), _P, _P]),
     "dm_bar_midpoints": (_INT, [C.POINTER(DmPlan), _P, _P, _P]),

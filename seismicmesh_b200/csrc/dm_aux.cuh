@@ -227,6 +227,50 @@ __global__ void sliver_apply_kernel(double* __restrict__ p, const int32_t* __res
   for (int k = 0; k < 3; ++k) p[3 * v0 + k] = p[3 * v0 + k] + delta[3 * i + k];
 }
 
+// Which vertex of a tetrahedron sits in column 0 decides which vertex the sliver perturbation moves
+// (mesh_generator.py:234,245-274: "vertex 0 of every sliver, last write wins"); the reference takes
+// whatever order CGAL hands out.  Our triangulation stage makes the choice explicit: among the
+// vertices that are well inside the domain (key = fd(p[v]) < thresh) one is picked by a hash of the
+// cell (so neighbouring slivers do not all move the same vertex), and when there is none the one with
+// the smallest key (the most interior).  Boundary vertices are therefore only moved when a cell has
+// nothing else to offer.  Applied as an EVEN permutation (orientation is preserved).
+__global__ void cells_lead_interior_kernel(const double* __restrict__ key, int32_t* __restrict__ t, int64_t T,
+                                           double thresh) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int4 q = *reinterpret_cast<const int4*>(t + 4 * c);
+  const int v[4] = {q.x, q.y, q.z, q.w};
+  double k[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) k[j] = key[v[j]];
+  int cnt = 0, amin = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    cnt += k[j] < thresh ? 1 : 0;
+    if (k[j] < k[amin]) amin = j;  // first minimum (np.argmin)
+  }
+  int sel = amin;
+  if (cnt > 0) {  // the pick-th interior column, pick = (sum of the ids) mod (number of interior columns)
+    const int pick = (int)(((int64_t)v[0] + v[1] + v[2] + v[3]) % cnt);
+    int seen = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = k[j] < thresh;
+      if (in && seen == pick) sel = j;
+      seen += in ? 1 : 0;
+    }
+  }
+  // even permutations that bring column `sel` to the front: (0 1 2 3), (1 2 0 3), (2 0 1 3), (3 1 0 2)
+  if (sel == 1)
+    q = make_int4(v[1], v[2], v[0], v[3]);
+  else if (sel == 2)
+    q = make_int4(v[2], v[0], v[1], v[3]);
+  else if (sel == 3)
+    q = make_int4(v[3], v[1], v[0], v[2]);
+  *reinterpret_cast<int4*>(t + 4 * c) = q;
+}
+
+
 // circumball of each cell vs the padded slab boxes of the rank below / above
 // (migration/cpp/cpputils.cpp:85-200, 247-383).  boxes: [min(dim), max(dim)] x 2.
 struct HaloBoxes {

@@ -379,6 +379,15 @@ int dm_sliver_perturb(double* p, int64_t N, const int32_t* t, const int32_t* ele
   return DM_OK;
 }
 
+int dm_cells_lead_interior(const double* key, int32_t* t, int64_t T, double thresh, void* stream) {
+  if (T < 0) return DM_ERR_ARG;
+  if (T == 0) return DM_OK;
+  if (!key || !t) return DM_ERR_ARG;
+  cells_lead_interior_kernel<<<nblk(T, 256), 256, 0, S(stream)>>>(key, t, T, thresh);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_level_set_newton(const double* prog, double* p, const int32_t* bid, int64_t nb, int dim, double deps,
                         void* stream) {
   if (!prog || nb < 0 || bad_dim(dim)) return DM_ERR_ARG;
@@ -458,9 +467,7 @@ int dm_stage_cull_count(const DmPlan* pl, const double* prog, const double* p, c
   return dm_stage_cull_chunk(pl, prog, p, t, 0, pl->T, geps, use_keep, stream);
 }
 
-int dm_stage_build_adjacency(const DmPlan* pl, const int32_t* t, int use_keep, void* stream) {
-  (void)t;
-  (void)use_keep;  // the kept cells were already scattered to the vertex buckets by stage A
+int dm_stage_build_adjacency(const DmPlan* pl, void* stream) {
   if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
   return pl->dim == 2 ? stage_adjacency<2>(pl, -1, nullptr, nullptr, st) : stage_adjacency<3>(pl, -1, nullptr, nullptr, st);

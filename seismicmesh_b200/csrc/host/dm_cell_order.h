@@ -1,12 +1,22 @@
-// Output order of the host triangulators: vertex ids ascending within a cell, cells in lexicographic
-// order.  This is the order the device pipeline likes best (dm_pipeline.cuh, stage A): consecutive
-// cells share their first vertices, so the warp-aggregated slot claims merge (2.4 atomics per cell
-// instead of 3.7 in creation order on the ball h0 = 0.03 mesh) and the position gathers of a warp
-// fall into few lines (10 distinct 128-B lines per warp instead of 58; Qhull's own order: 2.4 / 23).
-// Orientation is therefore NOT normalised (the loop body never uses it; the reference fixes it once,
-// at termination, in fix_mesh).
+// Output order of the host triangulators: cells GROUPED BY THEIR SMALLEST VERTEX ID (groups in
+// ascending order of that id, cells inside a group in lexicographic order of their sorted ids), every
+// cell keeping the triangulator's OWN column order.
+//
+// The grouping is what the device pipeline likes best (dm_pipeline.cuh, stage A): consecutive cells
+// share vertices, so the warp-aggregated slot claims merge and the position gathers of a warp fall
+// into few lines (the kernel sorts the four ids of a cell in registers where it needs them sorted).
+//
+// The column order inside a cell is deliberately NOT canonicalised: the reference's sliver_removal
+// moves "vertex 0 of every sliver, last write wins" (mesh_generator.py:234,245-274), which only
+// converges when column 0 is an unbiased choice among the cell's vertices.  With ids ascending inside
+// every cell column 0 was always the smallest id, the same low-id vertices were hit pass after pass
+// and hard inputs never got rid of their slivers (round-1 verdict; pinned by
+// tests/test_reference_with_native_triangulators.py::test_sliver_removal_hard_input_converges).
+// Orientation is not normalised either (the loop body never uses it; the reference fixes it once, at
+// termination, in fix_mesh).
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <vector>
 
@@ -14,32 +24,43 @@ namespace dmx {
 
 template <int K>
 inline void order_cells(int32_t* cells, int64_t T, int64_t N) {
-  if (T <= 0) return;
-  for (int64_t c = 0; c < T; ++c) std::sort(cells + K * c, cells + K * c + K);
-  // counting sort by the first (smallest) id, then a small sort inside every group
+  if (T <= 0 || T > (int64_t)INT32_MAX) return;  // (beyond int32 cell ids the list stays in creation order: still valid input)
+  struct Key {
+    int32_t s[K];   // the ids in ascending order (the sort key)
+    int32_t src;    // where the cell came from
+  };
+  std::vector<Key> keys((size_t)T);
+  // counting sort by the smallest id ...
   std::vector<int64_t> start(N + 1, 0);
-  for (int64_t c = 0; c < T; ++c) ++start[cells[K * c] + 1];
+  for (int64_t c = 0; c < T; ++c) {
+    int32_t m = cells[K * c];
+    for (int k = 1; k < K; ++k) m = std::min(m, cells[K * c + k]);
+    ++start[m + 1];
+  }
   for (int64_t v = 0; v < N; ++v) start[v + 1] += start[v];
-  std::vector<int32_t> tmp((size_t)(K * T));
   {
     std::vector<int64_t> pos(start.begin(), start.end() - 1);
     for (int64_t c = 0; c < T; ++c) {
-      const int64_t o = pos[cells[K * c]]++;
-      for (int k = 0; k < K; ++k) tmp[K * o + k] = cells[K * c + k];
+      Key key;
+      for (int k = 0; k < K; ++k) key.s[k] = cells[K * c + k];
+      std::sort(key.s, key.s + K);
+      key.src = (int32_t)c;
+      keys[(size_t)pos[key.s[0]]++] = key;
     }
   }
-  struct Cell {
-    int32_t v[K];
-  };
-  Cell* g = reinterpret_cast<Cell*>(tmp.data());
+  // ... then a small sort inside every group
   for (int64_t v = 0; v < N; ++v)
     if (start[v + 1] - start[v] > 1)
-      std::sort(g + start[v], g + start[v + 1], [](const Cell& a, const Cell& b) {
+      std::sort(keys.begin() + start[v], keys.begin() + start[v + 1], [](const Key& a, const Key& b) {
         for (int k = 1; k < K; ++k)
-          if (a.v[k] != b.v[k]) return a.v[k] < b.v[k];
-        return false;
+          if (a.s[k] != b.s[k]) return a.s[k] < b.s[k];
+        return a.src < b.src;
       });
-  std::copy(tmp.begin(), tmp.end(), cells);
+  std::vector<int32_t> tmp(cells, cells + (size_t)(K * T));
+  for (int64_t c = 0; c < T; ++c) {
+    const int32_t* from = tmp.data() + (size_t)K * keys[(size_t)c].src;
+    for (int k = 0; k < K; ++k) cells[K * c + k] = from[k];
+  }
 }
 
 }  // namespace dmx

@@ -159,7 +159,7 @@ class ForceLoop:
             return p_out, Ftot
         # ---- staged path: at least one opaque user callable ----
         self.cull(p, t)
-        check(lib.dm_stage_build_adjacency(C.byref(pl.c), D.ptr(t), 1, st), "build_bars")
+        check(lib.dm_stage_build_adjacency(C.byref(pl.c), st), "build_bars")
         f = self.size.struct()
         if not self.size.lowered:
             t0 = time.perf_counter()
@@ -336,7 +336,7 @@ def unique_bars(t, N=None):
     pl = D.Plan(N, td.shape[0], dim)
     st = D.stream_ptr()
     check(lib.dm_stage_cull_count(C.byref(pl.c), None, None, D.ptr(td), 0.0, 0, st), "cull_count")
-    check(lib.dm_stage_build_adjacency(C.byref(pl.c), D.ptr(td), 0, st), "build_bars")
+    check(lib.dm_stage_build_adjacency(C.byref(pl.c), st), "build_bars")
     check(lib.dm_stage_bar_index(C.byref(pl.c), st), "bar_index")
     E = pl.num_bars()
     pairs = torch.empty((E, 2), dtype=torch.int32, device=td.device)

@@ -142,7 +142,30 @@ def _initial_points(h0, geps, dim, bbox, size, level0, pfix, opts):
     else:
         r0m = r0.min()
     np.random.seed(opts["seed"])
-    return np.vstack((pfix, p[np.random.rand(p.shape[0]) < r0m**dim / r0**dim]))
+    p = p[np.random.rand(p.shape[0]) < r0m**dim / r0**dim]
+    if len(pfix) and len(p):
+        # A lattice point that coincides with a fixed point (the lattice origin and box corners ARE the
+        # corners of a Rectangle / Cube) would be an exact duplicate row: a Delaunay code keeps ONE copy,
+        # not necessarily the fixed row, and the constraint would silently move to a free vertex.  The
+        # reference gets away with it because CGAL merges duplicates and pfix is re-located by
+        # nearest-node search every iteration (mesh_generator.py:472-475); here the lattice copy goes.
+        # (The random stream above is drawn for the full lattice first, so the vertex set is the
+        # reference's minus those copies.)
+        _, d2 = _nearest_sq(pfix, p)
+        p = p[d2 > 0.0]
+    return np.vstack((pfix, p))
+
+
+def _nearest_sq(a, b):
+    """for every row of b: (index, squared distance) of the nearest row of a (a is small)."""
+    best = np.full(len(b), np.inf)
+    arg = np.zeros(len(b), dtype=np.int64)
+    for i, row in enumerate(np.asarray(a, dtype=np.float64)):
+        d = ((b - row) ** 2).sum(axis=1)
+        m = d < best
+        best[m] = d[m]
+        arg[m] = i
+    return arg, best
 
 
 def _termination(p, t, opts, dim, sliver=False, verbose=1):
@@ -152,7 +175,10 @@ def _termination(p, t, opts, dim, sliver=False, verbose=1):
         p, t = meshutil.delete_boundary_entities(p, t, dim=2, min_qual=0.15, verbose=verbose)
         if opts["subdomains"] is None and opts["mesh_improvement"]:
             p, t = meshutil.laplacian2_fixed_point(p, t)
-    p, t, _ = meshutil.fix_mesh(p, t, dim=dim, delete_unused=True)
+    if opts["perform_checks"]:  # reference :672-675
+        p, t = meshutil.linter(p, t, dim=dim)
+    else:
+        p, t, _ = meshutil.fix_mesh(p, t, dim=dim, delete_unused=True)
     return p, t
 
 
@@ -428,6 +454,14 @@ def sliver_removal(points, domain, edge_length, comm=None, **kwargs):  # noqa: C
         t_host = tri.triangulate(p_host)
         stats["delaunay"] += time.perf_counter() - t0
         t_dev = D.to_dev(t_host, torch.int32)
+        # which vertex sits in column 0 decides which vertex a sliver moves (reference :234,245-274 takes
+        # CGAL's order): prefer a vertex well inside the domain, see dm_cells_lead_interior
+        if level0.lowered:
+            key = torch.empty(N, dtype=torch.float64, device=p_dev.device)
+            check(lib.dm_sdf_eval(D.ptr(level0.prog), D.ptr(p_dev), N, dim, D.ptr(key), st()), "sdf_eval")
+        else:
+            key = D.to_dev(np.asarray(level0.func(p_host), dtype=np.float64), torch.float64)
+        check(lib.dm_cells_lead_interior(D.ptr(key), D.ptr(t_dev), t_dev.shape[0], -0.5 * h0, st()), "cells_lead_interior")
         if level0.lowered:
             # cull + dihedral bound test in ONE kernel on the uncompacted cell list; the kept cells are
             # only compacted when the loop ends (fix_mesh below)

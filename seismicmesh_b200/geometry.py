@@ -440,3 +440,79 @@ def from_spec(spec):
     if kind == "cylinder":
         return Cylinder(h=prm["h"], r=prm["r"], **kw)
     raise ValueError(kind)
+
+
+# ---------------------------------------------------------------------------------------------
+# The rest of the reference's `SeismicMesh.geometry` namespace that callers of the hot path use
+# (geometry/__init__.py): the reference's own tests and benchmarks reach the mesh helpers through
+# it (`SeismicMesh.geometry.simp_vol`, tests/test_2dmesher_SDF.py:29; `calc_dihedral_angles`,
+# tests/test_3d_sliver.py:13).  Host helpers come from meshutil; the two natives of
+# `_fast_geometry` that belong to the sliver loop run their CUDA kernels.
+# ---------------------------------------------------------------------------------------------
+from .meshutil import (  # noqa: E402,F401
+    delete_boundary_entities,
+    do_any_overlap,
+    fix_mesh,
+    get_boundary_edges,
+    get_boundary_entities,
+    get_boundary_facets,
+    get_boundary_vertices,
+    get_centroids,
+    get_edges,
+    get_facets,
+    is_manifold,
+    laplacian2_fixed_point,
+    linter,
+    simp_qual,
+    simp_vol,
+    unique_rows,
+    vertex_to_entities,
+)
+
+
+def calc_dihedral_angles(points, cells):
+    """The six dihedral angles of every tetrahedron, (6T, 1) float64 cell-major, like
+    `_fast_geometry.calc_dihedral_angles` (geometry/cpp/fast_geometry.cpp:351-452); device kernel."""
+    p = D.points_dev(points, 3)
+    t = D.to_dev(np.ascontiguousarray(cells), torch.int32)
+    T = t.shape[0]
+    out = torch.empty(6 * T, dtype=torch.float64, device=p.device)
+    check(lib.dm_dihedral(D.ptr(p), D.ptr(t), T, 0.0, 4.0, D.ptr(out), None, D.stream_ptr()), "dm_dihedral")
+    return out.cpu().numpy().reshape(-1, 1)
+
+
+def calc_circumsphere_grad(p0, p1, p2, p3):
+    """Gradient of the circumsphere radius with respect to p0, (S, 3), like
+    `_fast_geometry.calc_circumsphere_grad` (fast_geometry.cpp:580-703); device kernel."""
+    pts = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3) for a in (p0, p1, p2, p3)]
+    S = len(pts[0])
+    p = D.points_dev(np.concatenate(pts, axis=0), 3)
+    t = D.to_dev(np.arange(4 * S, dtype=np.int32).reshape(4, S).T.copy(), torch.int32)
+    out = torch.empty((S, 3), dtype=torch.float64, device=p.device)
+    check(lib.dm_circumsphere_grad(D.ptr(p), D.ptr(t), None, S, D.ptr(out), D.stream_ptr()), "dm_circumsphere_grad")
+    return out.cpu().numpy()
+
+
+def unique_edges(edges):
+    """Sorted unique (min, max) vertex pairs of an (K, 2) integer array, like
+    `_fast_geometry.unique_edges` (fast_geometry.cpp:49-77).  The device pipeline builds bars from
+    CELLS (engine.unique_bars, stage B); a bare edge list is handled as degenerate triangles (v, w, w)."""
+    from .engine import unique_bars
+
+    e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
+    if len(e) == 0:
+        return np.zeros((0, 2), dtype=np.int32)
+    tri = np.column_stack([e[:, 0], e[:, 1], e[:, 1]]).astype(np.int32)
+    out = unique_bars(tri)
+    # the degenerate triangle (v, w, w) also carries the pair (w, w): keep it only where the input has it
+    loops = np.unique(e[e[:, 0] == e[:, 1], 0])
+    keep = (out[:, 0] != out[:, 1]) | np.isin(out[:, 0], loops)
+    return np.ascontiguousarray(out[keep])
+
+
+__all__ += [
+    "simp_vol", "simp_qual", "fix_mesh", "get_edges", "get_facets", "get_centroids", "get_boundary_edges",
+    "get_boundary_facets", "get_boundary_vertices", "get_boundary_entities", "delete_boundary_entities",
+    "laplacian2_fixed_point", "linter", "do_any_overlap", "is_manifold", "vertex_to_entities", "unique_rows",
+    "calc_dihedral_angles", "calc_circumsphere_grad", "unique_edges",
+]

@@ -2,7 +2,8 @@
 row "next #2").  Own NumPy/SciPy implementations of the behaviour of the reference's
 geometry/utils.py helpers that `_termination` needs (mesh_generator.py:655-677):
 fix_mesh (:204-249), simp_vol (:175-199), simp_qual (:252-274), boundary queries (:310-437),
-delete_boundary_entities (:440-468) and laplacian2_fixed_point (:494-547).
+delete_boundary_entities (:440-468) and laplacian2_fixed_point (:494-547); plus the optional
+`perform_checks` pass: linter (:820-872) over do_any_overlap (:745-817) and is_manifold (:634-654).
 """
 import numpy as np
 import scipy.sparse as sp
@@ -11,7 +12,8 @@ from scipy.sparse.linalg import splu
 __all__ = [
     "simp_vol", "simp_qual", "fix_mesh", "get_edges", "get_facets", "get_boundary_edges",
     "get_boundary_facets", "get_boundary_vertices", "get_boundary_entities",
-    "delete_boundary_entities", "laplacian2_fixed_point",
+    "delete_boundary_entities", "laplacian2_fixed_point", "get_centroids", "vertex_to_entities",
+    "do_any_overlap", "is_manifold", "linter", "unique_rows",
 ]
 
 
@@ -177,3 +179,99 @@ def laplacian2_fixed_point(p, t):
     rhs[bnd] = p[bnd]
     lu = splu(A)
     return np.column_stack([lu.solve(rhs[:, 0]), lu.solve(rhs[:, 1])]), t
+
+
+def unique_rows(a, return_index=False, return_inverse=False):
+    """`geometry.unique_rows` (geometry/utils.py:141-172): unique rows in lexicographic order."""
+    out = _unique_rows(np.asarray(a), return_index=return_index, return_inverse=return_inverse)
+    return out
+
+
+def get_centroids(p, t, dim=2):
+    """p[t].sum(1)/(dim+1) (geometry/utils.py:729-742)."""
+    return p[t].sum(1) / (dim + 1)
+
+
+def vertex_to_entities(p, t, dim=2):
+    """CSR map vertex -> incident entities: (vtoe, ptr) as geometry/utils.py:577-602 returns it."""
+    t = np.asarray(t)
+    n = len(p)
+    flat = t.ravel()
+    order = np.argsort(flat, kind="stable")
+    vtoe = (order // t.shape[1]).astype(np.int64)
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=n))]).astype(np.int64)
+    return vtoe, ptr
+
+
+def do_any_overlap(p, t, dim=2):
+    """Pairs (ie, ele) where the centroid of entity `ie` lies inside an entity `ele` of its 1-ring
+    (geometry/utils.py:745-817; the point-in-entity tests are vertex_in_entity2 :657-679, closed
+    barycentric bounds, and vertex_in_entity3 :682-726, five determinants of one strict sign).
+    Vectorised over all (entity, ring neighbour) pairs instead of the reference's Python loops."""
+    t = np.asarray(t)
+    T, c = t.shape
+    if T == 0:
+        return []
+    vtoe, ptr = vertex_to_entities(p, t, dim=dim)
+    cnt = (ptr[1:] - ptr[:-1])[t]                      # (T, c) ring sizes per corner
+    tot = cnt.sum(axis=1)
+    ie = np.repeat(np.arange(T), tot)
+    # neighbour ids: for entity ie, concatenate vtoe[ptr[v]:ptr[v+1]] over its vertices (reference order)
+    starts = ptr[:-1][t].ravel()
+    lens = cnt.ravel()
+    seg = np.repeat(np.arange(len(lens)), lens)
+    within = np.arange(lens.sum()) - np.repeat(np.cumsum(lens) - lens, lens)
+    ele = vtoe[starts[seg] + within]
+    m = ie != ele
+    ie, ele = ie[m], ele[m]
+    cen = get_centroids(p, t, dim=dim)[ie]
+    q = p[t[ele]]                                      # (M, c, dim)
+    if dim == 2:
+        x, y = cen[:, 0], cen[:, 1]
+        x1, y1, x2, y2, x3, y3 = q[:, 0, 0], q[:, 0, 1], q[:, 1, 0], q[:, 1, 1], q[:, 2, 0], q[:, 2, 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            den = (y2 - y3) * (x1 - x3) + (x3 - x2) * (y1 - y3)
+            a = ((y2 - y3) * (x - x3) + (x3 - x2) * (y - y3)) / den
+            b = ((y3 - y1) * (x - x3) + (x1 - x3) * (y - y3)) / den
+        cc = 1 - a - b
+        inside = (0 <= a) & (a <= 1) & (0 <= b) & (b <= 1) & (0 <= cc) & (cc <= 1)
+    else:
+        def det4(rows):
+            A = np.concatenate([rows, np.ones(rows.shape[:2] + (1,))], axis=2)
+            return np.sign(np.linalg.det(A))
+
+        s0 = det4(q)
+        inside = s0 != 0
+        for k in range(4):
+            r = q.copy()
+            r[:, k, :] = cen
+            inside &= det4(r) == s0
+    return [(int(a_), int(b_)) for a_, b_ in zip(ie[inside], ele[inside])]
+
+
+def is_manifold(p, t, dim=2):
+    """geometry/utils.py:634-654: #boundary-edge endpoints == 2 * #boundary vertices."""
+    bedges = get_boundary_edges(t, dim=dim)
+    if bedges.size != p[np.unique(bedges), :].size:
+        print("Mesh has a non-manifold boundary...", flush=True)
+        return False
+    return True
+
+
+def linter(p, t, dim=2, min_qual=0.10):
+    """`perform_checks=True` clean-up (geometry/utils.py:820-872): of every overlapping pair the
+    lower-quality entity goes, then fix_mesh, poor boundary entities (2-D) and the manifold check."""
+    print("Performing mesh linting...", flush=True)
+    qual = simp_qual(p, t)
+    pairs = do_any_overlap(p, t, dim=dim)
+    delete = np.unique(np.array([pr[int(np.argmin(qual[list(pr)]))] for pr in pairs], dtype=int))
+    print("Deleting " + str(len(delete)) + " overlapped entities", flush=True)
+    t = np.delete(t, delete, axis=0)
+    p, t, _ = fix_mesh(p, t, delete_unused=True, dim=dim)
+    if dim == 2:
+        p, t = delete_boundary_entities(p, t, min_qual=min_qual)
+        is_manifold(p, t)
+    qual = simp_qual(p, t)
+    print("There are " + str(len(p)) + " vertices and " + str(len(t)) + " elements in the mesh", flush=True)
+    print("The minimum element quality is " + str(np.amin(qual)), flush=True)
+    return p, t

@@ -273,6 +273,19 @@ def _exchange_ghosts(below, above, rank, size, dim, cdev, group=None):
     return ga.cpu().numpy(), gb.cpu().numpy()
 
 
+def _broadcast_points(points, rank, dim, cdev, group=None):
+    """rank 0's (N,dim) array on every rank (the reference reads `points` on rank 0 only and sends each
+    rank its block, migration.localize_points, migration.py:55-69)."""
+    n = torch.tensor([0 if points is None else len(points)], dtype=torch.int64, device=cdev)
+    dist.broadcast(n, 0, group=group)
+    if rank == 0:
+        buf = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64).reshape(-1, dim)).to(cdev)
+    else:
+        buf = torch.empty((int(n.item()), dim), dtype=torch.float64, device=cdev)
+    dist.broadcast(buf, 0, group=group)
+    return buf.cpu().numpy()
+
+
 def _gather_points(points, rank, size, dim, cdev, group=None):
     """Owned vertices of every rank -> one array on rank 0, in rank order (None elsewhere)."""
     counts = torch.zeros(size, dtype=torch.int64, device=cdev)
@@ -303,6 +316,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
     (migration.localize_sizing_function), so parallel and serial runs see the same fh."""
     import ctypes as C
     import time
+    import warnings
 
     from . import device as D
     from . import generation as G
@@ -322,8 +336,11 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
     }
     gen_opts.update(kwargs)
     G._parse_kwargs(kwargs)
-    if gen_opts["points"] is not None:
-        raise NotImplementedError("user-defined initial points are not supported in parallel here")
+    if gen_opts["pfix"] is not None and rank == 0:
+        # the reference drops fixed points when comm.size > 1 (_unpack_pfix, mesh_generator.py:880-888)
+        warnings.warn("`pfix` is ignored when comm.size > 1 (as in the reference)")
+    if gen_opts["ttol"] is not None and rank == 0:
+        warnings.warn("`ttol` is ignored when comm.size > 1: every iteration retriangulates (twice, with the ghosts)")
     print_msg1, print_msg2 = G._printers(gen_opts)
     if rank != 0:
         print_msg1 = print_msg2 = lambda msg: None  # noqa: E731
@@ -354,30 +371,55 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
     dev = D.device()
     cdev = _comm_device(dev)
 
-    # ---- initial points of this rank's slab (make_init_points + rejection, :808-852) ----
-    lb = bbox_arr.copy()
-    lims = np.linspace(lb[axis, 0], lb[axis, 1], size_ + 1)
-    lb[axis, :] = lims[rank : rank + 2]
-    if rank != 0:  # "starting point must be lasts + h0"
-        prev = lims[rank - 1 : rank + 1]
-        lb[axis, 0] = prev[0] + (int(np.ceil((prev[1] + h0 - prev[0]) / h0)) - 1) * h0 + h0
-    p = G._staggered_grid(h0, dim, lb)
-    p = p[level0.eval_host(p) < geps]
-    r0 = size.eval_host(p)
-    r0m = float(r0.min()) if len(r0) else np.inf
-    if gen_opts["r0m_is_h0"]:
-        r0m = 1.1 * h0 if 1.1 * h0 < r0m else h0
-    t_r0m = torch.tensor([r0m], dtype=torch.float64, device=cdev)
-    dist.all_reduce(t_r0m, op=dist.ReduceOp.MIN, group=group)  # "decimation occurs uniformly across ranks"
-    r0m = float(t_r0m.item())
-    np.random.seed(gen_opts["seed"])
-    p = np.ascontiguousarray(p[np.random.rand(p.shape[0]) < r0m**dim / r0**dim])
-    assert len(p) > 0, "No vertices to mesh with!"
-    # extents of every rank: AABB of its points, padded by 5*h0 along the axis (_form_extents, :867-877)
+    def all_ranks_ok(ok, what):
+        """A failed check must stop EVERY rank (a rank that raises alone leaves the others blocked in
+        the next collective): agree on the outcome first, then raise everywhere."""
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int64, device=cdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        assert int(flag.item()) == 0, what
+
+    if gen_opts["points"] is None:
+        # ---- initial points of this rank's slab (make_init_points + rejection, :808-852) ----
+        lb = bbox_arr.copy()
+        lims = np.linspace(lb[axis, 0], lb[axis, 1], size_ + 1)
+        lb[axis, :] = lims[rank : rank + 2]
+        if rank != 0:  # "starting point must be lasts + h0"
+            prev = lims[rank - 1 : rank + 1]
+            lb[axis, 0] = prev[0] + (int(np.ceil((prev[1] + h0 - prev[0]) / h0)) - 1) * h0 + h0
+        p = G._staggered_grid(h0, dim, lb)
+        p = p[level0.eval_host(p) < geps]
+        r0 = size.eval_host(p)
+        r0m = float(r0.min()) if len(r0) else np.inf
+        if gen_opts["r0m_is_h0"]:
+            r0m = 1.1 * h0 if 1.1 * h0 < r0m else h0
+        t_r0m = torch.tensor([r0m], dtype=torch.float64, device=cdev)
+        dist.all_reduce(t_r0m, op=dist.ReduceOp.MIN, group=group)  # "decimation occurs uniformly across ranks"
+        r0m = float(t_r0m.item())
+        np.random.seed(gen_opts["seed"])
+        p = np.ascontiguousarray(p[np.random.rand(p.shape[0]) < r0m**dim / r0**dim])
+        pad = 5 * h0  # _form_extents pads the AABB of the owned points by 5*h0 along the axis (:867-877)
+        ext_axis = axis
+    else:
+        # ---- user-defined points (restart; _user_defined_points :787-805): rank 0's array is cut into
+        # comm.size blocks (decomp.blocker, decomp/blocker.py:4-111: `axis` 1 cuts along x, 0 along y,
+        # 2 along z; equal-width blocks of the points' bounding box) and every rank takes its block.
+        # Extents are the blocks' bounding boxes, unpadded, as blocker returns them.
+        pts = _broadcast_points(gen_opts["points"], rank, dim, cdev, group)
+        ext_axis = {0: 1, 1: 0, 2: 2}[axis]
+        if ext_axis >= dim:
+            raise ValueError("Dimensions of points are not supported")
+        eps_ = np.finfo(float).eps
+        lo_, hi_ = pts[:, ext_axis].min() - eps_, pts[:, ext_axis].max() + eps_
+        cuts = np.linspace(lo_, hi_, size_ + 1)
+        blk = np.clip(np.searchsorted(cuts, pts[:, ext_axis], side="right") - 1, 0, size_ - 1)
+        p = np.ascontiguousarray(pts[blk == rank])
+        pad = 0.0
+    all_ranks_ok(len(p) > 0, "No vertices to mesh with!")
+    # extents of every rank: bounding box of its points (padded, see above)
     ext = torch.zeros((size_, 2 * dim), dtype=torch.float64, device=cdev)
     mine = np.concatenate([p.min(0), p.max(0)])
-    mine[axis] -= 5 * h0
-    mine[axis + dim] += 5 * h0
+    mine[ext_axis] -= pad
+    mine[ext_axis + dim] += pad
     ext[rank] = torch.from_numpy(mine).to(cdev)
     dist.all_reduce(ext, op=dist.ReduceOp.SUM, group=group)
     extents = ext.cpu().numpy()
@@ -449,7 +491,6 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         stats["iterations"] += 1
         maxdp = loop.maxdp()
         print_msg2("Iteration #%d, max movement is %f, there are %d vertices and %d cells" % (count + 1, maxdp, len(p_loc), len(t_loc)))
-        if rank == 0:
-            assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
+        all_ranks_ok(maxdp < 1000 * h0, "max movement indicates there's a convergence problem")
         count += 1
         print_msg2("     Elapsed wall-clock time %f : " % (time.time() - start))

@@ -16,7 +16,7 @@ from . import _lib
 from . import device as D
 from ._lib import check, lib
 
-__all__ = ["SizeFunction", "GridInterpolant", "grid_axes", "get_sizing_function_from_segy", "limgrad"]
+__all__ = ["SizeFunction", "GridInterpolant", "grid_axes", "get_sizing_function_from_segy", "limgrad", "read_velocity_model"]
 
 
 def grid_axes(bbox, shape):
@@ -230,14 +230,26 @@ def _read_segy(filename):
     return np.flipud(vp), int(ns), int(ntr), 0
 
 
+def read_velocity_model(filename, nz=None, nx=None, ny=None, byte_order=None, axes_order=None, axes_order_sort=None,
+                        dtype=None):
+    """Read a velocity model: (vp, nz, nx, ny), z flipped (mesh_size_function.py:590-646).  SEG-Y through
+    our own reader (IBM / IEEE / integer sample formats), anything else as a raw binary."""
+    if str(filename).endswith(".segy"):
+        return _read_segy(filename)
+    return _read_bin(filename, nz, nx, ny, byte_order, axes_order, axes_order_sort, dtype)
+
+
 def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     """Build a mesh-size function from a seismic velocity model: same name, arguments, defaults,
     errors and step order as the reference (mesh_size_function.py:27-232).  ``velocity_data=`` arrays
     binary files and SEG-Y files (own reader, no ``segyio``) are supported."""
     opts = dict(_SIZING_DEFAULTS)
     opts.update(kwargs)
-    if comm is not None and getattr(comm, "rank", 0) != 0:
-        return SizeFunction(bbox, lambda p: 1, opts["hmin"])  # the reference computes on rank 0 only (:128,:220)
+    # The reference builds the grid on rank 0 only, hands the other ranks a placeholder (:128,:220) and
+    # later ships every rank its resampled slab of rank 0's grid (migration.localize_sizing_function).
+    # Here the grid is REPLICATED per GPU (DESIGN.md section 5), so every rank builds the same size function
+    # from the same input: same bbox (padded), same hmin, same grid everywhere, no placeholder to leak
+    # into generate_mesh.  `comm` is accepted for call compatibility.
     vp, nz, nx, ny = opts["velocity_data"], opts["nz"], opts["nx"], opts["ny"]
     if vp is None:
         if str(filename).endswith(".segy"):

@@ -375,6 +375,31 @@ def test_sliver_flags_fused_pass(sm):
     assert len(orc.sliver_cells(pts, cells, lo, hi)) == 0
 
 
+def test_cells_lead_interior_kernel(sm):
+    """dm_cells_lead_interior (the column order the sliver loop sees) against its NumPy restatement:
+    same cells, bit for bit, on cells with 0..4 interior vertices; even permutation (same orientation)."""
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+
+    dom = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    h0 = 0.12
+    p, t = _lattice_mesh(sm, dom, h0, 3, seed=5)
+    key = orc.sdf(dom.spec(), p)
+    for thresh in (-0.5 * h0, -10.0, 10.0):
+        td = dev(t, torch.int32).clone()
+        check(lib.dm_cells_lead_interior(D.ptr(dev(key, torch.float64)), D.ptr(td), len(t), thresh, D.stream_ptr()), "lead")
+        got = td.cpu().numpy()
+        ref = orc.cells_lead_interior(t, key, thresh)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(np.sort(got, axis=1), np.sort(t, axis=1))
+    v = p[ref]
+    vol = np.einsum("ij,ij->i", np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), v[:, 3] - v[:, 0])
+    v0 = p[t]
+    vol0 = np.einsum("ij,ij->i", np.cross(v0[:, 1] - v0[:, 0], v0[:, 2] - v0[:, 0]), v0[:, 3] - v0[:, 0])
+    assert np.array_equal(np.sign(vol), np.sign(vol0))
+    assert lib.dm_cells_lead_interior(None, None, 0, 0.0, None) == 0  # empty input
+
+
 def test_level_set_newton_kernel(sm):
     from seismicmesh_b200 import device as D
     from seismicmesh_b200._lib import check, lib
@@ -570,6 +595,36 @@ def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
 def _e2e():
     with open(os.path.join(GOLDEN, "e2e.json")) as f:
         return json.load(f)
+
+
+def test_initial_points_product_matches_reference(sm):
+    """SURVEY a11 on the PRODUCT side: generation._initial_points (device fd / fh evaluation, NumPy legacy
+    RNG for the rejection step) equals the reference's _generate_initial_points (mesh_generator.py:808-852,
+    goldens written by the unmodified reference) row for row: Disk, Ball and the gridded rectangle with
+    its four fixed corners."""
+    from seismicmesh_b200.engine import Level, SizeSpec
+    from seismicmesh_b200.generation import _initial_points
+
+    g = load_golden("init_points.npz")
+    opts = dict(seed=0, r0m_is_h0=False)
+    for name, dom, h0, dim in (("disk", sm.Disk([0.0, 0.0], 1.0), 0.05, 2), ("ball", sm.Ball([0.0, 0.0, 0.0], 1.0), 0.2, 3)):
+        bbox = np.array(dom.bbox).reshape(-1, 2)
+        p = _initial_points(h0, 0.1 * h0, dim, bbox, SizeSpec(dim, const=h0), Level(dom, dim), np.empty((0, dim)), opts)
+        assert np.array_equal(p, g[name])
+    gi = load_golden("interp_2d.npz")
+    bbox = tuple(gi["bbox"].tolist())
+    interp = sm.GridInterpolant([gi["axis0"], gi["axis1"]], gi["grid"])
+    rect = sm.Rectangle(bbox)
+    h0 = float(gi["hmin"])
+    p = _initial_points(h0, 0.1 * h0, 2, np.array(bbox).reshape(-1, 2), SizeSpec(2, interp=interp), Level(rect, 2),
+                        rect.corners, opts)
+    ref = g["grid2d"]
+    # the reference keeps a lattice point that coincides with a fixed corner (CGAL merges the duplicate);
+    # the product drops that lattice copy so that the FIXED row is the one the triangulation uses
+    nfix = len(rect.corners)
+    assert np.array_equal(p[:nfix], ref[:nfix])
+    dup = (np.abs(ref[nfix:, None, :] - ref[None, :nfix, :]).max(axis=2) == 0).any(axis=1)
+    assert np.array_equal(p[nfix:], ref[nfix:][~dup])
 
 
 def test_generate_mesh_disk_matches_reference(sm):

@@ -54,13 +54,26 @@ def _sgn(x):
 
 
 def _is_lex_sorted(t):
-    """ids ascending within a cell, cells in lexicographic order (the documented output order)."""
+    """The documented output order: cells in lexicographic order of their SORTED ids (hence grouped by
+    their smallest id), each cell keeping the triangulator's own column order."""
     t = np.asarray(t, dtype=np.int64)
     if len(t) == 0:
         return True
-    if not (np.diff(t, axis=1) > 0).all():
+    ts = np.sort(t, axis=1)
+    if not (np.diff(ts, axis=1) > 0).all():
         return False
-    return np.array_equal(t, t[np.lexsort(t.T[::-1])])
+    return np.array_equal(ts, ts[np.lexsort(ts.T[::-1])])
+
+
+def _column0_unbiased(t):
+    """Column 0 must not be systematically the smallest (or largest) id of its cell: the reference's
+    sliver_removal moves t[:,0] of every sliver (mesh_generator.py:245-274)."""
+    t = np.asarray(t, dtype=np.int64)
+    if len(t) < 200:
+        return True
+    frac_min = (t[:, 0] == t.min(axis=1)).mean()
+    frac_max = (t[:, 0] == t.max(axis=1)).mean()
+    return frac_min < 0.6 and frac_max < 0.6
 
 
 def _incircle(hl, p, i, j, k, m):

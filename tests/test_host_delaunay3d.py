@@ -11,7 +11,7 @@ from fractions import Fraction
 import numpy as np
 import pytest
 
-from test_host_delaunay import _is_lex_sorted, hl  # noqa: F401  (fixture: builds / loads libdistmesh_host.so)
+from test_host_delaunay import _column0_unbiased, _is_lex_sorted, hl  # noqa: F401  (fixture: builds / loads libdistmesh_host.so)
 
 
 @pytest.fixture(scope="module")
@@ -122,6 +122,7 @@ def test_same_cells_as_qhull_in_general_position(tri, n, seed):
     p = np.random.default_rng(seed).random((n, 3)) * [3.0, 1.0, 0.5] - [1.0, 0.5, 0.0]
     t = tri.triangulate(p)
     assert t.dtype == np.int32 and t.flags.c_contiguous and t.shape[1] == 4 and _is_lex_sorted(t)
+    assert _column0_unbiased(t)
     assert np.array_equal(_canon(t), _canon(Delaunay(p).simplices))
     assert tri.qhull_retries == 0
 

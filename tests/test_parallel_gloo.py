@@ -135,3 +135,83 @@ def test_ghost_exchange_and_gather_gloo(world):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+# ---- the reference's migration / decomp names over torch.distributed (seismicmesh_b200.migration) ----
+def _migration_worker(rank, world, port, q):
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200.parallel import TorchComm, _broadcast_points
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = TorchComm()
+        dim = 2
+        pts = _global_points(n=600, dim=dim, seed=5)[:, ::-1].copy()  # long along x: `axis=1` cuts x
+        ok = True
+        # restart path: rank 0's points reach everybody unchanged
+        got = _broadcast_points(pts if rank == 0 else None, rank, dim, torch.device("cpu"))
+        ok &= np.array_equal(got, pts)
+        # blocker on rank 0 + localize_points: every rank gets its block and all the extents
+        if rank == 0:
+            blocks, extents = sm.decomp.blocker(points=pts, rank=rank, num_blocks=world, axis=1)
+        else:
+            blocks, extents = None, None
+        mine, ext = sm.migration.localize_points(blocks, extents, comm, dim)
+        b_all, e_all = sm.decomp.blocker(points=pts, rank=0, num_blocks=world, axis=1)
+        ok &= np.array_equal(mine, b_all[rank]) and np.allclose(np.asarray(ext), np.asarray(e_all))
+        # exchange: the packed export table of enqueue ([NSB, NSA, ..]; rows (x, y, id)), built by hand here
+        nsb, nsa = (0 if rank == 0 else 2 + rank), (0 if rank == world - 1 else 1 + rank)
+        exports = np.zeros((1 + nsb + nsa, dim + 1))
+        exports[0, :2] = nsb, nsa
+        exports[1:, :dim] = 10.0 * rank + np.arange(nsb + nsa)[:, None]
+        recv = sm.migration.exchange(comm, rank, world, exports, dim=dim)
+        n_exp = (0 if rank == world - 1 else 2 + rank + 1) + (0 if rank == 0 else 1 + rank - 1)
+        ok &= (recv.size == 0 and n_exp == 0) or recv.shape == (n_exp, dim)
+        # aggregate: local meshes -> rank 0, cells renumbered by the running vertex offset
+        lp = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]) + [2.0 * rank, 0.0]
+        lt = np.array([[0, 1, 2], [1, 3, 2]])
+        gp, gt = sm.migration.aggregate(lp, lt, comm, world, rank, dim=dim)
+        if rank == 0:
+            ok &= gp.shape == (4 * world, dim) and gt.shape == (2 * world, dim + 1) and gt.max() == 4 * world - 1
+            ok &= abs(np.abs(sm.geometry.simp_vol(gp, gt)).sum() - world) < 1e-12
+        else:
+            ok &= gp is True and gt is True
+        ok &= sm.migration.localize_sizing_function("fh", 0.1, None, dim, 1, comm) == "fh"
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_migration_names_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migration_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_blocker_matches_reference():
+    from oracle import ref_harness
+
+    if not (ref_harness.reference_available() and ref_harness.native_available()):
+        pytest.skip("reference tree only exists in the build container")
+    import seismicmesh_b200 as sm
+
+    ref = ref_harness.load_reference()
+    for dim, axis, nb in ((2, 0, 3), (2, 1, 4), (3, 0, 2), (3, 1, 5)):
+        pts = _global_points(n=900, dim=dim, seed=dim + axis)
+        b0, e0 = ref.decomp.blocker(points=pts, rank=0, num_blocks=nb, axis=axis)
+        b1, e1 = sm.decomp.blocker(points=pts, rank=0, num_blocks=nb, axis=axis)
+        assert len(b0) == len(b1)
+        for x, y in zip(b0, b1):
+            assert np.array_equal(x, y)
+        assert np.allclose(np.asarray(e0), np.asarray(e1), rtol=0, atol=0)

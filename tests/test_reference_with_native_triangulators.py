@@ -63,3 +63,38 @@ def test_smooth_diff_and_ball_sliver_removal(ref_sm):
     assert sm.geometry.calc_dihedral_angles(p, c).min() * 180 / np.pi >= 10.0  # reference tests/test_3d_sliver.py
     assert abs(sm.geometry.simp_vol(p, c).sum() - ref["volume"]) < 0.02 * ref["volume"]
     assert tri[3].qhull_retries == 0
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_sliver_removal_hard_input_converges(ref_sm, seed):
+    """Round-1 regression, pinned on the CPU: a jittered lattice in the unit ball (h0 = 0.12; seed 3 is the
+    input of tests/test_gpu_parity.py::test_sliver_flags_fused_pass) starts with ~900 slivers.  The
+    UNMODIFIED reference loop, fed the default (native) triangulator's cells in the column order the
+    product's sliver_removal gives them (dm_cells_lead_interior, restated by
+    oracle.cells_lead_interior), must get rid of all of them within 60 passes.  The reference moves
+    "vertex 0 of every sliver" (mesh_generator.py:245-274): with ids ascending inside every cell
+    (round 1) 1972 slivers were left, with an unbiased column 0 ~650, because boundary vertices get
+    pushed out of the domain; leading with an interior vertex converges in 20-30 passes."""
+    sm, tri = ref_sm
+    from oracle import distmesh_oracle as orc
+    from seismicmesh_b200.generation import _staggered_grid
+
+    dom = sm.Ball([0.0, 0.0, 0.0], 1.0)
+    h0 = 0.12
+    rng = np.random.default_rng(seed)
+    p = _staggered_grid(h0, 3, np.array(dom.bbox).reshape(-1, 2))
+    p = p[dom.eval(p) < 0.1 * h0]
+    p = np.ascontiguousarray(p + rng.uniform(-0.15 * h0, 0.15 * h0, size=p.shape))
+    t = tri[3].triangulate(p)
+    frac_min = (t[:, 0] == t.min(axis=1)).mean()
+    assert 0.1 < frac_min < 0.6  # the triangulator itself does not canonicalise the columns
+    inner = ref_harness._qhull
+    ref_harness._qhull = lambda points, dim: orc.cells_lead_interior(
+        inner(points, dim), dom.eval(np.ascontiguousarray(points)), -0.5 * h0)
+    try:
+        pts, cells = _quiet(lambda: sm.sliver_removal(points=p, domain=dom, edge_length=h0, max_iter=60))
+    finally:
+        ref_harness._qhull = inner
+    dh = sm.geometry.calc_dihedral_angles(pts, cells)
+    assert dh.min() * 180 / np.pi >= 10.0
+    assert tri[3].qhull_retries == 0
