@@ -34,14 +34,15 @@ __device__ __forceinline__ void pdl_prologue() {
 #endif
 }
 
+// `smem`: dynamic shared memory in bytes (the caller has raised the kernel's limit beyond 48 KB)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st,
-                                       Args&&... args) {
+static inline cudaError_t launch_chain_smem(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                            cudaStream_t st, Args&&... args) {
 #if DM_PDL
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -50,9 +51,14 @@ static inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, un
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 #else
-  kern<<<grid, block, 0, st>>>(static_cast<KArgs>(args)...);
+  kern<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
   return cudaGetLastError();
 #endif
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st,
+                                       Args&&... args) {
+  return launch_chain_smem(kern, grid, block, 0, st, static_cast<Args&&>(args)...);
 }
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

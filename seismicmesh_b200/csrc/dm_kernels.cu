@@ -17,6 +17,7 @@
 
 #include "dm_aux.cuh"
 #include "dm_pipeline.cuh"
+#include "dm_rows.cuh"
 #include "dm_scan.cuh"
 
 using namespace dm;
@@ -59,7 +60,8 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   const int64_t K1 = K > 0 ? K : 1, T1 = T > 0 ? T : 1;
   const int64_t heap_ints = K1 + 4 * (N + 1);
   // bar sums: one per adjacency block + one per group of RG blocks + one per heavy vertex (dm_pipeline.cuh)
-  const int64_t nbm = cdiv(N > 0 ? N : 1, AB_THREADS / PCfg<DIM>::G);
+  // (the leaves are the 32-vertex warps of rows_kernel; the lane-group kernel of round 1 has fewer blocks)
+  const int64_t nbm = cdiv(N > 0 ? N : 1, 32);
   const int64_t ngrp = cdiv(nbm, RG);
   const int64_t nblocks = nbm + ngrp + (N + 2) + 8;
   size_t off = 0;
@@ -205,14 +207,28 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   return (int)cudaGetLastError();
 }
 
+// Stage B kernel choice: the thread-per-vertex rows kernel of round 2 (dm_rows.cuh) unless DM_ROWS=0 asks
+// for the lane-group kernel of round 1 (kept for comparison runs; same inputs, same outputs).
+static bool use_rows_kernel() {
+  static const bool on = [] {
+    const char* e = getenv("DM_ROWS");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int DIM, int BAR>
+static cudaError_t rows_smem_ready(size_t bytes) {
+  static cudaError_t st = cudaFuncSetAttribute(rows_kernel<DIM, BAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return st;
+}
+
 // bar: -1 rows only (staged path: a separate bar pass follows) ; otherwise f->kind (0 const, 1 grid):
 // the bar pass and the reduction to the scale are fused into the adjacency kernel
 template <int DIM>
 static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const double* p, cudaStream_t st) {
   typedef typename PCfg<DIM>::entry_t entry_t;
-  constexpr int VPB = AB_THREADS / PCfg<DIM>::G;
   const int64_t N = pl->N;
-  const unsigned nb = nblk(N, VPB);
   int2* degs = reinterpret_cast<int2*>(pl->degs);
   const entry_t* bucket = static_cast<const entry_t*>(pl->bucket);
   const entry_t* ovf_e = static_cast<const entry_t*>(pl->ovf_e);
@@ -220,6 +236,27 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   memset(&fz, 0, sizeof(fz));
   const DmSizeFn& ff = f ? *f : fz;
   const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
+  if (use_rows_kernel()) {
+    const unsigned nb = nblk(N, 32 * ROWS_WPB);  // the last block's spare warps are empty leaves
+    constexpr size_t ints = (size_t)ROWS_WPB * RowsCfg<DIM>::WARP_INTS > (size_t)HV_SMEM ? (size_t)ROWS_WPB * RowsCfg<DIM>::WARP_INTS
+                                                                                       : (size_t)HV_SMEM;
+    constexpr size_t smem = ints * sizeof(int32_t);
+#define DM_ROWS_LAUNCH(B)                                                                                          \
+  DM_CUDA_TRY((rows_smem_ready<DIM, B>(smem)));                                                                    \
+  launch_chain_smem(rows_kernel<DIM, B>, nb + HV_BLOCKS, ROWS_THREADS, smem, st, pl->cnt, bucket, pl->ovf_v, ovf_e, \
+                    N, pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone,   \
+                    pl->sync + 3, pl->scalars);                                                                    \
+  mark("adjacency", st)
+    switch (bar) {
+      case 0: DM_ROWS_LAUNCH(0); break;
+      case 1: DM_ROWS_LAUNCH(1); break;
+      default: DM_ROWS_LAUNCH(-1); break;
+    }
+#undef DM_ROWS_LAUNCH
+    return (int)cudaGetLastError();
+  }
+  constexpr int VPB = AB_THREADS / PCfg<DIM>::G;
+  const unsigned nb = nblk(N, VPB);
 #define DM_ADJ(B)                                                                                                   \
   launch_chain(adjacency_kernel<DIM, B>, nb + HV_BLOCKS, AB_THREADS, st, pl->cnt, bucket, pl->ovf_v, ovf_e, N,       \
                pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone,           \

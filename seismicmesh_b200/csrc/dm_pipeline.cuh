@@ -327,7 +327,7 @@ __device__ __forceinline__ void final_scale(const double* partials, int64_t nb, 
 
 // A vertex whose bucket overflowed (hull / hub vertices; listed by stage A): the whole block gathers
 // its star from the bucket and the spill list, sorts + de-duplicates it and writes the row.
-template <int DIM, int BAR>
+template <int DIM, int BAR, int THREADS = AB_THREADS>
 __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t* s_val, int* s_scan, double* s_dbl,
                                              int* s_base, int* s_pos, const int32_t* __restrict__ cnt,
                                              const typename PCfg<DIM>::entry_t* __restrict__ bucket,
@@ -352,7 +352,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
   __syncthreads();
   int32_t* reg = heap + *s_base;  // candidates, later the row, live here
   const bool in_smem = n <= HV_SMEM;
-  for (int i = tid; i < nb; i += AB_THREADS) {
+  for (int i = tid; i < nb; i += THREADS) {
     const typename PCfg<DIM>::entry_t e = bucket[(int64_t)v * CAP + i];
     const int* ei = reinterpret_cast<const int*>(&e);
 #pragma unroll
@@ -363,7 +363,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
         reg[i * DIM + c] = ei[c];
     }
   }
-  for (int k = tid; k < novf; k += AB_THREADS) {
+  for (int k = tid; k < novf; k += THREADS) {
     if (ovf_v[k] == v) {
       const int i = nb + atomicAdd(s_pos, 1);
       const typename PCfg<DIM>::entry_t e = ovf_e[k];
@@ -379,7 +379,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
   }
   // rank of v among the heavy vertices: where its bar sums go (see final_scale)
   int vrank = 0;
-  for (int j0 = 0; j0 < nheavy; j0 += AB_THREADS) {
+  for (int j0 = 0; j0 < nheavy; j0 += THREADS) {
     const int j = j0 + tid;
     vrank += __syncthreads_count(j < nheavy && hv[j] < v);
   }
@@ -388,12 +388,12 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
   if (n <= HV_RANK) {
     // one pass: candidate i is the first of its value if no equal value precedes it, and its
     // row position is the number of DISTINCT smaller values = #{j : val[j] < val[i], j first}.
-    constexpr int PER = HV_RANK / AB_THREADS;
+    constexpr int PER = HV_RANK / THREADS;
     bool first[PER];
     int x[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const int i = tid + u * AB_THREADS;
+      const int i = tid + u * THREADS;
       first[u] = i < n;
       x[u] = i < n ? s_val[i] : 0;
     }
@@ -401,13 +401,13 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
     for (int j = 0; j < n; ++j) {
       const int y = s_val[j];
 #pragma unroll
-      for (int u = 0; u < PER; ++u) first[u] = first[u] && !(y == x[u] && j < tid + u * AB_THREADS);
+      for (int u = 0; u < PER; ++u) first[u] = first[u] && !(y == x[u] && j < tid + u * THREADS);
     }
     __syncthreads();
     int32_t* s_first = s_val + HV_RANK;  // HV_SMEM >= 2 * HV_RANK
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-      const int i = tid + u * AB_THREADS;
+      const int i = tid + u * THREADS;
       if (i < n) s_first[i] = first[u] ? 1 : 0;
     }
     __syncthreads();
@@ -442,7 +442,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
       block_sort_ascending(reg, n);
     // unique: chunk by chunk; an element's output position never exceeds its input position and
     // all reads of a chunk complete before its writes, so compaction in place is safe
-    for (int c0 = 0; c0 < n; c0 += AB_THREADS) {
+    for (int c0 = 0; c0 < n; c0 += THREADS) {
       const int i = c0 + tid;
       int x = 0;
       bool first = false;
@@ -462,7 +462,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
   int32_t* row = adj + (int64_t)v * RS;
   int64_t sbase = (int64_t)v * RS;
   if (U <= RS) {
-    for (int i = tid; i < U; i += AB_THREADS) row[i] = reg[i];
+    for (int i = tid; i < U; i += THREADS) row[i] = reg[i];
   } else {
     if (tid == 0) row[0] = *s_base;
     sbase = N * RS + *s_base;
@@ -475,7 +475,7 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
     double sL = 0.0, sH = 0.0;
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
-    for (int j = lo + tid; j < U; j += AB_THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
+    for (int j = lo + tid; j < U; j += THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
     const double bl = block_sum(sL, s_dbl);
     const double bh = block_sum(sH, s_dbl);
     if (tid == 0) {
