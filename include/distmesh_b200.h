@@ -211,11 +211,19 @@ typedef struct DmPlan {
   int32_t *esc;      /* (N) vertices that left a level set in stage D, projected by its second kernel */
   void *scan_tmp;    /* scratch of the on-demand scans */
   size_t scan_tmp_bytes;
+  int64_t n_rows;    /* vertices [0, n_rows) get neighbour rows, bar sums, forces and an update (default N);
+                        the others are only NEIGHBOURS: the ghost copies of a slab (dm_plan_set_rows) */
 } DmPlan;
 
 size_t dm_plan_bytes(int64_t N, int64_t T, int dim);
 /* carve `ws` (device, 256-B aligned, >= dm_plan_bytes) into *plan (host struct). */
 int dm_plan_init(DmPlan *plan_host, int64_t N, int64_t T, int dim, void *ws, size_t ws_bytes);
+
+/* Multi-GPU slabs (mesh_generator.py:715-731): with the local vertices ordered [owned | ghosts], only the
+ * owned ones need rows / forces / an update -- the ghosts are somebody else's vertices and their new
+ * positions arrive through the halo exchange.  n_rows = number of owned vertices (1..N).  The bar sums
+ * (force scale) then run over the bars whose smaller LOCAL id is owned, i.e. every bar with an owned end. */
+int dm_plan_set_rows(DmPlan *plan_host, int64_t n_rows);
 
 /* stage A: keep flags (fd on centroids) + scatter of every kept cell to its vertices' buckets.
  * prog == NULL: plan->keep was filled by the caller (opaque fd), only count.
@@ -281,9 +289,12 @@ int dm_force_iteration_reuse(const DmPlan *plan_host, const double *const *progs
                              const DmSizeFn *fh_host, const double *p, double *p_out, double L0mult,
                              double delta_t, double deps, double h0, int64_t nfix,
                              const uint8_t *fixed, double *Ftot, void *stream);
-/* the `ttol` test: plan->scalars[5] = max_v |p[v] - p_ref[v]|_2 (p_ref = positions at the last
- * retriangulation). */
-int dm_stage_displacement(const DmPlan *plan_host, const double *p, const double *p_ref, void *stream);
+/* the `ttol` test: plan->scalars[5] = max_v |p[v] - p_ref[v]|_2 / h_v (p_ref = positions at the last
+ * retriangulation).  fh_host == NULL: h_v = 1 (absolute displacement, compare with ttol * h0 as DistMesh
+ * does); otherwise h_v = fh(p[v]) (constant or gridded; DM_SIZE_EXTERNAL is not accepted): displacement
+ * in units of the LOCAL mesh size, which is what makes the test usable on graded meshes. */
+int dm_stage_displacement(const DmPlan *plan_host, const double *p, const double *p_ref,
+                          const DmSizeFn *fh_host, void *stream);
 
 /* dm_force_iteration with a CUDA event recorded after every kernel (measurement only, used by
  * bench.py for the per-kernel roofline table; synchronises the stream).  ms_host[i] and the

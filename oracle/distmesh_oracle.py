@@ -265,10 +265,14 @@ def scatter_forces(bars, Fvec, N):
     return Ftot
 
 
-def compute_forces(p, t, fh, L0mult, return_parts=False):
-    """mesh_generator.py:691-712"""
+def compute_forces(p, t, fh, L0mult, return_parts=False, n_rows=None):
+    """mesh_generator.py:691-712.  n_rows (not in the reference; restates dm_plan_set_rows for the
+    multi-GPU slabs): only the bars with an end among the first n_rows vertices are kept, so the rows
+    >= n_rows of the result are meaningless (ghost copies, overwritten by the halo exchange)."""
     dim = p.shape[1]
     bars = unique_bars(t)
+    if n_rows is not None:
+        bars = bars[bars[:, 0] < n_rows]
     barvec, L = bar_lengths(p, bars)
     hbars = fh(p[bars].sum(1) / 2)
     scale = ((L**dim).sum() / (hbars**dim).sum()) ** (1.0 / dim)
@@ -300,14 +304,14 @@ def project_points_back_newton(p, fd, deps, hmin, idx):
     return p
 
 
-def force_iteration(p, t, levels, fh, h0, geps, deps, delta_t=0.30, ifix=()):
+def force_iteration(p, t, levels, fh, h0, geps, deps, delta_t=0.30, ifix=(), n_rows=None):
     """One pass of the body of the reference's while-loop AFTER the Delaunay step
     (mesh_generator.py:482, 497-521): cull, forces, pfix, update, projection, maxdp."""
     dim = p.shape[1]
     L0mult = 1 + 0.4 / 2 ** (dim - 1)
     keep = cull_mask(p, t, levels[0], geps)
     tk = t[keep]
-    Ftot, parts = compute_forces(p, tk, fh, L0mult, return_parts=True)
+    Ftot, parts = compute_forces(p, tk, fh, L0mult, return_parts=True, n_rows=n_rows)
     Ftot[list(ifix)] = 0
     pn = p + delta_t * Ftot
     for idx, lv in enumerate(levels):

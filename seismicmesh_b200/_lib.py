@@ -63,6 +63,7 @@ class DmPlan(C.Structure):
         ("esc", C.c_void_p),
         ("scan_tmp", C.c_void_p),
         ("scan_tmp_bytes", C.c_size_t),
+        ("n_rows", C.c_int64),
     ]
 
 
@@ -88,6 +89,7 @@ _SIGNATURES = {
     "dm_level_set_newton": (_INT, [_P, _P, _P, _I64, _INT, _D, _P]),
     "dm_plan_bytes": (_SZ, [_I64, _I64, _INT]),
     "dm_plan_init": (_INT, [C.POINTER(DmPlan), _I64, _I64, _INT, _P, _SZ]),
+    "dm_plan_set_rows": (_INT, [C.POINTER(DmPlan), _I64]),
     "dm_stage_prep": (_INT, [C.POINTER(DmPlan), _P, _P]),
     "dm_stage_cull_chunk": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _I64, _I64, _D, _INT, _P]),
     "dm_force_iteration_tail": (
@@ -114,7 +116,7 @@ _SIGNATURES = {
         _INT,
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _D, _D, _D, _D, _I64, _P, _P, _P],
     ),
-    "dm_stage_displacement": (_INT, [C.POINTER(DmPlan), _P, _P, _P]),
+    "dm_stage_displacement": (_INT, [C.POINTER(DmPlan), _P, _P, C.POINTER(DmSizeFn), _P]),
     "dm_force_iteration_profiled": (
         _INT,
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _P, _D, _D, _D, _D, _D, _I64, _P, _P,

@@ -124,6 +124,7 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
     pl->esc = reinterpret_cast<int32_t*>(esc);
     pl->scan_tmp = scan_tmp;
     pl->scan_tmp_bytes = scan_bytes;
+    pl->n_rows = N;
   }
   return off;
 }
@@ -144,9 +145,9 @@ Rows<DIM> rows_of(const DmPlan* pl) {
 
 template <int DIM>
 int launch_bar_pass(const DmPlan* pl, const double* p, const DmSizeFn& f, int hmode, double* mid, cudaStream_t st) {
-  const unsigned nb = nblk(pl->N, PL_THREADS);
+  const unsigned nb = nblk(pl->n_rows, PL_THREADS);
 #define DM_BP(H)                                                                                              \
-  bar_pass_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, rows_of<DIM>(pl), pl->rowptr, pl->N, pl->hslot,     \
+  bar_pass_kernel<DIM, H><<<nb, PL_THREADS, 0, st>>>(f, p, rows_of<DIM>(pl), pl->rowptr, pl->n_rows, pl->hslot, \
                                                      pl->hbar, mid, pl->partials, pl->sync + 1, pl->scalars)
   switch (hmode) {
     case 0: DM_BP(0); break;
@@ -163,11 +164,11 @@ template <int DIM>
 int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_out, const Levels& lv,
                          const DmSizeFn& f, int hmode, double L0mult, double delta_t, double deps, double h0,
                          int64_t nfix, const uint8_t* fixed, double* Ftot, cudaStream_t st) {
-  const unsigned nb = nblk(pl->N, VU_THREADS);
+  const unsigned nb = nblk(pl->n_rows, VU_THREADS);  // vertices without a row (ghost copies) are not updated
   const double* pg = pad ? pl->p4 : p;
 #define DM_VU(H, P)                                                                                              \
   launch_chain(vertex_update_kernel<DIM, H, P>, nb, VU_THREADS, st, f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr, \
-               pl->hslot, pl->hbar, pl->scalars, pl->N, lv, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,          \
+               pl->hslot, pl->hbar, pl->scalars, pl->n_rows, lv, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,     \
                pl->partials, pl->sync + 2, pl->scalars, pl->esc, pl->counters + 5)
   if (DIM == 3 && pad) {
     switch (hmode) {
@@ -202,17 +203,19 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
   launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, DM_CS_THREADS, st, prog, pc, t, ncells, geps, mode,
                pl->keep + cell0, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
-               static_cast<entry_t*>(pl->ovf_e), pl->hv, pl->counters);
+               static_cast<entry_t*>(pl->ovf_e), pl->hv, pl->counters, (int)pl->n_rows);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
 }
 
-// Stage B kernel choice: the thread-per-vertex rows kernel of round 2 (dm_rows.cuh) unless DM_ROWS=0 asks
-// for the lane-group kernel of round 1 (kept for comparison runs; same inputs, same outputs).
+// Stage B kernel choice: the lane-group kernel (adjacency_kernel, dm_pipeline.cuh) unless DM_ROWS=1 asks
+// for the thread-per-vertex rows kernel (dm_rows.cuh): same inputs, same outputs (the whole GPU suite
+// passes with either), measured SLOWER in round 2 -- see the header of dm_rows.cuh -- and kept for
+// comparison runs only.
 static bool use_rows_kernel() {
   static const bool on = [] {
     const char* e = getenv("DM_ROWS");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
@@ -256,10 +259,10 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
     return (int)cudaGetLastError();
   }
   constexpr int VPB = AB_THREADS / PCfg<DIM>::G;
-  const unsigned nb = nblk(N, VPB);
+  const unsigned nb = nblk(pl->n_rows, VPB);
 #define DM_ADJ(B)                                                                                                   \
   launch_chain(adjacency_kernel<DIM, B>, nb + HV_BLOCKS, AB_THREADS, st, pl->cnt, bucket, pl->ovf_v, ovf_e, N,       \
-               pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone,           \
+               pl->n_rows, pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone, \
                pl->sync + 3, pl->scalars);                                                                          \
   mark("adjacency", st)
   switch (bar) {
@@ -341,10 +344,10 @@ int dm_cull_cells(const double* prog, const double* p, const int32_t* t, int64_t
   if (!p || !t || !keep) return DM_ERR_ARG;
   if (dim == 2)
     cull_scatter_kernel<2><<<nblk(T, DM_CS_THREADS), DM_CS_THREADS, 0, S(stream)>>>(
-        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   else
     cull_scatter_kernel<3><<<nblk(T, DM_CS_THREADS), DM_CS_THREADS, 0, S(stream)>>>(
-        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        prog, p, t, T, geps, 0, keep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }
@@ -468,6 +471,12 @@ int dm_plan_init(DmPlan* plan, int64_t N, int64_t T, int dim, void* ws, size_t w
   return DM_OK;
 }
 
+int dm_plan_set_rows(DmPlan* plan, int64_t n_rows) {
+  if (!plan || n_rows < 1 || n_rows > plan->N) return DM_ERR_ARG;
+  plan->n_rows = n_rows;
+  return DM_OK;
+}
+
 int dm_stage_prep(const DmPlan* pl, const double* p, void* stream) {
   if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
@@ -513,16 +522,16 @@ int dm_stage_build_adjacency(const DmPlan* pl, void* stream) {
 int dm_stage_bar_index(const DmPlan* pl, void* stream) {
   if (!pl) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  upper_count_kernel<<<nblk(pl->N, 256), 256, 0, st>>>(reinterpret_cast<const int2*>(pl->degs), pl->N, pl->rowptr);
+  upper_count_kernel<<<nblk(pl->N, 256), 256, 0, st>>>(reinterpret_cast<const int2*>(pl->degs), pl->N, pl->n_rows, pl->rowptr);
   return exclusive_scan(pl->rowptr, pl->rowptr, pl->N, pl->scan_tmp, pl->scan_tmp_bytes, st);
 }
 
 int dm_bars_pairs(const DmPlan* pl, int32_t* pairs, void* stream) {
   if (!pl || !pairs) return DM_ERR_ARG;
   if (pl->dim == 2)
-    bars_pairs_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(rows_of<2>(pl), pl->rowptr, pl->N, pairs);
+    bars_pairs_kernel<2><<<nblk(pl->n_rows, 256), 256, 0, S(stream)>>>(rows_of<2>(pl), pl->rowptr, pl->n_rows, pairs);
   else
-    bars_pairs_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(rows_of<3>(pl), pl->rowptr, pl->N, pairs);
+    bars_pairs_kernel<3><<<nblk(pl->n_rows, 256), 256, 0, S(stream)>>>(rows_of<3>(pl), pl->rowptr, pl->n_rows, pairs);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }
@@ -530,11 +539,11 @@ int dm_bars_pairs(const DmPlan* pl, int32_t* pairs, void* stream) {
 int dm_bar_sizes(const DmPlan* pl, const DmSizeFn* f, double* out, void* stream) {
   if (!pl || !f || !out) return DM_ERR_ARG;
   if (pl->dim == 2)
-    bar_sizes_kernel<2><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, rows_of<2>(pl), pl->rowptr, pl->hslot, pl->hbar,
-                                                                 pl->N, out);
+    bar_sizes_kernel<2><<<nblk(pl->n_rows, 256), 256, 0, S(stream)>>>(*f, rows_of<2>(pl), pl->rowptr, pl->hslot, pl->hbar,
+                                                                      pl->n_rows, out);
   else
-    bar_sizes_kernel<3><<<nblk(pl->N, 256), 256, 0, S(stream)>>>(*f, rows_of<3>(pl), pl->rowptr, pl->hslot, pl->hbar,
-                                                                 pl->N, out);
+    bar_sizes_kernel<3><<<nblk(pl->n_rows, 256), 256, 0, S(stream)>>>(*f, rows_of<3>(pl), pl->rowptr, pl->hslot, pl->hbar,
+                                                                      pl->n_rows, out);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }
@@ -622,14 +631,22 @@ int dm_force_iteration_reuse(const DmPlan* pl, const double* const* progs, int n
   return vertex_update_impl(pl, p, false, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }
 
-int dm_stage_displacement(const DmPlan* pl, const double* p, const double* p_ref, void* stream) {
+int dm_stage_displacement(const DmPlan* pl, const double* p, const double* p_ref, const DmSizeFn* f, void* stream) {
   if (!pl || !p || !p_ref) return DM_ERR_ARG;
+  if (f && (f->kind == DM_SIZE_EXTERNAL || check_size_fn(f, pl->dim))) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
   const unsigned nb = nblk(pl->N, PL_THREADS);
-  if (pl->dim == 2)
-    displacement_kernel<2><<<nb, PL_THREADS, 0, st>>>(p, p_ref, pl->N, pl->partials, pl->sync + 5, pl->scalars);
-  else
-    displacement_kernel<3><<<nb, PL_THREADS, 0, st>>>(p, p_ref, pl->N, pl->partials, pl->sync + 5, pl->scalars);
+  DmSizeFn fz;
+  memset(&fz, 0, sizeof(fz));
+  const DmSizeFn& ff = f ? *f : fz;
+#define DM_DISP(D_, R_) \
+  displacement_kernel<D_, R_><<<nb, PL_THREADS, 0, st>>>(ff, p, p_ref, pl->N, pl->partials, pl->sync + 5, pl->scalars)
+  if (pl->dim == 2) {
+    if (f) DM_DISP(2, 1); else DM_DISP(2, 0);
+  } else {
+    if (f) DM_DISP(3, 1); else DM_DISP(3, 0);
+  }
+#undef DM_DISP
   DM_LAUNCH_CHECK();
   return DM_OK;
 }

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(DM_CS_THREADS, DM_CS_MINB) cull_scatter_kernel
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ cnt,
     typename PCfg<DIM>::entry_t* __restrict__ bucket, int32_t* __restrict__ ovf_v,
-    typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int32_t* __restrict__ hv, int32_t* __restrict__ counters) {
+    typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int32_t* __restrict__ hv, int32_t* __restrict__ counters,
+    int n_rows) {
   pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,13 +158,37 @@ __global__ void __launch_bounds__(DM_CS_THREADS, DM_CS_MINB) cull_scatter_kernel
     }
   }
   if (cnt == nullptr) return;
+  // The host triangulators hand the cells over grouped by their smallest id but with their own column
+  // order (dm_cell_order.h; the sliver loop needs an unbiased column 0).  The centroid above was summed
+  // in that order (bit-exactness); for the scatter the ids are sorted in registers, so that column j of
+  // consecutive lanes holds equal ids again and the slot claims below merge.
+  {
+    auto cx = [](int& a, int& b) {
+      const int lo_ = min(a, b), hi_ = max(a, b);
+      a = lo_;
+      b = hi_;
+    };
+    if (DIM == 3) {
+      cx(ids[0], ids[1]);
+      cx(ids[2], ids[3]);
+      cx(ids[0], ids[2]);
+      cx(ids[1], ids[3]);
+      cx(ids[1], ids[2]);
+    } else {
+      cx(ids[0], ids[1]);
+      cx(ids[1], ids[2]);
+      cx(ids[0], ids[1]);
+    }
+  }
   // Slot claims of the DIM+1 vertices are independent: issue all the atomics first and only then
   // wait for them, so a warp pays ONE L2 round trip instead of DIM+1.
   const unsigned lt = (1u << lane) - 1u;
   int base[DIM + 1], rank[DIM + 1], leader[DIM + 1];
 #pragma unroll
   for (int j = 0; j <= DIM; ++j) {
-    const int vj = k ? ids[j] : -1 - lane;  // a culled lane never continues a run
+    // (vertices >= n_rows are ghost copies: nobody builds their rows, so nothing is pushed to them)
+    const bool kj = k && ids[j] < n_rows;
+    const int vj = kj ? ids[j] : -1 - lane;  // a culled lane never continues a run
     const int prev = __shfl_up_sync(FULL, vj, 1);
     const unsigned heads = __ballot_sync(FULL, lane == 0 || vj != prev);
     const int start = 31 - __clz(heads & (lt | (1u << lane)));
@@ -172,12 +197,12 @@ __global__ void __launch_bounds__(DM_CS_THREADS, DM_CS_MINB) cull_scatter_kernel
     leader[j] = start;
     rank[j] = lane - start;
     base[j] = 0;
-    if (k && lane == start) base[j] = atomicAdd(cnt + ids[j], end - start);
+    if (kj && lane == start) base[j] = atomicAdd(cnt + ids[j], end - start);
   }
 #pragma unroll
   for (int j = 0; j <= DIM; ++j) {
     const int slot = __shfl_sync(FULL, base[j], leader[j]) + rank[j];
-    if (k) {
+    if (k && ids[j] < n_rows) {
       const typename PCfg<DIM>::entry_t e = others_of<DIM>(ids, j);
       if (slot < CAP) {
         bucket[(int64_t)ids[j] * CAP + slot] = e;
@@ -562,10 +587,11 @@ __device__ __noinline__ RowSums select_row(bool punt, int n, int v,
 template <int DIM, int BAR>
 __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     const int32_t* __restrict__ cnt, const typename PCfg<DIM>::entry_t* __restrict__ bucket,
-    const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N,
+    const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N, int64_t NR,
     int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
     int32_t* __restrict__ counters, const __grid_constant__ DmSizeFn f, const double* __restrict__ pp,
     double* __restrict__ hslot, double* partials, int32_t* gdone, int32_t* total_done, double* scalars) {
+  // N: vertices (sizes the per-slot arrays) ; NR <= N: vertices that get a row (the grid covers NR)
   pdl_prologue();
   constexpr int CAP = PCfg<DIM>::CAP, RS = PCfg<DIM>::RS, G = PCfg<DIM>::G, LOGH = PCfg<DIM>::LOGH;
   constexpr int H = 1 << LOGH;
@@ -620,7 +646,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     t4[1] = make_int4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
     tab[H + lg] = HASH_PARKED;  // the lane's parking word (see hash_insert_lockstep)
   }
-  int n = v < N ? cnt[v] : 0;
+  int n = v < NR ? cnt[v] : 0;
   const bool heavy = n > CAP;  // overflowed bucket: a heavy-vertex block builds this row
   if (heavy) n = 0;
   bool punt = false;
@@ -713,7 +739,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
   // ---- write the row
   int bars = 0;
   double sL = 0.0, sH = 0.0;
-  if (v < N && !heavy && !punt) {
+  if (v < NR && !heavy && !punt) {
     int32_t* row = adj + v * RS;
     int64_t sbase = v * RS;
     if (U <= RS) {
@@ -814,11 +840,15 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
 }
 
 // bar ids: rowptr[v] = #upper neighbours (scanned afterwards)
-__global__ void upper_count_kernel(const int2* __restrict__ degs, int64_t N, int32_t* __restrict__ rowptr) {
+__global__ void upper_count_kernel(const int2* __restrict__ degs, int64_t N, int64_t NR, int32_t* __restrict__ rowptr) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v < N) {
-    const int2 d = degs[v];
-    rowptr[v] = d.x - d.y;
+    int n = 0;
+    if (v < NR) {  // vertices without a row (ghost copies) own no bar
+      const int2 d = degs[v];
+      n = d.x - d.y;
+    }
+    rowptr[v] = n;
   }
 }
 
@@ -1098,10 +1128,14 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
   }
 }
 
-// max_v |p[v] - p_ref[v]|_2 -> scalars[5]: the displacement since the last retriangulation (the
-// `ttol` test of DistMesh, Persson & Strang; north_star (5)).  Last block reduces; self-resetting.
-template <int DIM>
-__global__ void __launch_bounds__(PL_THREADS) displacement_kernel(const double* __restrict__ p,
+// max_v |p[v] - p_ref[v]|_2 / h_v -> scalars[5]: the displacement since the last retriangulation (the
+// `ttol` test of DistMesh, Persson & Strang; north_star (5)), measured in units of the LOCAL mesh size:
+// h_v = 1 (REL = 0: absolute displacement), or fh(p[v]) for a constant / gridded size function
+// (REL = 1).  On a graded mesh the coarse regions move far more than ttol * hmin every iteration, so
+// an absolute test retriangulates every time; relative to the local size it behaves like the uniform
+// case.  Last block reduces; self-resetting.
+template <int DIM, int REL>
+__global__ void __launch_bounds__(PL_THREADS) displacement_kernel(const DmSizeFn f, const double* __restrict__ p,
                                                                  const double* __restrict__ p_ref, int64_t N,
                                                                  double* partials, int32_t* done, double* scalars) {
   pdl_prologue();
@@ -1116,6 +1150,10 @@ __global__ void __launch_bounds__(PL_THREADS) displacement_kernel(const double* 
     const double e0 = a0 - b0, e1 = a1 - b1, e2 = a2 - b2;
     d2 = e0 * e0 + e1 * e1;
     if (DIM == 3) d2 = d2 + e2 * e2;
+    if (REL) {
+      const double h = f.kind == DM_SIZE_GRID ? size_eval(f, a0, a1, a2) : f.hconst;
+      d2 = d2 / (h * h);
+    }
   }
   const double bm = block_max(d2, sm);
   if (threadIdx.x == 0) {

@@ -1,24 +1,22 @@
-// Stage B, second design (round 2): one THREAD per vertex, one private hash set per thread.
+// Stage B, alternative design (round 2 experiment; OFF by default, DM_ROWS=1 selects it): one THREAD per
+// vertex with a private hash set, instead of the 8-lane group per vertex of adjacency_kernel.
 //
-// The round-1 kernel (adjacency_kernel, dm_pipeline.cuh) gives a vertex to a group of 8 lanes that
-// share one open-addressing table and insert in warp lockstep (write, __syncwarp, verify): 270 warp
-// instructions per vertex, 33 M shared-memory wavefronts of which 29 % are bank conflicts, 72 % of
-// the issue slots busy -- it is issue / LDS bound, not byte bound (profiles/r1d_*).
-//
-// Here a warp takes a TILE of 32 consecutive vertices, lane = vertex:
-//   * the lane walks its own bucket (the DIM other ids of every incident kept cell, written by stage A)
-//     and inserts every id into its PRIVATE table tab[slot * 32 + lane]: the bank of every access is
-//     the lane id, so no access of the kernel's inner loop ever conflicts, nothing is shared between
-//     lanes, and there is no atomic, no __syncwarp and no verify pass; a new id is also appended to
-//     the lane's row buffer, so the de-duplicated neighbour set needs no compaction pass;
-//   * the <= RS ids of the row buffer are sorted by a compile-time bitonic network on REGISTERS
-//     (240 compare-exchanges in 3-D, no divergence), which also yields nlow = #{ids < v};
-//   * the 32 rows leave through shared memory as 128-B (3-D) / 64-B (2-D) coalesced stores;
-//   * the bar pass over the row's upper part (L, fh(midpoint), sum L^d, sum h^d) follows per lane.
-// A vertex with more than RS distinct neighbours (legal, rare: not a manifold star) is built by the
-// whole warp, minimum by minimum, straight from its bucket (slow_row); vertices whose bucket
-// overflowed (hubs) are built by the heavy-vertex blocks at the head of the grid, as before.
-// About 80 warp instructions per vertex; the reductions to the force scale are those of round 1.
+// A warp takes a TILE of 32 consecutive vertices, lane = vertex:
+//   * the lane walks its own bucket (stage A's output) and inserts every id into its PRIVATE table
+//     tab[slot * 32 + lane]: the bank of every access is the lane id, nothing is shared between lanes,
+//     no atomic, no __syncwarp, no verify pass;
+//   * the table column is compacted in place, sorted by a compile-time bitonic network on REGISTERS
+//     (which also yields nlow = #{ids < v}), and the 32 rows leave as coalesced 16-B stores;
+//   * the bar pass over the row's upper part follows per lane; rows with more than RS ids are built
+//     by the whole warp (slow_row), bucket overflows by the heavy-vertex blocks, as before.
+// Parity: the complete GPU suite passes with it (103 tests, gpurun_out r2b / r2d).
+// Measured on B200 (ball h0 = 0.02, profiles/r2d_*): 84 M warp instructions against 142 M for the
+// lane-group kernel, but only 21 of 64 warps resident (8 KB of table per warp, 80 registers) and
+// IPC 0.41 against 0.72: 207 us against 191 us; gridded fh: 100 us against 56 us (EAGE-shaped), since the
+// per-lane bar pass serialises seven trilinear lookups where the group spreads them over 8 lanes.
+// The cost is SIMT divergence: a warp executes the probe / insert path of an id whenever ANY of its
+// 32 lanes needs it (94 % of the id rounds), so the 80 % of ids that are duplicates save nothing.
+// Kept as the record of that measurement; adjacency_kernel stays the product path.
 #pragma once
 #include "dm_pipeline.cuh"
 

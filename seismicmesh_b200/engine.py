@@ -103,6 +103,7 @@ class ForceLoop:
         self.L0mult = 1 + 0.4 / 2 ** (dim - 1)
         self.nfix = int(nfix)
         self.fixed_mask = None  # optional (N,) uint8 device mask of additional fixed vertices
+        self.n_rows = None      # slabs: local vertices are [owned | ghosts] and only the first n_rows are owned
         self.plan = None
         self.all_lowered = all(lv.lowered for lv in levels) and size.lowered
         self._progs = [lv.prog for lv in levels if lv.lowered]
@@ -117,6 +118,8 @@ class ForceLoop:
         # the C plan is sized for capacity; the live cell count is set per call
         self.plan.c.T = T
         self.plan.c.K = self.dim * (self.dim + 1) * T
+        # multi-GPU slabs: only the first n_rows (owned) vertices get rows / forces / an update
+        check(lib.dm_plan_set_rows(C.byref(self.plan.c), N if self.n_rows is None else int(self.n_rows)), "dm_plan_set_rows")
         return self.plan
 
     # -- the iteration --------------------------------------------------------------------
@@ -191,53 +194,64 @@ class ForceLoop:
                     self.host_seconds += time.perf_counter() - t0
         return p_out, Ftot
 
-    def iterate_host(self, p_pin, t_pin, out_pin, chunks=8):
+    def iterate_host(self, p_pin, t_pin, out_pin, chunks=8, p_dev=None):
         """One force iteration with HOST buffers in and out (pinned torch CPU tensors: p (N,dim) f64,
         t (T,dim+1) i32, out (N,dim) f64): what a driver whose Delaunay lives on the host does every
-        iteration.  The cell list is uploaded in `chunks` pieces on a copy stream and stage A runs on
-        each piece as it lands, so the cull + scatter hides behind the PCIe transfer; stages B-D
-        follow, then the new positions go back.  Returns the device tensor of the new positions."""
+        iteration, and what `generate_mesh` itself calls.  The cell list is uploaded in `chunks` pieces
+        on a copy stream and stage A runs on each piece as it lands, so the cull + scatter hides behind
+        the PCIe transfer; stages B-D follow, then the new positions go back (asynchronously: the
+        caller synchronises before reading `out_pin`).  `p_dev`: the positions are already on the
+        device (the previous call's result) -- `p_pin` is then ignored and only the cells travel.
+        Returns the device tensor of the new positions (valid until the call after the next)."""
         if not self.all_lowered:
             raise RuntimeError("iterate_host needs lowered fd / fh")
-        N, T = p_pin.shape[0], t_pin.shape[0]
+        N, T = out_pin.shape[0], t_pin.shape[0]
         pl = self.ensure_plan(N, T)
         dev = D.device()
         hb = getattr(self, "_host_bufs", None)
         if hb is None or hb[0].shape[0] != N or hb[1].shape[0] < T:
-            hb = (torch.empty((N, self.dim), dtype=torch.float64, device=dev),
-                  torch.empty((max(T, 1), self.dim + 1), dtype=torch.int32, device=dev),
-                  torch.empty((N, self.dim), dtype=torch.float64, device=dev), torch.cuda.Stream(device=dev))
+            cap = max(T, 1) if hb is None or hb[0].shape[0] != N else max(T, int(hb[1].shape[0] * 1.25))
+            hb = [torch.empty((N, self.dim), dtype=torch.float64, device=dev),
+                  torch.empty((cap, self.dim + 1), dtype=torch.int32, device=dev),
+                  torch.empty((N, self.dim), dtype=torch.float64, device=dev), torch.cuda.Stream(device=dev),
+                  torch.empty((N, self.dim), dtype=torch.float64, device=dev)]
             self._host_bufs = hb
-        p_dev, t_dev, p_out, cs = hb
+        t_dev, cs = hb[1], hb[3]
+        # two result buffers, alternating: the caller may hand the previous result back as `p_dev`
+        p_out = hb[2] if (p_dev is None or p_dev.data_ptr() != hb[2].data_ptr()) else hb[4]
+        p_in = hb[0] if p_dev is None else p_dev
         ms = torch.cuda.current_stream()
         st = D.stream_ptr()
-        cs.wait_stream(ms)  # the previous call's kernels are done with p_dev / t_dev
+        cs.wait_stream(ms)  # the previous call's kernels are done with p_in / t_dev
         nch = max(1, min(int(chunks), T)) if T > 0 else 0
         bounds = [T * k // nch for k in range(nch + 1)] if nch else [0]
         evs = []
         with torch.cuda.stream(cs):
-            p_dev.copy_(p_pin, non_blocking=True)
-            ev_p = torch.cuda.Event()
-            ev_p.record(cs)
+            ev_p = None
+            if p_dev is None:
+                p_in.copy_(p_pin, non_blocking=True)
+                ev_p = torch.cuda.Event()
+                ev_p.record(cs)
             for k in range(nch):
                 a, b = bounds[k], bounds[k + 1]
                 t_dev[a:b].copy_(t_pin[a:b], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(cs)
                 evs.append(e)
-        ms.wait_event(ev_p)
-        check(lib.dm_stage_prep(C.byref(pl.c), D.ptr(p_dev), st), "dm_stage_prep")
+        if ev_p is not None:
+            ms.wait_event(ev_p)
+        check(lib.dm_stage_prep(C.byref(pl.c), D.ptr(p_in), st), "dm_stage_prep")
         prog0 = D.ptr(self._progs[0])
         for k in range(nch):
             a, b = bounds[k], bounds[k + 1]
             ms.wait_event(evs[k])
-            check(lib.dm_stage_cull_chunk(C.byref(pl.c), prog0, D.ptr(p_dev), C.c_void_p(t_dev.data_ptr() + 4 * (self.dim + 1) * a),
+            check(lib.dm_stage_cull_chunk(C.byref(pl.c), prog0, D.ptr(p_in), C.c_void_p(t_dev.data_ptr() + 4 * (self.dim + 1) * a),
                                           a, b - a, self.geps, 1, st), "dm_stage_cull_chunk")
         f = self.size.struct()
         progs = D.prog_array(self._progs)
         check(
             lib.dm_force_iteration_tail(
-                C.byref(pl.c), progs, len(self._progs), C.byref(f), D.ptr(p_dev), D.ptr(p_out), self.L0mult, self.delta_t,
+                C.byref(pl.c), progs, len(self._progs), C.byref(f), D.ptr(p_in), D.ptr(p_out), self.L0mult, self.delta_t,
                 self.deps, self.h0, self.nfix, D.ptr(self.fixed_mask), None, st,
             ),
             "dm_force_iteration_tail",
@@ -265,9 +279,21 @@ class ForceLoop:
         )
         return p_out, Ftot
 
-    def displacement(self, p, p_ref):
-        """max_v |p[v] - p_ref[v]| on the device (the DistMesh `ttol` test); returns a float."""
-        check(lib.dm_stage_displacement(C.byref(self.plan.c), D.ptr(p), D.ptr(p_ref), D.stream_ptr()), "displacement")
+    def spare_like(self, p):
+        """An (N,dim) device buffer that is not `p` (two alternate; for ping-pong callers)."""
+        sp = getattr(self, "_spare", None)
+        if sp is None or sp[0].shape != p.shape:
+            sp = [torch.empty_like(p), torch.empty_like(p)]
+            self._spare = sp
+        return sp[0] if p.data_ptr() != sp[0].data_ptr() else sp[1]
+
+    def displacement(self, p, p_ref, relative=False):
+        """max_v |p[v] - p_ref[v]| on the device (the DistMesh `ttol` test); returns a float.
+        relative=True: every vertex's displacement is divided by the local mesh size fh(p[v]), which is
+        what makes the test meaningful on graded meshes (lowered fh only)."""
+        f = self.size.struct() if relative and self.size.lowered else None
+        check(lib.dm_stage_displacement(C.byref(self.plan.c), D.ptr(p), D.ptr(p_ref), C.byref(f) if f is not None else None,
+                                        D.stream_ptr()), "displacement")
         return float(self.plan.scalars()[5].item())
 
     def maxdp(self):

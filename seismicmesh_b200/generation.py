@@ -216,6 +216,141 @@ def _comm_info(comm):
     return int(getattr(comm, "rank", 0)), int(getattr(comm, "size", 1))
 
 
+def _finish(loop, p_host, p_dev, t_dev, level0, size, h0, deps, dim, gen_opts, stats, print_msg1):
+    """max_iter reached (reference :485-494): cull, host clean-up, level-set Newton, final tight cull."""
+    print_msg1("Termination reached...maximum number of iterations reached.")
+    tt = time.perf_counter()
+    t_kept = loop.kept_cells(p_dev, t_dev).cpu().numpy()
+    p_out, t_out = _termination(p_host, t_kept, gen_opts, dim, verbose=gen_opts["verbose"])
+    p_out = _level_set_newton(p_out, t_out, level0, deps, dim)
+    # final cull with a tight tolerance (reference :493)
+    pd = D.to_dev(p_out, torch.float64)
+    td = D.to_dev(t_out, torch.int32)
+    fin = ForceLoop(dim, [level0], size, h0, h0 * 0.001, deps)
+    t_out = fin.kept_cells(pd, td).cpu().numpy().astype(t_out.dtype)
+    stats["termination"] += time.perf_counter() - tt
+    return p_out, t_out
+
+
+def _loop_pinned(loop, tri, p, N, dim, h0, deps, max_iter, ttol, level0, size, gen_opts, stats, print_msg1, print_msg2):
+    """The DistMesh loop (reference :460-527) for lowered fd / fh: positions live on the device, the host
+    Delaunay reads them from / writes its cells to PINNED staging buffers (raw-pointer triangulators,
+    no intermediate arrays), the cell list goes up in chunks overlapped with stage A and the new
+    positions come back asynchronously (ForceLoop.iterate_host -- the call bench.py's `e2e` leg times).
+    `ttol` (extension): iterations between two retriangulations re-use the neighbour rows and never
+    leave the device; the displacement test is relative to the local mesh size."""
+    pins = [torch.empty((N, dim), dtype=torch.float64).pin_memory() for _ in range(2)]
+    pins[0].copy_(torch.from_numpy(np.ascontiguousarray(p)))
+    cur = 0                       # pins[cur] mirrors the device positions whenever host_current
+    cap = max(int(tri.max_cells(N)) if hasattr(tri, "max_cells") else 8 * N + 64, 1)
+    t_pin = torch.empty((cap, dim + 1), dtype=torch.int32).pin_memory()
+    sc_pin = torch.empty(8, dtype=torch.float64).pin_memory()
+    p_dev = D.to_dev(p, torch.float64)
+    host_current = True
+    p_tri = None                  # positions at the last retriangulation (ttol test)
+    t_dev = None
+    T = 0
+    disp = float("inf")
+    count = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while True:
+        start = time.time()
+        last = count == (max_iter - 1)
+        retri = last or ttol is None or p_tri is None or disp > ttol
+        if retri:
+            if not host_current:
+                t3 = time.perf_counter()
+                pins[cur].copy_(p_dev, non_blocking=True)
+                torch.cuda.synchronize()
+                host_current = True
+                stats["d2h"] += time.perf_counter() - t3
+            t0 = time.perf_counter()
+            pts = pins[cur].numpy()
+            if hasattr(tri, "triangulate_into"):
+                T = tri.triangulate_into(pts, t_pin.numpy())
+                if T < 0:  # capacity: a pathological point set needs more than the usual bound
+                    t_pin = torch.empty((int(-T * 1.1) + 64, dim + 1), dtype=torch.int32).pin_memory()
+                    T = tri.triangulate_into(pts, t_pin.numpy())
+            else:
+                th = np.ascontiguousarray(tri.triangulate(pts), dtype=np.int32)
+                T = len(th)
+                if T > t_pin.shape[0]:
+                    t_pin = torch.empty((int(T * 1.1) + 64, dim + 1), dtype=torch.int32).pin_memory()
+                t_pin.numpy()[:T] = th
+            stats["delaunay"] += time.perf_counter() - t0
+            stats["triangulations"] += 1
+            if ttol is not None:
+                p_tri = p_dev.clone()
+
+        if last:
+            t_dev = D.to_dev(t_pin[:T], torch.int32)
+            return _finish(loop, pins[cur].numpy().copy(), p_dev, t_dev, level0, size, h0, deps, dim, gen_opts, stats,
+                           print_msg1)
+
+        ev0.record()
+        if retri:
+            nxt = cur ^ 1
+            p_dev = loop.iterate_host(None, t_pin[:T], pins[nxt], p_dev=p_dev)
+            cur = nxt
+            host_current = True
+        else:
+            p_dev, _ = loop.iterate_reuse(p_dev, p_out=loop.spare_like(p_dev))
+            host_current = False
+        sc_pin.copy_(loop.plan.scalars(), non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        stats["device"] += ev0.elapsed_time(ev1) * 1e-3
+        maxdp = float(sc_pin[4])
+        if ttol is not None:
+            disp = loop.displacement(p_dev, p_tri, relative=True)
+        stats["iterations"] += 1
+        print_msg2(
+            "Iteration #%d, max movement is %f, there are %d vertices and %d cells"
+            % (count + 1, maxdp, N, _kept_count(loop) if gen_opts["verbose"] > 1 else 0)
+        )
+        assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
+        count += 1
+        print_msg2("     Elapsed wall-clock time %f : " % (time.time() - start))
+
+
+def _loop_staged(loop, tri, p, N, dim, h0, deps, max_iter, level0, size, gen_opts, stats, print_msg1, print_msg2):
+    """The same loop when `domain` / `edge_length` is an opaque Python callable: user code is evaluated
+    on the host through staged copies inside ForceLoop.iterate (reported as `host_callables`)."""
+    p_dev = D.to_dev(p, torch.float64)
+    p_host = p
+    count = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while True:
+        start = time.time()
+        t0 = time.perf_counter()
+        t_host = tri.triangulate(p_host)
+        t1 = time.perf_counter()
+        t_dev = D.to_dev(t_host, torch.int32)
+        torch.cuda.synchronize()
+        stats["delaunay"] += t1 - t0
+        stats["h2d"] += time.perf_counter() - t1
+        stats["triangulations"] += 1
+        if count == (max_iter - 1):
+            return _finish(loop, p_host, p_dev, t_dev, level0, size, h0, deps, dim, gen_opts, stats, print_msg1)
+        ev0.record()
+        p_dev, _ = loop.iterate(p_dev, t_dev)
+        ev1.record()
+        torch.cuda.synchronize()
+        stats["device"] += ev0.elapsed_time(ev1) * 1e-3
+        t3 = time.perf_counter()
+        p_host = p_dev.cpu().numpy()
+        maxdp = loop.maxdp()
+        stats["d2h"] += time.perf_counter() - t3
+        stats["iterations"] += 1
+        print_msg2(
+            "Iteration #%d, max movement is %f, there are %d vertices and %d cells"
+            % (count + 1, maxdp, N, _kept_count(loop) if gen_opts["verbose"] > 1 else 0)
+        )
+        assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
+        count += 1
+        print_msg2("     Elapsed wall-clock time %f : " % (time.time() - start))
+
+
 def generate_mesh(domain, edge_length, comm=None, **kwargs):  # noqa: C901
     r"""Generate a 2D/3D simplicial mesh with DistMesh (see the reference docstring,
     mesh_generator.py:291-342, for the meaning of every keyword argument).
@@ -308,79 +443,12 @@ def generate_mesh(domain, edge_length, comm=None, **kwargs):  # noqa: C901
             ttol = None
     stats = dict(delaunay=0.0, h2d=0.0, device=0.0, d2h=0.0, termination=0.0, iterations=0, nverts=N,
                  triangulator=tri.name, triangulations=0)
-    p_dev = D.to_dev(p, torch.float64)
-    p_host = p
-    host_current = True  # p_host mirrors p_dev
-    p_tri = None         # positions at the last retriangulation (ttol test)
-    t_dev = None
-    disp = float("inf")
-    count = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while True:
-        start = time.time()
-        last = count == (max_iter - 1)
-        retri = last or ttol is None or p_tri is None or disp > ttol * h0
-        if retri:
-            if not host_current:
-                t3 = time.perf_counter()
-                p_host = p_dev.cpu().numpy()
-                host_current = True
-                stats["d2h"] += time.perf_counter() - t3
-            t0 = time.perf_counter()
-            t_host = tri.triangulate(p_host)
-            t1 = time.perf_counter()
-            t_dev = D.to_dev(t_host, torch.int32)
-            torch.cuda.synchronize()
-            t2 = time.perf_counter()
-            stats["delaunay"] += t1 - t0
-            stats["h2d"] += t2 - t1
-            stats["triangulations"] += 1
-            if ttol is not None:
-                p_tri = p_dev.clone()
-
-        if last:
-            print_msg1("Termination reached...maximum number of iterations reached.")
-            tt = time.perf_counter()
-            t_kept = loop.kept_cells(p_dev, t_dev).cpu().numpy()
-            p_out, t_out = _termination(p_host, t_kept, gen_opts, dim, verbose=gen_opts["verbose"])
-            p_out = _level_set_newton(p_out, t_out, level0, deps, dim)
-            # final cull with a tight tolerance (reference :493)
-            pd = D.to_dev(p_out, torch.float64)
-            td = D.to_dev(t_out, torch.int32)
-            fin = ForceLoop(dim, [level0], size, h0, h0 * 0.001, deps)
-            t_out = fin.kept_cells(pd, td).cpu().numpy().astype(t_out.dtype)
-            stats["termination"] += time.perf_counter() - tt
-            p_host = p_out
-            t_host = t_out
-            break
-
-        ev0.record()
-        if retri:
-            p_new, _ = loop.iterate(p_dev, t_dev)
-        else:
-            p_new, _ = loop.iterate_reuse(p_dev)
-        ev1.record()
-        torch.cuda.synchronize()
-        stats["device"] += ev0.elapsed_time(ev1) * 1e-3
-        t3 = time.perf_counter()
-        p_dev = p_new
-        if ttol is None:
-            p_host = p_dev.cpu().numpy()
-        else:  # positions stay on the device until the next retriangulation
-            host_current = False
-            disp = loop.displacement(p_dev, p_tri)
-        maxdp = loop.maxdp()
-        stats["d2h"] += time.perf_counter() - t3
-        stats["iterations"] += 1
-        print_msg2(
-            "Iteration #%d, max movement is %f, there are %d vertices and %d cells"
-            % (count + 1, maxdp, N, _kept_count(loop) if gen_opts["verbose"] > 1 else 0)
-        )
-        assert maxdp < 1000 * h0, "max movement indicates there's a convergence problem"
-        count += 1
-        end = time.time()
-        print_msg2("     Elapsed wall-clock time %f : " % (end - start))
-
+    if loop.all_lowered:
+        p_host, t_host = _loop_pinned(loop, tri, p, N, dim, h0, deps, max_iter, ttol, level0, size, gen_opts, stats,
+                                      print_msg1, print_msg2)
+    else:
+        p_host, t_host = _loop_staged(loop, tri, p, N, dim, h0, deps, max_iter, level0, size, gen_opts, stats,
+                                      print_msg1, print_msg2)
     stats["host_callables"] = loop.host_seconds
     last_run_stats.clear()
     last_run_stats.update(stats)

@@ -334,6 +334,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         "points": None, "delta_t": 0.30, "geps_mult": 0.1, "subdomains": None, "mesh_improvement": True,
         "r0m_is_h0": False, "triangulator": None, "ttol": None,
     }
+    return_state = bool(kwargs.pop("_return_state", False))  # bench.py: stop before the gather, hand the slab over
     gen_opts.update(kwargs)
     G._parse_kwargs(kwargs)
     if gen_opts["pfix"] is not None and rank == 0:
@@ -451,7 +452,8 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         fl = flags[:n_own].cpu().numpy()
         from_above, from_below = _exchange_ghosts(p[(fl & 1) != 0], p[(fl & 2) != 0], rank, size_, dim, cdev, group)
         stats["exchange"] += time.perf_counter() - t1
-        ghosts = [g for g in (from_above, from_below) if len(g)]
+        # local vertex order: [owned | ghosts from below | ghosts from above]
+        ghosts = [g for g in (from_below, from_above) if len(g)]
         p_loc = np.ascontiguousarray(np.vstack([p] + ghosts)) if ghosts else p
         t0 = time.perf_counter()
         t_loc = tri.triangulate(p_loc) if ghosts else t_own
@@ -464,6 +466,14 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         pd = D.to_dev(p_loc, torch.float64)
         td = D.to_dev(t_loc, torch.int32)
 
+        if count == (max_iter - 1) and return_state:
+            # the slab as the next force iteration would see it (bench.py's multi-GPU step): local points
+            # and cells, what this rank exports to rank-1 / rank+1 (rows of the owned block, in the order
+            # the neighbours hold them as ghosts) and how many ghosts it holds from each side
+            G.last_run_stats.clear()
+            G.last_run_stats.update(stats)
+            return dict(p=p_loc, t=t_loc, n_owned=n_own, export_below=np.nonzero(fl & 1)[0], export_above=np.nonzero(fl & 2)[0],
+                        n_ghost_below=len(from_below), n_ghost_above=len(from_above), extents=extents, dim=dim, h0=h0)
         if count == (max_iter - 1):
             # The reference gathers the local meshes (ghost copies included) and de-duplicates them on
             # rank 0 (migration.aggregate + fix_mesh); here rank 0 gathers the OWNED vertices and
@@ -484,6 +494,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
 
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        loop.n_rows = n_own  # rows, forces and the update for the owned vertices only; ghosts are just neighbours
         p_new, _ = loop.iterate(pd, td)
         ev1.record()
         p = np.ascontiguousarray(p_new[:n_own].cpu().numpy())  # "delete ghost points"

@@ -28,6 +28,18 @@ class QhullTriangulator:
 
         return np.ascontiguousarray(Delaunay(points).simplices, dtype=np.int32)
 
+    def max_cells(self, n):
+        return (2 * n if self.dim == 2 else 8 * n) + 64
+
+    def triangulate_into(self, points, cells):
+        """cells of `points` written into the caller's (cap, dim+1) int32 buffer; returns their number,
+        or minus the capacity that is needed when `cells` is too small."""
+        t = self.triangulate(points)
+        if len(t) > len(cells):
+            return -len(t)
+        cells[: len(t)] = t
+        return len(t)
+
 
 class SweepHullTriangulator:
     """2-D Delaunay by ``dmh_delaunay2d`` (exact predicates, vertex ids = input rows)."""
@@ -63,6 +75,26 @@ class SweepHullTriangulator:
             self.qhull_retries += 1
             return QhullTriangulator(2).triangulate(p)
         return np.ascontiguousarray(cells[: T.value])
+
+    def max_cells(self, n):
+        return int(self._lib.dmh_delaunay2d_max_cells(n))
+
+    def triangulate_into(self, points, cells):
+        """Raw-buffer form: `points` (N,2) float64 and `cells` (cap,3) int32 are the
+        caller's C-contiguous buffers (the pinned staging buffers of the device loop); the cells are
+        written in place, no intermediate array.  Returns the number of cells, or minus the capacity
+        that is needed."""
+        n = len(points)
+        T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        rc = self._lib.dmh_delaunay2d(points.ctypes.data, n, cells.ctypes.data, len(cells), C.byref(T), C.byref(dups), C.byref(lost))
+        if rc == -2:
+            return -int(T.value)
+        if rc != 0:
+            raise RuntimeError(f"dmh_delaunay2d failed with code {rc}")
+        if lost.value and T.value:
+            self.qhull_retries += 1
+            return QhullTriangulator(2).triangulate_into(points, cells)
+        return int(T.value)
 
 
 class BowyerWatsonTriangulator:
@@ -102,6 +134,23 @@ class BowyerWatsonTriangulator:
             self.qhull_retries += 1
             return QhullTriangulator(3).triangulate(p)
         return np.ascontiguousarray(cells[: T.value])
+
+    def max_cells(self, n):
+        return int(self._lib.dmh_delaunay3d_max_cells(n))
+
+    def triangulate_into(self, points, cells):
+        """Raw-buffer form: see SweepHullTriangulator.triangulate_into."""
+        n = len(points)
+        T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        rc = self._lib.dmh_delaunay3d(points.ctypes.data, n, cells.ctypes.data, len(cells), C.byref(T), C.byref(dups), C.byref(lost))
+        if rc == -2:
+            return -int(T.value)
+        if rc != 0:
+            raise RuntimeError(f"dmh_delaunay3d failed with code {rc}")
+        if lost.value and n >= 4:
+            self.qhull_retries += 1
+            return QhullTriangulator(3).triangulate_into(points, cells)
+        return int(T.value)
 
 
 def get_triangulator(spec, dim):

@@ -558,6 +558,38 @@ def test_hub_vertex_full_iteration_vs_oracle(sm, dim, grid):
     assert relerr(Fr.cpu().numpy(), ref["Ftot"]) < TOL and relerr(again.cpu().numpy(), ref["p"]) < PTOL
 
 
+@pytest.mark.parametrize("dim,h0", [(2, 0.03), (3, 0.1)])
+def test_owned_rows_only(sm, dim, h0):
+    """Multi-GPU slabs (dm_plan_set_rows): with the local vertices ordered [owned | ghosts], rows, bar sums,
+    forces and the update exist for the owned vertices only; the ghosts are only neighbours.  Owned rows
+    against the oracle restricted the same way; ghost rows of the output are left alone."""
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dom = sm.Disk([0.0, 0.0], 1.0) if dim == 2 else sm.Ball([0.0, 0.0, 0.0], 1.0)
+    p, t = _lattice_mesh(sm, dom, h0, dim, seed=2)
+    # "ghosts" = the vertices with the largest coordinate along axis 1, moved to the end of the numbering
+    order = np.argsort(p[:, 1], kind="stable")
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    p, t = np.ascontiguousarray(p[order]), np.ascontiguousarray(inv[t].astype(np.int32))
+    n_own = int(0.8 * len(p))
+    t = np.ascontiguousarray(t[(t < n_own).any(axis=1)])  # cells made only of ghosts belong to the neighbour
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    loop = ForceLoop(dim, [Level(dom, dim)], SizeSpec(dim, const=h0), h0, geps, deps)
+    loop.n_rows = n_own
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    out = torch.full_like(pd, 7.0)
+    p_new, F = loop.iterate(pd, td, p_out=out, want_forces=True)
+    spec = dom.spec()
+    ref = orc.force_iteration(p, t, [lambda x: orc.sdf(spec, x)], lambda x: np.array([h0] * len(x)), h0, geps, deps,
+                              n_rows=n_own)
+    assert np.array_equal(loop.bars().cpu().numpy(), ref["bars"])
+    assert relerr(F.cpu().numpy()[:n_own], ref["Ftot"][:n_own]) < TOL
+    assert relerr(p_new.cpu().numpy()[:n_own], ref["p"][:n_own]) < PTOL
+    assert (p_new.cpu().numpy()[n_own:] == 7.0).all()
+    assert abs(loop.maxdp() - 0.30 * np.sqrt((ref["Ftot"][:n_own] ** 2).sum(1)).max()) < 1e-12
+
+
 @pytest.mark.parametrize("dim,h0,grid", [(2, 0.02, False), (3, 0.08, False), (3, 0.1, True)])
 def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
     """The opt-in `ttol` path: an iteration that re-uses the neighbour rows (no retriangulation) must
@@ -587,6 +619,20 @@ def test_row_reuse_iteration_and_displacement(sm, dim, h0, grid):
     assert np.array_equal(twice.cpu().numpy(), again.cpu().numpy())
     d = loop.displacement(again, pd)
     assert d == np.sqrt(((again.cpu().numpy() - p) ** 2).sum(1)).max()
+    # relative to the local mesh size (what the graded `ttol` test uses): |dp| / fh(p_new)
+    a = again.cpu().numpy()
+    hloc = orc.interp_grid(ax, vals, a) if grid else np.full(len(a), h0)
+    dr = loop.displacement(again, pd, relative=True)
+    assert abs(dr - (np.sqrt(((a - p) ** 2).sum(1)) / hloc).max()) <= 1e-12 * dr
+    # the host-buffer call with the positions already resident (what generate_mesh does every iteration):
+    # same bits as the plain device call, results alternate between two buffers
+    t_pin = torch.from_numpy(t).pin_memory()
+    o1, o2 = torch.empty_like(torch.from_numpy(p)).pin_memory(), torch.empty_like(torch.from_numpy(p)).pin_memory()
+    q1 = loop.iterate_host(None, t_pin, o1, p_dev=pd)
+    q2 = loop.iterate_host(None, t_pin, o2, p_dev=q1)
+    torch.cuda.synchronize()
+    assert q1.data_ptr() != q2.data_ptr()
+    assert np.array_equal(o1.numpy(), p1.cpu().numpy()) and np.array_equal(o2.numpy(), full.cpu().numpy())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -658,6 +704,28 @@ def test_generate_mesh_ttol_opt_in(sm):
     assert abs(meshutil.simp_vol(p1, t1).sum() - np.pi) < 0.01 * np.pi
     with pytest.raises(ValueError, match="ttol"):
         sm.generate_mesh(dom, 0.05, max_iter=3, verbose=0, ttol=-1.0)
+
+
+def test_generate_mesh_ttol_on_a_graded_mesh(sm):
+    """The displacement test is relative to the LOCAL mesh size: on a graded size function (where the
+    coarse region moves far more than ttol * hmin every iteration, so an absolute test retriangulated
+    50 times out of 50 in round 1) `ttol` now skips retriangulations, at the quality of the reference
+    semantics."""
+    from seismicmesh_b200 import meshutil
+
+    g = load_golden("interp_2d.npz")
+    bbox = tuple(g["bbox"].tolist())
+    ef = sm.SizeFunction(bbox, sm.GridInterpolant([g["axis0"], g["axis1"]], g["grid"]), float(g["hmin"]))
+    rect = sm.Rectangle(bbox)
+    p0, t0 = sm.generate_mesh(rect, ef, max_iter=40, verbose=0)
+    base = dict(sm.last_run_stats)
+    p1, t1 = sm.generate_mesh(rect, ef, max_iter=40, verbose=0, ttol=0.1)
+    lazy = dict(sm.last_run_stats)
+    assert base["triangulations"] == 40 and lazy["iterations"] == 39
+    assert lazy["triangulations"] <= base["triangulations"] // 2
+    q0, q1 = meshutil.simp_qual(p0, t0), meshutil.simp_qual(p1, t1)
+    assert abs(len(p1) - len(p0)) <= 0.01 * len(p0)
+    assert abs(q1.mean() - q0.mean()) <= 0.01 * q0.mean()
 
 
 def test_generate_mesh_gridded_rectangle(sm):

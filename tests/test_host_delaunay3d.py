@@ -236,3 +236,25 @@ def test_random_degenerate_stress_3d(hl, tri):  # noqa: F811
         _check_triangulation(hl, p, _first_occurrence_cells(p, t), n_used=len(np.unique(p, axis=0)))
         done += 1
     assert done >= 90 and tri.qhull_retries == 0
+
+
+def test_triangulate_into_raw_buffers(hl):  # noqa: F811
+    """the triangulators write their cells straight into a caller-owned buffer (the
+    pinned staging buffer of the device loop); same cells as `triangulate`, and a buffer that is too
+    small is reported as minus the capacity that is needed, with nothing written past its end."""
+    from seismicmesh_b200.triangulator import get_triangulator
+
+    rng = np.random.default_rng(11)
+    for dim in (2, 3):
+        tri = get_triangulator(None, dim)
+        p = np.ascontiguousarray(rng.random((3000, dim)))
+        ref = tri.triangulate(p)
+        buf = np.full((tri.max_cells(len(p)) + 7, dim + 1), -7, dtype=np.int32)
+        T = tri.triangulate_into(p, buf)
+        assert T == len(ref) and np.array_equal(buf[:T], ref) and (buf[T:] == -7).all()
+        small = np.full((len(ref) // 2, dim + 1), -7, dtype=np.int32)
+        assert tri.triangulate_into(p, small) == -len(ref) and (small == -7).all()
+        q = get_triangulator("qhull", dim)
+        buf2 = np.empty((q.max_cells(len(p)), dim + 1), dtype=np.int32)
+        T2 = q.triangulate_into(p, buf2)
+        assert np.array_equal(_canon(buf2[:T2]), _canon(ref))
