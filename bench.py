@@ -9,10 +9,20 @@ call) over one synthetic (p, t).  Delaunay is host work in the reference's desig
 once in the untimed set-up; it is reported separately (`delaunay_s`).
 
 Prints ONE JSON line (contract in the task statement): `value` = vertex-updates/s with inputs
-resident in HBM, `e2e` = the same through the public host-buffer call (H2D of p and t from pinned
-memory + D2H of the new positions inside the timed region), `roofline` for the dominant kernel
-(algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json), `cpu_baseline` = the oracle
-port of the reference's NumPy loop body timed on one host core.
+resident in HBM, `e2e` = the same through the public host-buffer call generate_mesh itself uses
+(ForceLoop.iterate_host: H2D of p and t from pinned memory + D2H of the new positions inside the timed
+region), `roofline` for the dominant kernel (algorithmic bytes / CUDA-event time against
+MEASURED_PEAKS.json), `cpu_baseline` = the oracle port of the reference's NumPy loop body on one host core.
+
+The default invocation (N = 1) also carries, as sub-records of the same line:
+  `workloads`     the north_star target workloads: BP2004-shaped (hmin 25 m, 6 Hz) and EAGE-shaped
+                  (hmin 75 m, 4 Hz), gridded fh -- value, e2e, roofline, max|dp| against the oracle;
+  `time_to_mesh`  BASELINE.json's second metric: generate_mesh end to end (host Delaunay included) on
+                  disk h0 = 0.01 and ball h0 = 0.05, 25 iterations, reference semantics and `ttol`.
+With N > 1 the step is the slab-decomposed one (one slab per GPU, ghosts chosen by dm_halo_select, one
+halo exchange per step), on the ball-sized cylinder slabs and, as a sub-record, on EAGE-shaped slabs.
+`--impl reference` times the reference's own CPU loop body (oracle port + the reference's compiled
+unique_edges) on the SAME configuration, without importing the product package.
 """
 import argparse
 import ctypes as C
@@ -30,10 +40,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "DistMesh vertex-updates/sec (verts x iters / s), device-resident force iteration"
 UNIT = "vertex-updates/s"
+TRIANGULATOR = None  # --triangulator: None = the package default (native), "qhull", "native"
 
 
 # ------------------------------------------------------------------------------------------------
-# workloads (BASELINE.json configs)
+# workloads (BASELINE.json configs) -- the builders in this block use NumPy / SciPy
+# only, so the reference arm can share them without importing the product package
 # ------------------------------------------------------------------------------------------------
 def _lattice(h0, dim, bbox):
     axes = [np.arange(int(np.ceil((hi + h0 - lo) / h0)), dtype=float) * h0 + lo for lo, hi in bbox]
@@ -44,7 +56,7 @@ def _lattice(h0, dim, bbox):
     return np.stack([a.ravel() for a in g], axis=1)
 
 
-def make_points(workload, h0, seed=0, shift=0.0):
+def make_points(workload, h0, seed=0):
     """Synthetic input of BASELINE.json configs[1] (ball) / configs[0] (disk): the reference's
     initial lattice inside the domain (uniform h => no rejection), jittered by 0.1*h0 (seeded) so
     the host Delaunay is non-degenerate, as in a mid-run iteration."""
@@ -55,41 +67,28 @@ def make_points(workload, h0, seed=0, shift=0.0):
     p = p[r - 1.0 < 0.1 * h0]
     rng = np.random.default_rng(seed)
     p = p + rng.uniform(-0.1 * h0, 0.1 * h0, p.shape)
-    p[:, 1] += shift
     return np.ascontiguousarray(p), dim
 
 
-TRIANGULATOR = None  # --triangulator: None = the package default (native), "qhull", "native"
-
-
-def delaunay_backend(dim):
-    from seismicmesh_b200.triangulator import get_triangulator
-
-    return get_triangulator(TRIANGULATOR, dim).name
-
-
-def triangulate(p):
-    """Host Delaunay with the package's default triangulator (2-D: native sweep-hull, 3-D: Qhull).
-    DM_BENCH_CACHE=<dir> re-uses the cells of an identical point set between runs of one profiling
-    session (the set-up is untimed either way)."""
-    from seismicmesh_b200.triangulator import get_triangulator
-
-    cache = os.environ.get("DM_BENCH_CACHE")
-    key = None
-    if cache:
-        import hashlib
-
-        key = os.path.join(cache, f"tri_{TRIANGULATOR or 'default'}_" + hashlib.sha1(p.tobytes()).hexdigest()[:16] + ".npz")
-        if os.path.exists(key):
-            z = np.load(key)
-            return z["t"], float(z["dt"])
-    t0 = time.perf_counter()
-    t = get_triangulator(TRIANGULATOR, p.shape[1]).triangulate(p)
-    dt = time.perf_counter() - t0
-    if key:
-        os.makedirs(cache, exist_ok=True)
-        np.savez(key, t=t, dt=dt)
-    return t, dt
+def make_cylinder_points(workload, h0, world, seed=0):
+    """Weak-scaling input for N > 1: `world` slabs along axis 1 of a cylinder (3-D) / rectangle (2-D),
+    each slab with the volume (area) of the unit ball (disk), i.e. the per-GPU work of the N = 1 workload."""
+    if workload == "ball":
+        dim, ell = 3, 4.0 / 3.0
+    else:
+        dim, ell = 2, np.pi / 2.0
+    Ly = world * ell
+    lo, hi = [-1.0] * dim, [1.0] * dim
+    lo[1], hi[1] = -Ly / 2, Ly / 2
+    p = _lattice(h0, dim, list(zip(lo, hi)))
+    if dim == 3:
+        rad = np.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2)
+        inside = (rad - 1.0 < 0.1 * h0) & (np.abs(p[:, 1]) - Ly / 2 < 0.1 * h0)
+    else:
+        inside = (np.abs(p[:, 0]) - 1.0 < 0.1 * h0) & (np.abs(p[:, 1]) - Ly / 2 < 0.1 * h0)
+    p = p[inside]
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(p + rng.uniform(-0.1 * h0, 0.1 * h0, p.shape)), dim, Ly
 
 
 def synth_vp(workload):
@@ -115,6 +114,56 @@ def synth_vp(workload):
     return np.ascontiguousarray(vp), bbox
 
 
+def sizing_kwargs(workload, vp, h0=None, freq=None):
+    if workload == "bp2004":  # README.md:176-186, benchmarks/benchmark_BP2004.py:31-39
+        hmin, fr = h0 or 75.0, freq or 2.0
+        return hmin, fr, 2, dict(hmin=hmin, wl=10, freq=fr, dt=0.001, grade=0.15, domain_pad=1e3, pad_style="edge",
+                                 nz=vp.shape[0], nx=vp.shape[1])
+    hmin, fr = h0 or 150.0, freq or 2.0  # README.md:275-292
+    return hmin, fr, 3, dict(hmin=hmin, wl=5, freq=fr, dt=0.001, grade=0.15, hmax=5e3, domain_pad=250.0,
+                             pad_style="linear_ramp", nz=vp.shape[0], nx=vp.shape[1], ny=vp.shape[2])
+
+
+def domain_spec(workload, bbox=None):
+    if workload == "ball":
+        return ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0))
+    if workload == "disk":
+        return ("disk", dict(x0=[0.0, 0.0], r=1.0))
+    return ("rectangle", dict(bbox=tuple(bbox))) if len(bbox) == 4 else ("cube", dict(bbox=tuple(bbox)))
+
+
+# ------------------------------------------------------------------------------------------------
+# product-side set-up
+# ------------------------------------------------------------------------------------------------
+def delaunay_backend(dim):
+    from seismicmesh_b200.triangulator import get_triangulator
+
+    return get_triangulator(TRIANGULATOR, dim).name
+
+
+def triangulate(p):
+    """Host Delaunay with the package's default (native) triangulator.  DM_BENCH_CACHE=<dir> re-uses the
+    cells of an identical point set between runs of one profiling session (the set-up is untimed)."""
+    from seismicmesh_b200.triangulator import get_triangulator
+
+    cache = os.environ.get("DM_BENCH_CACHE")
+    key = None
+    if cache:
+        import hashlib
+
+        key = os.path.join(cache, f"tri2_{TRIANGULATOR or 'default'}_" + hashlib.sha1(p.tobytes()).hexdigest()[:16] + ".npz")
+        if os.path.exists(key):
+            z = np.load(key)
+            return z["t"], float(z["dt"])
+    t0 = time.perf_counter()
+    t = get_triangulator(TRIANGULATOR, p.shape[1]).triangulate(p)
+    dt = time.perf_counter() - t0
+    if key:
+        os.makedirs(cache, exist_ok=True)
+        np.savez(key, t=t, dt=dt)
+    return t, dt
+
+
 def build_workload(workload, h0=None, freq=None, settle=2):
     """-> dict(p, t, dim, dom, size, h0, spec, fh_grid, delaunay_s, desc).  ball / disk: the reference's
     lattice inside the SDF (uniform h).  bp2004 / eage: gridded fh from our own
@@ -129,8 +178,7 @@ def build_workload(workload, h0=None, freq=None, settle=2):
         p, dim = make_points(workload, h0)
         dom = sm.Ball([0.0, 0.0, 0.0], 1.0) if dim == 3 else sm.Disk([0.0, 0.0], 1.0)
         t, dt = triangulate(p)
-        spec = ("ball", dict(x0=[0.0, 0.0, 0.0], r=1.0)) if dim == 3 else ("disk", dict(x0=[0.0, 0.0], r=1.0))
-        return dict(p=p, t=t, dim=dim, dom=dom, size=SizeSpec(dim, const=h0), h0=h0, spec=spec, fh_grid=None,
+        return dict(p=p, t=t, dim=dim, dom=dom, size=SizeSpec(dim, const=h0), h0=h0, spec=domain_spec(workload), fh_grid=None,
                     delaunay_s=dt, desc=f"{workload}_h0={h0:g}", sizing_s=0.0, edge=h0)
     import torch
 
@@ -139,16 +187,7 @@ def build_workload(workload, h0=None, freq=None, settle=2):
     from seismicmesh_b200.generation import _initial_points
 
     vp, bbox = synth_vp(workload)
-    if workload == "bp2004":  # README.md:176-186, benchmarks/benchmark_BP2004.py:31-39
-        hmin, fr = h0 or 75.0, freq or 2.0
-        kw = dict(hmin=hmin, wl=10, freq=fr, dt=0.001, grade=0.15, domain_pad=1e3, pad_style="edge",
-                  nz=vp.shape[0], nx=vp.shape[1])
-        dim = 2
-    else:  # README.md:275-292
-        hmin, fr = h0 or 150.0, freq or 2.0
-        kw = dict(hmin=hmin, wl=5, freq=fr, dt=0.001, grade=0.15, hmax=5e3, domain_pad=250.0,
-                  pad_style="linear_ramp", nz=vp.shape[0], nx=vp.shape[1], ny=vp.shape[2])
-        dim = 3
+    hmin, fr, dim, kw = sizing_kwargs(workload, vp, h0, freq)
     t0 = time.perf_counter()
     ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, **kw)
     sizing_s = time.perf_counter() - t0
@@ -166,20 +205,64 @@ def build_workload(workload, h0=None, freq=None, settle=2):
         t, dt = triangulate(p)
         p = loop.iterate(D.to_dev(p, torch.float64), D.to_dev(t, torch.int32))[0].cpu().numpy()
     t, dt = triangulate(p)
-    spec = ("rectangle", dict(bbox=tuple(ef.bbox))) if dim == 2 else ("cube", dict(bbox=tuple(ef.bbox)))
     g = ef.interpolant()
-    return dict(p=p, t=t, dim=dim, dom=dom, size=size, h0=hmin, spec=spec, fh_grid=(g.grid, g.values),
+    return dict(p=p, t=t, dim=dim, dom=dom, size=size, h0=hmin, spec=domain_spec(workload, ef.bbox), fh_grid=(g.grid, g.values),
                 delaunay_s=dt, sizing_s=sizing_s, edge=ef,
                 desc=f"{workload}_shaped_grid{'x'.join(str(n) for n in g.values.shape)}_hmin={hmin:g}_freq={fr:g}")
 
 
-def oracle_step_fn(wl):
+def build_slab_workload(workload, rank, world, h0=None, freq=None):
+    """One slab per GPU through the package's own parallel path (generate_mesh(comm=...) stopped before
+    its gather): every rank triangulates its owned vertices, dm_halo_select picks the vertices whose
+    incident-cell circumballs reach a neighbour's extent, the neighbours receive them as ghosts and
+    the slab is retriangulated with them -- exactly what a parallel iteration feeds the device.
+    ball / disk: cylinder / rectangle slabs with the N = 1 work per GPU (restart from the jittered
+    lattice); eage: the EAGE-shaped domain cut along axis 1 with hmin / freq scaled so that the work per
+    GPU stays that of the hmin 75 m / 4 Hz single-GPU case (BASELINE.json configs[4])."""
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200.engine import SizeSpec
+    from seismicmesh_b200.parallel import SlabLayout, TorchComm
+
+    comm = TorchComm()
+    sizing_s = 0.0
+    if workload in ("ball", "disk"):
+        h0 = h0 or (0.02 if workload == "ball" else 0.01)
+        pts, dim, Ly = make_cylinder_points(workload, h0, world)
+        dom = sm.Cylinder(h=Ly, r=1.0) if dim == 3 else sm.Rectangle((-1.0, 1.0, -Ly / 2, Ly / 2))
+        edge, size, fh_grid = h0, SizeSpec(dim, const=h0), None
+        # `axis=0` is decomp.blocker's name for cuts along y (dimension 1), the cylinder's axis
+        st = sm.generate_mesh(dom, edge, comm=comm, points=pts, max_iter=1, axis=0, verbose=0, _return_state=True)
+        desc = f"{workload}_h0={h0:g} x {world} slabs (cylinder of {world} ball volumes)"
+    else:
+        vp, bbox = synth_vp(workload)
+        sc = world ** (1.0 / 3.0)
+        hmin, fr, dim, kw = sizing_kwargs(workload, vp, (h0 or 75.0) / sc, (freq or 4.0) * sc)
+        t0 = time.perf_counter()
+        ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, **kw)
+        sizing_s = time.perf_counter() - t0
+        del vp
+        dom = sm.Cube(ef.bbox)
+        edge, size = ef, SizeSpec(dim, interp=ef.interpolant())
+        g = ef.interpolant()
+        fh_grid = (g.grid, g.values)
+        h0 = hmin
+        st = sm.generate_mesh(dom, edge, comm=comm, max_iter=3, axis=1, verbose=0, _return_state=True)
+        desc = f"eage_shaped_grid{'x'.join(str(n) for n in g.values.shape)}_hmin={hmin:.4g}_freq={fr:.4g} x {world} slabs along axis 1"
+    n_own = st["n_owned"]
+    layout = SlabLayout(np.arange(n_own), np.zeros(st["n_ghost_below"], dtype=np.int64), np.zeros(st["n_ghost_above"], dtype=np.int64),
+                        st["export_below"].astype(np.int64), st["export_above"].astype(np.int64))
+    stats = dict(sm.last_run_stats)
+    return dict(p=np.ascontiguousarray(st["p"]), t=np.ascontiguousarray(st["t"], dtype=np.int32), dim=dim, dom=dom, size=size, h0=h0,
+                spec=None, fh_grid=fh_grid, delaunay_s=stats.get("delaunay", 0.0), sizing_s=sizing_s, edge=edge, desc=desc,
+                layout=layout, n_owned=n_own)
+
+
+def oracle_step_fn(spec, h0, fh_grid):
     """The reference's loop body (oracle port, + the reference's own native unique_edges from
     oracle/_ref when it was built) as a closure step(p, t) -> p_new."""
     from oracle import distmesh_oracle as orc
     from oracle import ref_harness
 
-    spec, h0 = wl["spec"], wl["h0"]
     native = None
     if ref_harness.native_available():
         try:
@@ -195,10 +278,10 @@ def oracle_step_fn(wl):
         orc.unique_bars = unique_bars
     geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
     fd = lambda x: orc.sdf(spec, x)  # noqa: E731
-    if wl["fh_grid"] is None:
+    if fh_grid is None:
         fh = lambda x: np.array([h0] * len(x))  # noqa: E731
     else:
-        axes, grid = wl["fh_grid"]
+        axes, grid = fh_grid
         fh = lambda x: orc.interp_grid(list(axes), grid, x)  # noqa: E731
 
     def step(p, t):
@@ -278,7 +361,8 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
 
 def ncu_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None if there is none."""
+    `ncu --set full` capture of THIS build on this workload (profiles/ncu_traffic.json, regenerated by
+    tools/gpu/profile.sh; the file names the capture it came from); None if there is none."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             return json.load(f).get(workload, {}).get(kernel)
@@ -295,43 +379,50 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU loop body on the SAME configuration, no product imports
+# ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path, on the host cores of this box."""
     if rank != 0:
         return
+    from scipy.spatial import Delaunay
+
     K, W = args.steps, args.warmup
     workload = args.workload
-    if workload in ("ball", "disk"):
-        base_h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
-        # bounded sample: coarsen h0 until (K+W) steps + set-up fit in ~150 s (cost ~ 1/h0^dim)
-        dim = 3 if workload == "ball" else 2
-        est_full = 8.0 if workload == "ball" else 0.12
-        h0 = base_h0
-        for cand in (1.0, 1.25, 1.5, 2.0, 3.0):
-            h0 = base_h0 * cand
-            if (K + W) * est_full / cand**dim + (30.0 if workload == "ball" else 1.0) / cand**dim <= 150.0:
-                break
-        wl = build_workload(workload, h0)
-    else:
-        # gridded workloads need the device for their set-up (sizing function, settling iterations);
-        # the timed loop body below is host-only
-        wl = build_workload(workload, args.h0, args.freq)
-        base_h0 = h0 = wl["h0"]
-    p, t, dim, tq = wl["p"], wl["t"], wl["dim"], wl["delaunay_s"]
-    step, kind = oracle_step_fn(wl)
-    for _ in range(W):
-        step(p, t)
+    if workload not in ("ball", "disk"):
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "gridded workloads need the sizing preprocessing; the reference arm runs the headline ball / disk configurations"}))
+        return
+    h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
+    p, dim = make_points(workload, h0)  # the GPU arm's exact point set (same seed, same jitter)
     t0 = time.perf_counter()
-    for _ in range(K):
+    t = np.ascontiguousarray(Delaunay(p).simplices, dtype=np.int32)  # Qhull stands in for the reference's CGAL
+    tq = time.perf_counter() - t0
+    step, kind = oracle_step_fn(domain_spec(workload), h0, None)
+    # a full-size ball step is ~3 s on one core: bound the run to ~4 minutes, say how many steps were taken
+    c0 = time.perf_counter()
+    step(p, t)
+    one = time.perf_counter() - c0
+    Wd = max(0, min(W, int(30.0 // max(one, 1e-9))) - 1)
+    Kd = max(1, min(K, int(200.0 // max(one, 1e-9))))
+    for _ in range(Wd):
         step(p, t)
-    dt = time.perf_counter() - t0
+    c0 = time.perf_counter()
+    for _ in range(Kd):
+        step(p, t)
+    dt = time.perf_counter() - c0
     N = len(p)
-    val = N * K / dt
-    sample = f"{wl['desc']} (N={N}, T={len(t)}), {K} steps of the full loop body on 1 core"
+    val = N * Kd / dt
+    sample = f"{workload}_h0={h0:g} (N={N}, T={len(t)}): {Kd} timed steps of the full loop body after {Wd + 1} warm-up steps, 1 core"
     out = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": wl["desc"] if workload not in ("ball", "disk") else f"{workload}_h0={base_h0:g}", "sample_h0": h0, "delaunay": "excluded (host, set-up)"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": Kd, "warmup": Wd + 1,
+        "ms_per_step": dt / Kd * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{workload}_h0={h0:g}", "N_per_gpu": N, "T_per_gpu": int(len(t)), "dim": dim, "same_config": True,
+                   "delaunay": "excluded (host, set-up; Qhull here, CGAL in the reference)",
+                   "note": "kind=port: the NumPy restatement of the reference's loop body with the reference's own compiled "
+                           "unique_edges; the unmodified reference measured through its public API is ~2.3x slower "
+                           "(BASELINE.md section 2), so this baseline is the conservative one"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "detail": kind},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "delaunay_s": tq,
@@ -339,84 +430,47 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ball", choices=["ball", "disk", "bp2004", "eage"])
-    ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing / hmin (scale-up runs)")
-    ap.add_argument("--freq", type=float, default=None, help="bp2004 / eage: override the sizing frequency")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--triangulator", default=None, choices=["native", "qhull"],
-                    help="host Delaunay of the set-up (untimed); it also decides the ORDER of the cell list the device "
-                         "step is fed, which stage A is sensitive to.  Default: the package's (native)")
-    ap.add_argument("--time-to-mesh", type=int, default=0, metavar="ITERS",
-                    help="also run generate_mesh(max_iter=ITERS) end to end (host Delaunay included) and report "
-                         "time-to-mesh, with the reference's retriangulate-every-iteration and with ttol=0.1")
-    ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
-    args = ap.parse_args()
-    global TRIANGULATOR
-    TRIANGULATOR = args.triangulator
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def timed(fn, K, flush, barrier):
+    import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for i in range(K):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
+        ev[i][0].record()
+        fn()
+        ev[i][1].record()
+    barrier()
+    return float(sum(a.elapsed_time(b) for a, b in ev))
 
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
 
+def measure(wl, K, W, rank, world, local_rank, full, flush, kernel_table=None, cpu_check=True):
+    """The timed legs on one workload.  full: also the clocks sampler, the opt-in row-reuse step, the
+    sliver pass and the timed CPU baseline (the headline record); otherwise the sub-record subset."""
     import torch
     import torch.distributed as dist
 
-    import seismicmesh_b200 as sm
     from seismicmesh_b200 import device as D
     from seismicmesh_b200._lib import check, lib
-    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+    from seismicmesh_b200.engine import ForceLoop, Level
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    workload = args.workload
-    K, W = args.steps, args.warmup
-
-    # ---- set-up (untimed): points + ONE host Delaunay per rank (weak scaling: one slab per GPU) ----
-    layout = None
-    if world == 1:
-        wl = build_workload(workload, args.h0, args.freq)
-        p, t, dim, dom, h0, t_delaunay = wl["p"], wl["t"], wl["dim"], wl["dom"], wl["h0"], wl["delaunay_s"]
-        size = wl["size"]
-        n_owned = len(p)
-    else:
-        # weak scaling: a cylinder (3-D) / rectangle (2-D) of `world` slabs along axis 1, each slab
-        # with the volume of the N=1 ball / disk; every rank meshes its slab + ghost layers
-        from seismicmesh_b200.parallel import make_slab_workload
-
-        if workload not in ("ball", "disk"):
-            raise SystemExit("multi-GPU bench: --workload ball|disk (slab workload)")
-        h0 = args.h0 or (0.02 if workload == "ball" else 0.01)
-        p, dim, dom, layout = make_slab_workload(workload, h0, rank, world)
-        n_owned = layout.n_owned
-        t, t_delaunay = triangulate(p)
-        t = np.ascontiguousarray(t[(t < n_owned).any(axis=1)])  # cells made only of ghosts belong to the neighbours
-        size = SizeSpec(dim, const=h0)
-        wl = dict(desc=f"{workload}_h0={h0:g}", fh_grid=None, sizing_s=0.0)
+    p, t, dim, dom, h0, size = wl["p"], wl["t"], wl["dim"], wl["dom"], wl["h0"], wl["size"]
+    layout = wl.get("layout")
+    n_owned = wl.get("n_owned", len(p))
     N, T = len(p), len(t)
     geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
     loop = ForceLoop(dim, [Level(dom, dim)], size, h0, geps, deps)
-
+    if layout is not None:
+        loop.n_rows = n_owned
     p_dev = D.to_dev(p, torch.float64)
     t_dev = D.to_dev(t, torch.int32)
-    p_out = torch.empty_like(p_dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=p_dev.device)  # > 126 MB L2
+    p_out = p_dev.clone()  # (ghost rows of the output are only ever written by the halo exchange)
 
     halo, halo_kind = None, None
-    if world > 1:
+    if layout is not None:
         from seismicmesh_b200.parallel import PeerHalo, RingHalo
 
         ring = RingHalo(layout, dim, p_dev.device, rank=rank, world=world)
@@ -446,6 +500,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=p_dev.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     # pinned host buffers of the e2e leg (allocated before the clocks sampler starts)
     p_pin = torch.from_numpy(p).pin_memory()
     t_pin = torch.from_numpy(t).pin_memory()
@@ -454,26 +515,13 @@ def main():
     for _ in range(W):
         one_step()
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if (full and rank == 0) else None
+    if sampler:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
     wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
-        ev[i][0].record()
-        one_step()
-        ev[i][1].record()
-    barrier()
+    total_ms = allmax(timed(one_step, K, flush, barrier))
     wall = time.perf_counter() - wall0
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(step_ms.sum())
     if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=p_dev.device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
         nn = torch.tensor([n_owned], dtype=torch.float64, device=p_dev.device)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
         N_all = int(nn.item())
@@ -481,86 +529,71 @@ def main():
         N_all = n_owned
     value = N_all * K / (total_ms * 1e-3)
 
-    # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----
-
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region: the call
+    #      generate_mesh makes every iteration (there with the positions already resident)
     def e2e_step():
-        # the public host-buffer call: H2D of p and t (t in chunks, stage A overlapped with the transfer),
-        # stages B-D, D2H of the new positions -- all inside the timed region
-        loop.iterate_host(p_pin, t_pin, out_pin)
+        q = loop.iterate_host(p_pin, t_pin, out_pin)
         if halo is not None:
-            halo.exchange(loop._host_bufs[2])
+            halo.exchange(q)
         sc_pin.copy_(loop.plan.scalars(), non_blocking=True)
 
     for _ in range(2):
         e2e_step()
-    barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for i in range(K):
-        flush.fill_(i & 0xFF)
-        ev2[i][0].record()
-        e2e_step()
-        ev2[i][1].record()
-    barrier()
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
-    if world > 1:
-        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=p_dev.device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+    e2e_ms = allmax(timed(e2e_step, K, flush, barrier))
     e2e_value = N_all * K / (e2e_ms * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None  # sampled every 20 ms across both timed regions
+    clocks = sampler.stop() if sampler else None  # sampled every 20 ms across both timed regions
     maxdp = float(sc_pin[4])
+    h2d = int(p.nbytes + t.nbytes)
+    rec = {
+        "value": value, "unit": UNIT, "ms_per_step": total_ms / K,
+        "config": {"workload": wl["desc"], "N_per_gpu": N, "T_per_gpu": T, "dim": dim,
+                   "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
+                   "parallelism": (f"{world} slabs (owned + dm_halo_select ghosts per GPU; rows / forces for owned vertices only), "
+                                   f"halo exchange per step: {halo_kind}; halo bytes/step/rank={halo.bytes_per_exchange}; "
+                                   f"owned={n_owned} ghosts={N - n_owned} on rank 0") if layout is not None else "single",
+                   "N_owned_total": N_all},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(p.nbytes + 64),
+                "ms_per_step": e2e_ms / K, "h2d_gbs_per_rank": h2d / (e2e_ms / K * 1e-3) / 1e9,
+                "call": "ForceLoop.iterate_host (the call generate_mesh makes every iteration): pinned H2D of p and t, t in "
+                        "chunks overlapped with stage A, async D2H of the new positions"},
+        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
+        "delaunay_s": wl["delaunay_s"], "sizing_s": wl["sizing_s"], "maxdp": maxdp,
+    }
+    if clocks is not None:
+        rec["clocks"] = clocks
+        rec["wall_s_timed_region"] = wall
 
     # ---- opt-in path (generate_mesh(ttol=...)): an iteration that re-uses the neighbour rows ----
-    reuse = None
-    if world == 1 and loop.all_lowered:
+    if full and world == 1 and loop.all_lowered:
+        def reuse_step():
+            loop.iterate_reuse(p_dev, p_out=p_out)
+
         for _ in range(3):
-            loop.iterate_reuse(p_dev, p_out=p_out)
-        barrier()
-        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for i in range(K):
-            flush.fill_(i & 0xFF)
-            ev3[i][0].record()
-            loop.iterate_reuse(p_dev, p_out=p_out)
-            ev3[i][1].record()
-        barrier()
-        r_ms = float(sum(a.elapsed_time(b) for a, b in ev3)) / K
-        reuse = {"ms_per_step": r_ms, "value": N * 1e3 / r_ms, "unit": UNIT,
-                 "what": "force iteration without retriangulation (bar pass + vertex update on the rows of the last Delaunay)"}
+            reuse_step()
+        r_ms = timed(reuse_step, K, flush, barrier) / K
+        rec["row_reuse_step"] = {"ms_per_step": r_ms, "value": N * 1e3 / r_ms, "unit": UNIT,
+                                 "what": "force iteration without retriangulation (bar pass + vertex update on the rows of the last Delaunay)"}
         loop.iterate(p_dev, t_dev, p_out=p_out)  # leave the plan as the full iteration leaves it
 
-    # ---- sliver_removal's device work per pass (configs[1]): cull + order-preserving compaction +
-    #      6 dihedral angles per kept cell + bound test (mesh_generator.py:204-243)
-    sliver = None
-    if world == 1 and dim == 3:
+    # ---- sliver_removal's device work per pass (configs[1]): cull + 6 dihedral angles per kept cell + bound test
+    if full and world == 1 and dim == 3:
         lo_b, hi_b = 10.0 * np.pi / 180, np.pi
-
         fl = torch.empty(T, dtype=torch.uint8, device=p_dev.device)
         prog0 = loop._progs[0]
 
         def sliver_pass():
             check(lib.dm_sliver_flags(D.ptr(prog0), D.ptr(p_dev), D.ptr(t_dev), T, geps, lo_b, hi_b, None, D.ptr(fl),
                                       D.stream_ptr()), "sliver_flags")
-            return fl
 
         for _ in range(2):
             sliver_pass()
-        barrier()
-        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for i in range(K):
-            flush.fill_(i & 0xFF)
-            ev4[i][0].record()
-            fl = sliver_pass()
-            ev4[i][1].record()
-        barrier()
-        s_ms = float(sum(a.elapsed_time(b) for a, b in ev4)) / K
-        sliver = {"ms_per_pass": s_ms, "cells_per_s": T * 1e3 / s_ms, "slivers_flagged": int(fl.sum().item()),
-                  "what": "cull + dihedral-angle bound test of one sliver_removal pass (one fused kernel)"}
+        s_ms = timed(sliver_pass, K, flush, barrier) / K
+        rec["sliver_pass"] = {"ms_per_pass": s_ms, "cells_per_s": T * 1e3 / s_ms, "slivers_flagged": int(fl.sum().item()),
+                              "what": "cull + dihedral-angle bound test of one sliver_removal pass (one fused kernel)"}
         loop.iterate(p_dev, t_dev, p_out=p_out)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- per-kernel timing (CUDA events recorded inside the library, same stream) ----
     E = loop.plan.num_bars()
@@ -582,7 +615,7 @@ def main():
         acc = cur if acc is None else acc + cur
         names = [nm.raw[i * stride : (i + 1) * stride].split(b"\0")[0].decode() for i in range(n.value)]
     kern_ms = acc / reps
-    alg = algorithmic_bytes(N, T, Tk, E, dim, grid_fh=wl["fh_grid"] is not None)
+    alg = algorithmic_bytes(n_owned if layout is not None else N, T, Tk, E, dim, grid_fh=wl["fh_grid"] is not None)
     alg = {k: v for k, v in alg.items() if k in names}
     peak, peak_src = measured_peak()
     table = []
@@ -593,73 +626,159 @@ def main():
                       "achieved_gbs": gbs, "frac": gbs / peak})
     dom_k = max(table, key=lambda r: r["ms"])
     step_bytes = sum(alg.values())
-    roofline = {
+    rec["roofline"] = {
         "bound": "hbm", "kernel": dom_k["kernel"], "achieved": dom_k["achieved_gbs"], "peak": peak, "unit": "GB/s",
         "frac": dom_k["frac"], "traffic": ncu_traffic(wl["desc"], dom_k["kernel"]), "peak_source": peak_src,
         "whole_step": {"alg_bytes": int(step_bytes), "achieved": step_bytes / (kern_ms.sum() * 1e-3) / 1e9,
                        "frac": step_bytes / (kern_ms.sum() * 1e-3) / 1e9 / peak,
                        "alg_bytes_per_vertex_update": step_bytes / N},
+        "kernels": [{"kernel": r["kernel"], "ms": r["ms"], "frac": r["frac"]} for r in table],
     }
-    if args.kernel_table:
-        os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
-        with open(args.kernel_table, "w") as fo:
+    rec["config"].update({"T_kept": Tk, "bars": E})
+    if kernel_table:
+        os.makedirs(os.path.dirname(os.path.abspath(kernel_table)), exist_ok=True)
+        with open(kernel_table, "w") as fo:
             json.dump({"workload": wl["desc"], "h0": h0, "N": N, "T": T, "T_kept": Tk, "E": E, "peak_gbs": peak,
                        "kernels": table}, fo, indent=1)
+    print(f"  [{wl['desc']}]", file=sys.stderr)
     for row in table:
         print("  %-26s %8.4f ms  %5.1f%%  %8.1f GB/s  %5.1f%% of peak" % (
             row["kernel"], row["ms"], 100 * row["share"], row["achieved_gbs"], 100 * row["frac"]), file=sys.stderr)
 
-    # ---- CPU baseline: the reference's loop body (oracle port) on one host core, same (p, t) ----
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        step, kind = oracle_step_fn(wl)
-        p0, t0_ = p, t
+    # ---- CPU: the reference's loop body (oracle port) on one host core, same (p, t): baseline + parity ----
+    if cpu_check and world == 1 and wl["spec"] is not None:
+        step, kind = oracle_step_fn(wl["spec"], h0, wl["fh_grid"])
         nrep = 1 if N > 200000 else max(1, int(2e5 // N))
         c0 = time.perf_counter()
         for _ in range(nrep):
-            ref_p = step(p0, t0_)
+            ref_p = step(p, t)
         cdt = time.perf_counter() - c0
-        cpu = {"value": len(p0) * nrep / cdt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{nrep} step(s) of the same (p,t): N={len(p0)}, T={len(t0_)}; {cdt:.1f} s", "detail": kind}
-        if world == 1:  # parity of the benchmarked step against the oracle
-            perr = float(np.abs(out_pin.numpy() - ref_p).max())
-            cpu["max_abs_dp_vs_oracle"] = perr
+        rec["cpu_baseline"] = {"value": N * nrep / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{nrep} step(s) of the same (p,t): N={N}, T={T}; {cdt:.1f} s", "detail": kind,
+                               "max_abs_dp_vs_oracle": float(np.abs(out_pin.numpy() - ref_p).max())}
+        rec["max_abs_dp_vs_oracle"] = rec["cpu_baseline"]["max_abs_dp_vs_oracle"]
+    return rec
 
-    ttm = None
-    if args.time_to_mesh > 0 and world == 1:
-        from seismicmesh_b200 import meshutil
 
-        edge = wl["edge"]
-        ttm = {}
-        for name, kw in (("reference_semantics", {}), ("ttol_0.1", {"ttol": 0.1})):
+def time_to_mesh(cases, iters):
+    """BASELINE.json's second metric: generate_mesh end to end -- host Delaunay every iteration included,
+    termination clean-up included -- with the reference's semantics (retriangulate every iteration) and
+    with the opt-in `ttol` (retriangulate when some vertex moved more than ttol local mesh sizes)."""
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200 import meshutil
+
+    out = {}
+    for name, dom, edge in cases:
+        res = {}
+        for mode, kw in (("reference_semantics", {}), ("ttol_0.1", {"ttol": 0.1})):
             c0 = time.perf_counter()
-            pm, tm = sm.generate_mesh(dom, edge, max_iter=args.time_to_mesh, verbose=0, **kw)
+            pm, tm = sm.generate_mesh(dom, edge, max_iter=iters, verbose=0, **kw)
             wall_m = time.perf_counter() - c0
             st_ = dict(sm.last_run_stats)
             qm = meshutil.simp_qual(pm, tm)
-            ttm[name] = {"wall_s": wall_m, "delaunay_s": st_["delaunay"], "device_s": st_["device"],
-                         "triangulations": st_["triangulations"], "vertices": int(len(pm)), "cells": int(len(tm)),
-                         "mean_quality": float(qm.mean()), "min_quality": float(qm.min())}
+            res[mode] = {"wall_s": wall_m, "delaunay_s": st_["delaunay"], "device_s": st_["device"],
+                         "termination_s": st_["termination"], "triangulations": st_["triangulations"],
+                         "vertices": int(len(pm)), "cells": int(len(tm)), "mean_quality": float(qm.mean()),
+                         "min_quality": float(qm.min()),
+                         "vertex_updates_per_s_wall": st_["nverts"] * st_["iterations"] / wall_m}
+        res["max_iter"] = iters
+        res["triangulator"] = st_["triangulator"]
+        out[name] = res
+    return out
 
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": wl["desc"], "N_per_gpu": N, "T_per_gpu": T, "T_kept": Tk, "bars": E, "dim": dim,
-                   "l2": "flushed between timed steps (512 MiB fill, untimed)", "delaunay": "host, set-up (untimed)",
-                   "parallelism": (f"{world} slabs along axis 1 (owned+ghost per GPU), halo exchange per step: {halo_kind}; "
-                                   f"halo bytes/step/rank={halo.bytes_per_exchange}") if world > 1 else "single",
-                   "N_owned_total": N_all},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(p.nbytes + t.nbytes),
-                "d2h_bytes_per_step": int(p.nbytes + 64), "ms_per_step": e2e_ms / K},
-        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
-        "roofline": roofline, "cpu_baseline": cpu, "row_reuse_step": reuse, "sliver_pass": sliver, "time_to_mesh": ttm,
-        "delaunay_s": t_delaunay, "delaunay_backend": delaunay_backend(dim), "sizing_s": wl["sizing_s"], "maxdp": maxdp,
-        "wall_s_timed_region": wall,
-    }
-    print(json.dumps(out), flush=True)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ball", choices=["ball", "disk", "bp2004", "eage"])
+    ap.add_argument("--h0", type=float, default=None, help="override the lattice spacing / hmin (scale-up runs)")
+    ap.add_argument("--freq", type=float, default=None, help="bp2004 / eage: override the sizing frequency")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline record only: skip the bp2004 / eage sub-records and the time-to-mesh block")
+    ap.add_argument("--triangulator", default=None, choices=["native", "qhull"],
+                    help="host Delaunay of the set-up (untimed); it also decides the ORDER of the cell list the device "
+                         "step is fed, which stage A is sensitive to.  Default: the package's (native)")
+    ap.add_argument("--time-to-mesh", type=int, default=25, metavar="ITERS",
+                    help="iterations of the time-to-mesh block (generate_mesh end to end, host Delaunay included)")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (json) here")
+    args = ap.parse_args()
+    global TRIANGULATOR
+    TRIANGULATOR = args.triangulator
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import seismicmesh_b200 as sm
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, args.warmup
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))  # > 126 MB L2
+    default_run = args.workload == "ball" and args.h0 is None and not args.no_extras
+
+    if world == 1:
+        wl = build_workload(args.workload, args.h0, args.freq)
+    else:
+        wl = build_slab_workload(args.workload, rank, world, args.h0, args.freq)
+    rec = measure(wl, K, W, rank, world, local_rank, True, flush, kernel_table=args.kernel_table,
+                  cpu_check=not args.no_cpu_baseline)
+    del wl
+
+    extras = {}
+    if default_run and world == 1:
+        subs = {}
+        for name, wk, h, fq in (("bp2004_hmin25_freq6", "bp2004", 25.0, 6.0), ("eage_hmin75_freq4", "eage", 75.0, 4.0)):
+            w2 = build_workload(wk, h, fq)
+            r2 = measure(w2, max(5, K // 2), 3, rank, world, local_rank, False, flush)
+            del w2
+            torch.cuda.empty_cache()
+            subs[name] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "max_abs_dp_vs_oracle",
+                                             "delaunay_s", "sizing_s") if k in r2}
+        extras["workloads"] = subs
+        if args.time_to_mesh > 1:
+            extras["time_to_mesh"] = time_to_mesh(
+                (("disk_h0=0.01", sm.Disk([0.0, 0.0], 1.0), 0.01), ("ball_h0=0.05", sm.Ball([0.0, 0.0, 0.0], 1.0), 0.05)),
+                args.time_to_mesh)
+    elif default_run and world > 1:
+        try:
+            w2 = build_slab_workload("eage", rank, world)
+            r2 = measure(w2, max(5, K // 2), 3, rank, world, local_rank, False, flush)
+            if rank == 0:
+                extras["workloads"] = {"eage_slabs": {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "roofline",
+                                                                          "delaunay_s", "sizing_s") if k in r2}}
+        except Exception as exc:  # never lose the headline line to a sub-record
+            if rank == 0:
+                extras["workloads"] = {"eage_slabs": {"error": f"{type(exc).__name__}: {exc}"}}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": rec["config"], "clocks": rec.get("clocks"), "e2e": rec["e2e"],
+            "gpu_launches": rec["gpu_launches"], "roofline": rec.get("roofline"), "cpu_baseline": rec.get("cpu_baseline"),
+            "row_reuse_step": rec.get("row_reuse_step"), "sliver_pass": rec.get("sliver_pass"),
+            "workloads": extras.get("workloads"), "time_to_mesh": extras.get("time_to_mesh"),
+            "delaunay_s": rec["delaunay_s"], "delaunay_backend": delaunay_backend(rec["config"]["dim"]), "sizing_s": rec["sizing_s"],
+            "maxdp": rec["maxdp"], "wall_s_timed_region": rec.get("wall_s_timed_region"),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -1063,10 +1063,30 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
         if (HMODE == 0) {
           h = f.hconst;
         } else if (HMODE == 1) {
-          if (j >= lo)
+          if (j >= lo) {
             h = j < m ? hslot[base + j] : 0.0;
-          else  // lower bar: same midpoint bits as its owner computed -> same h bits
-            h = size_eval(f, (b0 + a0) / 2, (b1 + a1) / 2, (b2 + a2) / 2);
+          } else {
+            // lower bar (w, v), w < v: its OWNER w evaluated fh at the midpoint already (bar pass) and left
+            // it at the slot of v in w's row; finding that slot (one row line + 8 B) is far cheaper than a
+            // second interpolation (three axis searches, three divisions, a 64-B corner record from DRAM).
+            // Same value bit for bit: both ends form the same midpoint.  A row that lives in the heap
+            // (more than RS neighbours) takes the interpolation.
+            const int2 dw = R.degs[w];
+            int pos = -1;
+            if (dw.x <= PCfg<DIM>::RS) {
+              const int32_t* rw = R.adj + (int64_t)w * PCfg<DIM>::RS;
+              for (int q0 = dw.y & ~3; q0 < dw.x; q0 += 4) {
+                const int4 c = *reinterpret_cast<const int4*>(rw + q0);
+                pos = c.x == (int)v ? q0 : pos;
+                pos = c.y == (int)v ? q0 + 1 : pos;
+                pos = c.z == (int)v ? q0 + 2 : pos;
+                pos = c.w == (int)v ? q0 + 3 : pos;
+              }
+              if (pos >= dw.x) pos = -1;  // (a stale id behind the end of the row)
+            }
+            h = pos >= 0 ? hslot[(int64_t)w * PCfg<DIM>::RS + pos]
+                         : size_eval(f, (b0 + a0) / 2, (b1 + a1) / 2, (b2 + a2) / 2);
+          }
         } else {
           h = 0.0;
           if (j < m) h = hbar[j >= lo ? rowptr[v] + (j - lo) : bar_id_of<DIM>(R, rowptr, w, (int)v)];
