@@ -469,28 +469,51 @@ def measure(wl, K, W, rank, world, local_rank, full, flush, kernel_table=None, c
     t_dev = D.to_dev(t, torch.int32)
     p_out = p_dev.clone()  # (ghost rows of the output are only ever written by the halo exchange)
 
-    halo, halo_kind = None, None
+    halo, halo_kind, direct = None, None, None
     if layout is not None:
-        from seismicmesh_b200.parallel import PeerHalo, RingHalo
+        from seismicmesh_b200.parallel import DirectHalo, PeerHalo, RingHalo
 
         ring = RingHalo(layout, dim, p_dev.device, rank=rank, world=world)
         halo, halo_kind = ring, "NCCL P2P send/recv (RingHalo)"
-        if os.environ.get("DM_HALO", "p2p") == "p2p":
-            try:  # NVLink peer-memory push with our own kernel; checked once against the NCCL exchange
-                peer = PeerHalo(layout, dim, p_dev.device, rank=rank, world=world)
-                a, b = p_dev.clone(), p_dev.clone()
+        mode = os.environ.get("DM_HALO", "direct")
+        if mode in ("direct", "p2p"):
+            try:  # NVLink peer-memory exchange with our own kernels; checked once against the NCCL exchange
+                a = p_dev.clone()
                 a[n_owned:] = float("nan")
-                b[n_owned:] = float("nan")
                 ring.exchange(a)
-                peer.exchange(b)
-                peer.exchange(b)  # both slots
-                torch.cuda.synchronize()
-                assert torch.equal(a, b), "PeerHalo and RingHalo disagree"
-                halo, halo_kind = peer, "NVLink peer-memory push, dm_halo_push + symmetric-memory signals (PeerHalo)"
+                if mode == "direct":
+                    direct = DirectHalo(layout, dim, p_dev.device, rank=rank, world=world)
+                    for _ in range(2):  # both slots
+                        b = direct.slot()
+                        b.copy_(p_dev)
+                        b[n_owned:] = float("nan")
+                        torch.cuda.synchronize()
+                        dist.barrier()
+                        direct.exchange(b)
+                        torch.cuda.synchronize()
+                        direct.check()
+                        assert torch.equal(a, b), "DirectHalo and RingHalo disagree"
+                    halo, halo_kind = direct, ("NVLink stores straight into the neighbours' ghost rows + stamps, 2 launches "
+                                               "(dm_halo_push2 + dm_halo_wait; DirectHalo)")
+                else:
+                    peer = PeerHalo(layout, dim, p_dev.device, rank=rank, world=world)
+                    b = p_dev.clone()
+                    b[n_owned:] = float("nan")
+                    peer.exchange(b)
+                    peer.exchange(b)  # both slots
+                    torch.cuda.synchronize()
+                    assert torch.equal(a, b), "PeerHalo and RingHalo disagree"
+                    halo, halo_kind = peer, "NVLink peer-memory push, dm_halo_push + symmetric-memory signals (PeerHalo)"
             except Exception as exc:  # no peer access / symmetric memory on this box: keep NCCL
+                direct = None
                 halo_kind += f" [peer-memory path unavailable: {type(exc).__name__}: {exc}]"
 
     def one_step():
+        if direct is not None:  # the result goes to this step's symmetric slot, whose ghost rows the neighbours fill
+            out = direct.slot()
+            loop.iterate(p_dev, t_dev, p_out=out)
+            direct.exchange(out)
+            return
         loop.iterate(p_dev, t_dev, p_out=p_out)
         if halo is not None:
             halo.exchange(p_out)
@@ -668,9 +691,9 @@ def time_to_mesh(cases, iters):
     from seismicmesh_b200 import meshutil
 
     out = {}
-    for name, dom, edge in cases:
+    for name, dom, edge, ttols in cases:
         res = {}
-        for mode, kw in (("reference_semantics", {}), ("ttol_0.1", {"ttol": 0.1})):
+        for mode, kw in [("reference_semantics", {})] + [(f"ttol_{v:g}", {"ttol": v}) for v in ttols]:
             c0 = time.perf_counter()
             pm, tm = sm.generate_mesh(dom, edge, max_iter=iters, verbose=0, **kw)
             wall_m = time.perf_counter() - c0
@@ -751,9 +774,20 @@ def main():
                                              "delaunay_s", "sizing_s") if k in r2}
         extras["workloads"] = subs
         if args.time_to_mesh > 1:
+            # ttol values: 0.1 is DistMesh's 2-D default; in 3-D the maximum over all vertices is carried by a
+            # few boundary vertices and 0.5 local mesh sizes is what skips retriangulations at equal quality
+            # (profiles/r2g_ttol_sweep.json)
+            vp, bbox = synth_vp("eage")
+            _, _, _, kw = sizing_kwargs("eage", vp, 150.0, 2.0)
+            ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, **kw)
+            del vp
             extras["time_to_mesh"] = time_to_mesh(
-                (("disk_h0=0.01", sm.Disk([0.0, 0.0], 1.0), 0.01), ("ball_h0=0.05", sm.Ball([0.0, 0.0, 0.0], 1.0), 0.05)),
+                (("disk_h0=0.01", sm.Disk([0.0, 0.0], 1.0), 0.01, (0.1, 0.3)),
+                 ("ball_h0=0.05", sm.Ball([0.0, 0.0, 0.0], 1.0), 0.05, (0.1, 0.5)),
+                 ("eage_shaped_hmin=150_freq=2", sm.Cube(ef.bbox), ef, (0.5,))),
                 args.time_to_mesh)
+            del ef
+            torch.cuda.empty_cache()
     elif default_run and world > 1:
         try:
             w2 = build_slab_workload("eage", rank, world)

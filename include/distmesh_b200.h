@@ -323,15 +323,31 @@ int dm_halo_select(const double *p, const int32_t *t, int64_t T, int64_t N, int 
 int dm_halo_push(const double *p, const int32_t *idx, int64_t n, int dim, double *dst_peer,
                  void *stream);
 
+/* The whole per-iteration ghost exchange (migration.exchange, migration.py:148-183) as TWO launches.
+ * dm_halo_push2: the rows of p listed in idx_below / idx_above go straight into the GHOST ROWS of the
+ * neighbours' position buffers (dst_*: peer-mapped addresses of the first ghost row this rank fills in the
+ * neighbour's buffer), then `stamp` is stored, with system-scope release, to flag_below / flag_above (peer
+ * addresses of the neighbour's arrival stamps; NULL = no neighbour on that side).  done_dev: one zeroed int32
+ * of LOCAL device scratch.  dm_halo_wait: holds the stream until this rank's own stamps (written by the
+ * neighbours) have reached `stamp`; stamps must grow from step to step.  A neighbour that does not arrive
+ * within ~2 s of SM clock sets *err_dev = 1 instead of hanging the device. */
+int dm_halo_push2(const double *p, int dim, const int32_t *idx_below, int64_t n_below, double *dst_below,
+                  unsigned long long *flag_below, const int32_t *idx_above, int64_t n_above,
+                  double *dst_above, unsigned long long *flag_above, unsigned long long stamp,
+                  int32_t *done_dev, void *stream);
+int dm_halo_wait(const unsigned long long *flag_from_below, const unsigned long long *flag_from_above,
+                 unsigned long long stamp, int32_t *err_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing: gradient limiting of a gridded size function in place (replaces
  * _FastHJ.limgrad, sizing/cpp/FastHJ.cpp:63-190, called from _enforce_gradation_sizing,
  * sizing/mesh_size_function.py:471-496).  f (n0,n1,n2) float64 C order (n2 = 1 in 2-D);
  * delta = elen*dfdx ; ftol = min(f)*sqrt(1e-9) as in the reference.  Relaxes to the reference's
- * fixed point (unique up to ftol).  changed_dev: one int32 of device scratch.  Synchronises the
- * stream every 32 sweeps; *sweeps_host = sweeps run.  DM_ERR_WORKSPACE if max_sweeps did not suffice.
+ * fixed point (unique up to ftol) with Jacobi sweeps between f and tmp (n0*n1*n2 float64 of device scratch),
+ * so the result is deterministic; it ends up in f.  changed_dev: one int32 of device scratch.  Synchronises
+ * the stream every 32 sweeps; *sweeps_host = sweeps run.  DM_ERR_WORKSPACE if max_sweeps did not suffice.
  * ------------------------------------------------------------------------------------------- */
-int dm_limgrad(double *f, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol,
+int dm_limgrad(double *f, double *tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol,
                int max_sweeps, int32_t *changed_dev, int *sweeps_host, void *stream);
 
 /* utilities */

@@ -359,30 +359,34 @@ __global__ void halo_select_kernel(const double* __restrict__ p, const int32_t* 
 // ---------------------------------------------------------------------------------------------
 // gradient limiting of a gridded size function (sizing/cpp/FastHJ.cpp:63-157, c_limgrad): the
 // reference relaxes node pairs of the 6-edge stencil in a sequential active-set sweep until no
-// pair differs by more than delta (+ ftol).  The operator only ever lowers values and its fixed
-// point is unique (min-plus closure over grid paths), so any relaxation order converges to it:
-// here every node is relaxed against its clamped neighbours in place, one launch per sweep.
+// pair differs by more than delta (+ ftol).  The operator only ever lowers values and, up to the ftol band
+// of its acceptance test, any relaxation order converges to the same fixed point (min-plus closure over
+// grid paths).  Here every sweep is a JACOBI step (read one buffer, write the other), so the result is
+// the same from run to run -- an in-place sweep is a chaotic Gauss-Seidel whose result can differ by about
+// ftol per node between runs, enough to flip a rejection-sampling decision of the initial points.
 // ---------------------------------------------------------------------------------------------
-__global__ void limgrad_sweep_kernel(double* f, int n0, int n1, int n2, double delta, double ftol,
-                                     int32_t* __restrict__ changed) {
+__global__ void limgrad_sweep_kernel(const double* __restrict__ src, double* __restrict__ dst, int n0, int n1, int n2,
+                                     double delta, double ftol, int32_t* __restrict__ changed) {
   const int64_t n = (int64_t)n0 * n1 * n2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k2 = (int)(i % n2), k1 = (int)((i / n2) % n1), k0 = (int)(i / ((int64_t)n2 * n1));
   const int64_t s1 = n2, s0 = (int64_t)n1 * n2;
-  const double v = __ldcg(f + i);
+  const double v = src[i];
   double m = v;
-  if (k2 > 0) m = fmin(m, __ldcg(f + i - 1));
-  if (k2 < n2 - 1) m = fmin(m, __ldcg(f + i + 1));
-  if (k1 > 0) m = fmin(m, __ldcg(f + i - s1));
-  if (k1 < n1 - 1) m = fmin(m, __ldcg(f + i + s1));
-  if (k0 > 0) m = fmin(m, __ldcg(f + i - s0));
-  if (k0 < n0 - 1) m = fmin(m, __ldcg(f + i + s0));
+  if (k2 > 0) m = fmin(m, src[i - 1]);
+  if (k2 < n2 - 1) m = fmin(m, src[i + 1]);
+  if (k1 > 0) m = fmin(m, src[i - s1]);
+  if (k1 < n1 - 1) m = fmin(m, src[i + s1]);
+  if (k0 > 0) m = fmin(m, src[i - s0]);
+  if (k0 < n0 - 1) m = fmin(m, src[i + s0]);
   const double cand = m + delta;  // FastHJ.cpp:138,147
+  double out = v;
   if (v > cand + ftol) {
-    f[i] = cand;
+    out = cand;
     *changed = 1;
   }
+  dst[i] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,6 +403,61 @@ __global__ void halo_push_kernel(const double* __restrict__ p, const int32_t* __
   double x0, x1, x2;
   load_pt<DIM>(p, idx[i], x0, x1, x2);
   store_pt<DIM>(dst, i, x0, x1, x2);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Halo exchange as TWO launches per iteration (round 2): `halo_push2_kernel` stores the rows this rank
+// exports to rank-1 and rank+1 straight into the GHOST ROWS of the neighbours' position buffers (peer
+// mappings of their symmetric-memory buffers: NVLink stores, no staging buffer, no unpack copy) and the
+// last block to finish raises a stamp on each neighbour; `halo_wait_kernel` holds the stream until both
+// neighbours' stamps for this step have arrived.  Every block makes its stores visible system-wide
+// (fence.sc.sys) before it arrives on the local counter; the last arrival (acquire) publishes the stamp
+// with a system-scope release store, the waiter reads it with a system-scope acquire load.
+// ---------------------------------------------------------------------------------------------
+struct HaloPush {
+  const int32_t* idx[2];   // local rows exported below / above
+  int64_t n[2];
+  double* dst[2];          // first ghost row of this rank's block in the neighbour's buffer (peer address)
+  unsigned long long* flag[2];  // the neighbour's "arrived from above" / "arrived from below" stamp (peer address)
+};
+template <int DIM>
+__global__ void halo_push2_kernel(const double* __restrict__ p, HaloPush h, unsigned long long stamp, int32_t* done) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = i < h.n[0] ? 0 : 1;
+  const int64_t k = side == 0 ? i : i - h.n[0];
+  if (k < h.n[side]) {
+    double x0, x1, x2;
+    load_pt<DIM>(p, h.idx[side][k], x0, x1, x2);
+    store_pt<DIM>(h.dst[side], k, x0, x1, x2);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && arrive_acq_rel(done) == (int)gridDim.x - 1) {
+    *done = 0;
+    for (int s = 0; s < 2; ++s)
+      if (h.flag[s] != nullptr)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.flag[s]), "l"(stamp) : "memory");
+  }
+}
+
+// One thread per awaited neighbour spins until its stamp reaches `stamp` (stamps only grow).  The spin is
+// bounded (~2 s of SM clock): a neighbour that never arrives raises *err instead of hanging the GPU.
+__global__ void halo_wait_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long stamp,
+                                 int32_t* err) {
+  const unsigned long long* f = threadIdx.x == 0 ? f0 : f1;
+  if (f == nullptr) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= stamp) break;
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(err, 1);
+      break;
+    }
+    __nanosleep(64);
+  }
 }
 
 }  // namespace dm

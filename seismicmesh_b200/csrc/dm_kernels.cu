@@ -681,22 +681,28 @@ int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, in
   return (int)e;
 }
 
-int dm_limgrad(double* f, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
+int dm_limgrad(double* f, double* tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
                int32_t* changed_dev, int* sweeps_host, void* stream) {
-  if (!f || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;
+  if (!f || !tmp || f == tmp || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;
   if (n0 > INT32_MAX || n1 > INT32_MAX || n2 > INT32_MAX) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
   const int64_t n = n0 * n1 * n2;
-  const int batch = 32;  // sweeps between two looks at the convergence flag
+  const int batch = 32;  // sweeps between two looks at the convergence flag (even: the result is back in f)
   int done = 0, flag = 1;
+  double *src = f, *dst = tmp;
   while (flag && done < max_sweeps) {
     DM_CUDA_TRY(cudaMemsetAsync(changed_dev, 0, sizeof(int32_t), st));
-    for (int b = 0; b < batch && done < max_sweeps; ++b, ++done)
-      limgrad_sweep_kernel<<<nblk(n, 256), 256, 0, st>>>(f, (int)n0, (int)n1, (int)n2, delta, ftol, changed_dev);
+    for (int b = 0; b < batch && done < max_sweeps; ++b, ++done) {
+      limgrad_sweep_kernel<<<nblk(n, 256), 256, 0, st>>>(src, dst, (int)n0, (int)n1, (int)n2, delta, ftol, changed_dev);
+      double* sw = src;
+      src = dst;
+      dst = sw;
+    }
     DM_LAUNCH_CHECK();
     DM_CUDA_TRY(cudaMemcpyAsync(&flag, changed_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DM_CUDA_TRY(cudaStreamSynchronize(st));
   }
+  if (src != f) DM_CUDA_TRY(cudaMemcpyAsync(f, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (sweeps_host) *sweeps_host = done;
   return flag ? DM_ERR_WORKSPACE : DM_OK;  // not converged within max_sweeps
 }
@@ -709,6 +715,38 @@ int dm_halo_push(const double* p, const int32_t* idx, int64_t n, int dim, double
     halo_push_kernel<2><<<nblk(n, 256), 256, 0, S(stream)>>>(p, idx, n, dst_peer);
   else
     halo_push_kernel<3><<<nblk(n, 256), 256, 0, S(stream)>>>(p, idx, n, dst_peer);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
+int dm_halo_push2(const double* p, int dim, const int32_t* idx_below, int64_t n_below, double* dst_below,
+                  unsigned long long* flag_below, const int32_t* idx_above, int64_t n_above, double* dst_above,
+                  unsigned long long* flag_above, unsigned long long stamp, int32_t* done_dev, void* stream) {
+  if (!p || bad_dim(dim) || n_below < 0 || n_above < 0 || !done_dev) return DM_ERR_ARG;
+  if ((n_below > 0 && (!idx_below || !dst_below)) || (n_above > 0 && (!idx_above || !dst_above))) return DM_ERR_ARG;
+  HaloPush h;
+  h.idx[0] = idx_below;
+  h.idx[1] = idx_above;
+  h.n[0] = n_below;
+  h.n[1] = n_above;
+  h.dst[0] = dst_below;
+  h.dst[1] = dst_above;
+  h.flag[0] = flag_below;
+  h.flag[1] = flag_above;
+  const unsigned nb = nblk(n_below + n_above, 256);
+  if (dim == 2)
+    halo_push2_kernel<2><<<nb, 256, 0, S(stream)>>>(p, h, stamp, done_dev);
+  else
+    halo_push2_kernel<3><<<nb, 256, 0, S(stream)>>>(p, h, stamp, done_dev);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
+int dm_halo_wait(const unsigned long long* flag_from_below, const unsigned long long* flag_from_above,
+                 unsigned long long stamp, int32_t* err_dev, void* stream) {
+  if (!err_dev) return DM_ERR_ARG;
+  if (!flag_from_below && !flag_from_above) return DM_OK;
+  halo_wait_kernel<<<1, 2, 0, S(stream)>>>(flag_from_below, flag_from_above, stamp, err_dev);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["slab_bounds", "slab_partition", "RingHalo", "PeerHalo", "SlabLayout", "TorchComm", "generate_mesh_parallel"]
+__all__ = ["slab_bounds", "slab_partition", "RingHalo", "PeerHalo", "DirectHalo", "SlabLayout", "TorchComm", "generate_mesh_parallel"]
 
 
 def slab_bounds(lo, hi, world):
@@ -178,6 +178,85 @@ class PeerHalo:
         if r < w - 1:
             self.hdl.wait_signal(r + 1, channel=1)
             p[self.ghost_a] = self.buf[s, 1, : self.na]
+
+
+class DirectHalo:
+    """The neighbour exchange as TWO launches per iteration, with no staging buffer and no unpack copy:
+    every rank keeps its position buffers in symmetric memory (`slot(k)`: where the force iteration of
+    step k writes its result); `exchange(p)` stores the rows this rank exports straight into the GHOST
+    ROWS of the neighbours' buffers of the same step (`dm_halo_push2`: NVLink stores + a stamp raised on
+    each neighbour by the kernel's last block) and then holds the stream until both neighbours' stamps
+    of this step have arrived (`dm_halo_wait`).  Two alternating slots suffice: a neighbour can be at most
+    one step ahead (it waits for this rank's stamp before its next iteration), and then it writes ghost rows
+    of the slot this rank is still computing its OWNED rows of.  Same values as RingHalo / PeerHalo."""
+
+    def __init__(self, layout, dim, device, rank=None, world=None, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.dim = dim
+        n0, nb, na = layout.n_owned, len(layout.ghost_below), len(layout.ghost_above)
+        self.n_local = n0 + nb + na
+        self.exp_b = torch.as_tensor(layout.export_below, dtype=torch.int32, device=device)
+        self.exp_a = torch.as_tensor(layout.export_above, dtype=torch.int32, device=device)
+        counts = torch.zeros((self.world, 3), dtype=torch.int64, device=device)
+        counts[self.rank] = torch.tensor([n0, nb, na], dtype=torch.int64, device=device)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        self.counts = counts.cpu().numpy()
+        self.cap = int(self.counts.sum(axis=1).max())  # rows per slot, the same on every rank (symmetric allocation)
+        grp = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty((2, self.cap, dim), dtype=torch.float64, device=device)
+        self.flags = symm.empty((2,), dtype=torch.int64, device=device)  # stamps: [from below, from above]
+        self.flags.zero_()
+        self.hbuf = symm.rendezvous(self.buf, grp)
+        self.hflag = symm.rendezvous(self.flags, grp)
+        self.pbuf = [int(a) for a in self.hbuf.buffer_ptrs]
+        self.pflag = [int(a) for a in self.hflag.buffer_ptrs]
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step = 0
+        self.bytes_per_exchange = 8 * dim * (len(self.exp_b) + len(self.exp_a) + nb + na)
+        torch.cuda.synchronize()
+        self.hbuf.barrier(channel=3)
+
+    def slot(self, k=None):
+        """(n_local, dim) position buffer of step k (default: the step the next exchange belongs to)."""
+        k = self.step if k is None else k
+        return self.buf[k % 2, : self.n_local]
+
+    def exchange(self, p):
+        """Push the exported rows of `p` into the neighbours' slot of this step and wait for theirs; the ghost
+        rows of `self.slot()` then hold the neighbours' new positions."""
+        import ctypes as C
+
+        from . import device as D
+        from ._lib import check, lib
+
+        r, w, s = self.rank, self.world, self.step % 2
+        row = 8 * self.dim
+        stamp = self.step + 1
+        db = fb = da = fa = None
+        if r > 0:      # my "below" exports are rank r-1's ghosts "from above": behind its owned + from-below rows
+            n0p, nbp, _ = self.counts[r - 1]
+            db = C.c_void_p(self.pbuf[r - 1] + row * (s * self.cap + int(n0p + nbp)))
+            fb = C.c_void_p(self.pflag[r - 1] + 8)
+        if r < w - 1:  # my "above" exports are rank r+1's ghosts "from below": right behind its owned rows
+            n0p = self.counts[r + 1][0]
+            da = C.c_void_p(self.pbuf[r + 1] + row * (s * self.cap + int(n0p)))
+            fa = C.c_void_p(self.pflag[r + 1])
+        st = D.stream_ptr()
+        check(lib.dm_halo_push2(D.ptr(p), self.dim, D.ptr(self.exp_b), len(self.exp_b) if r > 0 else 0, db, fb,
+                                D.ptr(self.exp_a), len(self.exp_a) if r < w - 1 else 0, da, fa, stamp, D.ptr(self.done), st),
+              "dm_halo_push2")
+        mine = self.flags.data_ptr()
+        check(lib.dm_halo_wait(C.c_void_p(mine) if r > 0 else None, C.c_void_p(mine + 8) if r < w - 1 else None, stamp,
+                               D.ptr(self.err), st), "dm_halo_wait")
+        self.step += 1
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("DirectHalo: a neighbour's stamp did not arrive (dm_halo_wait timed out)")
 
 
 def make_slab_workload(workload, h0, rank, world, halo_layers=5, seed=0):
@@ -404,7 +483,10 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         # ---- user-defined points (restart; _user_defined_points :787-805): rank 0's array is cut into
         # comm.size blocks (decomp.blocker, decomp/blocker.py:4-111: `axis` 1 cuts along x, 0 along y,
         # 2 along z; equal-width blocks of the points' bounding box) and every rank takes its block.
-        # Extents are the blocks' bounding boxes, unpadded, as blocker returns them.
+        # blocker returns the blocks' bounding boxes UNPADDED, and the export test (here and in the reference,
+        # cpputils.cpp:122-135) only looks at cells whose bounding box overlaps the neighbour's extent: with
+        # disjoint extents nothing would ever be exported.  The extents are therefore padded by 5*h0 along the
+        # cut, exactly as _form_extents does for generated points (:867-877).
         pts = _broadcast_points(gen_opts["points"], rank, dim, cdev, group)
         ext_axis = {0: 1, 1: 0, 2: 2}[axis]
         if ext_axis >= dim:
@@ -414,7 +496,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         cuts = np.linspace(lo_, hi_, size_ + 1)
         blk = np.clip(np.searchsorted(cuts, pts[:, ext_axis], side="right") - 1, 0, size_ - 1)
         p = np.ascontiguousarray(pts[blk == rank])
-        pad = 0.0
+        pad = 5 * h0
     all_ranks_ok(len(p) > 0, "No vertices to mesh with!")
     # extents of every rank: bounding box of its points (padded, see above)
     ext = torch.zeros((size_, 2 * dim), dtype=torch.float64, device=cdev)

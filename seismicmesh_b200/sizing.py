@@ -149,7 +149,8 @@ def limgrad(cell_size, grade, elen, max_sweeps=None):
     ftol = float(a.min()) * np.sqrt(1e-9)  # FastHJ.cpp:72 (EPS = 1e-9)
     sweeps = C.c_int(0)
     cap = int(max_sweeps) if max_sweeps is not None else 4 * int(sum(shp)) + 64
-    check(lib.dm_limgrad(D.ptr(f), shp[0], shp[1], shp[2], float(elen) * float(grade), ftol, cap, D.ptr(flag),
+    tmp = torch.empty_like(f)  # the sweeps are Jacobi steps between two buffers (deterministic result)
+    check(lib.dm_limgrad(D.ptr(f), D.ptr(tmp), shp[0], shp[1], shp[2], float(elen) * float(grade), ftol, cap, D.ptr(flag),
                          C.byref(sweeps), D.stream_ptr()), "dm_limgrad")
     limgrad.last_sweeps = sweeps.value
     return f.cpu().numpy().reshape(a.shape)
