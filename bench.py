@@ -345,7 +345,7 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
     gathers counted once per distinct element; DESIGN.md section 4 / SURVEY section 8d), from the
     ACTUAL sizes of the run."""
     c, d = dim + 1, dim
-    hs = 8 * E if grid_fh else 0
+    hs = 16 * E if grid_fh else 0  # gridded fh: h is stored at both slots of a bar (8 B each), written once, read once
     return {
         # zero the per-iteration counters; 3-D: p read once, the padded copy written once
         "prep(zero+pad)": 4 * (N + 1) + (56 * N if dim == 3 else 0),
@@ -355,7 +355,7 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
         # bar pass K3 fused in (positions read once, h written once per bar for gridded fh)
         "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E + 8 * d * N + hs,
         "bar_pass+scale": 8 * d * N + 4 * E + 8 * N + hs,
-        "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + 2 * hs,
+        "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + hs,
     }
 
 
@@ -579,7 +579,7 @@ def measure(wl, K, W, rank, world, local_rank, full, flush, kernel_table=None, c
                 "ms_per_step": e2e_ms / K, "h2d_gbs_per_rank": h2d / (e2e_ms / K * 1e-3) / 1e9,
                 "call": "ForceLoop.iterate_host (the call generate_mesh makes every iteration): pinned H2D of p and t, t in "
                         "chunks overlapped with stage A, async D2H of the new positions"},
-        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped
+        "gpu_launches": 5 * K,  # prep, cull_scatter, adjacency, vertex_update, project_escaped (rank 0 recounts below)
         "delaunay_s": wl["delaunay_s"], "sizing_s": wl["sizing_s"], "maxdp": maxdp,
     }
     if clocks is not None:
@@ -658,6 +658,7 @@ def measure(wl, K, W, rank, world, local_rank, full, flush, kernel_table=None, c
         "kernels": [{"kernel": r["kernel"], "ms": r["ms"], "frac": r["frac"]} for r in table],
     }
     rec["config"].update({"T_kept": Tk, "bars": E})
+    rec["gpu_launches"] = len(names) * K  # our kernels per step (counted from the events recorded inside the library) x steps
     if kernel_table:
         os.makedirs(os.path.dirname(os.path.abspath(kernel_table)), exist_ok=True)
         with open(kernel_table, "w") as fo:

@@ -339,6 +339,17 @@ int dm_halo_wait(const unsigned long long *flag_from_below, const unsigned long 
                  unsigned long long stamp, int32_t *err_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Sizing preprocessing, elementwise chain in one pass (replaces the NumPy expressions of
+ * get_sizing_function_from_segy, sizing/mesh_size_function.py:411-426 wavelength sizing, :180-181 clamp,
+ * :453-468 CFL bound): out[i] = clamp(min(vp[i] / (freq*wl), h_gr[i]), hmin, hmax), then the CFL bound
+ * (vp*dt)/(dim*cr_lim) where (vp*dt)/(dim*out) > cr_lim = cr_max/(dim*space_order).  wl <= 0: no wavelength
+ * term; h_gr NULL: no gradient term; dt, cr_max or space_order == 0: no CFL bound.  Bit-identical to NumPy.
+ * ------------------------------------------------------------------------------------------- */
+int dm_size_from_velocity(const double *vp, const double *h_gr, int64_t n, int dim, double freq, double wl,
+                          double hmin, double hmax, double dt, double cr_max, double space_order,
+                          double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing: gradient limiting of a gridded size function in place (replaces
  * _FastHJ.limgrad, sizing/cpp/FastHJ.cpp:63-190, called from _enforce_gradation_sizing,
  * sizing/mesh_size_function.py:471-496).  f (n0,n1,n2) float64 C order (n2 = 1 in 2-D);

@@ -15,9 +15,11 @@
  *
  *   - every pointer is a HOST pointer; float64 row-major coordinates, int32 row-major cells;
  *   - no global state, re-entrant; the only allocation is internal scratch freed before return;
- *   - Output order: vertex ids ascending within a cell, cells in lexicographic order.  Consecutive cells
- *     then share their leading vertices, which is what the device pipeline's warp-aggregated slot claims
- *     and position gathers like best (csrc/host/dm_cell_order.h has the numbers).  Orientation is NOT
+ *   - Output order: cells GROUPED BY THEIR SMALLEST VERTEX ID (groups ascending, cells of a group in
+ *     lexicographic order of their sorted ids); the column order inside a cell is the triangulator's own and
+ *     is NOT canonicalised.  The grouping is what the device pipeline's warp-aggregated slot claims and
+ *     position gathers like best (csrc/host/dm_cell_order.h); an unbiased column 0 is what the reference's
+ *     sliver loop needs ("vertex 0 of every sliver", mesh_generator.py:234,245-274).  Orientation is NOT
  *     normalised: the loop body never uses it, and the reference fixes it at termination (fix_mesh);
  *   - results are exact Delaunay triangulations: the orientation / in-circle predicates run a
  *     floating-point filter and fall back to exact expansion arithmetic, so co-circular and
@@ -47,8 +49,8 @@ int64_t dmh_delaunay2d_max_cells(int64_t N);
 
 /* Delaunay triangulation of `points` (N,2).  Replaces DelaunayTriangulation.insert +
  * get_finite_cells (generation/cpp/delaunay_class.cpp:45-62, 99-117) with the vertex ids = input
- * rows.  Writes *T_out triangles to `cells` (capacity `cap` rows), vertex ids ascending within a
- * triangle and the triangles in lexicographic order (see "Output order" above).  Input rows
+ * rows.  Writes *T_out triangles to `cells` (capacity `cap` rows) in the order described under "Output
+ * order" above.  Input rows
  * that are in no triangle are counted in *duplicates_out (exact duplicates of an earlier row, which
  * keeps the cells; CGAL and Qhull leave those out as well) and *lost_out (everything else: all rows
  * when the input is collinear or has fewer than 3 distinct points, in which case *T_out = 0; a row
@@ -65,7 +67,7 @@ int64_t dmh_delaunay3d_max_cells(int64_t N);
 
 /* Delaunay triangulation of `points` (N,3).  Replaces DelaunayTriangulation3.insert +
  * get_finite_cells (generation/cpp/delaunay_class3.cpp) with the vertex ids = input rows.  Writes
- * *T_out tetrahedra to `cells`, vertex ids ascending within a cell, cells in lexicographic order; with
+ * *T_out tetrahedra to `cells` (see "Output order" above); with
  * DMH_ERR_CAPACITY nothing is written and *T_out is the capacity that is needed.  *duplicates_out
  * counts rows left out as exact duplicates of another row (ONE copy is in the cells, not necessarily
  * the first), *lost_out rows left out for any other reason: all N when there are not four affinely

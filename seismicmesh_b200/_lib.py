@@ -122,6 +122,7 @@ _SIGNATURES = {
         [C.POINTER(DmPlan), C.POINTER(_P), _INT, C.POINTER(DmSizeFn), _P, _P, _P, _D, _D, _D, _D, _D, _I64, _P, _P,
          C.POINTER(C.c_float), C.c_char_p, _INT, _INT, C.POINTER(_INT)],
     ),
+    "dm_size_from_velocity": (_INT, [_P, _P, _I64, _INT, _D, _D, _D, _D, _D, _D, _D, _P, _P]),
     "dm_limgrad": (_INT, [_P, _P, _I64, _I64, _I64, _D, _D, _INT, _P, C.POINTER(_INT), _P]),
     "dm_halo_push": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "dm_halo_push2": (_INT, [_P, _INT, _P, _I64, _P, _P, _P, _I64, _P, _P, C.c_uint64, _P, _P]),

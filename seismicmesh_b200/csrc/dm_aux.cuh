@@ -357,6 +357,40 @@ __global__ void halo_select_kernel(const double* __restrict__ p, const int32_t* 
 
 
 // ---------------------------------------------------------------------------------------------
+// Sizing preprocessing, the elementwise chain of get_sizing_function_from_segy in ONE pass over the
+// velocity grid (sizing/mesh_size_function.py): wavelength sizing h = vp / (freq * wl) (:411-426),
+// optionally the minimum with a gradient-sizing field (:429-450, computed by the caller), the hmin / hmax
+// clamp (:180-181) and the CFL bound (:453-468).  Same operations in the same order as the NumPy
+// expressions (no FMA contraction), so the grid is bit-identical to the reference's.
+// ---------------------------------------------------------------------------------------------
+struct SizingParams {
+  double inv_denom;   // unused (kept 0): the division is by freq * wl, as NumPy does it
+  double freq_wl;     // freq * wl ; <= 0: no wavelength sizing (h = 99999)
+  double hmin, hmax;
+  double dt;          // 0: no CFL bound
+  double dimf;        // (double) dim
+  double cr_lim;      // cr_max / (dim * space_order)
+  double dim_cr_lim;  // dim * cr_lim
+};
+__global__ void sizing_elementwise_kernel(const double* __restrict__ vp, const double* __restrict__ h_gr, int64_t n,
+                                          SizingParams q, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = vp[i];
+  // np.minimum(h_wl, h_gr) with the reference's 99999 stand-ins for a term that is switched off; with both
+  // switched off the grid keeps its initial value hmin (:162-166)
+  double h = q.freq_wl > 0.0 ? v / q.freq_wl : (h_gr != nullptr ? 99999.0 : q.hmin);
+  h = fmin(h, h_gr != nullptr ? h_gr[i] : (q.freq_wl > 0.0 ? 99999.0 : h));
+  if (h < q.hmin) h = q.hmin;
+  if (h > q.hmax) h = q.hmax;
+  if (q.dt != 0.0) {
+    const double cr_old = (v * q.dt) / (q.dimf * h);
+    if (cr_old > q.cr_lim) h = (v * q.dt) / q.dim_cr_lim;
+  }
+  out[i] = h;
+}
+
+// ---------------------------------------------------------------------------------------------
 // gradient limiting of a gridded size function (sizing/cpp/FastHJ.cpp:63-157, c_limgrad): the
 // reference relaxes node pairs of the 6-edge stencil in a sequential active-set sweep until no
 // pair differs by more than delta (+ ftol).  The operator only ever lowers values and, up to the ftol band

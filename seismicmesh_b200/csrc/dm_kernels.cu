@@ -612,7 +612,7 @@ int dm_force_iteration_tail(const DmPlan* pl, const double* const* progs, int nl
   if (!pl || !progs || nlevels < 1 || nlevels > DM_MAX_LEVELS || !f || f->kind == DM_SIZE_EXTERNAL) return DM_ERR_ARG;
   if (!p || !p_out || p == p_out || check_size_fn(f, pl->dim)) return DM_ERR_ARG;
   cudaStream_t st = S(stream);
-  const int rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
+  int rc = pl->dim == 2 ? stage_adjacency<2>(pl, f->kind, f, p, st) : stage_adjacency<3>(pl, f->kind, f, p, st);
   if (rc) return rc;
   return vertex_update_impl(pl, p, true, p_out, progs, nlevels, f, L0mult, delta_t, deps, h0, nfix, fixed, Ftot, st);
 }
@@ -679,6 +679,26 @@ int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, in
   for (int i = 0; i <= PROF_MAX; ++i) cudaEventDestroy(pr.ev[i]);
   if (rc) return rc;
   return (int)e;
+}
+
+int dm_size_from_velocity(const double* vp, const double* h_gr, int64_t n, int dim, double freq, double wl, double hmin,
+                          double hmax, double dt, double cr_max, double space_order, double* out, void* stream) {
+  if (n < 0 || bad_dim(dim)) return DM_ERR_ARG;
+  if (n == 0) return DM_OK;
+  if (!vp || !out) return DM_ERR_ARG;
+  SizingParams q;
+  memset(&q, 0, sizeof(q));
+  q.freq_wl = wl > 0.0 ? freq * wl : 0.0;
+  q.hmin = hmin;
+  q.hmax = hmax;
+  q.dimf = (double)dim;
+  const bool cfl = !(cr_max == 0.0 || dt == 0.0 || space_order == 0.0);
+  q.dt = cfl ? dt : 0.0;
+  q.cr_lim = cfl ? cr_max / ((double)dim * space_order) : 0.0;
+  q.dim_cr_lim = (double)dim * q.cr_lim;
+  sizing_elementwise_kernel<<<nblk(n, 256), 256, 0, S(stream)>>>(vp, h_gr, n, q, out);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
 }
 
 int dm_limgrad(double* f, double* tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,

@@ -57,6 +57,15 @@ constexpr int HV_SMEM = 4608;    // heavy path: candidates sorted in shared memo
 #ifndef DM_VU_MINB
 #define DM_VU_MINB 8
 #endif
+// Gridded fh: the bar pass leaves h at EVERY slot of a row, lower neighbours included, so that the vertex
+// update reads h of all its bars from its own row and never interpolates (its per-vertex loop is latency
+// bound; the bar pass spreads the interpolations of a row over a lane group).  Every bar is therefore
+// interpolated twice, once per end, with the same midpoint bits and hence the same h.  Measured in round 2
+// and rejected: evaluating h once per bar and handing it to the other end through a search of the owner's
+// row -- inside the vertex update (+9 % on that kernel), in a split lower / upper loop (+7..35 %), or in a
+// mirror kernel of its own after the row build (0.130 ms against 0.087 ms for the second interpolation on
+// the EAGE-shaped workload): five dependent gathers cost more than three divisions and a 64-B record.
+constexpr bool H_ALL_SLOTS = true;
 
 template <int DIM>
 struct PCfg;
@@ -270,19 +279,23 @@ __device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC],
   } while (__any_sync(FULL, any));
 }
 
-// L^d and h^d of the bar (a, p[w]); GRID: h is interpolated at the midpoint and stored at `hout`
+// L^d and h^d of the bar (a, p[w]); GRID: h is interpolated at the midpoint and stored at `hout`.
+// upper == false (GRID only): the slot is a LOWER neighbour of the row's vertex -- h is evaluated and stored
+// for the vertex update to read (same midpoint bits as the bar's owner forms, hence the same h), but the
+// bar belongs to its other end and is not added to the sums.
 template <int DIM, bool GRID>
 __device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __restrict__ pp, double a0, double a1,
-                                          double a2, int w, double* hout, double& sL, double& sH) {
+                                          double a2, int w, double* hout, double& sL, double& sH, bool upper = true) {
   double b0, b1, b2, d0, d1, d2;
   load_pt<DIM, true>(pp, w, b0, b1, b2);  // pp: the plan's padded point copy
-  const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
   double h = f.hconst;
   if (GRID) {
     // midpoint p[edges].sum(1)/2 (mesh_generator.py:699)
     h = size_eval(f, (a0 + b0) / 2, (a1 + b1) / 2, (a2 + b2) / 2);
     *hout = h;
+    if (!upper) return;
   }
+  const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
   if (DIM == 2) {
     sL += L * L;
     sH += h * h;
@@ -500,7 +513,8 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
     double sL = 0.0, sH = 0.0;
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
-    for (int j = lo + tid; j < U; j += THREADS) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH);
+    for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lo) + tid; j < U; j += THREADS)
+      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH, j >= lo);
     const double bl = block_sum(sL, s_dbl);
     const double bh = block_sum(sH, s_dbl);
     if (tid == 0) {
@@ -571,11 +585,11 @@ __device__ __noinline__ RowSums select_row(bool punt, int n, int v,
     degs[v] = make_int2(Up, lop);
     out.bars = Up - lop;
   }
-  if (BAR >= 0 && Up > lop) {
+  if (BAR >= 0 && Up > (BAR == 1 && H_ALL_SLOTS ? 0 : lop)) {
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
-    for (int j = lop + lg; j < Up; j += G)
-      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, out.sL, out.sH);
+    for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lop) + lg; j < Up; j += G)
+      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, out.sL, out.sH, j >= lop);
   }
   return out;
 }
@@ -758,10 +772,12 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
       degs[v] = make_int2(U, lo);
       bars = U - lo;
     }
-    if (BAR >= 0 && U > lo) {  // bar pass over the upper neighbours (mesh_generator.py:696-700)
+    if (BAR >= 0 && U > (BAR == 1 && H_ALL_SLOTS ? 0 : lo)) {
+      // bar pass (mesh_generator.py:696-700): L^d, h^d of the row's upper bars; gridded fh: h of EVERY slot
       double a0, a1, a2;
       load_pt<DIM, true>(pp, v, a0, a1, a2);
-      for (int j = lo + lg; j < U; j += G) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH);
+      for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lo) + lg; j < U; j += G)
+        bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH, j >= lo);
     }
   }
   // ---- a neighbour set that does not fit the group table: rare, out of line.  Warp-uniform branch.
@@ -907,24 +923,31 @@ __global__ void __launch_bounds__(PL_THREADS) bar_pass_kernel(const DmSizeFn f, 
   if (v < N) {
     const int2 dg = R.degs[v];
     const int lo = dg.y, m = dg.x;
-    if (m > lo) {
+    // gridded fh (HMODE 1): h is left at EVERY slot of the row, lower neighbours included (the vertex update
+    // reads it there); the sums run over the upper bars only
+    const int first = (HMODE == 1 && H_ALL_SLOTS) ? 0 : lo;
+    if (m > first) {
       const int32_t* row = R.row(v, m);
       const int64_t base = R.slot_base(v, m);
       double a0, a1, a2;
       load_pt<DIM>(p, v, a0, a1, a2);
       // rows are 16-B aligned and padded to a multiple of 4 ints: walk them in int4 chunks
-      for (int j0 = lo & ~3; j0 < m; j0 += 4) {
+      for (int j0 = first & ~3; j0 < m; j0 += 4) {
         const int4 q = *reinterpret_cast<const int4*>(row + j0);
         const int wq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + u;
-          if (j < lo || j >= m) continue;
+          if (j < first || j >= m) continue;
           const int w = wq[u];
           double b0, b1, b2, d0, d1, d2;
           load_pt<DIM>(p, w, b0, b1, b2);
           // midpoint p[edges].sum(1)/2 (mesh_generator.py:699)
           const double m0 = (a0 + b0) / 2, m1 = (a1 + b1) / 2, m2 = (a2 + b2) / 2;
+          if (HMODE == 1 && j < lo) {
+            hslot[base + j] = size_eval(f, m0, m1, m2);
+            continue;
+          }
           if (HMODE == 3) {
             store_pt<DIM>(mid, rowptr[v] + (j - lo), m0, m1, m2);
             continue;
@@ -1063,30 +1086,10 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
         if (HMODE == 0) {
           h = f.hconst;
         } else if (HMODE == 1) {
-          if (j >= lo) {
-            h = j < m ? hslot[base + j] : 0.0;
-          } else {
-            // lower bar (w, v), w < v: its OWNER w evaluated fh at the midpoint already (bar pass) and left
-            // it at the slot of v in w's row; finding that slot (one row line + 8 B) is far cheaper than a
-            // second interpolation (three axis searches, three divisions, a 64-B corner record from DRAM).
-            // Same value bit for bit: both ends form the same midpoint.  A row that lives in the heap
-            // (more than RS neighbours) takes the interpolation.
-            const int2 dw = R.degs[w];
-            int pos = -1;
-            if (dw.x <= PCfg<DIM>::RS) {
-              const int32_t* rw = R.adj + (int64_t)w * PCfg<DIM>::RS;
-              for (int q0 = dw.y & ~3; q0 < dw.x; q0 += 4) {
-                const int4 c = *reinterpret_cast<const int4*>(rw + q0);
-                pos = c.x == (int)v ? q0 : pos;
-                pos = c.y == (int)v ? q0 + 1 : pos;
-                pos = c.z == (int)v ? q0 + 2 : pos;
-                pos = c.w == (int)v ? q0 + 3 : pos;
-              }
-              if (pos >= dw.x) pos = -1;  // (a stale id behind the end of the row)
-            }
-            h = pos >= 0 ? hslot[(int64_t)w * PCfg<DIM>::RS + pos]
-                         : size_eval(f, (b0 + a0) / 2, (b1 + a1) / 2, (b2 + a2) / 2);
-          }
+          // gridded fh: h of every bar (v, w) waits at its slot in v's row -- the bar pass that follows the
+          // row build evaluates it for the lower slots as well as the upper ones (same midpoint bits at both
+          // ends of a bar, hence the same h), with a lane group per vertex; here it is one coalesced read
+          h = j < m ? hslot[base + j] : 0.0;
         } else {
           h = 0.0;
           if (j < m) h = hbar[j >= lo ? rowptr[v] + (j - lo) : bar_id_of<DIM>(R, rowptr, w, (int)v)];

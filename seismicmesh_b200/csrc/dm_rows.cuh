@@ -109,10 +109,11 @@ __device__ __noinline__ void slow_row(int v, int n, const typename PCfg<DIM>::en
     degs[v] = make_int2(U, lo);
     bars += U - lo;
   }
-  if (BAR >= 0 && U > lo) {
+  if (BAR >= 0 && U > (BAR == 1 ? 0 : lo)) {
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
-    for (int j = lo + lane; j < U; j += 32) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, sL, sH);
+    for (int j = (BAR == 1 ? 0 : lo) + lane; j < U; j += 32)
+      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, sL, sH, j >= lo);
   }
 }
 
@@ -285,11 +286,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, DM_ROWS_MINB) rows_kernel(
   // ---- bar pass over the upper neighbours (mesh_generator.py:696-700)
   int bars = mine ? U - lo : 0;
   double sL = 0.0, sH = 0.0;
-  if (BAR >= 0 && mine && U > lo) {
+  if (BAR >= 0 && mine && U > (BAR == 1 ? 0 : lo)) {
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
     const int64_t sbase = v * RS;
-    for (int j = lo; j < U; ++j) bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j * 32], hslot + sbase + j, sL, sH);
+    for (int j = (BAR == 1 ? 0 : lo); j < U; ++j)
+      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j * 32], hslot + sbase + j, sL, sH, j >= lo);
   }
   // ---- vertices with more than RS distinct neighbours: the whole warp, one vertex at a time
   unsigned todo = __ballot_sync(FULL, over && v < N && !heavy);

@@ -123,9 +123,11 @@ class SizeFunction:
 
 # ----------------------------------------------------------------------------------------------
 # Sizing preprocessing (SURVEY section 8f "next #3"): velocity model -> gridded size function
-# with the reference's interface (sizing/mesh_size_function.py:27-232).  The elementwise steps
-# are host NumPy (one pass each, seconds at most); the gradient limiter -- the reference's only
-# native code on this path (sizing/cpp/FastHJ.cpp) -- runs on the device.
+# with the reference's interface (sizing/mesh_size_function.py:27-232).  The elementwise chain
+# (wavelength sizing, clamp, CFL bound) is ONE fused kernel over the velocity grid and the gradient
+# limiter -- the reference's only native code on this path (sizing/cpp/FastHJ.cpp) -- runs on the grid
+# where that kernel left it; the optional windowed-variance term (SciPy uniform_filter) and the domain
+# padding (np.pad) stay on the host.
 # ----------------------------------------------------------------------------------------------
 _SIZING_DEFAULTS = {  # mesh_size_function.py:103-126
     "velocity_data": None, "vp_water": 1500.0, "hmin": 150.0, "hmax": 10000.0, "wl": 0, "freq": 2.0, "grad": 0.0,
@@ -133,6 +135,20 @@ _SIZING_DEFAULTS = {  # mesh_size_function.py:103-126
     "domain_pad": 0.0, "units": "m-s", "nz": None, "nx": None, "ny": None, "byte_order": "byte_order",
     "axes_order": (0, 1, 2), "axes_order_sort": "F", "dtype": "float32",
 }
+
+
+def _limgrad_device(f, grade, elen, max_sweeps=None):
+    """dm_limgrad on a device tensor, in place (2-D or 3-D grid)."""
+    shp = tuple(f.shape) if f.ndim == 3 else (f.shape[0], f.shape[1], 1)
+    flag = torch.zeros(1, dtype=torch.int32, device=f.device)
+    ftol = float(f.min().item()) * np.sqrt(1e-9)  # FastHJ.cpp:72 (EPS = 1e-9)
+    sweeps = C.c_int(0)
+    cap = int(max_sweeps) if max_sweeps is not None else 4 * int(sum(shp)) + 64
+    tmp = torch.empty_like(f)  # the sweeps are Jacobi steps between two buffers (deterministic result)
+    check(lib.dm_limgrad(D.ptr(f), D.ptr(tmp), shp[0], shp[1], shp[2], float(elen) * float(grade), ftol, cap, D.ptr(flag),
+                         C.byref(sweeps), D.stream_ptr()), "dm_limgrad")
+    limgrad.last_sweeps = sweeps.value
+    return f
 
 
 def limgrad(cell_size, grade, elen, max_sweeps=None):
@@ -145,14 +161,7 @@ def limgrad(cell_size, grade, elen, max_sweeps=None):
     shp = a.shape if a.ndim == 3 else (a.shape[0], a.shape[1], 1)
     D.require_cuda()
     f = torch.from_numpy(a).to(D.device())
-    flag = torch.zeros(1, dtype=torch.int32, device=f.device)
-    ftol = float(a.min()) * np.sqrt(1e-9)  # FastHJ.cpp:72 (EPS = 1e-9)
-    sweeps = C.c_int(0)
-    cap = int(max_sweeps) if max_sweeps is not None else 4 * int(sum(shp)) + 64
-    tmp = torch.empty_like(f)  # the sweeps are Jacobi steps between two buffers (deterministic result)
-    check(lib.dm_limgrad(D.ptr(f), D.ptr(tmp), shp[0], shp[1], shp[2], float(elen) * float(grade), ftol, cap, D.ptr(flag),
-                         C.byref(sweeps), D.stream_ptr()), "dm_limgrad")
-    limgrad.last_sweeps = sweeps.value
+    _limgrad_device(f, grade, elen, max_sweeps)
     return f.cpu().numpy().reshape(a.shape)
 
 
@@ -275,18 +284,17 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     for key in kwargs:
         if key not in _SIZING_DEFAULTS:
             raise ValueError("Option %s with parameter %s not recognized " % (key, kwargs[key]))
-    cell_size = np.full((nz, nx) if dim == 2 else (nz, nx, ny), opts["hmin"], dtype=float)
+    # ---- wavelength / gradient sizing (:411-450), clamp (:180-181), CFL bound (:453-468): argument checks in
+    #      the reference's order, then ONE fused kernel over the velocity grid on the device
+    h_gr = None
     if opts["wl"] > 0 or opts["grad"] > 0:
-        # wavelength sizing (:411-426) and gradient sizing (:429-450)
         if opts["wl"] < 0:
             raise ValueError("Parameter `wl` must be set > 0")
         if opts["freq"] < 0.0:
             raise ValueError("Parameter `freq` must be set > 0.0")
-        h_wl = 99999 if opts["wl"] == 0.0 else vp / (opts["freq"] * opts["wl"])
-        h_gr = 99999
         if opts["grad"] < 0:
             raise ValueError("Parameter grad must be > 0")
-        if opts["grad"] != 0.0:
+        if opts["grad"] != 0.0:  # windowed variance of vp: SciPy's uniform_filter on the host, as the reference calls it
             from scipy import ndimage
 
             st = opts["stencil_size"]
@@ -297,10 +305,6 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
             win_var = np.divide(win_var, np.amax(win_var))
             win_var -= np.amin(win_var)
             h_gr = opts["grad"] / (win_var + 0.10)
-        cell_size = np.minimum(h_wl, h_gr)
-    cell_size[cell_size < opts["hmin"]] = opts["hmin"]
-    cell_size[cell_size > opts["hmax"]] = opts["hmax"]
-    # CFL limit (:453-468)
     cr_max, dt, so = opts["cr_max"], opts["dt"], opts["space_order"]
     if not ((cr_max == 0.0) or (dt == 0.0) or (so == 0.0)):
         if cr_max < 0:
@@ -309,19 +313,27 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
             raise ValueError("Parameter `dt` must be > 0.0")
         if so < 1:
             raise ValueError("Parameter `space_order` must be >= 1 ")
-        cr_old = (vp * dt) / (dim * cell_size)
-        cr_lim = cr_max / (dim * so)
-        cell_size = np.where(cr_old > cr_lim, (vp * dt) / (dim * cr_lim), cell_size)
-    # gradation (:471-496)
     grade = opts["grade"]
+    if grade < 0:
+        raise ValueError("Parameter `grade` must be > 0.0")
+    D.require_cuda()
+    vp = np.ascontiguousarray(vp, dtype=np.float64)
+    vp_dev = torch.from_numpy(vp).to(D.device())
+    gr_dev = None if h_gr is None else torch.from_numpy(np.ascontiguousarray(h_gr, dtype=np.float64)).to(D.device())
+    cs_dev = torch.empty_like(vp_dev)
+    check(lib.dm_size_from_velocity(D.ptr(vp_dev), D.ptr(gr_dev), vp_dev.numel(), dim, float(opts["freq"]), float(opts["wl"]),
+                                    float(opts["hmin"]), float(opts["hmax"]), float(dt), float(cr_max), float(so), D.ptr(cs_dev),
+                                    D.stream_ptr()), "dm_size_from_velocity")
+    del vp_dev, gr_dev
+    # gradation (:471-496): the limiter runs on the grid where it is
     if grade == 0.0:
         warnings.warn("Mesh size gradient is deactiavted. This may compromise mesh quality")
     else:
-        if grade < 0:
-            raise ValueError("Parameter `grade` must be > 0.0")
         if grade > 1.0:
             warnings.warn("Parameter `grade` is set pretty high (> 1.0)!")
-        cell_size = limgrad(cell_size, grade, (bbox[1] - bbox[0]) / nz)
+        _limgrad_device(cs_dev, grade, (bbox[1] - bbox[0]) / nz)
+    cell_size = cs_dev.cpu().numpy()
+    del cs_dev
     # domain extension (:526-572)
     pad = opts["domain_pad"]
     if pad < 0:

@@ -56,8 +56,8 @@ class SweepHullTriangulator:
         self.qhull_retries = 0
 
     def triangulate(self, points):
-        """points (N,2) float64 host array -> cells (T,3) int32, ids = input rows, ascending within a
-        cell, cells in lexicographic order (orientation not normalised)."""
+        """points (N,2) float64 host array -> cells (T,3) int32, ids = input rows; cells grouped by their
+        smallest id, column order inside a cell the triangulator's own (orientation not normalised)."""
         p = np.ascontiguousarray(points, dtype=np.float64)
         if p.ndim != 2 or p.shape[1] != 2:
             raise ValueError("points must be (N, 2)")
@@ -112,8 +112,8 @@ class BowyerWatsonTriangulator:
         self.qhull_retries = 0
 
     def triangulate(self, points):
-        """points (N,3) float64 host array -> cells (T,4) int32, ids = input rows, ascending within a
-        cell, cells in lexicographic order (orientation not normalised)."""
+        """points (N,3) float64 host array -> cells (T,4) int32, ids = input rows; cells grouped by their
+        smallest id, column order inside a cell the triangulator's own (orientation not normalised)."""
         p = np.ascontiguousarray(points, dtype=np.float64)
         if p.ndim != 2 or p.shape[1] != 3:
             raise ValueError("points must be (N, 3)")
