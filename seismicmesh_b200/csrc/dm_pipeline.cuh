@@ -57,6 +57,9 @@ constexpr int HV_SMEM = 4608;    // heavy path: candidates sorted in shared memo
 #ifndef DM_VU_MINB
 #define DM_VU_MINB 8
 #endif
+#ifndef DM_AB_BARRIER
+#define DM_AB_BARRIER 0  // 1: block totals of stage B through a block barrier instead of an arrival counter
+#endif
 // Gridded fh: the bar pass leaves h at EVERY slot of a row, lower neighbours included, so that the vertex
 // update reads h of all its bars from its own row and never interpolates (its per-vertex loop is latency
 // bound; the bar pass spreads the interpolations of a row over a lane group).  Every bar is therefore
@@ -799,6 +802,19 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     sH = warp_sum(sH);
   }
   int lead = 0;  // lane 0: 1 = this warp closes its reduction group
+#if DM_AB_BARRIER
+  if (lane == 0) {
+    s_wbars[wid] = bars;
+    if (BAR >= 0) {
+      s_wL[wid] = sL;
+      s_wH[wid] = sH;
+    }
+  }
+  __syncthreads();
+  if (wid != 0) return;
+  if (lane == 0) {
+    {
+#else
   if (lane == 0) {
     s_wbars[wid] = bars;
     if (BAR >= 0) {
@@ -808,6 +824,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
     __threadfence_block();
     if (atomicAdd(&s_arrived, 1) == AB_THREADS / 32 - 1) {  // the block's last warp
       __threadfence_block();
+#endif
       int tb = 0;
       double tL = 0.0, tH = 0.0;
 #pragma unroll
