@@ -17,8 +17,8 @@
 
 #include "dm_aux.cuh"
 #include "dm_pipeline.cuh"
-#include "dm_rows.cuh"
 #include "dm_scan.cuh"
+#include "dm_tiles.cuh"
 
 using namespace dm;
 
@@ -79,9 +79,13 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
   char* gdone = take((size_t)(ngrp + 1) * 4);
   const size_t zbytes = off - z0;
   // ----
-  char* bucket = take((size_t)(N + 1) * CAP * esz);
+  // third layout: per-vertex buckets ; fourth layout (dm_tiles.cuh, the default): per-tile record lists.
+  // One region, sized for either.
+  const size_t bucket_bytes = (size_t)(N + 1) * CAP * esz;
+  const size_t trec_bytes = (size_t)cdiv(N + 1, TL_R) * TCfg<DIM>::CAPT * sizeof(int4);
+  char* bucket = take(bucket_bytes > trec_bytes ? bucket_bytes : trec_bytes);
   char* ovf_v = take((size_t)(DIM + 1) * T1 * 4);
-  char* ovf_e = take((size_t)(DIM + 1) * T1 * esz);
+  char* ovf_e = take((size_t)(DIM + 1) * T1 * sizeof(int4));  // tile layout: 16-B records in 2-D as well
   char* hv = take((size_t)(N + 1) * 4);
   char* adj = take((size_t)(N + 1) * RS * 4);
   char* heap = take((size_t)heap_ints * 4);
@@ -193,6 +197,22 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
   return (int)cudaGetLastError();
 }
 
+// Stages A + B: the tile layout (dm_tiles.cuh) unless DM_TILES=0 asks for the per-vertex buckets of the third
+// layout (dm_pipeline.cuh), kept for comparison runs: same inputs, same rows, same tests.
+static bool use_tiles() {
+  static const bool on = [] {
+    const char* e = getenv("DM_TILES");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int DIM, int BAR>
+static cudaError_t tile_smem_ready(size_t bytes) {
+  static cudaError_t st = cudaFuncSetAttribute(tile_rows_kernel<DIM, BAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return st;
+}
+
 template <int DIM>
 static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double* p, const int32_t* t, double geps,
                               int mode, cudaStream_t st, int64_t cell0 = 0, int64_t ncells = -1) {
@@ -201,29 +221,18 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   // cells [cell0, cell0 + ncells): t points at the first of them
   const unsigned nb = nblk(ncells, DM_CS_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
+  if (use_tiles()) {
+    launch_chain(cull_bin_kernel<DIM, DIM == 3>, nb, DM_CS_THREADS, st, prog, pc, t, ncells, geps, mode, pl->keep + cell0,
+                 pl->cnt, static_cast<int4*>(pl->bucket), pl->ovf_v, static_cast<int4*>(pl->ovf_e), pl->counters,
+                 (int)pl->n_rows);
+    mark("cull_bin", st);
+    return (int)cudaGetLastError();
+  }
   launch_chain(cull_scatter_kernel<DIM, DIM == 3>, nb, DM_CS_THREADS, st, prog, pc, t, ncells, geps, mode,
                pl->keep + cell0, pl->cnt, static_cast<entry_t*>(pl->bucket), pl->ovf_v,
                static_cast<entry_t*>(pl->ovf_e), pl->hv, pl->counters, (int)pl->n_rows);
   mark("cull_scatter", st);
   return (int)cudaGetLastError();
-}
-
-// Stage B kernel choice: the lane-group kernel (adjacency_kernel, dm_pipeline.cuh) unless DM_ROWS=1 asks
-// for the thread-per-vertex rows kernel (dm_rows.cuh): same inputs, same outputs (the whole GPU suite
-// passes with either), measured SLOWER in round 2 -- see the header of dm_rows.cuh -- and kept for
-// comparison runs only.
-static bool use_rows_kernel() {
-  static const bool on = [] {
-    const char* e = getenv("DM_ROWS");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
-template <int DIM, int BAR>
-static cudaError_t rows_smem_ready(size_t bytes) {
-  static cudaError_t st = cudaFuncSetAttribute(rows_kernel<DIM, BAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return st;
 }
 
 // bar: -1 rows only (staged path: a separate bar pass follows) ; otherwise f->kind (0 const, 1 grid):
@@ -239,23 +248,21 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   memset(&fz, 0, sizeof(fz));
   const DmSizeFn& ff = f ? *f : fz;
   const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
-  if (use_rows_kernel()) {
-    const unsigned nb = nblk(N, 32 * ROWS_WPB);  // the last block's spare warps are empty leaves
-    constexpr size_t ints = (size_t)ROWS_WPB * RowsCfg<DIM>::WARP_INTS > (size_t)HV_SMEM ? (size_t)ROWS_WPB * RowsCfg<DIM>::WARP_INTS
-                                                                                       : (size_t)HV_SMEM;
-    constexpr size_t smem = ints * sizeof(int32_t);
-#define DM_ROWS_LAUNCH(B)                                                                                          \
-  DM_CUDA_TRY((rows_smem_ready<DIM, B>(smem)));                                                                    \
-  launch_chain_smem(rows_kernel<DIM, B>, nb + HV_BLOCKS, ROWS_THREADS, smem, st, pl->cnt, bucket, pl->ovf_v, ovf_e, \
-                    N, pl->adj, pl->heap, degs, pl->hv, pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone,   \
-                    pl->sync + 3, pl->scalars);                                                                    \
-  mark("adjacency", st)
+  if (use_tiles()) {
+    const unsigned nb = nblk(cdiv(pl->n_rows, TL_R), TL_WPB);
+    constexpr size_t smem = (size_t)TL_WPB * tile_warp_ints<DIM>() * sizeof(int32_t);
+#define DM_TILE_LAUNCH(B)                                                                                          \
+  DM_CUDA_TRY((tile_smem_ready<DIM, B>(smem)));                                                                    \
+  launch_chain_smem(tile_rows_kernel<DIM, B>, nb, TL_THREADS, smem, st, pl->cnt, static_cast<const int4*>(pl->bucket), \
+                    pl->ovf_v, static_cast<const int4*>(pl->ovf_e), N, pl->n_rows, pl->adj, pl->heap, degs,         \
+                    pl->counters, ff, pp, pl->hslot, pl->partials, pl->gdone, pl->sync + 3, pl->scalars);           \
+  mark("tile_rows", st)
     switch (bar) {
-      case 0: DM_ROWS_LAUNCH(0); break;
-      case 1: DM_ROWS_LAUNCH(1); break;
-      default: DM_ROWS_LAUNCH(-1); break;
+      case 0: DM_TILE_LAUNCH(0); break;
+      case 1: DM_TILE_LAUNCH(1); break;
+      default: DM_TILE_LAUNCH(-1); break;
     }
-#undef DM_ROWS_LAUNCH
+#undef DM_TILE_LAUNCH
     return (int)cudaGetLastError();
   }
   constexpr int VPB = AB_THREADS / PCfg<DIM>::G;

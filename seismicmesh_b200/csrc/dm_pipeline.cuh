@@ -287,14 +287,14 @@ __device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC],
 // for the vertex update to read (same midpoint bits as the bar's owner forms, hence the same h), but the
 // bar belongs to its other end and is not added to the sums.
 template <int DIM, bool GRID>
-__device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __restrict__ pp, double a0, double a1,
-                                          double a2, int w, double* hout, double& sL, double& sH, bool upper = true) {
-  double b0, b1, b2, d0, d1, d2;
-  load_pt<DIM, true>(pp, w, b0, b1, b2);  // pp: the plan's padded point copy
+__device__ __forceinline__ void bar_terms_at(const DmSizeFn& f, const GridGuess& gg, double a0, double a1, double a2,
+                                             double b0, double b1, double b2, double* hout, double& sL, double& sH,
+                                             bool upper = true) {
+  double d0, d1, d2;
   double h = f.hconst;
   if (GRID) {
     // midpoint p[edges].sum(1)/2 (mesh_generator.py:699)
-    h = size_eval(f, (a0 + b0) / 2, (a1 + b1) / 2, (a2 + b2) / 2);
+    h = size_eval(f, gg, (a0 + b0) / 2, (a1 + b1) / 2, (a2 + b2) / 2);
     *hout = h;
     if (!upper) return;
   }
@@ -306,6 +306,14 @@ __device__ __forceinline__ void bar_terms(const DmSizeFn& f, const double* __res
     sL += L * L * L;
     sH += h * h * h;
   }
+}
+template <int DIM, bool GRID>
+__device__ __forceinline__ void bar_terms(const DmSizeFn& f, const GridGuess& gg, const double* __restrict__ pp,
+                                          double a0, double a1, double a2, int w, double* hout, double& sL, double& sH,
+                                          bool upper = true) {
+  double b0, b1, b2;
+  load_pt<DIM, true>(pp, w, b0, b1, b2);  // pp: the plan's padded point copy
+  bar_terms_at<DIM, GRID>(f, gg, a0, a1, a2, b0, b1, b2, hout, sL, sH, upper);
 }
 
 // ---- heavy vertices: one block per vertex -------------------------------------------------------
@@ -516,8 +524,10 @@ __device__ __noinline__ void heavy_vertex(int ih, int nheavy, int novf, int32_t*
     double sL = 0.0, sH = 0.0;
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
+    GridGuess gg;
+    if (BAR == 1) gg = grid_guess(f);
     for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lo) + tid; j < U; j += THREADS)
-      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH, j >= lo);
+      bar_terms<DIM, BAR == 1>(f, gg, pp, a0, a1, a2, reg[j], hslot + sbase + j, sL, sH, j >= lo);
     const double bl = block_sum(sL, s_dbl);
     const double bh = block_sum(sH, s_dbl);
     if (tid == 0) {
@@ -591,8 +601,10 @@ __device__ __noinline__ RowSums select_row(bool punt, int n, int v,
   if (BAR >= 0 && Up > (BAR == 1 && H_ALL_SLOTS ? 0 : lop)) {
     double a0, a1, a2;
     load_pt<DIM, true>(pp, v, a0, a1, a2);
+    GridGuess gg;
+    if (BAR == 1) gg = grid_guess(f);
     for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lop) + lg; j < Up; j += G)
-      bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, srt[j], hslot + sbase + j, out.sL, out.sH, j >= lop);
+      bar_terms<DIM, BAR == 1>(f, gg, pp, a0, a1, a2, srt[j], hslot + sbase + j, out.sL, out.sH, j >= lop);
   }
   return out;
 }
@@ -779,8 +791,10 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
       // bar pass (mesh_generator.py:696-700): L^d, h^d of the row's upper bars; gridded fh: h of EVERY slot
       double a0, a1, a2;
       load_pt<DIM, true>(pp, v, a0, a1, a2);
+      GridGuess gg;
+      if (BAR == 1) gg = grid_guess(f);
       for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lo) + lg; j < U; j += G)
-        bar_terms<DIM, BAR == 1>(f, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH, j >= lo);
+        bar_terms<DIM, BAR == 1>(f, gg, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH, j >= lo);
     }
   }
   // ---- a neighbour set that does not fit the group table: rare, out of line.  Warp-uniform branch.
@@ -948,6 +962,8 @@ __global__ void __launch_bounds__(PL_THREADS) bar_pass_kernel(const DmSizeFn f, 
       const int64_t base = R.slot_base(v, m);
       double a0, a1, a2;
       load_pt<DIM>(p, v, a0, a1, a2);
+      GridGuess gg;
+      if (HMODE == 1) gg = grid_guess(f);
       // rows are 16-B aligned and padded to a multiple of 4 ints: walk them in int4 chunks
       for (int j0 = first & ~3; j0 < m; j0 += 4) {
         const int4 q = *reinterpret_cast<const int4*>(row + j0);
@@ -962,7 +978,7 @@ __global__ void __launch_bounds__(PL_THREADS) bar_pass_kernel(const DmSizeFn f, 
           // midpoint p[edges].sum(1)/2 (mesh_generator.py:699)
           const double m0 = (a0 + b0) / 2, m1 = (a1 + b1) / 2, m2 = (a2 + b2) / 2;
           if (HMODE == 1 && j < lo) {
-            hslot[base + j] = size_eval(f, m0, m1, m2);
+            hslot[base + j] = size_eval(f, gg, m0, m1, m2);
             continue;
           }
           if (HMODE == 3) {
@@ -974,7 +990,7 @@ __global__ void __launch_bounds__(PL_THREADS) bar_pass_kernel(const DmSizeFn f, 
           if (HMODE == 0) {
             h = f.hconst;
           } else if (HMODE == 1) {
-            h = size_eval(f, m0, m1, m2);
+            h = size_eval(f, gg, m0, m1, m2);
             hslot[base + j] = h;
           } else {
             h = hbar[rowptr[v] + (j - lo)];

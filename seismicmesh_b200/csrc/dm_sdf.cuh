@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define DM_HD __host__ __device__ __forceinline__
 #define DM_LDG(ptr) (*(ptr))
+#define DM_LDG_KEEP(ptr) ldg_keep(ptr)
 #else
 #define DM_HD inline
 #define DM_LDG(ptr) (*(ptr))
+#define DM_LDG_KEEP(ptr) ldg_keep(ptr)
 #endif
 
 #define DM_SDF_STACK 8
@@ -23,11 +25,24 @@
 
 namespace dm {
 
-// eight consecutive doubles of a 64-B aligned record: two 256-bit read-only loads on the device
+// a node of an interpolation axis: a few KB that every lookup of every thread reads -- kept in L1 ahead of
+// the streaming traffic (the corner records below, the position gathers)
+DM_HD double ldg_keep(const double* q) {
+#if defined(__CUDA_ARCH__)
+  double v;
+  asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(q));
+  return v;
+#else
+  return *q;
+#endif
+}
+
+// eight consecutive doubles of a 64-B aligned record: two 256-bit read-only loads on the device.  A record
+// is used once (the 3-D grid is far larger than any cache): it does not displace anything in L1.
 DM_HD void dm_load8(const double* c, double (&v)[8]) {
 #if defined(__CUDA_ARCH__)
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(c));
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(c + 4));
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(c));
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(c + 4));
 #else
   for (int k = 0; k < 8; ++k) v[k] = c[k];
 #endif
@@ -242,12 +257,33 @@ DM_HD bool sdf_project(const double* __restrict__ prog, int dim, double deps, do
 // gridded fh: scipy RegularGridInterpolator(linear, bounds_error=False, fill_value=None)
 // find_indices: largest i with axis[i] <= x, clamped to [0, n-2]  (== clip(searchsorted(right)-1))
 // ---------------------------------------------------------------------------------------------
-DM_HD int grid_find(const double* __restrict__ ax, int n, double x) {
+// What grid_find needs of an axis besides the nodes themselves: its first node and the float32 scale of the
+// uniform-spacing guess.  Loop invariant: a kernel builds it once per thread (grid_guess) instead of reading
+// the axis ends and dividing for every lookup.
+struct GridGuess {
+  double a0[3];
+  float scale[3];
+};
+DM_HD GridGuess grid_guess(const DmSizeFn& f) {
+  GridGuess g;
+  for (int k = 0; k < 3; ++k) {
+    g.a0[k] = 0.0;
+    g.scale[k] = 0.0f;
+    if (k < f.dim) {
+      const double a0 = DM_LDG(f.axis[k]), a1 = DM_LDG(f.axis[k] + f.n[k] - 1);
+      g.a0[k] = a0;
+      g.scale[k] = (float)(f.n[k] - 1) / (float)(a1 - a0);
+    }
+  }
+  return g;
+}
+
+// -> i, lo = ax[i], hi = ax[i+1]
+DM_HD int grid_find(const double* __restrict__ ax, int n, double x, double a0, float scale, double& lo, double& hi) {
   // uniform-spacing guess, then fix up against the ACTUAL (float32-rounded) axis.  The guess only
   // has to land within a node or two, so it is computed in float32 (a handful of instructions
   // instead of a float64 division); the loops below make the result exact whatever the guess.
-  const double a0 = DM_LDG(ax), a1 = DM_LDG(ax + n - 1);
-  const float g = (float)(x - a0) / (float)(a1 - a0) * (float)(n - 1);
+  const float g = (float)(x - a0) * scale;
   int i;
   if (!(g > 0.0f))
     i = 0;
@@ -255,17 +291,26 @@ DM_HD int grid_find(const double* __restrict__ ax, int n, double x) {
     i = n - 2;
   else
     i = (int)g;
-  while (i > 0 && x < DM_LDG(ax + i)) --i;
-  while (i < n - 2 && x >= DM_LDG(ax + i + 1)) ++i;
+  lo = DM_LDG_KEEP(ax + i);
+  hi = DM_LDG_KEEP(ax + i + 1);
+  while (i > 0 && x < lo) {
+    --i;
+    hi = lo;
+    lo = DM_LDG_KEEP(ax + i);
+  }
+  while (i < n - 2 && x >= hi) {
+    ++i;
+    lo = hi;
+    hi = DM_LDG_KEEP(ax + i + 1);
+  }
   return i;
 }
 
-DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
+DM_HD double size_eval(const DmSizeFn& f, const GridGuess& gg, double x0, double x1, double x2) {
   if (f.kind == DM_SIZE_CONST) return f.hconst;
-  const int i0 = grid_find(f.axis[0], f.n[0], x0);
-  const int i1 = grid_find(f.axis[1], f.n[1], x1);
-  const double a00 = DM_LDG(f.axis[0] + i0), a01 = DM_LDG(f.axis[0] + i0 + 1);
-  const double a10 = DM_LDG(f.axis[1] + i1), a11 = DM_LDG(f.axis[1] + i1 + 1);
+  double a00, a01, a10, a11;
+  const int i0 = grid_find(f.axis[0], f.n[0], x0, gg.a0[0], gg.scale[0], a00, a01);
+  const int i1 = grid_find(f.axis[1], f.n[1], x1, gg.a0[1], gg.scale[1], a10, a11);
   const double y0 = (x0 - a00) / (a01 - a00);
   const double y1 = (x1 - a10) / (a11 - a10);
   if (f.dim == 2) {
@@ -279,8 +324,8 @@ DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
     out = out + v11 * y0 * y1;
     return out;
   }
-  const int i2 = grid_find(f.axis[2], f.n[2], x2);
-  const double a20 = DM_LDG(f.axis[2] + i2), a21 = DM_LDG(f.axis[2] + i2 + 1);
+  double a20, a21;
+  const int i2 = grid_find(f.axis[2], f.n[2], x2, gg.a0[2], gg.scale[2], a20, a21);
   const double y2 = (x2 - a20) / (a21 - a20);
   const int64_t n1 = f.n[1], n2 = f.n[2];
   double cv[8];  // corner values in itertools.product order
@@ -306,6 +351,11 @@ DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
         out = out + cv[c0 * 4 + c1 * 2 + c2] * w;
       }
   return out;
+}
+
+DM_HD double size_eval(const DmSizeFn& f, double x0, double x1, double x2) {
+  if (f.kind == DM_SIZE_CONST) return f.hconst;
+  return size_eval(f, grid_guess(f), x0, x1, x2);
 }
 
 // ---------------------------------------------------------------------------------------------
