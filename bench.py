@@ -354,6 +354,9 @@ def algorithmic_bytes(N, T, Tk, E, dim, grid_fh=False):
         # SURVEY 8d K2 (+K5: rows are symmetric, every bar is stored at both of its ends) with the
         # bar pass K3 fused in (positions read once, h written once per bar for gridded fh)
         "adjacency": 4 * c * Tk + 8 * (N + 1) + 8 * E + 8 * d * N + hs,
+        # the tile layout of stages A + B (dm_tiles.cuh): the same compulsory traffic
+        "cull_bin": 4 * c * T + 8 * d * N + T + 4 * c * Tk,
+        "tile_rows": 4 * c * Tk + 8 * (N + 1) + 8 * E + 8 * d * N + hs,
         "bar_pass+scale": 8 * d * N + 4 * E + 8 * N + hs,
         "vertex_update+maxdp": 16 * d * N + 8 * E + 8 * N + hs,
     }
@@ -574,7 +577,8 @@ def measure(wl, K, W, rank, world, local_rank, full, flush, kernel_table=None, c
                    "parallelism": (f"{world} slabs (owned + dm_halo_select ghosts per GPU; rows / forces for owned vertices only), "
                                    f"halo exchange per step: {halo_kind}; halo bytes/step/rank={halo.bytes_per_exchange}; "
                                    f"owned={n_owned} ghosts={N - n_owned} on rank 0") if layout is not None else "single",
-                   "N_owned_total": N_all},
+                   "N_owned_total": N_all,
+                   "stage_ab_layout": f"{loop.layout} (include/distmesh_b200.h DM_LAYOUT_*; the kernel table names the kernels that ran)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(p.nbytes + 64),
                 "ms_per_step": e2e_ms / K, "h2d_gbs_per_rank": h2d / (e2e_ms / K * 1e-3) / 1e9,
                 "call": "ForceLoop.iterate_host (the call generate_mesh makes every iteration): pinned H2D of p and t, t in "

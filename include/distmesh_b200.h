@@ -166,10 +166,12 @@ int dm_level_set_newton(const double *prog, double *p, const int32_t *bid, int64
  * built around the observation that every scattered 4..16-byte access costs one 128-byte line
  * wavefront: per-vertex structures are fixed-stride, line-aligned rows.
  *   keep     (T)            cull flags
- *   cnt      (N+1)          kept cells incident to each vertex
+ *   cnt      (N+1)          kept cells incident to each vertex                       [tiles: records per tile]
  *   bucket   (N*CAP)        per vertex: the OTHER vertex ids of each incident kept cell
  *                           (3-D: CAP=48 entries of 4 ints; 2-D: CAP=16 entries of 2 ints)
- *   ovf_v/e  ((dim+1)*T)    spill records (vertex, entry) of buckets that overflowed
+ *                           [tiles: per tile of 32 vertices a list of 16-B records {other ids, vertex & 31},
+ *                            3-D: 1280 records per tile, 2-D: 320]
+ *   ovf_v/e  ((dim+1)*T)    spill records (vertex, entry) of buckets that overflowed  [tiles: (tile, record)]
  *   hv       (N)            vertices whose bucket spilled (hull / hub vertices): listed by stage A, their rows
  *                           are built one block per vertex by the first blocks of stage B's grid
  *   adj      (N*RS)         sorted unique neighbour ids of vertex v at adj[v*RS ...] (RS = 32 ints
@@ -213,7 +215,22 @@ typedef struct DmPlan {
   size_t scan_tmp_bytes;
   int64_t n_rows;    /* vertices [0, n_rows) get neighbour rows, bar sums, forces and an update (default N);
                         the others are only NEIGHBOURS: the ghost copies of a slab (dm_plan_set_rows) */
+  int64_t layout;    /* DM_LAYOUT_*: how stages A + B pass the kept cells to the vertices (dm_plan_set_layout) */
 } DmPlan;
+
+/* Stages A + B exist in two layouts with identical outputs (rows are sorted sets):
+ *   DM_LAYOUT_BUCKETS  every kept cell is pushed into a fixed-capacity bucket of each of its vertices; a lane
+ *                      group per vertex de-duplicates and sorts its bucket (many short-lived warps: the faster
+ *                      one on small meshes and with a 3-D gridded fh);
+ *   DM_LAYOUT_TILES    every kept cell leaves one 16-B record per vertex in the list of the vertex's TILE of 32
+ *                      consecutive ids (`bucket` then holds the lists, `cnt` their lengths); one warp per tile
+ *                      builds the 32 rows (fewer scattered accesses and fewer instructions: the faster one on
+ *                      large meshes);
+ *   DM_LAYOUT_AUTO     tiles from 200 000 rows on (the default). */
+#define DM_LAYOUT_AUTO 0
+#define DM_LAYOUT_BUCKETS 1
+#define DM_LAYOUT_TILES 2
+int dm_plan_set_layout(DmPlan *plan_host, int layout);
 
 size_t dm_plan_bytes(int64_t N, int64_t T, int dim);
 /* carve `ws` (device, 256-B aligned, >= dm_plan_bytes) into *plan (host struct). */

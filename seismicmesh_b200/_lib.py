@@ -64,6 +64,7 @@ class DmPlan(C.Structure):
         ("scan_tmp", C.c_void_p),
         ("scan_tmp_bytes", C.c_size_t),
         ("n_rows", C.c_int64),
+        ("layout", C.c_int64),
     ]
 
 
@@ -90,6 +91,7 @@ _SIGNATURES = {
     "dm_plan_bytes": (_SZ, [_I64, _I64, _INT]),
     "dm_plan_init": (_INT, [C.POINTER(DmPlan), _I64, _I64, _INT, _P, _SZ]),
     "dm_plan_set_rows": (_INT, [C.POINTER(DmPlan), _I64]),
+    "dm_plan_set_layout": (_INT, [C.POINTER(DmPlan), _INT]),
     "dm_stage_prep": (_INT, [C.POINTER(DmPlan), _P, _P]),
     "dm_stage_cull_chunk": (_INT, [C.POINTER(DmPlan), _P, _P, _P, _I64, _I64, _D, _INT, _P]),
     "dm_force_iteration_tail": (

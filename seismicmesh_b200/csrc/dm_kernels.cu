@@ -129,6 +129,7 @@ size_t plan_layout_dim(DmPlan* pl, int64_t N, int64_t T, char* base) {
     pl->scan_tmp = scan_tmp;
     pl->scan_tmp_bytes = scan_bytes;
     pl->n_rows = N;
+    pl->layout = DM_LAYOUT_AUTO;
   }
   return off;
 }
@@ -197,14 +198,18 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
   return (int)cudaGetLastError();
 }
 
-// Stages A + B: the tile layout (dm_tiles.cuh) unless DM_TILES=0 asks for the per-vertex buckets of the third
-// layout (dm_pipeline.cuh), kept for comparison runs: same inputs, same rows, same tests.
-static bool use_tiles() {
-  static const bool on = [] {
+// Stages A + B: which layout (include/distmesh_b200.h, DM_LAYOUT_*).  A pure function of the plan, so the
+// stages of one iteration agree; DM_TILES=0 / 1 in the environment overrides the plan (comparison runs, and
+// the GPU suite is run both ways).
+constexpr int64_t TILES_FROM_ROWS = 200000;
+static bool use_tiles(const DmPlan* pl) {
+  static const int forced = [] {
     const char* e = getenv("DM_TILES");
-    return !(e && e[0] == '0');
+    return !e ? -1 : (e[0] == '0' ? 0 : 1);
   }();
-  return on;
+  if (forced >= 0) return forced == 1;
+  if (pl->layout == DM_LAYOUT_AUTO) return pl->n_rows >= TILES_FROM_ROWS;
+  return pl->layout == DM_LAYOUT_TILES;
 }
 
 template <int DIM, int BAR>
@@ -221,8 +226,9 @@ static int stage_cull_scatter(const DmPlan* pl, const double* prog, const double
   // cells [cell0, cell0 + ncells): t points at the first of them
   const unsigned nb = nblk(ncells, DM_CS_THREADS);
   const double* pc = DIM == 3 ? pl->p4 : p;  // 3-D: the padded copy made by the prep kernel
-  if (use_tiles()) {
-    launch_chain(cull_bin_kernel<DIM, DIM == 3>, nb, DM_CS_THREADS, st, prog, pc, t, ncells, geps, mode, pl->keep + cell0,
+  if (use_tiles(pl)) {
+    launch_chain(cull_bin_kernel<DIM, DIM == 3, DM_CB_CPT>, nblk(ncells, DM_CS_THREADS * DM_CB_CPT), DM_CS_THREADS, st, prog, pc, t,
+                 ncells, geps, mode, pl->keep + cell0,
                  pl->cnt, static_cast<int4*>(pl->bucket), pl->ovf_v, static_cast<int4*>(pl->ovf_e), pl->counters,
                  (int)pl->n_rows);
     mark("cull_bin", st);
@@ -248,7 +254,7 @@ static int stage_adjacency(const DmPlan* pl, int bar, const DmSizeFn* f, const d
   memset(&fz, 0, sizeof(fz));
   const DmSizeFn& ff = f ? *f : fz;
   const double* pp = (DIM == 3 && p) ? pl->p4 : p;  // bar pass gathers from the padded copy
-  if (use_tiles()) {
+  if (use_tiles(pl)) {
     const unsigned nb = nblk(cdiv(pl->n_rows, TL_R), TL_WPB);
     constexpr size_t smem = (size_t)TL_WPB * tile_warp_ints<DIM>() * sizeof(int32_t);
 #define DM_TILE_LAUNCH(B)                                                                                          \
@@ -481,6 +487,12 @@ int dm_plan_init(DmPlan* plan, int64_t N, int64_t T, int dim, void* ws, size_t w
 int dm_plan_set_rows(DmPlan* plan, int64_t n_rows) {
   if (!plan || n_rows < 1 || n_rows > plan->N) return DM_ERR_ARG;
   plan->n_rows = n_rows;
+  return DM_OK;
+}
+
+int dm_plan_set_layout(DmPlan* plan, int layout) {
+  if (!plan || layout < DM_LAYOUT_AUTO || layout > DM_LAYOUT_TILES) return DM_ERR_ARG;
+  plan->layout = layout;
   return DM_OK;
 }
 

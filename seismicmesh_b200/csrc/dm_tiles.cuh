@@ -101,74 +101,106 @@ __device__ __forceinline__ int4 record_of(const int (&ids)[4], int j) {
   return make_int4(ids[j == 0 ? 1 : 0], ids[j <= 1 ? 2 : 1], 0, ids[j] & (TL_R - 1));
 }
 
-template <int DIM, bool PAD>
-__global__ void __launch_bounds__(DM_CS_THREADS, DM_CS_MINB) cull_bin_kernel(
+// CPT cells per thread (cells c, c + blockDim.x, ...): the kernel is bound by the LATENCY of its dependent
+// chain -- cell ids (DRAM) -> position gathers (L2) -> SDF -> position claims (L2 atomics, hot counters) ->
+// stores -- at the occupancy its registers allow, so every phase is written for all CPT cells of a thread
+// before the next one starts: their chains are independent and overlap.
+#ifndef DM_CB_CPT
+#define DM_CB_CPT 2
+#endif
+#ifndef DM_CB_MINB
+#define DM_CB_MINB 6
+#endif
+template <int DIM, bool PAD, int CPT>
+__global__ void __launch_bounds__(DM_CS_THREADS, DM_CB_MINB) cull_bin_kernel(
     const double* __restrict__ prog, const double* __restrict__ p, const int32_t* __restrict__ t, int64_t T,
     double geps, int mode, uint8_t* __restrict__ keep, int32_t* __restrict__ tcnt, int4* __restrict__ trec,
     int32_t* __restrict__ ovf_v, int4* __restrict__ ovf_e, int32_t* __restrict__ counters, int n_rows) {
   pdl_prologue();
   constexpr int CAPT = TCfg<DIM>::CAPT;
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * (blockDim.x * CPT) + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool k = false;
-  int ids[4] = {0, 0, 0, 0};
-  if (c < T) {
-    load_cell<DIM>(t, c, ids);
-    k = true;
-    if (mode == 0) {
-      double c0, c1, c2;
-      cell_centroid<DIM, PAD>(p, ids, c0, c1, c2);  // summed in the cell's own column order (bit-exactness)
-      k = sdf_eval(prog, DIM, c0, c1, c2) < -geps;
-      keep[c] = k ? 1 : 0;
-    } else if (mode == 1) {
-      k = keep[c] != 0;
+  bool k[CPT];
+  int ids[CPT][4];
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
+    const int64_t c = c0 + (int64_t)u * blockDim.x;
+    k[u] = c < T;
+    ids[u][0] = ids[u][1] = ids[u][2] = ids[u][3] = 0;
+    if (k[u]) load_cell<DIM>(t, c, ids[u]);
+  }
+  if (mode == 0) {
+    double cc[CPT][3];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)  // (a cell past the end gathers vertex 0: a valid address)
+      cell_centroid<DIM, PAD>(p, ids[u], cc[u][0], cc[u][1], cc[u][2]);  // summed in the cell's own column order
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+      const int64_t c = c0 + (int64_t)u * blockDim.x;
+      if (k[u]) {
+        k[u] = sdf_eval(prog, DIM, cc[u][0], cc[u][1], cc[u][2]) < -geps;
+        keep[c] = k[u] ? 1 : 0;
+      }
+    }
+  } else if (mode == 1) {
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+      const int64_t c = c0 + (int64_t)u * blockDim.x;
+      if (k[u]) k[u] = keep[c] != 0;
     }
   }
   // ids sorted in registers: column j of the lanes of a warp then holds ids of few tiles
-  {
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
     auto cx = [](int& a, int& b) {
       const int lo_ = min(a, b), hi_ = max(a, b);
       a = lo_;
       b = hi_;
     };
     if (DIM == 3) {
-      cx(ids[0], ids[1]);
-      cx(ids[2], ids[3]);
-      cx(ids[0], ids[2]);
-      cx(ids[1], ids[3]);
-      cx(ids[1], ids[2]);
+      cx(ids[u][0], ids[u][1]);
+      cx(ids[u][2], ids[u][3]);
+      cx(ids[u][0], ids[u][2]);
+      cx(ids[u][1], ids[u][3]);
+      cx(ids[u][1], ids[u][2]);
     } else {
-      cx(ids[0], ids[1]);
-      cx(ids[1], ids[2]);
-      cx(ids[0], ids[1]);
+      cx(ids[u][0], ids[u][1]);
+      cx(ids[u][1], ids[u][2]);
+      cx(ids[u][0], ids[u][1]);
     }
   }
-  // one list-position claim per (column, tile) of the warp; all claims issued before any is waited on
+  // one list-position claim per (cell slot, column, tile) of the warp; all claims issued before any is waited on
   const unsigned lt = (1u << lane) - 1u;
-  int base[DIM + 1], rank[DIM + 1], leader[DIM + 1];
+  int base[CPT][DIM + 1], rl[CPT][DIM + 1];  // rl: rank | leader << 8
 #pragma unroll
-  for (int j = 0; j <= DIM; ++j) {
-    // (vertices >= n_rows are ghost copies: nobody builds their rows, so they get no records)
-    const bool kj = k && ids[j] < n_rows;
-    const int key = kj ? ids[j] / TL_R : -1 - lane;  // a lane without a record is alone in its class
-    const unsigned m = __match_any_sync(FULL, key);
-    leader[j] = __ffs(m) - 1;
-    rank[j] = __popc(m & lt);
-    base[j] = 0;
-    if (kj && lane == leader[j]) base[j] = atomicAdd(tcnt + key, __popc(m));
+  for (int u = 0; u < CPT; ++u) {
+#pragma unroll
+    for (int j = 0; j <= DIM; ++j) {
+      // (vertices >= n_rows are ghost copies: nobody builds their rows, so they get no records)
+      const bool kj = k[u] && ids[u][j] < n_rows;
+      const int key = kj ? ids[u][j] / TL_R : -1 - lane;  // a lane without a record is alone in its class
+      const unsigned m = __match_any_sync(FULL, key);
+      const int leader = __ffs(m) - 1;
+      rl[u][j] = __popc(m & lt) | (leader << 8);
+      base[u][j] = 0;
+      if (kj && lane == leader) base[u][j] = atomicAdd(tcnt + key, __popc(m));
+    }
   }
 #pragma unroll
-  for (int j = 0; j <= DIM; ++j) {
-    const int slot = __shfl_sync(FULL, base[j], leader[j]) + rank[j];
-    if (k && ids[j] < n_rows) {
-      const int tile = ids[j] / TL_R;
-      const int4 rec = record_of<DIM>(ids, j);
-      if (slot < CAPT) {
-        trec[(int64_t)tile * CAPT + slot] = rec;
-      } else {  // list full (hub vertices): the record goes to the global spill list with its tile
-        const int o = atomicAdd(counters + 2, 1);
-        ovf_v[o] = tile;
-        ovf_e[o] = rec;
+  for (int u = 0; u < CPT; ++u) {
+#pragma unroll
+    for (int j = 0; j <= DIM; ++j) {
+      const int slot = __shfl_sync(FULL, base[u][j], rl[u][j] >> 8) + (rl[u][j] & 0xff);
+      if (k[u] && ids[u][j] < n_rows) {
+        const int tile = ids[u][j] / TL_R;
+        const int4 rec = record_of<DIM>(ids[u], j);
+        if (slot < CAPT) {
+          trec[(int64_t)tile * CAPT + slot] = rec;
+        } else {  // list full (hub vertices): the record goes to the global spill list with its tile
+          const int o = atomicAdd(counters + 2, 1);
+          ovf_v[o] = tile;
+          ovf_e[o] = rec;
+        }
       }
     }
   }

@@ -13,6 +13,7 @@ One :class:`ForceLoop` owns the per-iteration workspace (a torch uint8 blob carv
 staged copies (their time is reported as host time), everything else stays on the device.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -93,9 +94,21 @@ def _project_host(p, fd, deps, hmin, idx):
     return p
 
 
+LAYOUTS = {"auto": 0, "buckets": 1, "tiles": 2}  # DM_LAYOUT_* of include/distmesh_b200.h
+
+
 class ForceLoop:
-    def __init__(self, dim, levels, size, h0, geps, deps, delta_t=0.30, nfix=0):
+    def __init__(self, dim, levels, size, h0, geps, deps, delta_t=0.30, nfix=0, layout=None):
+        """layout: how stages A + B pass the kept cells to the vertices ("buckets" / "tiles" / "auto"; same
+        rows either way).  None: DM_LAYOUT from the environment, else the measured choice -- per-vertex
+        buckets with a 3-D gridded fh (its bar pass wants many short-lived warps), otherwise auto (the
+        library takes the tile layout from 200 000 rows on)."""
         D.require_cuda()
+        if layout is None:
+            layout = os.environ.get("DM_LAYOUT") or ("buckets" if dim == 3 and size.interp is not None else "auto")
+        if layout not in LAYOUTS:
+            raise ValueError(f"layout must be one of {sorted(LAYOUTS)}")
+        self.layout = layout
         self.dim = dim
         self.levels = levels
         self.size = size
@@ -120,6 +133,7 @@ class ForceLoop:
         self.plan.c.K = self.dim * (self.dim + 1) * T
         # multi-GPU slabs: only the first n_rows (owned) vertices get rows / forces / an update
         check(lib.dm_plan_set_rows(C.byref(self.plan.c), N if self.n_rows is None else int(self.n_rows)), "dm_plan_set_rows")
+        check(lib.dm_plan_set_layout(C.byref(self.plan.c), LAYOUTS[self.layout]), "dm_plan_set_layout")
         return self.plan
 
     # -- the iteration --------------------------------------------------------------------

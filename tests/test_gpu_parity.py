@@ -558,6 +558,64 @@ def test_hub_vertex_full_iteration_vs_oracle(sm, dim, grid):
     assert relerr(Fr.cpu().numpy(), ref["Ftot"]) < TOL and relerr(again.cpu().numpy(), ref["p"]) < PTOL
 
 
+@pytest.mark.parametrize("case", ["disk", "ball", "cube_grid", "hub2", "hub3", "hub3_grid", "slab2", "slab3"])
+def test_tile_layout_equals_bucket_layout(sm, case):
+    """Stages A + B exist in two layouts (include/distmesh_b200.h, DM_LAYOUT_*): per-vertex buckets and
+    per-tile record lists.  Same (p, t) in, the same rows out: bars / degrees bit-identical, forces and new
+    positions equal up to the order in which the global bar sums are added, and the tile layout against the
+    oracle.  Hubs overflow a tile's record list (spill records) and the fixed row (heap rows); slabs give
+    rows to the owned vertices only."""
+    from scipy.spatial import Delaunay
+    from seismicmesh_b200.engine import ForceLoop, Level, SizeSpec
+
+    dim = 2 if case in ("disk", "hub2", "slab2") else 3
+    n_rows = None
+    if case in ("disk", "ball", "slab2", "slab3"):
+        h0 = {"disk": 0.02, "ball": 0.07, "slab2": 0.03, "slab3": 0.1}[case]
+        dom = sm.Disk([0.0, 0.0], 1.0) if dim == 2 else sm.Ball([0.0, 0.0, 0.0], 1.0)
+        p, t = _lattice_mesh(sm, dom, h0, dim)
+        if case.startswith("slab"):
+            n_rows = int(0.6 * len(p)) + 7
+    else:
+        rng = np.random.default_rng(11 + dim)
+        h0 = 0.08
+        pts = [rng.uniform(-1.0, 1.0, (4000 if dim == 3 else 2500, dim))]
+        if case.startswith("hub"):
+            n_shell = 150 if dim == 2 else 400
+            u = rng.normal(size=(n_shell, dim))
+            pts = [np.zeros((1, dim)), 0.45 * u / np.linalg.norm(u, axis=1)[:, None], pts[0][np.linalg.norm(pts[0], axis=1) > 0.5]]
+        p = np.ascontiguousarray(np.vstack(pts))
+        t = Delaunay(p).simplices.astype(np.int32)
+        dom = sm.Rectangle((-1.0, 1.0, -1.0, 1.0)) if dim == 2 else sm.Cube((-1.0, 1.0, -1.0, 1.0, -1.0, 1.0))
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(np.double).eps) * h0
+    if case.endswith("grid"):
+        ax = [np.linspace(-1.3, 1.3, 31)] * dim
+        X = np.meshgrid(*ax, indexing="ij")
+        interp = sm.GridInterpolant(ax, h0 * (1.0 + 0.8 * np.sqrt(sum(x**2 for x in X))))
+        size = SizeSpec(dim, interp=interp)
+        fh = lambda x: orc.interp_grid(list(interp.grid), interp.values, x)  # noqa: E731
+    else:
+        size = SizeSpec(dim, const=h0)
+        fh = lambda x: np.array([h0] * len(x))  # noqa: E731
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    out = {}
+    for layout in ("buckets", "tiles"):
+        loop = ForceLoop(dim, [Level(dom, dim)], size, h0, geps, deps, layout=layout)
+        loop.n_rows = n_rows
+        p_new, F = loop.iterate(pd, td, want_forces=True)
+        nr = len(p) if n_rows is None else n_rows
+        out[layout] = (loop.bars().cpu().numpy(), loop.plan.degs().cpu().numpy()[:nr].copy(), F.cpu().numpy()[:nr].copy(),
+                       p_new.cpu().numpy()[:nr].copy())
+    (b0, d0, F0, p0), (b1, d1, F1, p1) = out["buckets"], out["tiles"]
+    assert np.array_equal(b0, b1) and np.array_equal(d0, d1)
+    assert relerr(F1, F0) < TOL and relerr(p1, p0) < PTOL
+    if n_rows is None:
+        spec = dom.spec()
+        ref = orc.force_iteration(p, t, [lambda x: orc.sdf(spec, x)], fh, h0, geps, deps)
+        assert np.array_equal(b1, ref["bars"])
+        assert relerr(F1, ref["Ftot"]) < TOL and relerr(p1, ref["p"]) < PTOL
+
+
 @pytest.mark.parametrize("dim,h0", [(2, 0.03), (3, 0.1)])
 def test_owned_rows_only(sm, dim, h0):
     """Multi-GPU slabs (dm_plan_set_rows): with the local vertices ordered [owned | ghosts], rows, bar sums,

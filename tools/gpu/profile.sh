@@ -11,6 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
 # the full-set capture: skip the set-up + warm-up launches, take the five kernels of one timed step
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:'prep_kernel|cull_scatter_kernel|adjacency_kernel|vertex_update_kernel|project_list_kernel' -s 20 -c 5 \
+  -k regex:'prep_kernel|cull_scatter_kernel|cull_bin_kernel|adjacency_kernel|tile_rows_kernel|vertex_update_kernel|project_list_kernel' -s 20 -c 5 \
   -o gpurun_out/${TAG}_full python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}

@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 NAMES = {"prep_kernel": "prep(zero+pad)", "cull_scatter_kernel": "cull_scatter", "adjacency_kernel": "adjacency",
-         "rows_kernel": "adjacency", "vertex_update_kernel": "vertex_update+maxdp", "project_list_kernel": "project_escaped"}
+         "cull_bin_kernel": "cull_bin", "tile_rows_kernel": "tile_rows", "vertex_update_kernel": "vertex_update+maxdp", "project_list_kernel": "project_escaped"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
