@@ -378,6 +378,24 @@ int dm_size_from_velocity(const double *vp, const double *h_gr, int64_t n, int d
 int dm_limgrad(double *f, double *tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol,
                int max_sweeps, int32_t *changed_dev, int *sweeps_host, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Termination path: Laplacian smoothing of a 2-D mesh as one linear solve (replaces
+ * geometry.laplacian2_fixed_point, geometry/utils.py:494-547: SciPy assembly + pyamg Ruge-Stuben solve).
+ * Every interior vertex goes to the average of its neighbours; the boundary vertices -- those with more
+ * neighbours than incident triangles, i.e. the vertices of edges that belong to one triangle only
+ * (get_boundary_vertices, geometry/utils.py:399-417) -- stay where they are.  Needs the neighbour rows of
+ * stage B for the cells t (dm_stage_cull_count(..., use_keep = 0) + dm_stage_build_adjacency on this plan).
+ * Matrix-free Jacobi-preconditioned conjugate gradients on the interior block, both coordinates at once, two
+ * launches per iteration, scalars on the device; the host looks at the residual every 32 iterations and
+ * stops when |r| <= rtol * |diag(A) x| for both coordinates.  x (N,2): in = the vertices, out = the solution.
+ * work: dm_laplacian_work_bytes(N) of device scratch, 256-B aligned.  DM_ERR_WORKSPACE if max_iter did not
+ * suffice.  *iters_host = iterations run, resid_host[2] = the relative residuals reached.
+ * ------------------------------------------------------------------------------------------- */
+size_t dm_laplacian_work_bytes(int64_t N);
+int dm_laplacian_smooth(const DmPlan *plan_host, const int32_t *t, int64_t T, double *x, void *work,
+                        size_t work_bytes, double rtol, int max_iter, int *iters_host, double *resid_host,
+                        void *stream);
+
 /* utilities */
 size_t dm_scan_scratch_bytes(int64_t n);
 /* exclusive scan of int32 in[0..n) -> out[0..n], out[n] = total (in == out allowed) */

@@ -18,6 +18,7 @@
 #include "dm_aux.cuh"
 #include "dm_pipeline.cuh"
 #include "dm_scan.cuh"
+#include "dm_smooth.cuh"
 #include "dm_tiles.cuh"
 
 using namespace dm;
@@ -698,6 +699,80 @@ int dm_force_iteration_profiled(const DmPlan* pl, const double* const* progs, in
   for (int i = 0; i <= PROF_MAX; ++i) cudaEventDestroy(pr.ev[i]);
   if (rc) return rc;
   return (int)e;
+}
+
+static size_t lap_layout(LapWork* w, int64_t N, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* ptr = base ? base + off : nullptr;
+    off += align256(bytes);
+    return ptr;
+  };
+  const int64_t nb = nblk(N, LS_THREADS);
+  char* ntri = take((size_t)N * 4);
+  char* done = take(2 * 4);
+  char* interior = take((size_t)N);
+  char* v[5];
+  for (int k = 0; k < 5; ++k) v[k] = take((size_t)N * 16);
+  char* partials = take((size_t)nb * 4 * 8);
+  char* sc = take(LS_SCALARS * 8);
+  if (w) {
+    w->ntri = reinterpret_cast<int32_t*>(ntri);
+    w->done = reinterpret_cast<int32_t*>(done);
+    w->interior = reinterpret_cast<uint8_t*>(interior);
+    w->r = reinterpret_cast<double2*>(v[0]);
+    w->z = reinterpret_cast<double2*>(v[1]);
+    w->p0 = reinterpret_cast<double2*>(v[2]);
+    w->p1 = reinterpret_cast<double2*>(v[3]);
+    w->Ap = reinterpret_cast<double2*>(v[4]);
+    w->partials = reinterpret_cast<double*>(partials);
+    w->sc = reinterpret_cast<double*>(sc);
+  }
+  return off;
+}
+
+size_t dm_laplacian_work_bytes(int64_t N) { return N > 0 ? lap_layout(nullptr, N, nullptr) : 0; }
+
+int dm_laplacian_smooth(const DmPlan* pl, const int32_t* t, int64_t T, double* x, void* work, size_t work_bytes, double rtol,
+                        int max_iter, int* iters_host, double* resid_host, void* stream) {
+  if (!pl || pl->dim != 2 || pl->n_rows != pl->N || T < 0 || (!t && T > 0) || !x || !work || max_iter < 0 || !(rtol >= 0.0))
+    return DM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(work) & 255) != 0) return DM_ERR_ARG;
+  const int64_t N = pl->N;
+  if (work_bytes < lap_layout(nullptr, N, nullptr)) return DM_ERR_WORKSPACE;
+  LapWork w;
+  lap_layout(&w, N, static_cast<char*>(work));
+  cudaStream_t st = S(stream);
+  const Rows<2> R = rows_of<2>(pl);
+  double2* xs = reinterpret_cast<double2*>(x);
+  const unsigned nb = nblk(N, LS_THREADS);
+  // [ntri | done] are contiguous in the layout
+  DM_CUDA_TRY(cudaMemsetAsync(w.ntri, 0, (size_t)(reinterpret_cast<char*>(w.interior) - reinterpret_cast<char*>(w.ntri)), st));
+  if (T > 0) lap_count_kernel<<<nblk(T, 256), 256, 0, st>>>(t, T, w.ntri);
+  lap_init_kernel<<<nb, LS_THREADS, 0, st>>>(R, xs, N, w);
+  DM_LAUNCH_CHECK();
+  const int look = 32;  // iterations between two looks at the residual
+  int it = 0;
+  double sc[4] = {0.0, 0.0, 0.0, 0.0};  // r.r (2), scale (2)
+  bool conv = false;
+  while (!conv && it < max_iter) {
+    for (int k = 0; k < look && it < max_iter; ++k, ++it) {
+      double2* po = (it & 1) ? w.p1 : w.p0;
+      double2* pn = (it & 1) ? w.p0 : w.p1;
+      lap_ap_kernel<<<nb, LS_THREADS, 0, st>>>(R, N, w, po, pn);
+      lap_update_kernel<<<nb, LS_THREADS, 0, st>>>(R, N, w, pn, xs);
+    }
+    DM_LAUNCH_CHECK();
+    DM_CUDA_TRY(cudaMemcpyAsync(sc, w.sc + 6, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    DM_CUDA_TRY(cudaStreamSynchronize(st));
+    conv = sc[0] <= rtol * rtol * sc[2] && sc[1] <= rtol * rtol * sc[3];
+  }
+  if (iters_host) *iters_host = it;
+  if (resid_host) {  // relative residuals of the two coordinates
+    resid_host[0] = sc[2] > 0.0 ? sqrt(sc[0] / sc[2]) : 0.0;
+    resid_host[1] = sc[3] > 0.0 ? sqrt(sc[1] / sc[3]) : 0.0;
+  }
+  return conv || max_iter == 0 ? DM_OK : DM_ERR_WORKSPACE;  // not converged within max_iter
 }
 
 int dm_size_from_velocity(const double* vp, const double* h_gr, int64_t n, int dim, double freq, double wl, double hmin,

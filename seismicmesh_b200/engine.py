@@ -383,3 +383,31 @@ def unique_bars(t, N=None):
     if E > 0:
         check(lib.dm_bars_pairs(C.byref(pl.c), D.ptr(pairs), st), "bars_pairs")
     return pairs if as_torch else pairs.cpu().numpy()
+
+
+def laplacian_smooth(p, t, rtol=1e-13, max_iter=200000):
+    """geometry.laplacian2_fixed_point (geometry/utils.py:494-547) on the device: every interior vertex of the
+    2-D mesh (p, t) at the average of its neighbours, boundary vertices fixed -- neighbour rows from stage B,
+    then matrix-free preconditioned conjugate gradients (dm_laplacian_smooth).  Host arrays in and out;
+    `laplacian_smooth.last` = (iterations, relative residuals)."""
+    D.require_cuda()
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    t32 = np.ascontiguousarray(t, dtype=np.int32)
+    if p.ndim != 2 or p.shape[1] != 2:
+        raise NotImplementedError("Laplacian smoothing only works in 2D for now")
+    N, T = len(p), len(t32)
+    if N == 0 or T == 0:
+        return p, t
+    pd, td = D.to_dev(p, torch.float64), D.to_dev(t32, torch.int32)
+    plan = D.Plan(N, T, 2)
+    st = D.stream_ptr()
+    check(lib.dm_stage_cull_count(C.byref(plan.c), None, D.ptr(pd), D.ptr(td), 0.0, 0, st), "cull_count")  # every cell kept
+    check(lib.dm_stage_build_adjacency(C.byref(plan.c), st), "build_adjacency")
+    nbytes = lib.dm_laplacian_work_bytes(N)
+    work = torch.empty(nbytes + 256, dtype=torch.uint8, device=D.device())
+    wptr = (work.data_ptr() + 255) & ~255
+    iters, resid = C.c_int(0), (C.c_double * 2)()
+    check(lib.dm_laplacian_smooth(C.byref(plan.c), D.ptr(td), T, D.ptr(pd), C.c_void_p(wptr), nbytes, float(rtol), int(max_iter),
+                                  C.byref(iters), resid, st), "dm_laplacian_smooth")
+    laplacian_smooth.last = (iters.value, (resid[0], resid[1]))
+    return pd.cpu().numpy(), t

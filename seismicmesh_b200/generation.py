@@ -15,7 +15,7 @@ import torch
 from . import device as D
 from . import geometry, meshutil
 from ._lib import check, lib
-from .engine import ForceLoop, Level, SizeSpec
+from .engine import ForceLoop, Level, SizeSpec, laplacian_smooth
 from .sizing import SizeFunction
 from .triangulator import get_triangulator
 
@@ -174,7 +174,7 @@ def _termination(p, t, opts, dim, sliver=False, verbose=1):
         p, t, _ = meshutil.fix_mesh(p, t, dim=dim, delete_unused=True)
         p, t = meshutil.delete_boundary_entities(p, t, dim=2, min_qual=0.15, verbose=verbose)
         if opts["subdomains"] is None and opts["mesh_improvement"]:
-            p, t = meshutil.laplacian2_fixed_point(p, t)
+            p, t = laplacian_smooth(p, t)  # the linear solve of geometry.laplacian2_fixed_point, on the device
     if opts["perform_checks"]:  # reference :672-675
         p, t = meshutil.linter(p, t, dim=dim)
     else:

@@ -701,6 +701,43 @@ def _e2e():
         return json.load(f)
 
 
+@pytest.mark.parametrize("case", ["golden", "disk", "annulus_graded"])
+def test_laplacian_smoothing_on_device(sm, case):
+    """Termination path: the Laplacian linear solve (geometry.laplacian2_fixed_point, geometry/utils.py:494-547)
+    as matrix-free conjugate gradients on the device against the direct sparse solve on the host (which the CPU
+    suite pins to the reference's golden): same boundary vertices, same solution."""
+    from scipy.spatial import Delaunay
+    from seismicmesh_b200 import meshutil as mu
+    from seismicmesh_b200.engine import laplacian_smooth
+
+    if case == "golden":
+        g = load_golden("meshutil_2d.npz")
+        p, t = g["p"].copy(), g["t"].copy()
+    else:
+        rng = np.random.default_rng(5)
+        if case == "disk":
+            dom, h0 = sm.Disk([0.0, 0.0], 1.0), 0.02
+            p, t = _lattice_mesh(sm, dom, h0, 2)
+        else:  # graded point cloud in an annulus: vertices of very different degree, two boundary loops
+            r = 0.3 + 0.7 * rng.uniform(0, 1, 6000) ** 2
+            a = rng.uniform(0, 2 * np.pi, 6000)
+            p = np.column_stack([r * np.cos(a), r * np.sin(a)])
+            t = Delaunay(p).simplices.astype(np.int32)
+            c = p[t].sum(1) / 3
+            t = t[np.hypot(c[:, 0], c[:, 1]) > 0.32]
+        p, t, _ = mu.fix_mesh(p, t, dim=2, delete_unused=True)
+    ref, _ = mu.laplacian2_fixed_point(p.copy(), t.copy())
+    got, t2 = laplacian_smooth(p.copy(), t.copy())
+    assert t2 is t or np.array_equal(t2, t)
+    bnd = mu.get_boundary_vertices(t)
+    assert np.array_equal(got[bnd], p[bnd])            # boundary vertices did not move
+    assert np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+    iters, resid = laplacian_smooth.last
+    assert max(resid) <= 1e-12 and iters < 100000
+    if case == "golden":
+        assert np.abs(got - g["lap_p"]).max() <= 1e-9
+
+
 def test_initial_points_product_matches_reference(sm):
     """SURVEY a11 on the PRODUCT side: generation._initial_points (device fd / fh evaluation, NumPy legacy
     RNG for the rejection step) equals the reference's _generate_initial_points (mesh_generator.py:808-852,
