@@ -663,7 +663,11 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
   int32_t* s_lst = s_raw + VPB * GS;
   const int lg = tid % G, grp = tid / G;
   const int64_t v = bidx * VPB + grp;
-  if (tid == 0) s_arrived = 0;
+  __shared__ GridGuess s_gg;  // gridded fh: what the index search needs of the axes, once per block
+  if (tid == 0) {
+    s_arrived = 0;
+    if (BAR == 1) s_gg = grid_guess(f);
+  }
   __syncthreads();  // the only block barrier: at the very start, where no warp has to wait long
   int32_t* tab = s_tab + grp * GS;
   int32_t* lst = s_lst + grp * GS;
@@ -792,7 +796,7 @@ __global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
       double a0, a1, a2;
       load_pt<DIM, true>(pp, v, a0, a1, a2);
       GridGuess gg;
-      if (BAR == 1) gg = grid_guess(f);
+      if (BAR == 1) gg = s_gg;
       for (int j = (BAR == 1 && H_ALL_SLOTS ? 0 : lo) + lg; j < U; j += G)
         bar_terms<DIM, BAR == 1>(f, gg, pp, a0, a1, a2, tab[j], hslot + sbase + j, sL, sH, j >= lo);
     }

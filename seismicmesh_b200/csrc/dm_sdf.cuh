@@ -263,18 +263,21 @@ DM_HD bool sdf_project(const double* __restrict__ prog, int dim, double deps, do
 struct GridGuess {
   double a0[3];
   float scale[3];
+  int cells32;  // the corner-record index of a 3-D grid fits 32 bits (it nearly always does): one 32-bit product chain
 };
 DM_HD GridGuess grid_guess(const DmSizeFn& f) {
   GridGuess g;
   for (int k = 0; k < 3; ++k) {
-    g.a0[k] = 0.0;
-    g.scale[k] = 0.0f;
-    if (k < f.dim) {
-      const double a0 = DM_LDG(f.axis[k]), a1 = DM_LDG(f.axis[k] + f.n[k] - 1);
-      g.a0[k] = a0;
-      g.scale[k] = (float)(f.n[k] - 1) / (float)(a1 - a0);
-    }
+    // (an axis that does not exist reads axis 0 instead: every load below is from a valid address whether or
+    //  not the compiler turns the guard into a select)
+    const int kk = k < f.dim ? k : 0;
+    const double* ax = f.axis[kk];
+    const int n = f.n[kk];
+    const double a0 = DM_LDG(ax), a1 = DM_LDG(ax + n - 1);
+    g.a0[k] = a0;
+    g.scale[k] = (float)(n - 1) / (float)(a1 - a0);
   }
+  g.cells32 = f.dim == 3 && (int64_t)(f.n[0] - 1) * (f.n[1] - 1) * (f.n[2] - 1) < ((int64_t)1 << 31) ? 1 : 0;
   return g;
 }
 
@@ -283,25 +286,22 @@ DM_HD int grid_find(const double* __restrict__ ax, int n, double x, double a0, f
   // uniform-spacing guess, then fix up against the ACTUAL (float32-rounded) axis.  The guess only
   // has to land within a node or two, so it is computed in float32 (a handful of instructions
   // instead of a float64 division); the loops below make the result exact whatever the guess.
-  const float g = (float)(x - a0) * scale;
-  int i;
-  if (!(g > 0.0f))
-    i = 0;
-  else if (g >= (float)(n - 2))
-    i = n - 2;
-  else
-    i = (int)g;
+  // Clamp to [0, n-2] without branches (a NaN guess becomes 0: fmaxf returns the other operand).
+  const float g = fminf(fmaxf((float)(x - a0) * scale, 0.0f), (float)(n - 2));
+  int i = (int)g;
   lo = DM_LDG_KEEP(ax + i);
   hi = DM_LDG_KEEP(ax + i + 1);
-  while (i > 0 && x < lo) {
-    --i;
-    hi = lo;
-    lo = DM_LDG_KEEP(ax + i);
-  }
-  while (i < n - 2 && x >= hi) {
-    ++i;
-    lo = hi;
-    hi = DM_LDG_KEEP(ax + i + 1);
+  if ((x < lo && i > 0) || (x >= hi && i < n - 2)) {  // the guess is off (a node boundary, or far outside): walk
+    while (i > 0 && x < lo) {
+      --i;
+      hi = lo;
+      lo = DM_LDG_KEEP(ax + i);
+    }
+    while (i < n - 2 && x >= hi) {
+      ++i;
+      lo = hi;
+      hi = DM_LDG_KEEP(ax + i + 1);
+    }
   }
   return i;
 }
@@ -330,7 +330,8 @@ DM_HD double size_eval(const DmSizeFn& f, const GridGuess& gg, double x0, double
   const int64_t n1 = f.n[1], n2 = f.n[2];
   double cv[8];  // corner values in itertools.product order
   if (f.cells != nullptr) {
-    const double* c = f.cells + (((int64_t)i0 * (n1 - 1) + i1) * (n2 - 1) + i2) * 8;
+    const double* c = gg.cells32 ? f.cells + (size_t)(((unsigned)i0 * (unsigned)(f.n[1] - 1) + (unsigned)i1) * (unsigned)(f.n[2] - 1) + (unsigned)i2) * 8
+                                 : f.cells + (((int64_t)i0 * (n1 - 1) + i1) * (n2 - 1) + i2) * 8;
     dm_load8(c, cv);
   } else {
     const double* g = f.grid + ((int64_t)i0 * n1 + i1) * n2 + i2;
