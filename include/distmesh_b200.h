@@ -367,6 +367,18 @@ int dm_size_from_velocity(const double *vp, const double *h_gr, int64_t n, int d
                           double *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Sizing preprocessing: domain extension of the gridded size function (replaces np.pad as called by
+ * get_sizing_function_from_segy, sizing/mesh_size_function.py:526-587) with NumPy's semantics and arithmetic:
+ * in (shape) -> out (shape + before + after), C order, dim 2 or 3; axes padded one after the other, axis 0 first,
+ * each from the edge planes of NumPy's region of interest.  mode 0 = "edge", 1 = "constant" (end_before /
+ * end_after are the constant values), 2 = "linear_ramp" (end values; np.linspace(end, edge, width,
+ * endpoint=False) including its any-zero-step rule).  Bit-identical to np.pad.  flags_dev: two int32 of scratch.
+ * ------------------------------------------------------------------------------------------- */
+int dm_pad(const double *in, double *out, int dim, const int64_t *shape_host, const int64_t *before_host,
+           const int64_t *after_host, int mode, double end_before, double end_after, int32_t *flags_dev,
+           void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing: gradient limiting of a gridded size function in place (replaces
  * _FastHJ.limgrad, sizing/cpp/FastHJ.cpp:63-190, called from _enforce_gradation_sizing,
  * sizing/mesh_size_function.py:471-496).  f (n0,n1,n2) float64 C order (n2 = 1 in 2-D);

@@ -586,3 +586,41 @@ def cells_lead_interior(t, key, thresh):
     sel = np.where(cnt > 0, sel, np.argmin(kk, axis=1))
     even = np.array([[0, 1, 2, 3], [1, 2, 0, 3], [2, 0, 1, 3], [3, 1, 0, 2]])
     return np.ascontiguousarray(np.take_along_axis(t, even[sel], axis=1))
+
+
+def pad_staged(a, padding, mode, end_values):
+    """np.pad(a, padding, mode) for mode in ("edge", "constant", "linear_ramp"), restated the way
+    numpy/lib/_arraypad_impl.py works (NumPy 2.3; the reference calls it at sizing/mesh_size_function.py:575-587):
+    one axis after the other, axis 0 first; while axis k is padded the region of interest is the full (already
+    padded) extent along the axes before k and the original extent along the axes after k (_view_roi); a linear
+    ramp is np.linspace(end_value, edge, width, endpoint=False), i.e. j * ((edge - end) / width) + end, or --
+    when ANY element of the edge plane has a zero step -- (j / width) * (edge - end) + end for the whole plane
+    (numpy/_core/function_base.py: any_step_zero).  The CUDA kernel dm_pad follows this restatement."""
+    a = np.asarray(a, dtype=np.float64)
+    nd = a.ndim
+    sl = tuple(slice(padding[k][0], padding[k][0] + a.shape[k]) for k in range(nd))
+    P = np.empty([a.shape[k] + padding[k][0] + padding[k][1] for k in range(nd)])
+    P[sl] = a
+    for k in range(nd):
+        roi = P[tuple(slice(None) if j <= k else sl[j] for j in range(nd))]
+        lw, rw = padding[k]
+        n = roi.shape[k]
+        for lower, W, ev in ((True, lw, end_values[0]), (False, rw, end_values[1])):
+            if W == 0:
+                continue
+            ix = [slice(None)] * nd
+            ix[k] = slice(lw, lw + 1) if lower else slice(n - rw - 1, n - rw)
+            edge = roi[tuple(ix)]
+            if mode == "edge":
+                y = np.repeat(edge, W, axis=k)
+            elif mode == "constant":
+                y = np.full_like(np.repeat(edge, W, axis=k), ev)
+            else:
+                delta = edge - ev
+                step = delta / W
+                j = np.arange(W, dtype=np.float64).reshape([-1 if q == k else 1 for q in range(nd)])
+                y = (j / W) * delta if (step == 0).any() else j * step
+                y = y + ev
+            ix[k] = slice(0, W) if lower else slice(n - W, n)
+            roi[tuple(ix)] = y if lower else np.flip(y, axis=k)
+    return P

@@ -494,4 +494,105 @@ __global__ void halo_wait_kernel(const unsigned long long* f0, const unsigned lo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// np.pad on the device (domain extension of the sizing grid, sizing/mesh_size_function.py:526-587, which calls
+// np.pad with mode "edge", "constant" or "linear_ramp").  NumPy pads one axis after the other, axis 0 first, and
+// while it pads axis k its region of interest is the full (already padded) extent along the axes before k and the
+// ORIGINAL extent along the axes after k (numpy/lib/_arraypad_impl.py, _view_roi); the pads of axis k are computed
+// from the edge planes of that region.  One launch per stage here, the same order, the same arithmetic:
+// linear_ramp is np.linspace(end_value, edge, width, endpoint=False): j * ((edge - end) / width) + end -- or, when
+// ANY element of the edge plane equals the end value (a zero step somewhere), (j / width) * (edge - end) + end for
+// the whole plane (numpy/_core/function_base.py linspace: `any_step_zero`); hence the flag pass before each fill.
+// ---------------------------------------------------------------------------------------------
+struct PadGeom {
+  int n[3];   // padded shape (2-D: n[2] = 1)
+  int lo[3];  // original area [lo, hi) along every axis
+  int hi[3];
+};
+
+__global__ void pad_copy_kernel(const double* __restrict__ in, double* __restrict__ out, PadGeom g) {
+  const int64_t m0 = g.hi[0] - g.lo[0], m1 = g.hi[1] - g.lo[1], m2 = g.hi[2] - g.lo[2];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m0 * m1 * m2) return;
+  const int64_t i2 = i % m2, i1 = (i / m2) % m1, i0 = i / (m2 * m1);
+  out[((i0 + g.lo[0]) * g.n[1] + (i1 + g.lo[1])) * g.n[2] + (i2 + g.lo[2])] = in[i];
+}
+
+// extent of the region of interest of stage `axis` along axis q
+__device__ __forceinline__ void pad_roi(const PadGeom& g, int axis, int q, int& b, int& e) {
+  if (q < axis) {
+    b = 0;
+    e = g.n[q];
+  } else {
+    b = g.lo[q];
+    e = g.hi[q];
+  }
+}
+
+// flags[0] / flags[1] = 1 if some element of the lower / upper edge plane equals end_lo / end_hi
+__global__ void pad_flags_kernel(const double* __restrict__ out, PadGeom g, int axis, double end_lo, double end_hi,
+                                 int32_t* __restrict__ flags) {
+  int b[3], e[3];
+  for (int q = 0; q < 3; ++q) pad_roi(g, axis, q, b[q], e[q]);
+  const int qa = axis == 0 ? 1 : 0, qb = axis == 2 ? 1 : 2;  // the two other axes
+  const int64_t na = e[qa] - b[qa], nb = e[qb] - b[qb];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na * nb) return;
+  int idx[3];
+  idx[qa] = b[qa] + (int)(i / nb);
+  idx[qb] = b[qb] + (int)(i % nb);
+  idx[axis] = g.lo[axis];
+  if (out[((int64_t)idx[0] * g.n[1] + idx[1]) * g.n[2] + idx[2]] == end_lo) flags[0] = 1;
+  idx[axis] = g.hi[axis] - 1;
+  if (out[((int64_t)idx[0] * g.n[1] + idx[1]) * g.n[2] + idx[2]] == end_hi) flags[1] = 1;
+}
+
+// mode 0 edge, 1 constant (= end value), 2 linear_ramp
+__global__ void pad_fill_kernel(double* __restrict__ out, PadGeom g, int axis, int mode, double end_lo, double end_hi,
+                                const int32_t* __restrict__ flags) {
+  int b[3], e[3];
+  for (int q = 0; q < 3; ++q) pad_roi(g, axis, q, b[q], e[q]);
+  const int qa = axis == 0 ? 1 : 0, qb = axis == 2 ? 1 : 2;
+  const int64_t na = e[qa] - b[qa], nb = e[qb] - b[qb];
+  const int wl = g.lo[axis], wr = g.n[axis] - g.hi[axis];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na * nb * (wl + wr)) return;
+  // the pad index runs fastest when the padded axis is the last one (coalesced stores), else the last other axis does
+  int64_t r = i;
+  int jj, ia, ib;
+  if (axis == 2) {
+    jj = (int)(r % (wl + wr));
+    r /= (wl + wr);
+    ib = (int)(r % nb);
+    ia = (int)(r / nb);
+  } else {
+    ib = (int)(r % nb);
+    r /= nb;
+    jj = (int)(r % (wl + wr));
+    ia = (int)(r / (wl + wr));
+  }
+  int idx[3];
+  idx[qa] = b[qa] + ia;
+  idx[qb] = b[qb] + ib;
+  const bool lower = jj < wl;
+  const int W = lower ? wl : wr;
+  const int j = lower ? jj : wr - 1 - (jj - wl);  // position on the ramp counted from the OUTER end
+  idx[axis] = lower ? g.lo[axis] : g.hi[axis] - 1;
+  const double edge = out[((int64_t)idx[0] * g.n[1] + idx[1]) * g.n[2] + idx[2]];
+  const double endv = lower ? end_lo : end_hi;
+  double v;
+  if (mode == 0) {
+    v = edge;
+  } else if (mode == 1) {
+    v = endv;
+  } else {
+    const double delta = edge - endv;
+    const double step = delta / (double)W;
+    v = flags[lower ? 0 : 1] ? ((double)j / (double)W) * delta : (double)j * step;
+    v = v + endv;
+  }
+  idx[axis] = lower ? j : g.n[axis] - 1 - j;
+  out[((int64_t)idx[0] * g.n[1] + idx[1]) * g.n[2] + idx[2]] = v;
+}
+
 }  // namespace dm

@@ -795,6 +795,40 @@ int dm_size_from_velocity(const double* vp, const double* h_gr, int64_t n, int d
   return DM_OK;
 }
 
+int dm_pad(const double* in, double* out, int dim, const int64_t* shape_host, const int64_t* before_host,
+           const int64_t* after_host, int mode, double end_before, double end_after, int32_t* flags_dev, void* stream) {
+  if (!in || !out || in == out || bad_dim(dim) || !shape_host || !before_host || !after_host || mode < 0 || mode > 2 || !flags_dev)
+    return DM_ERR_ARG;
+  PadGeom g;
+  int64_t total = 1, inner = 1;
+  for (int q = 0; q < 3; ++q) {
+    const int64_t m = q < dim ? shape_host[q] : 1, bq = q < dim ? before_host[q] : 0, aq = q < dim ? after_host[q] : 0;
+    if (m < 1 || bq < 0 || aq < 0 || m + bq + aq > INT32_MAX) return DM_ERR_ARG;
+    g.n[q] = (int)(m + bq + aq);
+    g.lo[q] = (int)bq;
+    g.hi[q] = (int)(bq + m);
+    total *= g.n[q];
+    inner *= m;
+  }
+  (void)total;
+  cudaStream_t st = S(stream);
+  pad_copy_kernel<<<nblk(inner, 256), 256, 0, st>>>(in, out, g);
+  for (int axis = 0; axis < dim; ++axis) {
+    const int64_t w = (int64_t)g.lo[axis] + (g.n[axis] - g.hi[axis]);
+    if (w == 0) continue;
+    int64_t plane = 1;
+    for (int q = 0; q < 3; ++q)
+      if (q != axis) plane *= q < axis ? g.n[q] : g.hi[q] - g.lo[q];
+    if (mode == 2) {
+      DM_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 2 * sizeof(int32_t), st));
+      pad_flags_kernel<<<nblk(plane, 256), 256, 0, st>>>(out, g, axis, end_before, end_after, flags_dev);
+    }
+    pad_fill_kernel<<<nblk(plane * w, 256), 256, 0, st>>>(out, g, axis, mode, end_before, end_after, flags_dev);
+  }
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_limgrad(double* f, double* tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
                int32_t* changed_dev, int* sweeps_host, void* stream) {
   if (!f || !tmp || f == tmp || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;

@@ -37,27 +37,45 @@ class GridInterpolant:
     """
 
     def __init__(self, axes, values, cell_records=True):
+        """values: host array, or a float64 CUDA tensor (the grid get_sizing_function_from_segy leaves on the
+        device: it is used where it is and only comes to the host if somebody reads ``.values``)."""
         self.cell_records = bool(cell_records)  # 3-D: keep per-cell 64-B corner records on the device (8x the grid)
         self.grid = tuple(np.ascontiguousarray(a, dtype=np.float64) for a in axes)
-        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        self._values_dev = None
+        if isinstance(values, torch.Tensor) and values.is_cuda:
+            self._values_dev = values.to(torch.float64).contiguous()
+            self._values = None
+            self.shape = tuple(int(n) for n in values.shape)
+        else:
+            self._values = np.ascontiguousarray(values, dtype=np.float64)
+            self.shape = self._values.shape
         self.dim = len(self.grid)
-        if self.dim not in (2, 3) or self.values.ndim != self.dim:
+        if self.dim not in (2, 3) or len(self.shape) != self.dim:
             raise ValueError("Dimension not supported")
-        for a, n in zip(self.grid, self.values.shape):
+        for a, n in zip(self.grid, self.shape):
             if a.ndim != 1 or len(a) != n or n < 2 or not np.all(np.diff(a) > 0):
                 raise ValueError("grid axes must be strictly ascending and match the values' shape")
         self._dev = None
+
+    @property
+    def values(self):
+        if self._values is None:
+            self._values = self._values_dev.cpu().numpy()
+        return self._values
 
     def device_arrays(self):
         dev = D.device()
         if self._dev is None or self._dev[1].device != dev:
             axes = [torch.from_numpy(a).to(dev) for a in self.grid]
-            grid = torch.from_numpy(self.values).to(dev)
+            if self._values_dev is not None and self._values_dev.device == dev:
+                grid = self._values_dev
+            else:
+                grid = torch.from_numpy(self.values).to(dev)
             cells = None
             if self.dim == 3 and self.cell_records:
                 # a trilinear lookup then touches one aligned 64-B record instead of 4 sectors in 4 DRAM
                 # pages; skipped when it would take more than a quarter of the free device memory
-                nc = int(np.prod([n - 1 for n in self.values.shape]))
+                nc = int(np.prod([n - 1 for n in self.shape]))
                 if 64 * nc <= torch.cuda.mem_get_info(dev)[0] // 4:
                     cells = torch.empty(nc * 8, dtype=torch.float64, device=dev)
                     f = D.size_fn_struct(_lib.SIZE_GRID, 3, axes=axes, grid=grid)
@@ -126,8 +144,8 @@ class SizeFunction:
 # with the reference's interface (sizing/mesh_size_function.py:27-232).  The elementwise chain
 # (wavelength sizing, clamp, CFL bound) is ONE fused kernel over the velocity grid and the gradient
 # limiter -- the reference's only native code on this path (sizing/cpp/FastHJ.cpp) -- runs on the grid
-# where that kernel left it; the optional windowed-variance term (SciPy uniform_filter) and the domain
-# padding (np.pad) stay on the host.
+# where that kernel left it, and so does the domain padding (np.pad's algorithm, dm_pad): the grid never leaves
+# the device.  The optional windowed-variance term (SciPy uniform_filter) stays on the host.
 # ----------------------------------------------------------------------------------------------
 _SIZING_DEFAULTS = {  # mesh_size_function.py:103-126
     "velocity_data": None, "vp_water": 1500.0, "hmin": 150.0, "hmax": 10000.0, "wl": 0, "freq": 2.0, "grad": 0.0,
@@ -178,14 +196,30 @@ def _read_bin(filename, nz, nx, ny, byte_order, axes_order, axes_order_sort, dty
     return np.flipud(vp.transpose((*axes_order,))), nz, nx, ny
 
 
+_PAD_MODES = {"edge": 0, "constant": 1, "linear_ramp": 2}
+
+
 def _pad(array, padding, style, extra):  # mesh_size_function.py:575-587
+    """np.pad(array, padding, style, ...) with the reference's three styles.  A CUDA tensor is padded on the
+    device (dm_pad: NumPy's axis-by-axis algorithm and arithmetic, bit-identical) and stays there."""
+    if style not in _PAD_MODES:
+        raise ValueError("pad style currently not supported. Try `linear_ramp`, `edge`, or `constant`")
+    if isinstance(array, torch.Tensor):
+        a = array.to(torch.float64).contiguous()
+        dim = a.ndim
+        shape = (C.c_int64 * dim)(*a.shape)
+        before = (C.c_int64 * dim)(*[int(w[0]) for w in padding])
+        after = (C.c_int64 * dim)(*[int(w[1]) for w in padding])
+        out = torch.empty(tuple(int(n + w[0] + w[1]) for n, w in zip(a.shape, padding)), dtype=torch.float64, device=a.device)
+        flags = torch.zeros(2, dtype=torch.int32, device=a.device)
+        check(lib.dm_pad(D.ptr(a), D.ptr(out), dim, shape, before, after, _PAD_MODES[style], float(extra[0]), float(extra[1]),
+                         D.ptr(flags), D.stream_ptr()), "dm_pad")
+        return out
     if style == "edge":
         return np.pad(array, padding, "edge")
     if style == "constant":
         return np.pad(array, padding, "constant", constant_values=tuple(extra))
-    if style == "linear_ramp":
-        return np.pad(array, padding, "linear_ramp", end_values=tuple(extra))
-    raise ValueError("pad style currently not supported. Try `linear_ramp`, `edge`, or `constant`")
+    return np.pad(array, padding, "linear_ramp", end_values=tuple(extra))
 
 
 _SEGY_FORMATS = {  # data sample format code (binary header bytes 3225-3226) -> big-endian dtype
@@ -332,9 +366,8 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
         if grade > 1.0:
             warnings.warn("Parameter `grade` is set pretty high (> 1.0)!")
         _limgrad_device(cs_dev, grade, (bbox[1] - bbox[0]) / nz)
-    cell_size = cs_dev.cpu().numpy()
-    del cs_dev
-    # domain extension (:526-572)
+    # domain extension (:526-572): np.pad's algorithm on the device, on the grid where the limiter left it.  (The
+    # reference also pads vp, which nothing reads afterwards.)
     pad = opts["domain_pad"]
     if pad < 0:
         raise ValueError("Domain extension must be >= 0")
@@ -344,8 +377,8 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
         nn = [int(pad / dk) for dk in d]
         bbox = tuple(v for k in range(dim) for v in ((bbox[2 * k] - pad, bbox[2 * k + 1] + (pad if k > 0 else 0.0))))
         padding = tuple((nn[k], 0) if k == 0 else (nn[k], nn[k]) for k in range(dim))
-        mx_h, mx_v = np.amax(cell_size), np.amax(vp)
-        cell_size = _pad(cell_size, padding, opts["pad_style"], [mx_h] * 2)
-        vp = _pad(vp, padding, opts["pad_style"], [mx_v] * 2)
+        mx_h = float(cs_dev.max().item())
+        cs_dev = _pad(cs_dev, padding, opts["pad_style"], [mx_h] * 2)
+    cell_size = cs_dev
     # gridded interpolant with the reference's float32-linspace axes (:391-408, :514-523)
     return SizeFunction(tuple(bbox), GridInterpolant(grid_axes(bbox, cell_size.shape), cell_size), opts["hmin"])

@@ -942,6 +942,29 @@ def test_reference_segy_domain_extension_answers(sm, tmp_path, style):
     assert np.allclose([len(p), len(t)], case["reference_run_here"], atol=100)  # and the unmodified reference run here
 
 
+@pytest.mark.parametrize("style", ["edge", "constant", "linear_ramp"])
+def test_pad_kernel_equals_numpy(sm, style):
+    """dm_pad against np.pad, bit for bit (domain extension of the sizing grid, mesh_size_function.py:526-587):
+    2-D and 3-D, the reference's one-sided padding of axis 0, end values = the array maximum with the maximum
+    inside and on the boundary (NumPy's zero-step rule for ramps), and a grid large enough for many blocks."""
+    from seismicmesh_b200.sizing import _pad
+
+    rng = np.random.default_rng(3)
+    cases = [((7, 9), ((3, 0), (2, 2))), ((5, 6, 4), ((2, 0), (3, 3), (1, 1))), ((6, 5), ((0, 0), (4, 4))),
+             ((4, 3, 5), ((1, 0), (0, 0), (2, 2))), ((61, 130, 97), ((12, 0), (7, 7), (9, 9))), ((300, 211), ((40, 0), (33, 33)))]
+    for shape, padding in cases:
+        for on_boundary in (False, True):
+            a = rng.uniform(1.0, 5.0, shape)
+            if on_boundary:
+                a[(0,) * len(shape)] = 9.0
+            for ev in ([float(a.max())] * 2, [7.5, 0.25]):
+                kw = {"edge": {}, "constant": {"constant_values": tuple(ev)}, "linear_ramp": {"end_values": tuple(ev)}}[style]
+                ref = np.pad(a, padding, style, **kw)
+                got = _pad(dev(a, torch.float64), padding, style, ev)
+                assert got.is_cuda and tuple(got.shape) == ref.shape
+                assert np.array_equal(got.cpu().numpy(), ref), (shape, padding, on_boundary, ev)
+
+
 def test_limgrad_kernel_vs_oracle_large(sm):
     """BP2004-shaped grid (1911 x 5395): the CUDA limiter against the oracle's fixed point through
     size-independent properties (gradient bound, never raises a value, idempotent) and against the

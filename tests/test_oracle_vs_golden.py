@@ -172,3 +172,22 @@ def test_limgrad_oracle_vs_reference_native(shape):
     out = np.asarray(hj.limgrad([*shape], elen, grade, 10000, f0.flatten("F"))).reshape(shape, order="F")
     mine = orc.limgrad(f0, elen * grade, f0.min() * np.sqrt(1e-9))
     assert np.abs(mine - out).max() <= 4 * f0.min() * np.sqrt(1e-9)
+
+
+def test_pad_restatement_equals_numpy():
+    """The staged restatement of np.pad that the CUDA kernel dm_pad follows (oracle.pad_staged) against
+    np.pad itself: the reference's three pad styles, its one-sided padding of axis 0, end values equal to the
+    array maximum (the reference's choice) with the maximum inside and on the boundary (NumPy's zero-step rule)."""
+    rng = np.random.default_rng(0)
+    for shape, padding in (((7, 9), ((3, 0), (2, 2))), ((5, 6, 4), ((2, 0), (3, 3), (1, 1))), ((6, 5), ((0, 0), (4, 4))),
+                           ((4, 3, 5), ((1, 0), (0, 0), (2, 2)))):
+        for on_boundary in (False, True):
+            a = rng.uniform(1.0, 5.0, shape)
+            if on_boundary:
+                a[(0,) * len(shape)] = 9.0
+            ev = [float(a.max())] * 2
+            assert np.array_equal(orc.pad_staged(a, padding, "edge", ev), np.pad(a, padding, "edge"))
+            assert np.array_equal(orc.pad_staged(a, padding, "constant", ev), np.pad(a, padding, "constant", constant_values=tuple(ev)))
+            assert np.array_equal(orc.pad_staged(a, padding, "linear_ramp", ev), np.pad(a, padding, "linear_ramp", end_values=tuple(ev)))
+            assert np.array_equal(orc.pad_staged(a, padding, "linear_ramp", [7.5, 0.25]),
+                                  np.pad(a, padding, "linear_ramp", end_values=(7.5, 0.25)))
