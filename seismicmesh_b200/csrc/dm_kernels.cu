@@ -213,10 +213,10 @@ static bool use_tiles(const DmPlan* pl) {
   return pl->layout == DM_LAYOUT_TILES;
 }
 
+// (per call, not once per process: the attribute belongs to the CURRENT device's copy of the kernel)
 template <int DIM, int BAR>
 static cudaError_t tile_smem_ready(size_t bytes) {
-  static cudaError_t st = cudaFuncSetAttribute(tile_rows_kernel<DIM, BAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return st;
+  return cudaFuncSetAttribute(tile_rows_kernel<DIM, BAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 template <int DIM>
