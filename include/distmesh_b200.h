@@ -367,6 +367,21 @@ int dm_size_from_velocity(const double *vp, const double *h_gr, int64_t n, int d
                           double *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Sizing preprocessing, the `grad=` option: windowed variance of the velocity model (replaces the two
+ * scipy.ndimage.uniform_filter calls and the NumPy expressions of sizing/mesh_size_function.py:428-448).
+ * dm_uniform_filter: out = uniform_filter(in, size) with SciPy's defaults (mode "reflect", origin 0), axis after
+ * axis with SciPy's running-sum recurrence per line, bit-identical; in (n0,n1,n2) C order (n2 = 1 and ndim = 2
+ * for a 2-D grid), size_host[ndim] window lengths (<= the axis lengths), tmp: n0*n1*n2 float64 of scratch;
+ * square_input != 0: the filter of in*in (the reference's uniform_filter(vp**2)) without a squared copy.
+ * dm_variance_size: pass 0: out = sqr_mean - mean*mean ; pass 1 (in place on out, with vmax = max(out) and
+ * vmin_scaled = min(out)/vmax taken by the caller): out = grad / ((out / vmax - vmin_scaled) + 0.10).
+ * ------------------------------------------------------------------------------------------- */
+int dm_uniform_filter(const double *in, double *out, double *tmp, int64_t n0, int64_t n1, int64_t n2,
+                      const int *size_host, int ndim, int square_input, void *stream);
+int dm_variance_size(const double *mean, const double *sqr_mean, int64_t n, int pass, double vmax,
+                     double vmin_scaled, double grad, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing: domain extension of the gridded size function (replaces np.pad as called by
  * get_sizing_function_from_segy, sizing/mesh_size_function.py:526-587) with NumPy's semantics and arithmetic:
  * in (shape) -> out (shape + before + after), C order, dim 2 or 3; axes padded one after the other, axis 0 first,

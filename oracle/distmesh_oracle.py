@@ -624,3 +624,34 @@ def pad_staged(a, padding, mode, end_values):
             ix[k] = slice(0, W) if lower else slice(n - W, n)
             roi[tuple(ix)] = y if lower else np.flip(y, axis=k)
     return P
+
+
+def uniform_filter1d_lines(a, size, axis):
+    """scipy.ndimage.uniform_filter1d(a, size, axis=axis) (mode "reflect", origin 0; SciPy 1.18, C source
+    ni_filters.c NI_UniformFilter1D), restated: per line a running sum over the reflect-extended samples --
+    tmp = sum(ext[0:size]); out[0] = tmp / size; tmp += ext[i + size - 1] - ext[i - 1]; out[i] = tmp / size.
+    scipy.ndimage.uniform_filter applies it axis after axis (axis 0 first); the reference calls that at
+    sizing/mesh_size_function.py:436-437.  The CUDA kernel dm_uniform_filter follows this restatement."""
+    a = np.moveaxis(np.asarray(a, dtype=np.float64), axis, -1)
+    n = a.shape[-1]
+    left = size // 2
+    idx = np.arange(n + size - 1) - left
+    idx = np.where(idx < 0, -idx - 1, idx)
+    idx = np.where(idx >= n, 2 * n - 1 - idx, idx)
+    ext = a[..., idx]
+    out = np.empty_like(a)
+    tmp = np.zeros(a.shape[:-1])
+    for k in range(size):
+        tmp = tmp + ext[..., k]
+    out[..., 0] = tmp / size
+    for i in range(1, n):
+        tmp = tmp + (ext[..., i + size - 1] - ext[..., i - 1])
+        out[..., i] = tmp / size
+    return np.moveaxis(out, -1, axis)
+
+
+def uniform_filter(a, size):
+    out = np.asarray(a, dtype=np.float64)
+    for axis, s in enumerate(size):
+        out = uniform_filter1d_lines(out, int(s), axis)
+    return out

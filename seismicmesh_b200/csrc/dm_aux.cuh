@@ -595,4 +595,65 @@ __global__ void pad_fill_kernel(double* __restrict__ out, PadGeom g, int axis, i
   out[((int64_t)idx[0] * g.n[1] + idx[1]) * g.n[2] + idx[2]] = v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// scipy.ndimage.uniform_filter along ONE axis (mode "reflect", origin 0), as the `grad=` option of the sizing
+// preprocessing calls it (sizing/mesh_size_function.py:428-448).  SciPy's uniform_filter1d keeps a running
+// sum per line -- tmp = sum of the first `size` extended samples; out[0] = tmp / size; then
+// tmp += ext[i + size - 1] - ext[i - 1]; out[i] = tmp / size -- and uniform_filter applies it axis after axis;
+// the same recurrence here (one thread per line, so the rounding sequence is SciPy's), bit-identical
+// (restated and checked against SciPy on the CPU: oracle.uniform_filter1d_lines).
+// ---------------------------------------------------------------------------------------------
+__global__ void uniform_filter_axis_kernel(const double* __restrict__ in, double* __restrict__ out, int n0, int n1, int n2,
+                                           int axis, int size, int square) {
+  const int n[3] = {n0, n1, n2};
+  const int len = n[axis];
+  const int64_t lines = (int64_t)n0 * n1 * n2 / len;
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= lines) return;
+  // line l: position along the two other axes; consecutive threads walk the last remaining axis
+  int64_t base, stride;
+  if (axis == 2) {
+    base = l * n2;
+    stride = 1;
+  } else if (axis == 1) {
+    base = (l / n2) * (int64_t)n1 * n2 + l % n2;
+    stride = n2;
+  } else {
+    base = l;
+    stride = (int64_t)n1 * n2;
+  }
+  const int left = size / 2;
+  // extended sample e (0 <= e < len + size - 1) -> reflected index into the line: (d c b a | a b c d | d c b a)
+  auto ext = [&](int e) {
+    int i = e - left;
+    if (i < 0) i = -i - 1;
+    if (i >= len) i = 2 * len - 1 - i;
+    const double x = in[base + (int64_t)i * stride];
+    return square ? x * x : x;  // (the filter of vp**2 without a squared copy of the model)
+  };
+  double tmp = 0.0;
+  for (int k = 0; k < size; ++k) tmp += ext(k);
+  out[base] = tmp / (double)size;
+  for (int i = 1; i < len; ++i) {
+    tmp += ext(i + size - 1) - ext(i - 1);
+    out[base + (int64_t)i * stride] = tmp / (double)size;
+  }
+}
+
+// h_gr = grad / ((var / vmax - vmin_scaled) + 0.10), var = sqr_mean - mean * mean (mesh_size_function.py:441-448);
+// pass 0 leaves var in `out` (the caller takes its extrema), pass 1 finishes in place
+__global__ void variance_size_kernel(const double* __restrict__ mean, const double* __restrict__ sqr_mean, int64_t n, int pass,
+                                     double vmax, double vmin_scaled, double grad, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (pass == 0) {
+    const double m = mean[i];
+    out[i] = sqr_mean[i] - m * m;
+  } else {
+    double v = out[i] / vmax;
+    v = v - vmin_scaled;
+    out[i] = grad / (v + 0.10);
+  }
+}
+
 }  // namespace dm

@@ -829,6 +829,36 @@ int dm_pad(const double* in, double* out, int dim, const int64_t* shape_host, co
   return DM_OK;
 }
 
+int dm_uniform_filter(const double* in, double* out, double* tmp, int64_t n0, int64_t n1, int64_t n2, const int* size_host,
+                      int ndim, int square_input, void* stream) {
+  if (!in || !out || !tmp || in == out || in == tmp || out == tmp || !size_host || (ndim != 2 && ndim != 3)) return DM_ERR_ARG;
+  if (n0 < 1 || n1 < 1 || n2 < 1 || n0 * n1 * n2 > (int64_t)INT32_MAX * 64 || n0 > INT32_MAX || n1 > INT32_MAX || n2 > INT32_MAX) return DM_ERR_ARG;
+  const int64_t n[3] = {n0, n1, n2};
+  for (int a = 0; a < ndim; ++a)
+    if (size_host[a] < 1 || size_host[a] > n[a]) return DM_ERR_ARG;  // (SciPy's multiple reflections of very short lines are not reproduced)
+  cudaStream_t st = S(stream);
+  // axis after axis, ping-pong between tmp and out so that the last axis lands in `out`
+  const double* src = in;
+  for (int a = 0; a < ndim; ++a) {
+    double* dst = ((ndim - 1 - a) % 2 == 0) ? out : tmp;
+    const int64_t lines = n0 * n1 * n2 / n[a];
+    uniform_filter_axis_kernel<<<nblk(lines, 128), 128, 0, st>>>(src, dst, (int)n0, (int)n1, (int)n2, a, size_host[a],
+                                                                  a == 0 && square_input ? 1 : 0);
+    src = dst;
+  }
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
+int dm_variance_size(const double* mean, const double* sqr_mean, int64_t n, int pass, double vmax, double vmin_scaled, double grad,
+                     double* out, void* stream) {
+  if (n < 0 || pass < 0 || pass > 1 || !out || (pass == 0 && (!mean || !sqr_mean))) return DM_ERR_ARG;
+  if (n == 0) return DM_OK;
+  variance_size_kernel<<<nblk(n, 256), 256, 0, S(stream)>>>(mean, sqr_mean, n, pass, vmax, vmin_scaled, grad, out);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_limgrad(double* f, double* tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
                int32_t* changed_dev, int* sweeps_host, void* stream) {
   if (!f || !tmp || f == tmp || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;

@@ -145,7 +145,7 @@ class SizeFunction:
 # (wavelength sizing, clamp, CFL bound) is ONE fused kernel over the velocity grid and the gradient
 # limiter -- the reference's only native code on this path (sizing/cpp/FastHJ.cpp) -- runs on the grid
 # where that kernel left it, and so does the domain padding (np.pad's algorithm, dm_pad): the grid never leaves
-# the device.  The optional windowed-variance term (SciPy uniform_filter) stays on the host.
+# the device; the optional windowed-variance term likewise (dm_uniform_filter: SciPy's recurrence, bit-identical).
 # ----------------------------------------------------------------------------------------------
 _SIZING_DEFAULTS = {  # mesh_size_function.py:103-126
     "velocity_data": None, "vp_water": 1500.0, "hmin": 150.0, "hmax": 10000.0, "wl": 0, "freq": 2.0, "grad": 0.0,
@@ -283,6 +283,41 @@ def read_velocity_model(filename, nz=None, nx=None, ny=None, byte_order=None, ax
     return _read_bin(filename, nz, nx, ny, byte_order, axes_order, axes_order_sort, dtype)
 
 
+def uniform_filter(a_dev, size, square_input=False):
+    """scipy.ndimage.uniform_filter(a, size) (mode "reflect") of a 2-D / 3-D float64 CUDA tensor on the device
+    (dm_uniform_filter: SciPy's running-sum recurrence per line, axis after axis: bit-identical)."""
+    a = a_dev.contiguous()
+    shp = tuple(a.shape) + (1,) * (3 - a.ndim)
+    sz = (C.c_int * a.ndim)(*[int(s) for s in size])
+    out, tmp = torch.empty_like(a), torch.empty_like(a)
+    check(lib.dm_uniform_filter(D.ptr(a), D.ptr(out), D.ptr(tmp), shp[0], shp[1], shp[2], sz, a.ndim, 1 if square_input else 0,
+                                D.stream_ptr()), "dm_uniform_filter")
+    return out
+
+
+def _gradient_sizing(vp, vp_dev, grad, stencil):
+    """h_gr = grad / (normalised windowed variance of vp + 0.10)  (mesh_size_function.py:428-448) -> CUDA tensor."""
+    window = [stencil] * vp.ndim if np.isscalar(stencil) else list(stencil)
+    window = [int(w) for w in window]
+    if any(w < 1 or w > n for w, n in zip(window, vp.shape)):  # windows longer than the grid: SciPy on the host
+        from scipy import ndimage
+
+        win_mean = ndimage.uniform_filter(vp, tuple(window))
+        win_var = ndimage.uniform_filter(vp**2, tuple(window)) - win_mean**2
+        win_var = np.divide(win_var, np.amax(win_var))
+        win_var -= np.amin(win_var)
+        return torch.from_numpy(np.ascontiguousarray(grad / (win_var + 0.10))).to(vp_dev.device)
+    mean = uniform_filter(vp_dev, window)
+    sqr_mean = uniform_filter(vp_dev, window, square_input=True)
+    var = torch.empty_like(vp_dev)
+    st = D.stream_ptr()
+    check(lib.dm_variance_size(D.ptr(mean), D.ptr(sqr_mean), var.numel(), 0, 0.0, 0.0, 0.0, D.ptr(var), st), "dm_variance_size")
+    vmax, vmin = float(var.max().item()), float(var.min().item())
+    # min(var / vmax) == min(var) / vmax: a correctly rounded division by a positive number is monotone
+    check(lib.dm_variance_size(None, None, var.numel(), 1, vmax, vmin / vmax, float(grad), D.ptr(var), st), "dm_variance_size")
+    return var
+
+
 def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     """Build a mesh-size function from a seismic velocity model: same name, arguments, defaults,
     errors and step order as the reference (mesh_size_function.py:27-232).  ``velocity_data=`` arrays
@@ -320,7 +355,7 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
             raise ValueError("Option %s with parameter %s not recognized " % (key, kwargs[key]))
     # ---- wavelength / gradient sizing (:411-450), clamp (:180-181), CFL bound (:453-468): argument checks in
     #      the reference's order, then ONE fused kernel over the velocity grid on the device
-    h_gr = None
+    want_grad = False
     if opts["wl"] > 0 or opts["grad"] > 0:
         if opts["wl"] < 0:
             raise ValueError("Parameter `wl` must be set > 0")
@@ -328,17 +363,7 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
             raise ValueError("Parameter `freq` must be set > 0.0")
         if opts["grad"] < 0:
             raise ValueError("Parameter grad must be > 0")
-        if opts["grad"] != 0.0:  # windowed variance of vp: SciPy's uniform_filter on the host, as the reference calls it
-            from scipy import ndimage
-
-            st = opts["stencil_size"]
-            window = [st] * vp.ndim if np.isscalar(st) else st
-            win_mean = ndimage.uniform_filter(vp, tuple(window))
-            win_sqr_mean = ndimage.uniform_filter(vp**2, tuple(window))
-            win_var = win_sqr_mean - win_mean**2
-            win_var = np.divide(win_var, np.amax(win_var))
-            win_var -= np.amin(win_var)
-            h_gr = opts["grad"] / (win_var + 0.10)
+        want_grad = opts["grad"] != 0.0
     cr_max, dt, so = opts["cr_max"], opts["dt"], opts["space_order"]
     if not ((cr_max == 0.0) or (dt == 0.0) or (so == 0.0)):
         if cr_max < 0:
@@ -353,7 +378,7 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     D.require_cuda()
     vp = np.ascontiguousarray(vp, dtype=np.float64)
     vp_dev = torch.from_numpy(vp).to(D.device())
-    gr_dev = None if h_gr is None else torch.from_numpy(np.ascontiguousarray(h_gr, dtype=np.float64)).to(D.device())
+    gr_dev = _gradient_sizing(vp, vp_dev, opts["grad"], opts["stencil_size"]) if want_grad else None
     cs_dev = torch.empty_like(vp_dev)
     check(lib.dm_size_from_velocity(D.ptr(vp_dev), D.ptr(gr_dev), vp_dev.numel(), dim, float(opts["freq"]), float(opts["wl"]),
                                     float(opts["hmin"]), float(opts["hmax"]), float(dt), float(cr_max), float(so), D.ptr(cs_dev),

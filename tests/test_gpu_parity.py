@@ -965,6 +965,33 @@ def test_pad_kernel_equals_numpy(sm, style):
                 assert np.array_equal(got.cpu().numpy(), ref), (shape, padding, on_boundary, ev)
 
 
+def test_uniform_filter_and_gradient_sizing_equal_scipy(sm):
+    """dm_uniform_filter against scipy.ndimage.uniform_filter, bit for bit (2-D, 3-D, odd and even windows, the
+    squared-input variant), and the whole `grad=` term h_gr = grad / (normalised windowed variance + 0.10) against
+    the reference's NumPy / SciPy expressions (sizing/mesh_size_function.py:428-448)."""
+    from scipy import ndimage
+    from seismicmesh_b200.sizing import _gradient_sizing, uniform_filter
+
+    rng = np.random.default_rng(2)
+    for shape, size in (((140, 257), (10, 10)), ((33, 61, 47), (10, 10, 10)), ((15, 40), (3, 7)), ((22, 13, 14), (5, 4, 9))):
+        a = rng.uniform(1500.0, 4500.0, shape)
+        ad = dev(a, torch.float64)
+        assert np.array_equal(uniform_filter(ad, size).cpu().numpy(), ndimage.uniform_filter(a, size))
+        assert np.array_equal(uniform_filter(ad, size, square_input=True).cpu().numpy(), ndimage.uniform_filter(a**2, size))
+    for shape in ((120, 300), (40, 70, 55)):
+        z = np.linspace(0, 1, shape[0]).reshape((-1,) + (1,) * (len(shape) - 1))
+        vp = 1500.0 + 3000.0 * z + 200.0 * rng.uniform(size=shape)
+        vp[shape[0] // 3 : shape[0] // 2] = 4500.0
+        window = [10] * vp.ndim
+        win_mean = ndimage.uniform_filter(vp, tuple(window))
+        win_var = ndimage.uniform_filter(vp**2, tuple(window)) - win_mean**2
+        win_var = np.divide(win_var, np.amax(win_var))
+        win_var -= np.amin(win_var)
+        ref = 50.0 / (win_var + 0.10)
+        got = _gradient_sizing(vp, dev(vp, torch.float64), 50.0, 10.0)
+        assert np.array_equal(got.cpu().numpy(), ref)
+
+
 def test_limgrad_kernel_vs_oracle_large(sm):
     """BP2004-shaped grid (1911 x 5395): the CUDA limiter against the oracle's fixed point through
     size-independent properties (gradient bound, never raises a value, idempotent) and against the

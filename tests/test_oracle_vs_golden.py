@@ -191,3 +191,15 @@ def test_pad_restatement_equals_numpy():
             assert np.array_equal(orc.pad_staged(a, padding, "linear_ramp", ev), np.pad(a, padding, "linear_ramp", end_values=tuple(ev)))
             assert np.array_equal(orc.pad_staged(a, padding, "linear_ramp", [7.5, 0.25]),
                                   np.pad(a, padding, "linear_ramp", end_values=(7.5, 0.25)))
+
+
+def test_uniform_filter_restatement_equals_scipy():
+    """oracle.uniform_filter (the recurrence dm_uniform_filter follows) against scipy.ndimage.uniform_filter,
+    bit for bit: the `grad=` option's windowed mean of vp and of vp**2 (mesh_size_function.py:428-448)."""
+    from scipy import ndimage
+
+    rng = np.random.default_rng(1)
+    for shape, size in (((40, 57), (10, 10)), ((23, 31, 19), (10, 10, 10)), ((15, 40), (3, 7)), ((12, 13, 14), (5, 4, 9))):
+        a = rng.uniform(1500.0, 4500.0, shape)
+        assert np.array_equal(orc.uniform_filter(a, size), ndimage.uniform_filter(a, size))
+        assert np.array_equal(orc.uniform_filter(a**2, size), ndimage.uniform_filter(a**2, size))
