@@ -216,11 +216,13 @@ __global__ void __launch_bounds__(DM_CS_THREADS, DM_CB_MINB) cull_bin_kernel(
 // on the lane's private word behind the sets (it "finds itself" there without conflicts from then on).
 // No second barrier: a slot that is being verified was written before the barrier, so it is not EMPTY any
 // more and nobody writes it in the next step.
-template <int NC, int LOGH>
+template <int NC, int LOGH, bool PARTIAL>
 __device__ __forceinline__ void tile_insert_lockstep(int32_t* tab, unsigned park, const int4& rec, bool valid,
                                                      unsigned& pmask) {
+  // PARTIAL: some lanes of this batch hold no record (`valid` false; the last batch of a list, the spill scan)
   constexpr unsigned HM = (1u << LOGH) - 1u;
   constexpr int TS = (1 << LOGH) + 1;
+  constexpr int MAXS = DM_TL_MAXSTEPS < (1 << LOGH) ? DM_TL_MAXSTEPS : (1 << LOGH);
   const unsigned tb = (unsigned)rec.w * TS;
   int x[NC];
   x[0] = rec.x;
@@ -229,8 +231,11 @@ __device__ __forceinline__ void tile_insert_lockstep(int32_t* tab, unsigned park
   unsigned h[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    h[c] = valid ? tb + hash_slot<LOGH>(x[c]) : park;
-    x[c] = valid ? x[c] : HASH_PARKED;
+    h[c] = tb + hash_slot<LOGH>(x[c]);
+    if (PARTIAL && !valid) {
+      h[c] = park;
+      x[c] = HASH_PARKED;
+    }
   }
   int steps = 0;
   bool any;
@@ -252,11 +257,10 @@ __device__ __forceinline__ void tile_insert_lockstep(int32_t* tab, unsigned park
       h[c] = hit ? park : nxt;
       x[c] = hit ? HASH_PARKED : x[c];
     }
-    if (++steps > (DM_TL_MAXSTEPS < (1 << LOGH) ? DM_TL_MAXSTEPS : (1 << LOGH))) {  // set full: the vertex is rebuilt exactly afterwards
-      if (any) pmask |= 1u << rec.w;
-      any = false;
-    }
-  } while (__any_sync(FULL, any));
+  } while (__any_sync(FULL, any) && ++steps < MAXS);
+  // a key that walked the whole set without finding a place (the loop only ends early when every lane is done):
+  // the set is full, the vertex is rebuilt exactly afterwards
+  if (any) pmask |= 1u << rec.w;
 }
 
 // ascending sort of RS registers: bitonic network, every index static
@@ -482,7 +486,10 @@ __global__ void __launch_bounds__(TL_THREADS, DM_TL_MINB) tile_rows_kernel(
       for (int b = 0; b < n; b += 32) {
         cp_async_wait<TL_STAGES - 1>();
         const int4 cur = ring[slot * TL_R + lane];
-        tile_insert_lockstep<DIM, LOGH>(tab, park, cur, b + lane < n, pmask);
+        if (b + 32 <= n)
+          tile_insert_lockstep<DIM, LOGH, false>(tab, park, cur, true, pmask);
+        else
+          tile_insert_lockstep<DIM, LOGH, true>(tab, park, cur, b + lane < n, pmask);
         const int ia = b + TL_STAGES * TL_R + lane;
         cp_async16(ring + slot * TL_R + lane, tr.recs + (ia < CAPT ? ia : lane));
         cp_async_commit();
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(TL_THREADS, DM_TL_MINB) tile_rows_kernel(
         if (!__any_sync(FULL, mine)) continue;
         int4 r = make_int4(0, 0, 0, 0);
         if (mine) r = ovf_e[i];
-        tile_insert_lockstep<DIM, LOGH>(tab, park, r, mine, pmask);
+        tile_insert_lockstep<DIM, LOGH, true>(tab, park, r, mine, pmask);
       }
     }
     __syncwarp();
