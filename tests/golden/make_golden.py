@@ -34,7 +34,7 @@ Everything written here is produced by calling the *unmodified* reference functi
   reference_tests.json  : the reference's known-answer tests (2dmesher_SDF, immersion, smooth_sets,
                           pfix, verbose) replayed, next to the answers they assert  [`reftests`]
 
-`python tests/golden/make_golden.py segy|meshutil|reftests` regenerates only those.
+`python tests/golden/make_golden.py segy|meshutil|reftests|reftests3d` regenerates only those.
 """
 import json
 import os
@@ -494,9 +494,78 @@ def gen_segy():
     print(json.dumps(res, indent=1))
 
 
+def gen_reference_tests_3d():
+    """bin3d_testing.npz / reference_tests_3d.json: the reference's 20x10x10 binary velocity fixture
+    (tests/test3D.bin, float32 little-endian, kept as raw values) and the outcome of the reference tests that
+    mesh it or exercise the 3-D / water-layer paths, replayed with the unmodified reference next to the answers
+    those tests state: tests/test_3dmesher.py, test_3dmesher_domain_extension.py, test_3dmesher_SDF.py,
+    test_2dmesher_vs_water.py."""
+    import contextlib
+    import io
+
+    fname = os.path.join(ref_harness.REF_ROOT, "tests", "test3D.bin")
+    np.savez(os.path.join(HERE, "bin3d_testing.npz"), raw=np.fromfile(fname, dtype="<f4"))
+    res = {}
+    bbox = (-2e3, 0.0, 0.0, 1e3, 0.0, 1e3)
+    cube = sm.Cube(bbox)
+
+    def dh_range(p, c):
+        dh = np.asarray(sm.geometry.calc_dihedral_angles(p, c)).reshape(-1) * 180.0 / np.pi
+        return [float(dh.min()), float(dh.max())]
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        ef = sm.get_sizing_function_from_segy(fname, bbox, grade=0.005, grad=50, freq=2, wl=10, hmin=50, nz=20, nx=10, ny=10,
+                                              byte_order="little", domain_pad=0.0, axes_order=(2, 0, 1))
+        p, c = sm.generate_mesh(domain=cube, edge_length=ef, h0=50, max_iter=25, perform_checks=False)
+        p, c = sm.sliver_removal(points=p, edge_length=ef, domain=cube, h0=50)
+        res["test_3dmesher"] = {"stated_by_reference_test": [16459, 89240], "atol": 100, "reference_run_here": [len(p), len(c)],
+                                "dihedral_range_deg": dh_range(p, c)}
+        ext = {}
+        for style, answer in (("linear_ramp", [1388, 6592]), ("edge", [1383, 6545]), ("constant", [1406, 6622])):
+            ef = sm.get_sizing_function_from_segy(fname, bbox, grade=0.005, grad=150, freq=2, wl=5, hmin=150, nz=20, nx=10, ny=10,
+                                                  byte_order="little", domain_pad=200, pad_style=style, axes_order=(2, 0, 1))
+            p, c = sm.generate_mesh(domain=cube, edge_length=ef, h0=150, perform_checks=False)
+            p, c = sm.sliver_removal(points=p, domain=cube, edge_length=ef, h0=150)
+            ext[style] = {"stated_by_reference_test": answer, "reference_run_here": [len(p), len(c)], "dihedral_range_deg": dh_range(p, c)}
+        res["test_3dmesher_domain_extension"] = {"atol": 100, "styles": ext}
+
+        def cylinder(q):
+            r, z = np.sqrt(q[:, 0] ** 2 + q[:, 1] ** 2), q[:, 2]
+            d1, d2, d3 = r - 1.0, z - 1.0, -z - 1.0
+            d4, d5 = np.sqrt(d1**2 + d2**2), np.sqrt(d1**2 + d3**2)
+            d = np.maximum.reduce([d1, d2, d3])
+            ix = (d1 > 0) * (d2 > 0)
+            d[ix] = d4[ix]
+            ix = (d1 > 0) * (d3 > 0)
+            d[ix] = d5[ix]
+            return d
+
+        cb = (-1.0, 1.0, -1.0, 1.0, -1.0, 1.0)
+        p, c = sm.generate_mesh(bbox=cb, domain=cylinder, h0=0.10, edge_length=lambda q: np.array([0.10] * len(q)), max_iter=100)
+        p, c = sm.sliver_removal(points=p, domain=cylinder, edge_length=lambda q: np.array([0.10] * len(q)), h0=0.10, bbox=cb)
+        res["test_3dmesher_SDF"] = {"asserted": {"volume": 6.28, "atol": 0.10}, "stated_counts": [6825, 36206],
+                                    "reference_run_here": [len(p), len(c), float(np.sum(sm.geometry.simp_vol(p, c)))]}
+        vs = np.zeros((200, 200))
+        vs[0:150, :] = 1000
+        rb = (-10000.0, 0.0, 0.0, 10000.0)
+        ef = sm.get_sizing_function_from_segy(None, bbox=rb, grade=0.0, grad=0.0, wl=5, freq=2.0, hmin=10, hmax=10e6, velocity_data=vs,
+                                              nz=200, nx=200)
+        probes = [float(ef.eval((-5000, 5000))), float(ef.eval((-1, 5000)))]
+        ef.hmin = None
+        p, c = sm.generate_mesh(sm.Rectangle(rb), ef, h0=125, perform_checks=True)
+        res["test_2dmesher_vs_water"] = {"asserted": {"probes": [100, 150], "counts": [5616, 10955], "atol": 100},
+                                         "reference_run_here": {"probes": probes, "counts": [len(p), len(c)]}}
+    with open(os.path.join(HERE, "reference_tests_3d.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     if "reftests" in sys.argv[1:]:
         gen_reference_tests()
+        sys.exit(0)
+    if "reftests3d" in sys.argv[1:]:
+        gen_reference_tests_3d()
         sys.exit(0)
     if "segy" in sys.argv[1:] or "meshutil" in sys.argv[1:]:
         if "segy" in sys.argv[1:]:
@@ -514,4 +583,5 @@ if __name__ == "__main__":
     gen_segy()
     gen_meshutil()
     gen_reference_tests()
+    gen_reference_tests_3d()
     print("golden vectors written to", HERE)
