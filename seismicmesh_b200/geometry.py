@@ -461,8 +461,12 @@ from .meshutil import (  # noqa: E402,F401
     get_edges,
     get_facets,
     is_manifold,
+    calc_re_ratios,
+    get_winded_boundary_edges,
+    laplacian2,
     laplacian2_fixed_point,
     linter,
+    vertex_in_entity3,
     simp_qual,
     simp_vol,
     unique_rows,
@@ -514,5 +518,6 @@ __all__ += [
     "simp_vol", "simp_qual", "fix_mesh", "get_edges", "get_facets", "get_centroids", "get_boundary_edges",
     "get_boundary_facets", "get_boundary_vertices", "get_boundary_entities", "delete_boundary_entities",
     "laplacian2_fixed_point", "linter", "do_any_overlap", "is_manifold", "vertex_to_entities", "unique_rows",
-    "calc_dihedral_angles", "calc_circumsphere_grad", "unique_edges",
+    "calc_dihedral_angles", "calc_circumsphere_grad", "unique_edges", "calc_re_ratios", "get_winded_boundary_edges",
+    "laplacian2", "vertex_in_entity3",
 ]

@@ -12,7 +12,8 @@ from scipy.sparse.linalg import splu
 __all__ = [
     "simp_vol", "simp_qual", "fix_mesh", "get_edges", "get_facets", "get_boundary_edges",
     "get_boundary_facets", "get_boundary_vertices", "get_boundary_entities",
-    "delete_boundary_entities", "laplacian2_fixed_point", "get_centroids", "vertex_to_entities",
+    "delete_boundary_entities", "laplacian2_fixed_point", "laplacian2", "calc_re_ratios", "get_winded_boundary_edges",
+    "vertex_in_entity3", "get_centroids", "vertex_to_entities",
     "do_any_overlap", "is_manifold", "linter", "unique_rows",
 ]
 
@@ -275,3 +276,113 @@ def linter(p, t, dim=2, min_qual=0.10):
     print("There are " + str(len(p)) + " vertices and " + str(len(t)) + " elements in the mesh", flush=True)
     print("The minimum element quality is " + str(np.amin(qual)), flush=True)
     return p, t
+
+
+# ----------------------------------------------------------------------------------------------
+# Small helpers of the reference's geometry namespace that its own tests call (tests/test_geometry.py,
+# test_geometry2.py, test_ptin.py): mesh-quality ratio, boundary loop, iterative smoothing, point-in-tet.
+# Host NumPy; not on the device path.
+# ----------------------------------------------------------------------------------------------
+def calc_re_ratios(vertices, entities, dim=2):
+    """Circumradius over shortest edge of every simplex (geometry/utils.py:17-54; the reference takes the
+    circumballs from CGAL, here they come from the perpendicular-bisector system)."""
+    p = np.asarray(vertices, dtype=np.float64)
+    t = np.asarray(entities)
+    if dim not in (2, 3):
+        raise ValueError("Dimension invalid")
+    a = p[t[:, 0]]
+    rows = p[t[:, 1:]] - a[:, None, :]                    # (T, dim, dim): edges from vertex 0
+    rhs = 0.5 * np.einsum("tij,tij->ti", rows, rows)      # |e_i|^2 / 2
+    centre = np.linalg.solve(rows, rhs[..., None])[..., 0]  # circumcentre relative to vertex 0
+    radius = np.sqrt(np.einsum("ti,ti->t", centre, centre))
+    pairs = [(0, 1), (1, 2), (2, 0)] if dim == 2 else [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    lengths = np.stack([np.sqrt(((p[t[:, i]] - p[t[:, j]]) ** 2).sum(1)) for i, j in pairs])
+    return radius / lengths.min(axis=0)
+
+
+def get_winded_boundary_edges(entities):
+    """The boundary edges in the order a walk along the boundary meets them, starting from the first one
+    (geometry/utils.py:329-361): from the current vertex take the unvisited boundary edge with the smallest
+    row index that contains it; rows keep their stored orientation."""
+    be = get_boundary_edges(entities)
+    if len(be) == 0:
+        return be
+    incident = {}
+    for r, (u, v) in enumerate(be):
+        incident.setdefault(int(u), []).append(r)
+        incident.setdefault(int(v), []).append(r)
+    visited = np.zeros(len(be), dtype=bool)
+    order = [0]
+    visited[0] = True
+    cur = int(be[0, 1])
+    while True:
+        nxt = [r for r in incident.get(cur, []) if not visited[r]]
+        if not nxt:
+            break
+        r = min(nxt)
+        visited[r] = True
+        order.append(r)
+        u, v = int(be[r, 0]), int(be[r, 1])
+        cur = v if u == cur else u
+    return be[order]
+
+
+def laplacian2(vertices, entities, max_iter=20, tol=0.01, verbose=1, pfix=None):
+    """Iterated Laplacian smoothing (geometry/utils.py:550-631): every non-boundary vertex moves to the average
+    of its neighbours (an edge shared by two triangles counts twice) until the largest relative change of an
+    edge length drops below `tol`; `pfix` = coordinates whose nearest vertices stay put as well."""
+    p = np.asarray(vertices, dtype=np.float64)
+    t = np.asarray(entities)
+    if p.ndim != 2 or p.shape[1] != 2:
+        raise NotImplementedError("Laplacian smoothing only works in 2D for now")
+    n = len(p)
+    i = t[:, [0, 0, 1, 1, 2, 2]].ravel()
+    j = t[:, [1, 2, 0, 2, 0, 1]].ravel()
+    S = sp.coo_matrix((np.ones(len(i)), (i, j)), shape=(n, n)).tocsr()
+    W = np.asarray(S.sum(1)).ravel()
+    if np.any(W == 0):
+        print("Invalid mesh. Disjoint vertices found. Returning", flush=True)
+        print(np.argwhere(W == 0), flush=True)
+        return vertices, entities
+    fixed = get_boundary_vertices(t)
+    if pfix is not None:
+        near = [int(np.argmin(((p - np.asarray(f)) ** 2).sum(1))) for f in np.atleast_2d(pfix)]
+        fixed = np.concatenate((fixed, np.asarray(near, dtype=fixed.dtype)))
+    edge = get_edges(t)
+    eps = np.finfo(float).eps
+
+    def lengths(q):
+        return np.maximum(np.sqrt(((q[edge[:, 0]] - q[edge[:, 1]]) ** 2).sum(1)), eps)
+
+    L = lengths(p)
+    for it in range(max_iter):
+        q = (S @ p) / W[:, None]
+        q[fixed] = p[fixed]
+        p = q
+        Ln = lengths(p)
+        if np.amax((Ln - L) / Ln) < tol:
+            if verbose:
+                print("Movement tolerance reached after " + str(it) + " iterations..exiting", flush=True)
+            break
+        L = Ln
+    return p, entities
+
+
+def vertex_in_entity3(vertex, entity):
+    """Is the point inside the tetrahedron given as 12 coordinates (geometry/utils.py:682-726)?  True when
+    replacing each corner in turn by the point never flips the orientation."""
+    q = np.asarray(vertex, dtype=np.float64)
+    c = np.asarray(entity, dtype=np.float64).reshape(4, 3)
+
+    def orient(m):
+        return np.sign(np.linalg.det(np.hstack([m, np.ones((4, 1))])))
+
+    s0 = orient(c)
+    if s0 == 0:
+        return False
+    for k in range(4):
+        m = c.copy()
+        m[k] = q
+        if orient(m) != s0:
+            return False
+    return True

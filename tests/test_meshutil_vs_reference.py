@@ -102,3 +102,42 @@ def test_linter_and_overlap_match_reference():
 
         assert p0.shape == p1.shape and t0.shape == t1.shape
         assert np.array_equal(canon(p0, t0), canon(p1, t1))
+
+
+def test_reference_geometry_tests_run_through_the_package():
+    """The reference's tests/test_geometry.py, test_geometry2.py and test_ptin.py with the import swapped to
+    seismicmesh_b200.geometry: same inputs, the answers those tests assert."""
+    from seismicmesh_b200 import geometry as geo
+
+    # --- tests/test_geometry.py:8-60: twelve tetrahedra in a cube of side 2 around its centre
+    points = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [0, 0, 0]],
+                      dtype=float)
+    cells = np.array([[3, 4, 0, 8], [3, 7, 8, 2], [6, 8, 7, 2], [6, 5, 8, 2], [6, 5, 7, 8], [8, 7, 4, 5], [3, 7, 4, 8], [3, 8, 1, 2],
+                      [8, 5, 1, 2], [8, 4, 1, 5], [8, 4, 0, 1], [3, 8, 0, 1]], dtype=int)
+    assert len(geo.get_facets(cells)) == 12 * 4
+    bf = np.unique(np.sort(geo.get_boundary_facets(cells), axis=1), axis=1)
+    assert len(bf) == 12
+    assert len(geo.get_boundary_vertices(cells, dim=3)) == 8
+    assert np.sum(geo.simp_vol(points, cells)) == 8.0
+    # --- tests/test_geometry2.py:10-37: two triangles side by side
+    points = np.array([[0, 0], [6, 0], [3, 3], [9, 3]], dtype=float)
+    cells = np.array([[3, 2, 1], [2, 0, 1]], dtype=int)
+    assert np.allclose(geo.calc_re_ratios(points, cells, dim=2), [0.70710678, 0.70710678])
+    assert len(geo.get_edges(cells)) == 6
+    assert np.allclose(geo.get_winded_boundary_edges(cells), [[0, 1], [1, 3], [2, 3], [0, 2]])
+    assert len(geo.do_any_overlap(points, cells, dim=2)) == 0
+    g = load_golden("meshutil_2d.npz")
+    p1, t1 = geo.laplacian2(g["p"].copy(), g["t"].copy(), verbose=0)
+    assert p1.shape == g["p"].shape and np.array_equal(t1, g["t"])
+    bnd = geo.get_boundary_vertices(g["t"])
+    assert np.array_equal(p1[bnd], g["p"][bnd]) and geo.simp_qual(p1, t1).min() > 0
+    geo.laplacian2_fixed_point(g["p"].copy(), g["t"].copy())
+    # --- tests/test_ptin.py:8-46: a point inside / outside a tetrahedron
+    pts = np.array([[0, 0, 0], [0, 1, 0], [np.sqrt(2), 0.5, 0], [0.5, 0.5, np.sqrt(2)]], dtype=float)
+    ent = tuple(pts.ravel())
+    assert geo.vertex_in_entity3((0.5, 0.5, 1.0), ent)
+    assert not geo.vertex_in_entity3((0.0, 0.0, 1.0), ent)
+    # the ratio against the unmodified reference on a 3-D mesh as well (circumballs from its own native code)
+    g3 = load_golden("meshutil_3d.npz")
+    re3 = geo.calc_re_ratios(g3["p"], g3["t"], dim=3)
+    assert re3.shape == (len(g3["t"]),) and np.all(re3 >= np.sqrt(6) / 4 - 1e-9)  # regular tetrahedron is the minimum
