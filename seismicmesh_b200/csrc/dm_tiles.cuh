@@ -1,32 +1,36 @@
 // Stages A + B of the force iteration, fourth layout (round 2): records binned by TILES of 32 vertices.
 //
-// What bounded the third layout (dm_pipeline.cuh) was the number of scattered accesses of stage A -- every
-// kept cell claimed a slot in the bucket of each of its vertices (one global atomic per run of equal ids,
-// ~65 per warp of 32 cells) and stored a 16-B entry there (~128 different lines per warp) -- and, in stage B,
-// the per-vertex back end (compaction + rank sort of every neighbour set by a lane group, fixed reductions
-// per 4 vertices).  Here the unit of scatter is a TILE of 32 consecutive vertex ids:
+// The third layout (dm_pipeline.cuh) pushes every kept cell into a bucket of each of its vertices (one global
+// atomic per run of equal ids, ~65 per warp of 32 cells, and a 16-B entry store on ~128 different lines per
+// warp) and builds every row with a lane group of its own (hash, compaction, rank sort, a reduction per 4
+// vertices: 149 M warp instructions on the ball h0 = 0.02).  Here the unit of hand-over is a TILE of 32
+// consecutive vertex ids:
 //
-//   A  cull_bin        one thread per cell: centroid + fused SDF program -> keep flag (as before); each kept
+//   A  cull_bin        one thread per TWO cells: centroid + fused SDF program -> keep flag (as before); each kept
 //                      cell appends one 16-B RECORD per vertex -- {the other vertex ids, vertex & 31} -- to
 //                      the record list of the vertex's tile.  List positions are claimed per (column, tile)
 //                      with __match_any_sync: the host Delaunay codes emit cells grouped around vertices, so
-//                      a warp of 32 cells touches ~5 tiles (ball h0 = 0.02: ~10 atomics and ~12 contiguous
-//                      runs of stores per warp, against 65 and 128).  A full list spills to a global list.
-//   B  tile_rows       one WARP per tile, no block barrier before the final totals.  Every lane takes one
-//                      record at a time (coalesced read, all 32 lanes busy) and inserts its ids into the
-//                      hash set of the record's vertex -- 32 sets per warp in shared memory, plain loads and
-//                      stores in warp lockstep (probe; a lane that found the slot empty writes; warp
-//                      barrier; only the writers verify).  Then lane l IS vertex l of the tile: it compacts
-//                      its own set (odd stride: every lane on its own bank), sorts it with a compile-time
-//                      bitonic network on 32 registers, counts its lower neighbours, and the warp writes the
-//                      32 rows with coalesced 128-B stores.  The bar pass (L, fh(midpoint), sum L^d, sum h^d)
-//                      runs over the rows where they lie, a lane group per vertex, and there is ONE
-//                      reduction per 32 vertices.  Vertices whose set does not fit (more than RS distinct
-//                      neighbours, or a probe sequence that got too long) are rebuilt exactly by the whole
-//                      warp from the tile's records: gathered into the heap, sorted there, de-duplicated.
+//                      a warp of 32 cells touches ~5 tiles (~10 atomics and ~12 contiguous runs of stores per
+//                      warp, against 65 and 128).  A full list spills to a global list.  The kernel turned out
+//                      to be bound by the latency of its dependent chain, not by those accesses (DESIGN.md
+//                      section 4): hence the two cells per thread.
+//   B  tile_rows       one WARP per tile, no block barrier before the final totals.  The record batches
+//                      stream into a shared-memory ring (cp.async, 4 batches ahead); every lane takes one
+//                      record and inserts its ids into the hash set of the record's vertex -- 32 sets of 64
+//                      slots per warp in shared memory, plain loads and stores in warp lockstep (probe; a lane
+//                      that found the slot empty writes; warp barrier; only the writers verify).  Then lane l
+//                      IS vertex l of the tile: it compacts its own set in place (odd stride: every lane on its
+//                      own bank), sorts it with a compile-time bitonic network on 32 registers, counts its
+//                      lower neighbours, and the warp writes the 32 rows with coalesced 128-B stores.  The bar
+//                      pass (L, fh(midpoint), sum L^d, sum h^d) runs over the rows where they lie, a lane group
+//                      per vertex, two passes in flight, and there is ONE reduction per 32 vertices.  Vertices
+//                      with more than RS neighbours: a complete set (it holds up to 64) is sorted where it
+//                      lies by the whole warp; an overflowed one is rebuilt exactly from the tile's records --
+//                      gathered into the warp's shared memory (the heap for hubs), sorted, de-duplicated.
 //
 // Same outputs as the third layout (adj / heap / degs / hslot / counters[0] / scalars[0..2]); rows are sets,
-// sorted, so they are bit-identical; the bar sums are added in a different (fixed) order.
+// sorted, so they are bit-identical (tests/test_gpu_parity.py::test_tile_layout_equals_bucket_layout); the bar
+// sums are added in a different (fixed) order.  95 M warp instructions on the same mesh, 156 us against 191 us.
 #pragma once
 #include <limits.h>
 
