@@ -1,10 +1,12 @@
-// The force-iteration pipeline (stages A-D of include/distmesh_b200.h), third layout.
+// The force-iteration pipeline (stages A-D of include/distmesh_b200.h), third layout ("buckets"; stages A + B
+// also exist in a fourth, "tiles": dm_tiles.cuh, the choice is a plan setting).
 //
-// What bounds these kernels on B200 is not DRAM bytes but the number of distinct 128-B lines the
-// LSU / L2 have to touch: every scattered 4..16-B access (gather, store or atomic) costs about one
-// L1 wavefront (~1.3 cycles per lane per SM, measured), no matter how few bytes it moves.  The
-// layout is therefore chosen to minimise scattered accesses per cell and to make every per-vertex
-// structure one aligned 128-B line (or a few), read / written by a lane group in one wavefront:
+// What bounds these kernels on B200 is not DRAM bytes.  Every scattered 4..16-B access (gather, store or
+// atomic) costs about one L1 wavefront however few bytes it moves, so the layout makes every per-vertex
+// structure one aligned 128-B line (or a few), read / written by a lane group in one wavefront; beyond that,
+// round 2 found stage A bound by the latency of its dependent chain (cell ids -> gathers -> SDF -> claims ->
+// stores), stage B by instruction issue and shared-memory wavefronts, stage D by its gathers and the fp64
+// square roots / divisions:
 //
 //   0  prep              zero the per-iteration counters; 3-D: padded point copy p4 (one 256-bit gather per point)
 //   A  cull_scatter      one thread per cell: centroid + fused SDF program -> keep flag; each kept
@@ -139,9 +141,9 @@ __device__ __forceinline__ int2 others_of<2>(const int (&ids)[4], int j) {
 
 // Lanes that claim a slot of the same vertex in the same step share one atomic when they are
 // consecutive (equal-id runs: host Delaunay codes emit cells grouped around vertices).
-// The kernel sits at the L1 data-pipe bound of its access pattern: about one scattered access (a
-// position gather, a slot claim, an entry store: ~33 M of them on the ball h0=0.02 mesh) per SM per
-// cycle; l1tex__data_pipe_lsu_wavefronts is its top ncu metric.  Measured and rejected: claiming the
+// ~33 M scattered accesses on the ball h0=0.02 mesh (position gathers, slot claims, entry stores);
+// l1tex__data_pipe_lsu_wavefronts is its top ncu metric, but removing most of them (dm_tiles.cuh) did not
+// make stage A faster: the chain of dependent accesses is what it waits for.  Measured and rejected: claiming the
 // slots before the cull decision is known + prefetching the next cell in a grid-stride loop (the
 // longer live ranges spill and cost more than the overlap gains), more resident blocks, 4-byte entries.
 template <int DIM, bool PAD = false>
