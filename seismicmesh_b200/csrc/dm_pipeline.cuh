@@ -1120,6 +1120,12 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
         const int w = j < m ? wq[u] : (int)v;
         double b0, b1, b2, d0, d1, d2;
         load_pt<DIM, PAD>(pg, w, b0, b1, b2);
+        // (a slot past the end of the row is a bar of length 1, its term discarded: sqrt(0) would send the whole
+        //  warp through the square root's special-case subroutine in nearly every chunk)
+        if (j >= m) {
+          b0 = a0 - 1.0;
+          asm("" : "+d"(b0));
+        }
         const double L = bar_length<DIM>(a0, a1, a2, b0, b1, b2, d0, d1, d2);
         double h;
         if (HMODE == 0) {
@@ -1135,7 +1141,15 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
         }
         double Fs = h * k0 * scale - L;  // L0 - L  (mesh_generator.py:700-702)
         if (Fs < 0) Fs = 0;
-        const double qf = Fs / L;
+        // F / L.  A bar longer than L0 carries no force, and a ZERO numerator is the one operand that takes the
+        // fp64 division off its fast path (ncu: four warps in five went through the ~70-instruction subroutine
+        // because one of their lanes had Fs == 0).  0 / L is +0 exactly, so those lanes divide 1 / L instead and
+        // the quotient is replaced by 0: same bits, no subroutine.  (Written with selects on the OPERANDS: a
+        // branch around the division is turned back into "divide, then select" by the compiler.)
+        double qn = Fs > 0.0 ? Fs : 1.0;
+        asm("" : "+d"(qn));  // opaque to the optimiser, or it folds the select back into "Fs / L, then select"
+        const double qq = qn / L;
+        const double qf = Fs > 0.0 ? qq : 0.0;
         c0[u] = qf * d0;
         c1[u] = qf * d1;
         c2[u] = qf * d2;

@@ -47,6 +47,9 @@ namespace dm {
 #ifndef DM_TL_LOGH3
 #define DM_TL_LOGH3 6
 #endif
+#ifndef DM_TL_LOGH2
+#define DM_TL_LOGH2 5
+#endif
 #ifndef DM_TL_MAXSTEPS
 #define DM_TL_MAXSTEPS 64
 #endif
@@ -67,7 +70,7 @@ struct TCfg<3> {
 template <>
 struct TCfg<2> {
   static constexpr int RS = PCfg<2>::RS;
-  static constexpr int LOGH = 5;
+  static constexpr int LOGH = DM_TL_LOGH2;
   static constexpr int CAPT = 10 * TL_R;  // mean 6 triangles per vertex
   static constexpr int G = 4;
 };
