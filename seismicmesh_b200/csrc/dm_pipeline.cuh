@@ -615,8 +615,10 @@ __device__ __noinline__ RowSums select_row(bool punt, int n, int v,
 //      1 the same with gridded fh (h stored per upper slot).
 // Grid = HV_BLOCKS heavy-vertex blocks (they start first and run beside the main blocks; the heavy
 // list is complete when the kernel starts) + one main block per VPB vertices.
+// (gridded fh: one resident block less, so that the interpolation does not spill: -2..-10 % on the EAGE-shaped
+//  workloads; constant h is 5 % faster with the fifth block)
 template <int DIM, int BAR>
-__global__ void __launch_bounds__(AB_THREADS, DM_AB_MINB) adjacency_kernel(
+__global__ void __launch_bounds__(AB_THREADS, BAR == 1 ? DM_AB_MINB - 1 : DM_AB_MINB) adjacency_kernel(
     const int32_t* __restrict__ cnt, const typename PCfg<DIM>::entry_t* __restrict__ bucket,
     const int32_t* __restrict__ ovf_v, const typename PCfg<DIM>::entry_t* __restrict__ ovf_e, int64_t N, int64_t NR,
     int32_t* __restrict__ adj, int32_t* __restrict__ heap, int2* __restrict__ degs, const int32_t* __restrict__ hv,
