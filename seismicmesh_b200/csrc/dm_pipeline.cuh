@@ -1098,8 +1098,10 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     double deps, double h0, int64_t nfix, const uint8_t* __restrict__ fixed, double* __restrict__ Ftot,
     double* partials, int32_t* done, double* scalars, int32_t* __restrict__ esc, int32_t* __restrict__ esc_count) {
   pdl_prologue();
-  __shared__ double sm[32];
-  __shared__ bool s_last;
+  __shared__ double s_wmax[VU_THREADS / 32];
+  __shared__ int s_arrived;
+  if (threadIdx.x == 0) s_arrived = 0;
+  __syncthreads();  // the only block barrier: at the very start, where no warp has to wait
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double f2 = 0.0;
   if (v < N) {
@@ -1112,9 +1114,13 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     const int lo = dg.y, m = dg.x;
     const int32_t* row = R.row(v, m);
     const int64_t base = R.slot_base(v, m);
-    for (int j0 = 0; j0 < m; j0 += 4) {  // rows are 16-B aligned and padded to a multiple of 4 ints
-      const int4 q = *reinterpret_cast<const int4*>(row + j0);
+    // rows are 16-B aligned and padded to a multiple of 4 ints; the next chunk of the row is requested before
+    // this chunk's gathers (the row load is otherwise the head of every chunk's dependent chain)
+    int4 q = make_int4(0, 0, 0, 0);
+    if (m > 0) q = *reinterpret_cast<const int4*>(row);
+    for (int j0 = 0; j0 < m; j0 += 4) {
       const int wq[4] = {q.x, q.y, q.z, q.w};
+      if (j0 + 4 < m) q = *reinterpret_cast<const int4*>(row + j0 + 4);
       double c0[4], c1[4], c2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -1186,23 +1192,34 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     }
     if (out) esc[atomicAdd(esc_count, 1)] = (int32_t)v;
   }
-  const double bm = block_max(f2, sm);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = bm;
-    __threadfence();
-    s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    double mx = 0.0;
-    for (int64_t i = threadIdx.x; i < (int64_t)gridDim.x; i += VU_THREADS) mx = fmax(mx, __ldcg(partials + i));
-    const double r = block_max(mx, sm);
-    if (threadIdx.x == 0) {
-      scalars[3] = r;
-      scalars[4] = delta_t * sqrt(r);  // maxdp, mesh_generator.py:514
-      *done = 0;
+  // max |F|^2 without a block barrier (the warps of a block finish at different times: rows differ in length):
+  // every warp leaves its maximum in shared memory, the warp that arrives last publishes the block's, and the
+  // warp that sees the last block arrive reduces the blocks' maxima (a maximum does not depend on the order).
+  constexpr int NW = VU_THREADS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double wm = warp_max(f2);
+  int last = 0;
+  if (lane == 0) {
+    s_wmax[wid] = wm;
+    __threadfence_block();
+    if (atomicAdd(&s_arrived, 1) == NW - 1) {
+      __threadfence_block();
+      double bm = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) bm = fmax(bm, s_wmax[w]);
+      partials[blockIdx.x] = bm;
+      last = arrive_acq_rel(done) == (int)gridDim.x - 1 ? 1 : 0;
     }
+  }
+  if (!__shfl_sync(FULL, last, 0)) return;
+  __syncwarp();  // lane 0's acquire orders the other lanes' reads as well
+  double mx = 0.0;
+  for (int64_t i = lane; i < (int64_t)gridDim.x; i += 32) mx = fmax(mx, __ldcg(partials + i));
+  mx = warp_max(mx);
+  if (lane == 0) {
+    scalars[3] = mx;
+    scalars[4] = delta_t * sqrt(mx);  // maxdp, mesh_generator.py:514
+    *done = 0;
   }
 }
 
