@@ -137,35 +137,92 @@ __global__ void dihedral_kernel(const double* __restrict__ p, const int32_t* __r
 // mesh_generator.py:734-738) + dihedral bound test of the kept cells (:532-540); flags[c] = 1 for a
 // kept cell with an angle out of bounds.  Cell ids stay those of the UNcompacted list: the order of
 // the flagged cells is the order the reference sees after its order-preserving cull.
-__global__ void sliver_flags_kernel(const double* __restrict__ prog, const double* __restrict__ p,
-                                    const int32_t* __restrict__ t, int64_t T, double geps, double min_dh,
-                                    double max_dh, uint8_t* __restrict__ keep, uint8_t* __restrict__ flags) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= T) return;
-  int v[4];
-  load_cell<3>(t, c, v);
-  double P[4][3];
+// cos of dihedral angle i from the UNNORMALISED edge vectors: with u1, u2, u3 the three edges from one end of
+// the tetrahedron's edge i, cos = ((u2.u3)|u1|^2 - (u1.u2)(u1.u3)) / (|u1 x u2| |u1 x u3|) -- the same quantity
+// dihedral_angle feeds to acos, without its three normalisations (nine divisions, three square roots) and with
+// one reciprocal square root.  Equal to it up to rounding (~1e-15): good for a SCREEN, not for the answer.
+__device__ __forceinline__ double dihedral_cos_screen(const double P[4][3], int i) {
+  const int e[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+  const int i0 = e[i][0], i1 = e[i][1], i2 = e[5 - i][0], i3 = e[5 - i][1];
+  double u1[3], u2[3], u3[3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
-  // centroid p[t].sum(1)/4, vertices added in order (mesh_generator.py:737)
-  double c0 = P[0][0], c1 = P[0][1], c2 = P[0][2];
-#pragma unroll
-  for (int k = 1; k < 4; ++k) {
-    c0 = c0 + P[k][0];
-    c1 = c1 + P[k][1];
-    c2 = c2 + P[k][2];
+  for (int j = 0; j < 3; ++j) {
+    u1[j] = P[i1][j] - P[i0][j];
+    u2[j] = P[i2][j] - P[i0][j];
+    u3[j] = P[i3][j] - P[i0][j];
   }
-  const bool kept = sdf_eval(prog, 3, c0 / 4.0, c1 / 4.0, c2 / 4.0) < -geps;
-  bool bad = false;
-  if (kept) {
+  const double n11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+  const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+  const double d13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
+  const double d23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
+  const double a0 = u1[1] * u2[2] - u1[2] * u2[1], a1 = u1[2] * u2[0] - u1[0] * u2[2], a2 = u1[0] * u2[1] - u1[1] * u2[0];
+  const double b0 = u1[1] * u3[2] - u1[2] * u3[1], b1 = u1[2] * u3[0] - u1[0] * u3[2], b2 = u1[0] * u3[1] - u1[1] * u3[0];
+  const double aa = a0 * a0 + a1 * a1 + a2 * a2, bb = b0 * b0 + b1 * b1 + b2 * b2;
+  return (d23 * n11 - d12 * d13) * rsqrt(aa * bb);
+}
+
+// cos_hi = cos(min_dh), cos_lo = cos(max_dh): an angle whose screened cosine lies inside (cos_lo, cos_hi) by
+// SCREEN_MARGIN is inside (min_dh, max_dh) whatever the last bits of the reference formula and of acos say
+// (near the 10 / 170 degree bounds a cosine margin of 1e-9 is 6e-9 rad, against ~1e-15 of rounding); every other
+// angle -- 3 % of them on the ball -- is computed with the reference's own operation order and compared as the
+// reference compares it, so the flags are the reference's.
+constexpr double SCREEN_MARGIN = 1e-9;
+constexpr int SF_THREADS = 128;
+__global__ void __launch_bounds__(SF_THREADS) sliver_flags_kernel(const double* __restrict__ prog, const double* __restrict__ p,
+                                                                 const int32_t* __restrict__ t, int64_t T, double geps,
+                                                                 double min_dh, double max_dh, double cos_lo, double cos_hi,
+                                                                 uint8_t* __restrict__ keep, uint8_t* __restrict__ flags) {
+  // The angles that need the reference formula are few and scattered over the lanes (a warp would run the whole
+  // formula for one lane's sake), so they are QUEUED per block -- (cell, angle) pairs in shared memory -- and
+  // worked off densely afterwards, one pair per thread.
+  __shared__ unsigned short s_q[6 * SF_THREADS];
+  __shared__ int s_n;
+  __shared__ unsigned char s_bad[SF_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + tid;
+  if (tid == 0) s_n = 0;
+  s_bad[tid] = 0;
+  __syncthreads();
+  bool kept = false;
+  if (c < T) {
+    int v[4];
+    load_cell<3>(t, c, v);
+    double P[4][3];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double a = dihedral_angle(P, i);
-      bad = bad || (a < min_dh) || (a > max_dh);
+    for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], P[k][0], P[k][1], P[k][2]);
+    // centroid p[t].sum(1)/4, vertices added in order (mesh_generator.py:737)
+    double c0 = P[0][0], c1 = P[0][1], c2 = P[0][2];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      c0 = c0 + P[k][0];
+      c1 = c1 + P[k][1];
+      c2 = c2 + P[k][2];
     }
+    kept = sdf_eval(prog, 3, c0 / 4.0, c1 / 4.0, c2 / 4.0) < -geps;
+    if (kept) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double cs = dihedral_cos_screen(P, i);
+        if (!(cs > cos_lo + SCREEN_MARGIN && cs < cos_hi - SCREEN_MARGIN))  // (a NaN is queued as well)
+          s_q[atomicAdd(&s_n, 1)] = (unsigned short)(tid << 3 | i);
+      }
+    }
+    if (keep != nullptr) keep[c] = kept ? 1 : 0;
   }
-  if (keep != nullptr) keep[c] = kept ? 1 : 0;
-  flags[c] = bad ? 1 : 0;
+  __syncthreads();
+  const int nq = s_n;
+  for (int e = tid; e < nq; e += SF_THREADS) {
+    const int cell = s_q[e] >> 3, i = s_q[e] & 7;
+    int v[4];
+    load_cell<3>(t, (int64_t)blockIdx.x * blockDim.x + cell, v);
+    double Q[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) load_pt<3>(p, v[k], Q[k][0], Q[k][1], Q[k][2]);
+    const double a = dihedral_angle(Q, i);  // the reference's operation order
+    if ((a < min_dh) || (a > max_dh)) s_bad[cell] = 1;
+  }
+  __syncthreads();
+  if (c < T) flags[c] = s_bad[tid];
 }
 
 __global__ void circumsphere_grad_kernel(const double* __restrict__ p, const int32_t* __restrict__ t,

@@ -11,6 +11,7 @@
 //   dm_pipeline.cuh  stages A-D of the force iteration
 //   dm_aux.cuh       stand-alone kernels (fd/fh eval, projection, compaction, sliver, halo)
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -404,7 +405,12 @@ int dm_sliver_flags(const double* prog, const double* p, const int32_t* t, int64
   if (!prog || T < 0) return DM_ERR_ARG;
   if (T == 0) return DM_OK;
   if (!p || !t || !flags) return DM_ERR_ARG;
-  sliver_flags_kernel<<<nblk(T, 128), 128, 0, S(stream)>>>(prog, p, t, T, geps, min_dh, max_dh, keep, flags);
+  // the screen's bounds: cos is decreasing on [0, pi]; bounds outside it switch the screen off on that side
+  const double cos_hi = (min_dh > 0.0 && min_dh < 3.14159) ? cos(min_dh) : 2.0;
+  const double cos_lo = (max_dh > 0.0 && max_dh < 3.14159) ? cos(max_dh) : -2.0;
+  const bool screen = min_dh < max_dh && cos_lo < cos_hi;
+  sliver_flags_kernel<<<nblk(T, SF_THREADS), SF_THREADS, 0, S(stream)>>>(prog, p, t, T, geps, min_dh, max_dh, screen ? cos_lo : 2.0,
+                                                           screen ? cos_hi : -2.0, keep, flags);
   DM_LAUNCH_CHECK();
   return DM_OK;
 }

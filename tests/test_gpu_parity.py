@@ -375,6 +375,41 @@ def test_sliver_flags_fused_pass(sm):
     assert len(orc.sliver_cells(pts, cells, lo, hi)) == 0
 
 
+@pytest.mark.parametrize("lo_deg,hi_deg", [(10.0, 170.0), (10.0, 180.0), (25.0, 140.0), (0.0, 180.0)])
+def test_sliver_flags_screen_equals_exact_angles(sm, lo_deg, hi_deg):
+    """dm_sliver_flags screens every dihedral angle with a cheap cosine and computes the reference formula only
+    near the bounds: its flags must equal those taken from the exactly computed angles (dm_dihedral), on a mesh
+    with many poor cells, with one-sided and two-sided bounds, and with angles pushed right onto a bound."""
+    from seismicmesh_b200 import device as D
+    from seismicmesh_b200._lib import check, lib
+    from seismicmesh_b200.geometry import lower
+
+    rng = np.random.default_rng(9)
+    dom = sm.Cube((-2.0, 2.0, -2.0, 2.0, -2.0, 2.0))  # everything kept: the cull is not what is tested here
+    p = rng.uniform(-1.0, 1.0, (20000, 3))
+    from scipy.spatial import Delaunay
+    t = Delaunay(p).simplices.astype(np.int32)
+    lo, hi = lo_deg * np.pi / 180, hi_deg * np.pi / 180
+    pd, td = dev(p, torch.float64), dev(t, torch.int32)
+    T = len(t)
+    ang = torch.empty(6 * T, dtype=torch.float64, device="cuda")
+    f_exact = torch.empty(T, dtype=torch.uint8, device="cuda")
+    check(lib.dm_dihedral(D.ptr(pd), D.ptr(td), T, lo, hi, D.ptr(ang), D.ptr(f_exact), D.stream_ptr()), "dihedral")
+    a = ang.cpu().numpy().reshape(T, 6)
+    want = ((a < lo) | (a > hi)).any(axis=1)
+    assert np.array_equal(f_exact.cpu().numpy().astype(bool), want)
+    prog = lower(dom)
+    flags = torch.empty(T, dtype=torch.uint8, device="cuda")
+    check(lib.dm_sliver_flags(D.ptr(prog), D.ptr(pd), D.ptr(td), T, 1e-3, lo, hi, None, D.ptr(flags), D.stream_ptr()), "sliver_flags")
+    got = flags.cpu().numpy().astype(bool)
+    assert np.array_equal(got, want) and 0 < want.sum() < T or (lo_deg == 0.0 and not want.any() and not got.any())
+    # bounds set to angles that occur in the mesh: the cells whose angle IS the bound are decided by the exact path
+    for b in np.sort(a.ravel())[[T // 7, 3 * T, 5 * T]]:
+        for lo2, hi2 in ((float(b), np.pi), (0.0, float(b))):
+            check(lib.dm_sliver_flags(D.ptr(prog), D.ptr(pd), D.ptr(td), T, 1e-3, lo2, hi2, None, D.ptr(flags), D.stream_ptr()), "sliver_flags")
+            assert np.array_equal(flags.cpu().numpy().astype(bool), ((a < lo2) | (a > hi2)).any(axis=1))
+
+
 def test_cells_lead_interior_kernel(sm):
     """dm_cells_lead_interior (the column order the sliver loop sees) against its NumPy restatement:
     same cells, bit for bit, on cells with 0..4 interior vertices; even permutation (same orientation)."""
