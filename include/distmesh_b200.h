@@ -366,6 +366,12 @@ int dm_size_from_velocity(const double *vp, const double *h_gr, int64_t n, int d
                           double hmin, double hmax, double dt, double cr_max, double space_order,
                           double *out, void *stream);
 
+/* Sizing preprocessing: a[i] < thresh -> value in place (do_replace != 0) and *count_dev += the number of such
+ * entries (one zeroed uint64 of device memory): the water layer of a shear-velocity model
+ * (sizing/mesh_size_function.py:148-159: vp[vp < 1e-3] = vp_water), without a pass over the model on the host. */
+int dm_replace_below(double *a, int64_t n, double thresh, double value, int do_replace,
+                     unsigned long long *count_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Sizing preprocessing, the `grad=` option: windowed variance of the velocity model (replaces the two
  * scipy.ndimage.uniform_filter calls and the NumPy expressions of sizing/mesh_size_function.py:428-448).

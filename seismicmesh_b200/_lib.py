@@ -95,6 +95,7 @@ _SIGNATURES = {
     "dm_pad": (_INT, [_P, _P, _INT, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _INT, _D, _D, _P, _P]),
     "dm_uniform_filter": (_INT, [_P, _P, _P, _I64, _I64, _I64, C.POINTER(C.c_int), _INT, _INT, _P]),
     "dm_variance_size": (_INT, [_P, _P, _I64, _INT, _D, _D, _D, _P, _P]),
+    "dm_replace_below": (_INT, [_P, _I64, _D, _D, _INT, _P, _P]),
     "dm_laplacian_work_bytes": (_SZ, [_I64]),
     "dm_laplacian_smooth": (_INT, [C.POINTER(DmPlan), _P, _I64, _P, _P, _SZ, _D, _INT, C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
     "dm_stage_prep": (_INT, [C.POINTER(DmPlan), _P, _P]),

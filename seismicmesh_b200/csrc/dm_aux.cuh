@@ -713,4 +713,15 @@ __global__ void variance_size_kernel(const double* __restrict__ mean, const doub
   }
 }
 
+// vp[i] < thresh -> value, in place; *count += how many (the water layer of a shear-velocity model,
+// sizing/mesh_size_function.py:148-159)
+__global__ void replace_below_kernel(double* __restrict__ a, int64_t n, double thresh, double value, int do_replace,
+                                     unsigned long long* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hit = i < n && a[i] < thresh;
+  if (hit && do_replace) a[i] = value;
+  const unsigned m = __ballot_sync(FULL, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 }  // namespace dm

@@ -865,6 +865,16 @@ int dm_variance_size(const double* mean, const double* sqr_mean, int64_t n, int 
   return DM_OK;
 }
 
+int dm_replace_below(double* a, int64_t n, double thresh, double value, int do_replace, unsigned long long* count_dev,
+                     void* stream) {
+  if (n < 0 || !count_dev) return DM_ERR_ARG;
+  if (n == 0) return DM_OK;
+  if (!a) return DM_ERR_ARG;
+  replace_below_kernel<<<nblk(n, 256), 256, 0, S(stream)>>>(a, n, thresh, value, do_replace, count_dev);
+  DM_LAUNCH_CHECK();
+  return DM_OK;
+}
+
 int dm_limgrad(double* f, double* tmp, int64_t n0, int64_t n1, int64_t n2, double delta, double ftol, int max_sweeps,
                int32_t* changed_dev, int* sweeps_host, void* stream) {
   if (!f || !tmp || f == tmp || !changed_dev || n0 < 1 || n1 < 1 || n2 < 1 || max_sweeps < 0 || !(delta >= 0.0)) return DM_ERR_ARG;

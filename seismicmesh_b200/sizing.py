@@ -302,6 +302,7 @@ def _gradient_sizing(vp, vp_dev, grad, stencil):
     if any(w < 1 or w > n for w, n in zip(window, vp.shape)):  # windows longer than the grid: SciPy on the host
         from scipy import ndimage
 
+        vp = vp_dev.cpu().numpy()  # (with the water layer filled in)
         win_mean = ndimage.uniform_filter(vp, tuple(window))
         win_var = ndimage.uniform_filter(vp**2, tuple(window)) - win_mean**2
         win_var = np.divide(win_var, np.amax(win_var))
@@ -340,11 +341,6 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
         vp *= 1000.0
     elif opts["units"] == "ft-s":
         vp *= 0.30
-    pos = np.where(vp < 1e-3)  # water positions in shear-velocity data (:148-159)
-    if len(pos) > 0 and any(pos[0]):
-        if opts["vp_water"] is None or opts["vp_water"] < 1300 or opts["vp_water"] > 1800:
-            raise ValueError("vp_water is None or out of bounds. It should be >1300 and <1800 m/s")
-        vp[pos] = opts["vp_water"]
     if len(bbox) not in (4, 6):
         raise ValueError("Dimension not supported")
     dim = len(bbox) // 2
@@ -378,6 +374,14 @@ def get_sizing_function_from_segy(filename, bbox, comm=None, **kwargs):
     D.require_cuda()
     vp = np.ascontiguousarray(vp, dtype=np.float64)
     vp_dev = torch.from_numpy(vp).to(D.device())
+    # water positions in shear-velocity data (:148-159: vp[vp < 1e-3] = vp_water), counted and replaced on the device
+    cnt = torch.zeros(1, dtype=torch.int64, device=vp_dev.device)
+    water = opts["vp_water"]
+    ok = water is not None and 1300 <= water <= 1800
+    check(lib.dm_replace_below(D.ptr(vp_dev), vp_dev.numel(), 1e-3, float(water) if ok else 0.0, 1 if ok else 0, D.ptr(cnt),
+                               D.stream_ptr()), "dm_replace_below")
+    if int(cnt.item()) > 0 and not ok:
+        raise ValueError("vp_water is None or out of bounds. It should be >1300 and <1800 m/s")
     gr_dev = _gradient_sizing(vp, vp_dev, opts["grad"], opts["stencil_size"]) if want_grad else None
     cs_dev = torch.empty_like(vp_dev)
     check(lib.dm_size_from_velocity(D.ptr(vp_dev), D.ptr(gr_dev), vp_dev.numel(), dim, float(opts["freq"]), float(opts["wl"]),
