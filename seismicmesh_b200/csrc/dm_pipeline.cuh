@@ -260,28 +260,33 @@ __device__ __forceinline__ void hash_insert_lockstep(int32_t* tab, int (&x)[NC],
   unsigned h[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) h[c] = hash_slot<LOGH>(x[c]);
+  // A step (round 2, as in dm_tiles.cuh): every unfinished key reads its slot ONCE; whoever finds its own key is
+  // done, whoever finds the slot empty writes its key; after the warp barrier only the writers look again (they
+  // either won the slot or lost it -- to an equal key: done, to another: next slot).  No second barrier: a slot
+  // that is being verified was written before the barrier, so it is not EMPTY any more and nobody writes it in
+  // the next step.
   int steps = 0;
   bool any;
   do {
+    int v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = tab[h[c]];
 #pragma unroll
     for (int c = 0; c < NC; ++c)
-      if (tab[h[c]] == HASH_EMPTY) tab[h[c]] = x[c];
+      if (v[c] == HASH_EMPTY) tab[h[c]] = x[c];
     __syncwarp();
     any = false;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const bool hit = tab[h[c]] == x[c];
+      bool hit = v[c] == x[c];
+      if (v[c] == HASH_EMPTY) hit = tab[h[c]] == x[c];
       const unsigned nxt = (h[c] + 1u) & HM;
       any = any | !hit;
       h[c] = hit ? park : nxt;
       x[c] = hit ? HASH_PARKED : x[c];
     }
-    __syncwarp();
-    if (++steps > HASH_MAXSTEPS) {  // table (nearly) full: give up, the heavy path takes the vertex
-      punt = punt | any;
-      any = false;
-    }
-  } while (__any_sync(FULL, any));
+  } while (__any_sync(FULL, any) && ++steps <= HASH_MAXSTEPS);
+  punt = punt | any;  // (only possible when the step limit ended the loop) table (nearly) full: the heavy path takes the vertex
 }
 
 // L^d and h^d of the bar (a, p[w]); GRID: h is interpolated at the midpoint and stored at `hout`.
