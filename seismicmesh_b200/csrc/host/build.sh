@@ -4,6 +4,6 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../../libdistmesh_host.so"
-"${CXX:-g++}" -O2 -std=c++17 -ffp-contract=off -fPIC -shared -Wall -I"$HERE/../../../include" \
+"${CXX:-g++}" -O2 -std=c++17 -ffp-contract=off -fPIC -shared -pthread -Wall -I"$HERE/../../../include" \
   "$HERE/dm_delaunay2d.cpp" "$HERE/dm_delaunay3d.cpp" -o "$OUT"
 echo "built $OUT"

@@ -18,49 +18,106 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <memory>
+#include <thread>
 #include <vector>
 
 namespace dmx {
 
-template <int K>
-inline void order_cells(int32_t* cells, int64_t T, int64_t N) {
-  if (T <= 0 || T > (int64_t)INT32_MAX) return;  // (beyond int32 cell ids the list stays in creation order: still valid input)
-  struct Key {
-    int32_t s[K];   // the ids in ascending order (the sort key)
-    int32_t src;    // where the cell came from
-  };
-  std::vector<Key> keys((size_t)T);
-  // counting sort by the smallest id ...
-  std::vector<int64_t> start(N + 1, 0);
-  for (int64_t c = 0; c < T; ++c) {
-    int32_t m = cells[K * c];
-    for (int k = 1; k < K; ++k) m = std::min(m, cells[K * c + k]);
-    ++start[m + 1];
+template <class F>
+inline void order_threads(int nth, F&& fn) {
+  if (nth <= 1) {
+    fn(0);
+    return;
   }
-  for (int64_t v = 0; v < N; ++v) start[v + 1] += start[v];
+  std::vector<std::thread> th;
+  th.reserve(nth - 1);
+  for (int j = 1; j < nth; ++j) th.emplace_back([&fn, j] { fn(j); });
+  fn(0);
+  for (auto& t : th) t.join();
+}
+
+// Two cache-friendly passes instead of one random scatter over the whole list: the cells are first
+// streamed into a few hundred buckets of consecutive smallest ids (every thread with its own write
+// cursors), then every bucket -- small enough for the cache -- is filed by smallest id, its groups
+// sorted and written out.  The result does not depend on the number of threads.
+template <int K>
+inline void order_cells(int32_t* cells, int64_t T, int64_t N, int nth = 1) {
+  if (T <= 0 || T > (int64_t)INT32_MAX) return;  // (beyond int32 cell ids the list stays in creation order: still valid input)
+  if (T < 100000) nth = 1;
+  struct Key {
+    int32_t s[K];  // the ids in ascending order (the sort key)
+    int32_t v[K];  // the cell as it came
+  };
+  int shift = 0;
+  while ((N >> shift) > 1024) ++shift;
+  const int64_t B = (N >> shift) + 1;  // buckets
+  std::unique_ptr<Key[]> k1(new Key[(size_t)T]), k2(new Key[(size_t)T]);  // (plain arrays: not worth initialising twice)
+  std::vector<int64_t> start(N + 1, 0);                  // cells per smallest id, then the first slot of its group
+  std::vector<int64_t> cursor((size_t)(nth * B), 0);     // cells per (thread, bucket), then the thread's write position
+  order_threads(nth, [&](int j) {
+    int64_t* mine = cursor.data() + (size_t)j * B;
+    for (int64_t c = T * j / nth; c < T * (j + 1) / nth; ++c) {
+      int32_t m = cells[K * c];
+      for (int k = 1; k < K; ++k) m = std::min(m, cells[K * c + k]);
+      ++mine[m >> shift];
+      if (nth > 1)
+        __atomic_fetch_add(&start[m], (int64_t)1, __ATOMIC_RELAXED);
+      else
+        ++start[m];
+    }
+  });
   {
-    std::vector<int64_t> pos(start.begin(), start.end() - 1);
-    for (int64_t c = 0; c < T; ++c) {
-      Key key;
-      for (int k = 0; k < K; ++k) key.s[k] = cells[K * c + k];
-      std::sort(key.s, key.s + K);
-      key.src = (int32_t)c;
-      keys[(size_t)pos[key.s[0]]++] = key;
+    int64_t at = 0;
+    for (int64_t v = 0; v <= N; ++v) {
+      const int64_t k = start[v];
+      start[v] = at;
+      at += k;
+    }
+    for (int64_t b = 0; b < B; ++b) {
+      int64_t pos = start[std::min<int64_t>(N, b << shift)];
+      for (int j = 0; j < nth; ++j) {
+        const int64_t k = cursor[(size_t)j * B + b];
+        cursor[(size_t)j * B + b] = pos;
+        pos += k;
+      }
     }
   }
-  // ... then a small sort inside every group
-  for (int64_t v = 0; v < N; ++v)
-    if (start[v + 1] - start[v] > 1)
-      std::sort(keys.begin() + start[v], keys.begin() + start[v + 1], [](const Key& a, const Key& b) {
-        for (int k = 1; k < K; ++k)
-          if (a.s[k] != b.s[k]) return a.s[k] < b.s[k];
-        return a.src < b.src;
-      });
-  std::vector<int32_t> tmp(cells, cells + (size_t)(K * T));
-  for (int64_t c = 0; c < T; ++c) {
-    const int32_t* from = tmp.data() + (size_t)K * keys[(size_t)c].src;
-    for (int k = 0; k < K; ++k) cells[K * c + k] = from[k];
+  order_threads(nth, [&](int j) {
+    int64_t* mine = cursor.data() + (size_t)j * B;
+    for (int64_t c = T * j / nth; c < T * (j + 1) / nth; ++c) {
+      Key key;
+      for (int k = 0; k < K; ++k) key.s[k] = key.v[k] = cells[K * c + k];
+      std::sort(key.s, key.s + K);
+      k1[(size_t)mine[key.s[0] >> shift]++] = key;
+    }
+  });
+  // buckets of about the same number of cells per thread
+  std::vector<int64_t> bcut(nth + 1, B);
+  bcut[0] = 0;
+  {
+    int j = 1;
+    for (int64_t b = 0; b < B && j < nth; ++b)
+      while (j < nth && start[std::min<int64_t>(N, b << shift)] >= T * j / nth) bcut[j++] = b;
   }
+  order_threads(nth, [&](int j) {
+    std::vector<int64_t> pos;
+    for (int64_t b = bcut[j]; b < bcut[j + 1]; ++b) {
+      const int64_t v0 = std::min<int64_t>(N, b << shift), v1 = std::min<int64_t>(N, (b + 1) << shift);
+      pos.assign(start.begin() + v0, start.begin() + v1);
+      for (int64_t c = start[v0]; c < start[v1]; ++c) k2[(size_t)pos[k1[(size_t)c].s[0] - v0]++] = k1[(size_t)c];
+      // ... then a small sort inside every group
+      for (int64_t v = v0; v < v1; ++v)
+        if (start[v + 1] - start[v] > 1)
+          std::sort(k2.get() + start[v], k2.get() + start[v + 1], [](const Key& a, const Key& b) {
+            for (int k = 1; k < K; ++k)
+              if (a.s[k] != b.s[k]) return a.s[k] < b.s[k];
+            return false;
+          });
+      for (int64_t c = start[v0]; c < start[v1]; ++c)
+        for (int k = 0; k < K; ++k) cells[K * c + k] = k2[(size_t)c].v[k];
+    }
+  });
 }
 
 }  // namespace dmx

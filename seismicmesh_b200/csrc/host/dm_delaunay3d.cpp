@@ -20,10 +20,18 @@
 // nevertheless checked (every new finite tetrahedron positively oriented) and a violation is
 // reported as `lost`, never papered over.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
+#include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include "distmesh_host.h"
 #include "dm_cell_order.h"
@@ -221,42 +229,95 @@ inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
 }
 
 constexpr int32_t INF = -1;
+constexpr int MAX_THREADS = 32;      // stamps of thread j are j + 1 + k * MAX_THREADS: unique over the whole run
+constexpr int64_t CHUNK = 512;       // tetrahedron slots a thread claims at a time
+constexpr int64_t PAR_MIN_ROUND = 8000;   // rounds smaller than this are inserted by one thread
+constexpr int64_t PAR_MIN_PER_THREAD = 1500;
+constexpr int PAR_PASSES = 5;
 
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline bool trace_on() {
+  static const bool on = std::getenv("DM_HOST_TRACE") != nullptr;
+  return on;
+}
+
+template <class F>
+void run_threads(int nth, F&& fn) {
+  if (nth <= 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nth - 1);
+  for (int j = 1; j < nth; ++j) th.emplace_back([&fn, j] { fn(j); });
+  fn(0);
+  for (auto& t : th) t.join();
+}
+
+struct Facet {
+  int32_t t, k, nb;
+};
+struct Slot {
+  uint64_t key;
+  int32_t t, j, tag;
+};
+
+// what one inserting thread owns
+struct Ctx {
+  std::vector<int32_t> freelist, stack, cav, newt, deferred;
+  std::vector<Facet> bnd;
+  std::vector<Slot> table;
+  int32_t stamp = 0, stamp_next = 1, last = -1;
+  int64_t dups = 0, lost = 0;
+  bool failed = false, exhausted = false;
+  int me = 0;
+};
+
+// The triangulation.  Serial phases may grow the arrays; during a parallel phase their size is fixed
+// and every thread touches only tetrahedra whose finite vertices all belong to its own partition
+// (see insert<true>), so no two threads ever read or write the same tetrahedron.
 struct Delaunay3 {
   const double* P = nullptr;  // coordinates in insertion order
   int64_t n = 0;
   std::vector<int32_t> tv, tn;  // 4 vertices / 4 neighbours (opposite the vertex of the same slot) per tetrahedron
-  std::vector<int32_t> mark;    // +stamp: in the current cavity, -stamp: tested and not in conflict
-  std::vector<uint8_t> dead;
-  std::vector<int32_t> freelist, stack, cav, newt;
-  struct Facet {
-    int32_t t, k, nb;
-  };
-  std::vector<Facet> bnd;
-  struct Slot {
-    uint64_t key;
-    int32_t t, j, tag;
-  };
-  std::vector<Slot> table;
-  int32_t stamp = 0, last = 0;
-  int64_t dups = 0, lost = 0;
-  bool failed = false;
+  std::vector<int32_t> mark;    // +stamp: in the cavity of that insertion, -stamp: tested and not in conflict
+  std::vector<uint8_t> dead;    // 1: slot unused
+  std::vector<uint8_t> owner;   // partition of every vertex during a parallel phase
+  std::atomic<int64_t> top{0};  // slots handed out so far
+  bool parallel = false;
 
   const double* pt(int32_t v) const { return P + 3 * (int64_t)v; }
-  int64_t ntets() const { return (int64_t)dead.size(); }
+  int64_t slots() const { return top.load(std::memory_order_relaxed); }
 
-  int32_t new_tet() {
-    int32_t t;
-    if (!freelist.empty()) {
-      t = freelist.back();
-      freelist.pop_back();
-    } else {
-      t = (int32_t)dead.size();
-      tv.resize(tv.size() + 4);
-      tn.resize(tn.size() + 4);
-      mark.push_back(0);
-      dead.push_back(0);
+  void grow(int64_t want) {
+    if ((int64_t)dead.size() >= want) return;
+    const int64_t sz = std::max<int64_t>(want, (int64_t)dead.size() * 3 / 2);
+    tv.resize(4 * sz);
+    tn.resize(4 * sz);
+    mark.resize(sz, 0);
+    dead.resize(sz, 1);
+  }
+  // make sure the thread has `need` free slots; false: the arrays are full and may not grow now
+  bool reserve_slots(Ctx& c, int64_t need) {
+    while ((int64_t)c.freelist.size() < need) {
+      const int64_t k = std::max<int64_t>(CHUNK, need - (int64_t)c.freelist.size());
+      const int64_t at = top.fetch_add(k, std::memory_order_relaxed);
+      if (at + k > (int64_t)dead.size()) {
+        if (parallel) {
+          top.fetch_sub(k, std::memory_order_relaxed);
+          return false;
+        }
+        grow(at + k);
+      }
+      for (int64_t t = at + k - 1; t >= at; --t) c.freelist.push_back((int32_t)t);  // lowest slot on top
     }
+    return true;
+  }
+  int32_t new_tet(Ctx& c) {  // after reserve_slots
+    const int32_t t = c.freelist.back();
+    c.freelist.pop_back();
     dead[t] = 0;
     mark[t] = 0;
     return t;
@@ -264,6 +325,14 @@ struct Delaunay3 {
   int inf_slot(int32_t t) const {
     const int32_t* v = &tv[4 * (int64_t)t];
     return v[0] == INF ? 0 : v[1] == INF ? 1 : v[2] == INF ? 2 : v[3] == INF ? 3 : -1;
+  }
+  // every finite vertex of t in partition `me` (the vertex at infinity belongs to everybody: two
+  // tetrahedra of different partitions never share a facet, which has at least two finite vertices)
+  bool own(int32_t t, int me) const {
+    const int32_t* v = &tv[4 * (int64_t)t];
+    for (int k = 0; k < 4; ++k)
+      if (v[k] != INF && owner[v[k]] != me) return false;
+    return true;
   }
   // orientation of tetrahedron t with the vertex of slot k replaced by the point p
   double orient_with(int32_t t, int k, const double* p) const {
@@ -285,16 +354,17 @@ struct Delaunay3 {
 
   // neighbours of the first five tetrahedra by matching faces
   void link_all() {
-    const int64_t m = ntets();
+    const int64_t m = slots();
     for (int64_t t = 0; t < m; ++t)
       for (int k = 0; k < 4; ++k) {
+        if (dead[t]) continue;
         int32_t f[3];
         int c = 0;
         for (int j = 0; j < 4; ++j)
           if (j != k) f[c++] = tv[4 * t + j];
         std::sort(f, f + 3);
         for (int64_t u = 0; u < m; ++u) {
-          if (u == t) continue;
+          if (u == t || dead[u]) continue;
           for (int kk = 0; kk < 4; ++kk) {
             int32_t g[3];
             int d = 0;
@@ -307,13 +377,14 @@ struct Delaunay3 {
       }
   }
 
-  bool init(int32_t a, int32_t b, int32_t c, int32_t d) {
+  void init(Ctx& cx, int32_t a, int32_t b, int32_t c, int32_t d) {
     if (orient3d(pt(a), pt(b), pt(c), pt(d)) < 0.0) std::swap(a, b);
-    const int32_t t0 = new_tet();
+    reserve_slots(cx, 5);
+    const int32_t t0 = new_tet(cx);
     int32_t* v = &tv[4 * (int64_t)t0];
     v[0] = a, v[1] = b, v[2] = c, v[3] = d;
     for (int k = 0; k < 4; ++k) {  // ghost behind face k: the vertex at infinity in slot k, orientation flipped
-      const int32_t g = new_tet();
+      const int32_t g = new_tet(cx);
       int32_t* w = &tv[4 * (int64_t)g];
       const int32_t* s = &tv[4 * (int64_t)t0];
       for (int j = 0; j < 4; ++j) w[j] = s[j];
@@ -322,19 +393,18 @@ struct Delaunay3 {
       std::swap(w[x], w[y]);
     }
     link_all();
-    last = t0;
-    return true;
+    cx.last = t0;
   }
 
-  void match_face(int32_t t, int j, int32_t u, int32_t w) {
+  void match_face(Ctx& c, int32_t t, int j, int32_t u, int32_t w) {
     if (u > w) std::swap(u, w);
     const uint64_t key = (uint64_t)(u + 1) * (uint64_t)(n + 2) + (uint64_t)(w + 1);
-    const size_t mask = table.size() - 1;
+    const size_t mask = c.table.size() - 1;
     size_t h = (size_t)(key * 0x9E3779B97F4A7C15ULL >> 20) & mask;
     for (;;) {
-      Slot& s = table[h];
-      if (s.tag != stamp) {
-        s = Slot{key, t, j, stamp};
+      Slot& s = c.table[h];
+      if (s.tag != c.stamp) {
+        s = Slot{key, t, j, c.stamp};
         return;
       }
       if (s.key == key) {
@@ -346,42 +416,49 @@ struct Delaunay3 {
     }
   }
 
-  void insert(int32_t i) {
+  // Insert row i.  PAR: the thread may only look at tetrahedra of its own partition; as soon as the
+  // walk, the cavity or the ring of tetrahedra around the cavity reaches one that is not, the point is
+  // given back (false) before anything has been modified.
+  template <bool PAR>
+  bool insert(Ctx& c, int32_t i) {
     const double* p = pt(i);
     // ---- locate: walk from the tetrahedron created last
-    int32_t t = last;
-    const int64_t limit = 4 * ntets() + 64;
+    int32_t t = c.last;
+    if (PAR && (t < 0 || !own(t, c.me))) return false;
+    const int64_t limit = PAR ? 4096 : 4 * slots() + 64;
     bool found = false;
     for (int64_t steps = 0; steps < limit; ++steps) {
+      int32_t nxt = -1;
       const int ki = inf_slot(t);
       if (ki >= 0) {
         if (conflict(t, p)) {
           found = true;
           break;
         }
-        t = tn[4 * (int64_t)t + ki];
-        continue;
-      }
-      bool moved = false;
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = (kk + (int)(steps & 3)) & 3;
-        if (orient_with(t, k, p) < 0.0) {
-          t = tn[4 * (int64_t)t + k];
-          moved = true;
+        nxt = tn[4 * (int64_t)t + ki];
+      } else {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = (kk + (int)(steps & 3)) & 3;
+          if (orient_with(t, k, p) < 0.0) {
+            nxt = tn[4 * (int64_t)t + k];
+            if (!PAR || own(nxt, c.me)) break;  // (any face that separates t from p will do)
+          }
+        }
+        if (nxt < 0) {
+          found = true;
           break;
         }
       }
-      if (!moved) {
-        found = true;
-        break;
-      }
+      if (PAR && !own(nxt, c.me)) return false;
+      t = nxt;
     }
     if (!found) {  // the walk did not settle: exhaustive search
-      for (int64_t u = 0; u < ntets() && !found; ++u)
+      if (PAR) return false;
+      for (int64_t u = 0; u < slots() && !found; ++u)
         if (!dead[u] && conflict((int32_t)u, p)) t = (int32_t)u, found = true;
       if (!found) {
-        ++lost;
-        return;
+        ++c.lost;
+        return true;
       }
     }
     if (inf_slot(t) < 0) {
@@ -389,48 +466,55 @@ struct Delaunay3 {
       for (int k = 0; k < 4; ++k) {
         const double* q = pt(v[k]);
         if (q[0] == p[0] && q[1] == p[1] && q[2] == p[2]) {  // exact duplicate of an earlier row
-          ++dups;
-          return;
+          ++c.dups;
+          return true;
         }
       }
       if (!conflict(t, p)) {
-        ++lost;
-        return;
+        ++c.lost;
+        return true;
       }
     }
     // ---- cavity: flood fill over the tetrahedra in conflict
-    ++stamp;
-    cav.clear();
-    bnd.clear();
-    stack.clear();
-    stack.push_back(t);
+    c.stamp = c.stamp_next;
+    c.stamp_next += MAX_THREADS;
+    const int32_t stamp = c.stamp;
+    c.cav.clear();
+    c.bnd.clear();
+    c.stack.clear();
+    c.stack.push_back(t);
     mark[t] = stamp;
-    while (!stack.empty()) {
-      const int32_t c = stack.back();
-      stack.pop_back();
-      cav.push_back(c);
+    while (!c.stack.empty()) {
+      const int32_t cc = c.stack.back();
+      c.stack.pop_back();
+      c.cav.push_back(cc);
       for (int k = 0; k < 4; ++k) {
-        const int32_t nb = tn[4 * (int64_t)c + k];
+        const int32_t nb = tn[4 * (int64_t)cc + k];
         if (mark[nb] == stamp) continue;
         if (mark[nb] != -stamp) {
+          if (PAR && !own(nb, c.me)) return false;
           if (conflict(nb, p)) {
             mark[nb] = stamp;
-            stack.push_back(nb);
+            c.stack.push_back(nb);
             continue;
           }
           mark[nb] = -stamp;
         }
-        bnd.push_back(Facet{c, k, nb});
+        c.bnd.push_back(Facet{cc, k, nb});
       }
     }
     // ---- the fan: one new tetrahedron per boundary facet
+    if (!reserve_slots(c, (int64_t)c.bnd.size())) {
+      c.exhausted = true;
+      return false;
+    }
     size_t want = 64;
-    while (want < 8 * bnd.size()) want <<= 1;
-    if (table.size() < want) table.assign(want, Slot{0, 0, 0, 0});
+    while (want < 8 * c.bnd.size()) want <<= 1;
+    if (c.table.size() < want) c.table.assign(want, Slot{0, 0, 0, 0});
     int32_t fin = -1;
-    newt.clear();
-    for (const Facet& f : bnd) {
-      const int32_t nt = new_tet();
+    c.newt.clear();
+    for (const Facet& f : c.bnd) {
+      const int32_t nt = new_tet(c);
       int32_t* w = &tv[4 * (int64_t)nt];
       const int32_t* s = &tv[4 * (int64_t)f.t];
       for (int j = 0; j < 4; ++j) w[j] = s[j];
@@ -443,26 +527,142 @@ struct Delaunay3 {
           break;
         }
       if (w[0] != INF && w[1] != INF && w[2] != INF && w[3] != INF) {
-        if (!(orient3d(pt(w[0]), pt(w[1]), pt(w[2]), pt(w[3])) > 0.0)) failed = true;  // cavity not star-shaped
+        if (!(orient3d(pt(w[0]), pt(w[1]), pt(w[2]), pt(w[3])) > 0.0)) c.failed = true;  // cavity not star-shaped
         fin = nt;
       }
       for (int j = 0; j < 4; ++j) {
         if (j == f.k) continue;
         int32_t e[2];
-        int c = 0;
+        int cnt = 0;
         for (int m = 0; m < 4; ++m)
-          if (m != j && m != f.k) e[c++] = w[m];
-        match_face(nt, j, e[0], e[1]);
+          if (m != j && m != f.k) e[cnt++] = w[m];
+        match_face(c, nt, j, e[0], e[1]);
       }
-      newt.push_back(nt);
+      c.newt.push_back(nt);
     }
-    for (int32_t c : cav) {
-      dead[c] = 1;
-      freelist.push_back(c);
+    for (int32_t cc : c.cav) {
+      dead[cc] = 1;
+      c.freelist.push_back(cc);
     }
-    last = fin >= 0 ? fin : newt.back();
+    c.last = fin >= 0 ? fin : c.newt.back();
+    return true;
   }
 };
+
+int pick_threads(int threads) {
+  if (threads <= 0) {
+    const char* e = std::getenv("DM_HOST_THREADS");
+    threads = e != nullptr ? std::atoi(e) : 0;
+  }
+  if (threads <= 0) {
+    threads = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) threads = std::min(threads > 0 ? threads : 1 << 20, CPU_COUNT(&set));
+#endif
+    threads = std::min(threads, 16);
+  }
+  return std::max(1, std::min(threads, MAX_THREADS - 1));
+}
+
+// Partition of space into `cnt` boxes holding about the same number of points each: a k-d tree over
+// a sample of the points, every node cutting `cnt` boxes into a and cnt - a at the a / cnt quantile of
+// the node's axis.  Boxes are convex, so a straight walk between two points of a box stays in it.
+struct KdTree {
+  struct Node {
+    int axis;
+    double plane;
+    int left, right;  // >= 0: node, < 0: -(box + 1)
+  };
+  std::vector<Node> nodes;
+  int root = -1;
+  int build(const double* P, int32_t* lo, int32_t* hi, int cnt, int first, int axis, int rule) {
+    if (cnt <= 1 || hi - lo < 2) return -(first + 1);
+    int a = rule == 0 ? cnt / 2 : rule == 1 ? (3 * cnt + 4) / 8 : (5 * cnt + 3) / 8;
+    a = std::max(1, std::min(cnt - 1, a));
+    int32_t* mid = lo + (hi - lo) * (int64_t)a / cnt;
+    std::nth_element(lo, mid, hi, [&](int32_t x, int32_t y) { return P[3 * (int64_t)x + axis] < P[3 * (int64_t)y + axis]; });
+    const int me = (int)nodes.size();
+    nodes.push_back(Node{axis, P[3 * (int64_t)*mid + axis], 0, 0});
+    const int l = build(P, lo, mid, a, first, (axis + 1) % 3, rule);
+    const int r = build(P, mid, hi, cnt - a, first + a, (axis + 1) % 3, rule);
+    nodes[me].left = l;
+    nodes[me].right = r;
+    return me;
+  }
+  int box_of(const double* x) const {
+    int ref = root;
+    while (ref >= 0) {
+      const Node& nd = nodes[ref];
+      ref = x[nd.axis] < nd.plane ? nd.left : nd.right;
+    }
+    return -ref - 1;
+  }
+};
+
+// One round of the insertion order by several threads.  `pending`: rows of the round in Morton order.
+// Every pass cuts space into boxes along other planes, so that what a pass had to give back because it
+// touched a border of its box is inside a box of the next one; what is left after the last pass goes to
+// the serial code.
+void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& pending, int nth) {
+  const int64_t n = D.n;
+  std::vector<int32_t> sample;
+  {
+    const int64_t stride = std::max<int64_t>(1, n / 32768);
+    for (int64_t v = 0; v < n; v += stride) sample.push_back((int32_t)v);
+  }
+  for (int pass = 0; pass < PAR_PASSES; ++pass) {
+    if ((int64_t)pending.size() < 2 * PAR_MIN_PER_THREAD) break;
+    const int parts = std::min<int>((int)ctx.size(), nth + (pass >= 3 ? 1 : 0));
+    KdTree kd;
+    kd.root = kd.build(D.P, sample.data(), sample.data() + sample.size(), parts, 0, pass % 3, pass % 3);
+    run_threads(nth, [&](int j) {
+      const int64_t lo = n * j / nth, hi = n * (j + 1) / nth;
+      for (int64_t v = lo; v < hi; ++v) D.owner[v] = (uint8_t)kd.box_of(D.pt((int32_t)v));
+    });
+    // every thread: its rows of `pending` (in order) and a tetrahedron of its box to start from
+    const int64_t m = D.slots();
+    std::vector<std::vector<int32_t>> mine(parts);
+    run_threads(parts, [&](int j) {
+      Ctx& c = ctx[j];
+      c.me = j;
+      c.last = -1;
+      c.deferred.clear();
+      c.exhausted = false;
+      for (int32_t r : pending)
+        if (D.owner[r] == j) mine[j].push_back(r);
+      if (mine[j].empty()) return;
+      const int64_t from = m * j / parts;
+      for (int64_t s = 0; s < m; ++s) {
+        const int64_t t = from + s < m ? from + s : from + s - m;
+        if (!D.dead[t] && D.own((int32_t)t, j)) {
+          c.last = (int32_t)t;
+          break;
+        }
+      }
+    });
+    D.parallel = true;
+    const double tp0 = now_s();
+    const size_t before = pending.size();
+    run_threads(parts, [&](int j) {
+      Ctx& c = ctx[j];
+      for (int32_t r : mine[j])
+        if (c.failed || c.exhausted || !D.insert<true>(c, r)) c.deferred.push_back(r);
+    });
+    D.parallel = false;
+    // what is left, back in the order of the round
+    std::vector<int32_t> next;
+    bool stop = false;
+    for (int j = 0; j < parts; ++j) {
+      next.insert(next.end(), ctx[j].deferred.begin(), ctx[j].deferred.end());
+      stop = stop || ctx[j].failed || ctx[j].exhausted;
+    }
+    std::sort(next.begin(), next.end());
+    pending.swap(next);
+    if (trace_on()) std::fprintf(stderr, "[dmh3d] pass %d: %d parts, %zu -> %zu pending, %.3f s\n", pass, parts, before, pending.size(), now_s() - tp0);
+    if (stop) break;
+  }
+}
 
 }  // namespace
 
@@ -470,8 +670,8 @@ extern "C" {
 
 int64_t dmh_delaunay3d_max_cells(int64_t N) { return N < 4 ? 1 : 8 * N + 64; }
 
-int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
-                   int64_t* duplicates_out, int64_t* lost_out) {
+int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                      int64_t* duplicates_out, int64_t* lost_out, int threads) {
   if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
       N > (int64_t)std::numeric_limits<int32_t>::max() / 64)
     return DMH_ERR_ARG;
@@ -479,6 +679,9 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
   if (duplicates_out != nullptr) *duplicates_out = 0;
   if (lost_out != nullptr) *lost_out = N;
   if (N < 4) return DMH_OK;
+  int nth = pick_threads(threads);
+  if (N < PAR_MIN_ROUND) nth = 1;
+  const double t_begin = now_s();
 
   // ---- insertion order: rounds of growing size, Morton order within a round
   double lo[3], hi[3];
@@ -495,40 +698,67 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
     int32_t id;
   };
   std::vector<Item> items(N);
-  for (int64_t i = 0; i < N; ++i) {
-    uint64_t q[3];
-    for (int k = 0; k < 3; ++k) {
-      const double w = hi[k] - lo[k];
-      q[k] = w > 0.0 ? (uint64_t)std::min(2097151.0, (points[3 * i + k] - lo[k]) / w * 2097152.0) : 0;
+  run_threads(nth, [&](int j) {
+    for (int64_t i = N * j / nth; i < N * (j + 1) / nth; ++i) {
+      uint64_t q[3];
+      for (int k = 0; k < 3; ++k) {
+        const double w = hi[k] - lo[k];
+        q[k] = w > 0.0 ? (uint64_t)std::min(2097151.0, (points[3 * i + k] - lo[k]) / w * 2097152.0) : 0;
+      }
+      const uint64_t morton = spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2;
+      // round: 0 for 7 points in 8, 1 for 7 in 64, ... (a fixed hash of the row number: deterministic)
+      uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ULL;
+      h ^= h >> 29;
+      h *= 0xBF58476D1CE4E5B9ULL;
+      h ^= h >> 32;
+      int round = 0;
+      while (round < 20 && (h & 7) == 0) {
+        ++round;
+        h >>= 3;
+      }
+      items[i] = Item{((uint64_t)(20 - round) << 58) | (morton >> 6), (int32_t)i};  // later rounds sort last
     }
-    const uint64_t morton = spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2;
-    // round: 0 for 7 points in 8, 1 for 7 in 64, ... (a fixed hash of the row number: deterministic)
-    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ULL;
-    h ^= h >> 29;
-    h *= 0xBF58476D1CE4E5B9ULL;
-    h ^= h >> 32;
-    int round = 0;
-    while (round < 20 && (h & 7) == 0) {
-      ++round;
-      h >>= 3;
-    }
-    items[i] = Item{((uint64_t)(20 - round) << 58) | (morton >> 6), (int32_t)i};  // later rounds sort last
+  });
+  auto less = [](const Item& a, const Item& b) { return a.key != b.key ? a.key < b.key : a.id < b.id; };
+  if (nth > 1) {  // sorted runs, then pairwise merges
+    std::vector<int64_t> edge(nth + 1);
+    for (int j = 0; j <= nth; ++j) edge[j] = N * j / nth;
+    run_threads(nth, [&](int j) { std::sort(items.begin() + edge[j], items.begin() + edge[j + 1], less); });
+    for (int w = 1; w < nth; w *= 2)
+      run_threads((nth + 2 * w - 1) / (2 * w), [&](int g) {
+        const int a = g * 2 * w, mid = std::min(nth, a + w), b = std::min(nth, a + 2 * w);
+        if (mid < b) std::inplace_merge(items.begin() + edge[a], items.begin() + edge[mid], items.begin() + edge[b], less);
+      });
+  } else {
+    std::sort(items.begin(), items.end(), less);
   }
-  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key != b.key ? a.key < b.key : a.id < b.id; });
   std::vector<double> sorted(3 * N);
   std::vector<int32_t> ids(N);
-  for (int64_t r = 0; r < N; ++r) {
-    ids[r] = items[r].id;
-    for (int k = 0; k < 3; ++k) sorted[3 * r + k] = points[3 * (int64_t)items[r].id + k];
+  run_threads(nth, [&](int j) {
+    for (int64_t r = N * j / nth; r < N * (j + 1) / nth; ++r) {
+      ids[r] = items[r].id;
+      for (int k = 0; k < 3; ++k) sorted[3 * r + k] = points[3 * (int64_t)items[r].id + k];
+    }
+  });
+  // where the rounds start (the round number is in the top bits of the key)
+  std::vector<int64_t> round_start;
+  if (nth > 1) {
+    round_start.push_back(0);
+    for (int64_t r = 1; r < N; ++r)
+      if ((items[r].key >> 58) != (items[r - 1].key >> 58)) round_start.push_back(r);
+    round_start.push_back(N);
   }
   items.clear();
   items.shrink_to_fit();
 
+  const double t_sorted = now_s();
   Delaunay3 D;
   D.P = sorted.data();
   D.n = N;
-  D.tv.reserve(4 * (7 * N + 64));
-  D.tn.reserve(4 * (7 * N + 64));
+  D.grow(7 * N + 64 + (nth > 1 ? (int64_t)nth * 4 * CHUNK + N : 0));
+  std::vector<Ctx> ctx(nth + 1);  // (a pass with shifted bounds has one partition more)
+  for (int j = 0; j <= nth; ++j) ctx[j].stamp_next = j + 1;
+  Ctx& c0 = ctx[0];
   // ---- four affinely independent points to start from
   int32_t a = 0, b = -1, c = -1, d = -1;
   for (int64_t r = 1; r < N && b < 0; ++r)
@@ -538,28 +768,80 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
   for (int64_t r = 1; r < N && c >= 0 && d < 0; ++r)
     if (r != b && r != c && orient3d(D.pt(a), D.pt(b), D.pt(c), D.pt((int32_t)r)) != 0.0) d = (int32_t)r;
   if (d < 0) return DMH_OK;  // fewer than four affinely independent points: no cell, every row lost
-  D.init(a, b, c, d);
-  for (int64_t r = 1; r < N; ++r) {
-    if (r == b || r == c || r == d) continue;
-    D.insert((int32_t)r);
-    if (D.failed) break;
+  D.init(c0, a, b, c, d);
+  bool failed = false;
+  auto serial = [&](int64_t r) {
+    if (r == a || r == b || r == c || r == d) return;
+    D.insert<false>(c0, (int32_t)r);
+    failed = failed || c0.failed;
+  };
+  if (nth == 1) {
+    for (int64_t r = 1; r < N && !failed; ++r) serial(r);
+  } else {
+    D.owner.assign(N, 0);
+    for (size_t g = 0; g + 1 < round_start.size() && !failed; ++g) {
+      const int64_t r0 = round_start[g], r1 = round_start[g + 1];
+      const int use = (int)std::min<int64_t>(nth, (r1 - r0) / PAR_MIN_PER_THREAD);
+      if (r1 - r0 < PAR_MIN_ROUND || use < 2 || r0 < 64) {
+        for (int64_t r = std::max<int64_t>(r0, 1); r < r1 && !failed; ++r) serial(r);
+        continue;
+      }
+      std::vector<int32_t> pending;
+      pending.reserve(r1 - r0);
+      for (int64_t r = r0; r < r1; ++r)
+        if (r != a && r != b && r != c && r != d) pending.push_back((int32_t)r);
+      const double tr0 = now_s();
+      parallel_round(D, ctx, pending, use);
+      const double tr1 = now_s();
+      for (int j = 0; j <= nth; ++j) failed = failed || ctx[j].failed;
+      // the serial code starts its walk from a live tetrahedron
+      if (c0.last < 0 || D.dead[c0.last]) {
+        c0.last = -1;
+        for (int64_t t = 0; t < D.slots() && c0.last < 0; ++t)
+          if (!D.dead[t]) c0.last = (int32_t)t;
+      }
+      for (size_t x = 0; x < pending.size() && !failed; ++x) serial(pending[x]);
+      if (trace_on()) std::fprintf(stderr, "[dmh3d] round of %ld: parallel %.3f s, serial rest (%zu) %.3f s\n", (long)(r1 - r0), tr1 - tr0, pending.size(), now_s() - tr1);
+    }
   }
-  if (D.failed) D.lost += 1;
-  int64_t T = 0;
-  for (int64_t t = 0; t < D.ntets(); ++t)
-    if (!D.dead[t] && D.inf_slot((int32_t)t) < 0) ++T;
+  const double t_built = now_s();
+  int64_t dups = 0, lost = 0;
+  for (int j = 0; j <= nth; ++j) dups += ctx[j].dups, lost += ctx[j].lost;
+  if (failed) lost += 1;
+  // ---- the finite tetrahedra, in the caller's numbering
+  const int64_t m = D.slots();
+  std::vector<int64_t> cnt(nth + 1, 0);
+  run_threads(nth, [&](int j) {
+    int64_t k = 0;
+    for (int64_t t = m * j / nth; t < m * (j + 1) / nth; ++t)
+      if (!D.dead[t] && D.inf_slot((int32_t)t) < 0) ++k;
+    cnt[j + 1] = k;
+  });
+  for (int j = 0; j < nth; ++j) cnt[j + 1] += cnt[j];
+  const int64_t T = cnt[nth];
   *T_out = T;
-  if (duplicates_out != nullptr) *duplicates_out = D.dups;
-  if (lost_out != nullptr) *lost_out = D.lost;
+  if (duplicates_out != nullptr) *duplicates_out = dups;
+  if (lost_out != nullptr) *lost_out = lost;
   if (T > cap) return DMH_ERR_CAPACITY;
-  int64_t o = 0;
-  for (int64_t t = 0; t < D.ntets(); ++t) {
-    if (D.dead[t] || D.inf_slot((int32_t)t) >= 0) continue;
-    for (int k = 0; k < 4; ++k) cells[4 * o + k] = ids[D.tv[4 * t + k]];
-    ++o;
-  }
-  dmx::order_cells<4>(cells, T, N);
+  run_threads(nth, [&](int j) {
+    int64_t o = cnt[j];
+    for (int64_t t = m * j / nth; t < m * (j + 1) / nth; ++t) {
+      if (D.dead[t] || D.inf_slot((int32_t)t) >= 0) continue;
+      for (int k = 0; k < 4; ++k) cells[4 * o + k] = ids[D.tv[4 * t + k]];
+      ++o;
+    }
+  });
+  const double t_out = now_s();
+  dmx::order_cells<4>(cells, T, N, nth);
+  if (trace_on())
+    std::fprintf(stderr, "[dmh3d] N=%ld threads=%d: sort %.3f, build %.3f, extract %.3f, order %.3f s\n", (long)N, nth, t_sorted - t_begin,
+                 t_built - t_sorted, t_out - t_built, now_s() - t_out);
   return DMH_OK;
+}
+
+int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                   int64_t* duplicates_out, int64_t* lost_out) {
+  return dmh_delaunay3d_mt(points, N, cells, cap, T_out, duplicates_out, lost_out, 1);
 }
 
 double dmh_orient3d(const double* a, const double* b, const double* c, const double* d) { return orient3d(a, b, c, d); }

@@ -16,6 +16,21 @@ import ctypes as C
 import numpy as np
 
 
+def host_threads():
+    """Host threads one rank may use for the 3-D retriangulation."""
+    import os
+
+    env = os.environ.get("DM_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(16, cores // ranks))
+
+
 class QhullTriangulator:
     name = "qhull (scipy.spatial.Delaunay)"
 
@@ -102,7 +117,9 @@ class BowyerWatsonTriangulator:
 
     name = "bowyer-watson (libdistmesh_host)"
 
-    def __init__(self, dim):
+    def __init__(self, dim, threads=None):
+        """threads: host threads of the construction (dmh_delaunay3d_mt); None = DM_HOST_THREADS if set,
+        else the cores this process may use divided among the ranks of the node, at most 16."""
         if dim != 3:
             raise ValueError("BowyerWatsonTriangulator is 3-D; the 2-D native triangulator is SweepHullTriangulator")
         from ._hostlib import lib
@@ -110,6 +127,8 @@ class BowyerWatsonTriangulator:
         self.dim = dim
         self._lib = lib()
         self.qhull_retries = 0
+        self.threads = host_threads() if threads is None else max(1, int(threads))
+        self.name = f"bowyer-watson (libdistmesh_host, {self.threads} thread{'s' if self.threads > 1 else ''})"
 
     def triangulate(self, points):
         """points (N,3) float64 host array -> cells (T,4) int32, ids = input rows; cells grouped by their
@@ -122,7 +141,7 @@ class BowyerWatsonTriangulator:
         T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         for _ in range(2):
             cells = np.empty((cap, 4), dtype=np.int32)
-            rc = self._lib.dmh_delaunay3d(p.ctypes.data, n, cells.ctypes.data, cap, C.byref(T), C.byref(dups), C.byref(lost))
+            rc = self._lib.dmh_delaunay3d_mt(p.ctypes.data, n, cells.ctypes.data, cap, C.byref(T), C.byref(dups), C.byref(lost), self.threads)
             if rc != -2:  # DMH_ERR_CAPACITY: *T_out holds the size that is needed
                 break
             cap = T.value
@@ -142,7 +161,7 @@ class BowyerWatsonTriangulator:
         """Raw-buffer form: see SweepHullTriangulator.triangulate_into."""
         n = len(points)
         T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
-        rc = self._lib.dmh_delaunay3d(points.ctypes.data, n, cells.ctypes.data, len(cells), C.byref(T), C.byref(dups), C.byref(lost))
+        rc = self._lib.dmh_delaunay3d_mt(points.ctypes.data, n, cells.ctypes.data, len(cells), C.byref(T), C.byref(dups), C.byref(lost), self.threads)
         if rc == -2:
             return -int(T.value)
         if rc != 0:

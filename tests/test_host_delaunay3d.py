@@ -258,3 +258,109 @@ def test_triangulate_into_raw_buffers(hl):  # noqa: F811
         buf2 = np.empty((q.max_cells(len(p)), dim + 1), dtype=np.int32)
         T2 = q.triangulate_into(p, buf2)
         assert np.array_equal(_canon(buf2[:T2]), _canon(ref))
+
+
+# ---- dmh_delaunay3d_mt: the same triangulation built by several host threads -----------------------
+
+def _rows_sorted(t):
+    return np.sort(np.asarray(t), axis=1)
+
+
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_threads_same_cells_in_the_same_order(hl, threads):  # noqa: F811
+    """Points in general position (large enough for the partitioned rounds: 8000+ rows per round): the
+    threaded construction returns the cell list of the serial one, cell for cell (the column order
+    inside a cell is the construction's own and may differ)."""
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    p = np.random.default_rng(5).random((60000, 3)) * [2.0, 1.0, 1.0]
+    one = BowyerWatsonTriangulator(3, threads=1).triangulate(p)
+    tri = BowyerWatsonTriangulator(3, threads=threads)
+    many = tri.triangulate(p)
+    assert many.dtype == np.int32 and many.flags.c_contiguous and _is_lex_sorted(many) and _column0_unbiased(many)
+    assert np.array_equal(_rows_sorted(one), _rows_sorted(many))
+    assert tri.qhull_retries == 0
+    # raw-buffer form, and the capacity report
+    buf = np.full((tri.max_cells(len(p)), 4), -7, dtype=np.int32)
+    T = tri.triangulate_into(p, buf)
+    assert T == len(one) and np.array_equal(_rows_sorted(buf[:T]), _rows_sorted(one)) and (buf[T:] == -7).all()
+    small = np.full((1000, 4), -7, dtype=np.int32)
+    assert tri.triangulate_into(p, small) == -len(one) and (small == -7).all()
+
+
+def test_threads_distmesh_ball_iterates(hl):  # noqa: F811
+    """What the loop feeds it: the reference's staggered lattice clipped to a ball (co-spherical
+    everywhere: any valid Delaunay triangulation will do, checked exactly), then jittered and moved by
+    force iterations (general position: the serial cell set)."""
+    from oracle import distmesh_oracle as orc
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    h0 = 0.06
+    spec = ("ball", {"x0": [0.0, 0.0, 0.0], "r": 1.0})
+    fd = lambda x: orc.sdf(spec, x)  # noqa: E731
+    fh = lambda x: np.full(len(x), h0)  # noqa: E731
+    geps, deps = 0.1 * h0, np.sqrt(np.finfo(float).eps) * h0
+    p0 = orc.initial_points(h0, geps, 3, np.array([[-1.0, 1.0]] * 3), fh, fd, np.empty((0, 3)))
+    assert len(p0) > 16000
+    one, many = BowyerWatsonTriangulator(3, threads=1), BowyerWatsonTriangulator(3, threads=4)
+    t = many.triangulate(p0)
+    assert np.unique(t).size == len(p0)
+    _check_triangulation(hl, p0, t)
+    p = p0 + np.random.default_rng(0).uniform(-0.1 * h0, 0.1 * h0, p0.shape)
+    for it in range(2):
+        t = many.triangulate(p)
+        assert np.array_equal(_rows_sorted(t), _rows_sorted(one.triangulate(p)))
+        p = orc.force_iteration(p, t, [fd], fh, h0, geps, deps)["p"]
+    assert many.qhull_retries == 0
+
+
+def test_threads_degenerate_inputs(hl):  # noqa: F811
+    """Degenerate input through the partitioned rounds: a cubic lattice (every cube co-spherical, every
+    lattice plane co-planar), duplicated rows, points on the faces of a cube."""
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    tri = BowyerWatsonTriangulator(3, threads=4)
+    g = np.stack(np.meshgrid(np.arange(22.0), np.arange(23.0), np.arange(24.0), indexing="ij"), -1).reshape(-1, 3) * 0.1
+    t = tri.triangulate(np.ascontiguousarray(g))
+    assert len(t) >= 5 * 21 * 22 * 23
+    _check_triangulation(hl, g, t)
+    rng = np.random.default_rng(3)
+    c = rng.random((12000, 3))
+    for k in range(3):
+        c[500 * (2 * k): 500 * (2 * k + 1), k] = 0.0
+        c[500 * (2 * k + 1): 500 * (2 * k + 2), k] = 1.0
+    d2 = np.ascontiguousarray(np.r_[c, c[:700]])  # 700 exact duplicates
+    t = tri.triangulate(d2)
+    assert _is_lex_sorted(t)
+    _check_triangulation(hl, c, _first_occurrence_cells(d2, t), n_used=len(c))
+    assert tri.qhull_retries == 0
+
+
+def test_threads_error_paths(hl):  # noqa: F811
+    T, dups, lost = C.c_int64(), C.c_int64(), C.c_int64()
+    p = np.random.default_rng(1).random((20000, 3))
+    out = np.empty((64, 4), np.int32)
+    assert hl.dmh_delaunay3d_mt(p.ctypes.data, 20000, out.ctypes.data, 64, C.byref(T), None, None, 4) == -2
+    assert T.value > 64
+    flat = np.ascontiguousarray(np.c_[p[:, :2], np.zeros(len(p))])
+    big = np.empty((hl.dmh_delaunay3d_max_cells(len(p)), 4), np.int32)
+    assert hl.dmh_delaunay3d_mt(flat.ctypes.data, len(p), big.ctypes.data, len(big), C.byref(T), C.byref(dups), C.byref(lost), 4) == 0
+    assert (T.value, lost.value) == (0, len(p))
+    bad = p.copy()
+    bad[77, 2] = np.inf
+    assert hl.dmh_delaunay3d_mt(bad.ctypes.data, len(p), big.ctypes.data, len(big), C.byref(T), None, None, 4) == -1
+
+
+def test_host_threads_split_among_ranks(monkeypatch):
+    import os
+
+    from seismicmesh_b200 import triangulator as tr
+
+    cores = len(os.sched_getaffinity(0))
+    monkeypatch.delenv("DM_HOST_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert tr.host_threads() == max(1, min(16, cores))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert tr.host_threads() == max(1, min(16, cores // 8))
+    monkeypatch.setenv("DM_HOST_THREADS", "5")
+    assert tr.host_threads() == 5
