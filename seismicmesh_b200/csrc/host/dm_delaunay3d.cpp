@@ -228,7 +228,7 @@ inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
   return x;
 }
 
-constexpr int32_t INF = -1;
+constexpr int32_t INF = -1, DEAD = -2;
 constexpr int MAX_THREADS = 32;      // stamps of thread j are j + 1 + k * MAX_THREADS: unique over the whole run
 constexpr int64_t CHUNK = 512;       // tetrahedron slots a thread claims at a time
 constexpr int64_t PAR_MIN_ROUND = 8000;   // rounds smaller than this are inserted by one thread
@@ -281,30 +281,32 @@ struct Ctx {
 struct Delaunay3 {
   const double* P = nullptr;  // coordinates in insertion order
   int64_t n = 0;
-  std::vector<int32_t> tv, tn;  // 4 vertices / 4 neighbours (opposite the vertex of the same slot) per tetrahedron
+  struct alignas(32) Tet {
+    int32_t v[4];  // vertices (INF: the vertex at infinity; v[0] == DEAD: slot unused)
+    int32_t n[4];  // neighbours, opposite the vertex of the same slot
+  };
+  std::vector<Tet> T;           // (vertices and neighbours of a tetrahedron share half a cache line)
   std::vector<int32_t> mark;    // +stamp: in the cavity of that insertion, -stamp: tested and not in conflict
-  std::vector<uint8_t> dead;    // 1: slot unused
   std::vector<uint8_t> owner;   // partition of every vertex during a parallel phase
   std::atomic<int64_t> top{0};  // slots handed out so far
   bool parallel = false;
 
   const double* pt(int32_t v) const { return P + 3 * (int64_t)v; }
+  bool is_dead(int64_t t) const { return T[t].v[0] == DEAD; }
   int64_t slots() const { return top.load(std::memory_order_relaxed); }
 
   void grow(int64_t want) {
-    if ((int64_t)dead.size() >= want) return;
-    const int64_t sz = std::max<int64_t>(want, (int64_t)dead.size() * 3 / 2);
-    tv.resize(4 * sz);
-    tn.resize(4 * sz);
+    if ((int64_t)T.size() >= want) return;
+    const int64_t sz = std::max<int64_t>(want, (int64_t)T.size() * 3 / 2);
+    T.resize(sz, Tet{{DEAD, DEAD, DEAD, DEAD}, {0, 0, 0, 0}});
     mark.resize(sz, 0);
-    dead.resize(sz, 1);
   }
   // make sure the thread has `need` free slots; false: the arrays are full and may not grow now
   bool reserve_slots(Ctx& c, int64_t need) {
     while ((int64_t)c.freelist.size() < need) {
       const int64_t k = std::max<int64_t>(CHUNK, need - (int64_t)c.freelist.size());
       const int64_t at = top.fetch_add(k, std::memory_order_relaxed);
-      if (at + k > (int64_t)dead.size()) {
+      if (at + k > (int64_t)T.size()) {
         if (parallel) {
           top.fetch_sub(k, std::memory_order_relaxed);
           return false;
@@ -318,30 +320,30 @@ struct Delaunay3 {
   int32_t new_tet(Ctx& c) {  // after reserve_slots
     const int32_t t = c.freelist.back();
     c.freelist.pop_back();
-    dead[t] = 0;
+    T[t].v[0] = 0;
     mark[t] = 0;
     return t;
   }
   int inf_slot(int32_t t) const {
-    const int32_t* v = &tv[4 * (int64_t)t];
+    const int32_t* v = T[t].v;
     return v[0] == INF ? 0 : v[1] == INF ? 1 : v[2] == INF ? 2 : v[3] == INF ? 3 : -1;
   }
   // every finite vertex of t in partition `me` (the vertex at infinity belongs to everybody: two
   // tetrahedra of different partitions never share a facet, which has at least two finite vertices)
   bool own(int32_t t, int me) const {
-    const int32_t* v = &tv[4 * (int64_t)t];
+    const int32_t* v = T[t].v;
     for (int k = 0; k < 4; ++k)
       if (v[k] != INF && owner[v[k]] != me) return false;
     return true;
   }
   // orientation of tetrahedron t with the vertex of slot k replaced by the point p
   double orient_with(int32_t t, int k, const double* p) const {
-    const int32_t* v = &tv[4 * (int64_t)t];
+    const int32_t* v = T[t].v;
     const double* q[4] = {k == 0 ? p : pt(v[0]), k == 1 ? p : pt(v[1]), k == 2 ? p : pt(v[2]), k == 3 ? p : pt(v[3])};
     return orient3d(q[0], q[1], q[2], q[3]);
   }
   double insphere_of(int32_t t, const double* p) const {
-    const int32_t* v = &tv[4 * (int64_t)t];
+    const int32_t* v = T[t].v;
     return insphere(pt(v[0]), pt(v[1]), pt(v[2]), pt(v[3]), p);
   }
   bool conflict(int32_t t, const double* p) const {
@@ -349,7 +351,7 @@ struct Delaunay3 {
     if (ki < 0) return insphere_of(t, p) > 0.0;
     const double o = orient_with(t, ki, p);  // > 0: strictly beyond the hull facet
     if (o != 0.0) return o > 0.0;
-    return insphere_of(tn[4 * (int64_t)t + ki], p) > 0.0;  // in the facet's plane: as the tetrahedron behind it
+    return insphere_of(T[t].n[ki], p) > 0.0;  // in the facet's plane: as the tetrahedron behind it
   }
 
   // neighbours of the first five tetrahedra by matching faces
@@ -357,21 +359,21 @@ struct Delaunay3 {
     const int64_t m = slots();
     for (int64_t t = 0; t < m; ++t)
       for (int k = 0; k < 4; ++k) {
-        if (dead[t]) continue;
+        if (is_dead(t)) continue;
         int32_t f[3];
         int c = 0;
         for (int j = 0; j < 4; ++j)
-          if (j != k) f[c++] = tv[4 * t + j];
+          if (j != k) f[c++] = T[t].v[j];
         std::sort(f, f + 3);
         for (int64_t u = 0; u < m; ++u) {
-          if (u == t || dead[u]) continue;
+          if (u == t || is_dead(u)) continue;
           for (int kk = 0; kk < 4; ++kk) {
             int32_t g[3];
             int d = 0;
             for (int j = 0; j < 4; ++j)
-              if (j != kk) g[d++] = tv[4 * u + j];
+              if (j != kk) g[d++] = T[u].v[j];
             std::sort(g, g + 3);
-            if (f[0] == g[0] && f[1] == g[1] && f[2] == g[2]) tn[4 * t + k] = (int32_t)u;
+            if (f[0] == g[0] && f[1] == g[1] && f[2] == g[2]) T[t].n[k] = (int32_t)u;
           }
         }
       }
@@ -381,12 +383,12 @@ struct Delaunay3 {
     if (orient3d(pt(a), pt(b), pt(c), pt(d)) < 0.0) std::swap(a, b);
     reserve_slots(cx, 5);
     const int32_t t0 = new_tet(cx);
-    int32_t* v = &tv[4 * (int64_t)t0];
+    int32_t* v = T[t0].v;
     v[0] = a, v[1] = b, v[2] = c, v[3] = d;
     for (int k = 0; k < 4; ++k) {  // ghost behind face k: the vertex at infinity in slot k, orientation flipped
       const int32_t g = new_tet(cx);
-      int32_t* w = &tv[4 * (int64_t)g];
-      const int32_t* s = &tv[4 * (int64_t)t0];
+      int32_t* w = T[g].v;
+      const int32_t* s = T[t0].v;
       for (int j = 0; j < 4; ++j) w[j] = s[j];
       w[k] = INF;
       const int x = k == 0 ? 1 : 0, y = k <= 1 ? 2 : 1;  // two of the other slots
@@ -408,17 +410,18 @@ struct Delaunay3 {
         return;
       }
       if (s.key == key) {
-        tn[4 * (int64_t)t + j] = s.t;
-        tn[4 * (int64_t)s.t + s.j] = t;
+        T[t].n[j] = s.t;
+        T[s.t].n[s.j] = t;
         return;
       }
       h = (h + 1) & mask;
     }
   }
 
-  // Insert row i.  PAR: the thread may only look at tetrahedra of its own partition; as soon as the
-  // walk, the cavity or the ring of tetrahedra around the cavity reaches one that is not, the point is
-  // given back (false) before anything has been modified.
+  // Insert row i.  PAR: the walk and the cavity may only contain tetrahedra of the thread's own box (all
+  // finite vertices in it); as soon as one of them reaches another tetrahedron the point is given back
+  // (false) before anything has been modified.  The ring of tetrahedra around the cavity may contain
+  // tetrahedra with vertices of several boxes -- those are frozen during the phase.
   template <bool PAR>
   bool insert(Ctx& c, int32_t i) {
     const double* p = pt(i);
@@ -435,12 +438,12 @@ struct Delaunay3 {
           found = true;
           break;
         }
-        nxt = tn[4 * (int64_t)t + ki];
+        nxt = T[t].n[ki];
       } else {
         for (int kk = 0; kk < 4; ++kk) {
           const int k = (kk + (int)(steps & 3)) & 3;
           if (orient_with(t, k, p) < 0.0) {
-            nxt = tn[4 * (int64_t)t + k];
+            nxt = T[t].n[k];
             if (!PAR || own(nxt, c.me)) break;  // (any face that separates t from p will do)
           }
         }
@@ -455,14 +458,14 @@ struct Delaunay3 {
     if (!found) {  // the walk did not settle: exhaustive search
       if (PAR) return false;
       for (int64_t u = 0; u < slots() && !found; ++u)
-        if (!dead[u] && conflict((int32_t)u, p)) t = (int32_t)u, found = true;
+        if (!is_dead(u) && conflict((int32_t)u, p)) t = (int32_t)u, found = true;
       if (!found) {
         ++c.lost;
         return true;
       }
     }
     if (inf_slot(t) < 0) {
-      const int32_t* v = &tv[4 * (int64_t)t];
+      const int32_t* v = T[t].v;
       for (int k = 0; k < 4; ++k) {
         const double* q = pt(v[k]);
         if (q[0] == p[0] && q[1] == p[1] && q[2] == p[2]) {  // exact duplicate of an earlier row
@@ -489,10 +492,18 @@ struct Delaunay3 {
       c.stack.pop_back();
       c.cav.push_back(cc);
       for (int k = 0; k < 4; ++k) {
-        const int32_t nb = tn[4 * (int64_t)cc + k];
+        const int32_t nb = T[cc].n[k];
         if (mark[nb] == stamp) continue;
+        if (PAR && !own(nb, c.me)) {
+          // A tetrahedron with vertices of several boxes: nobody deletes it or moves its vertices in this
+          // phase, so it can be tested; it cannot join the cavity, but it may sit in the ring around it
+          // (only the neighbour slot facing the cavity is written, see below).  Never marked: no thread
+          // writes the mark of a tetrahedron that is not its own.
+          if (conflict(nb, p)) return false;
+          c.bnd.push_back(Facet{cc, k, nb});
+          continue;
+        }
         if (mark[nb] != -stamp) {
-          if (PAR && !own(nb, c.me)) return false;
           if (conflict(nb, p)) {
             mark[nb] = stamp;
             c.stack.push_back(nb);
@@ -515,15 +526,18 @@ struct Delaunay3 {
     c.newt.clear();
     for (const Facet& f : c.bnd) {
       const int32_t nt = new_tet(c);
-      int32_t* w = &tv[4 * (int64_t)nt];
-      const int32_t* s = &tv[4 * (int64_t)f.t];
+      int32_t* w = T[nt].v;
+      const int32_t* s = T[f.t].v;
       for (int j = 0; j < 4; ++j) w[j] = s[j];
       w[f.k] = i;
-      tn[4 * (int64_t)nt + f.k] = f.nb;
-      int32_t* back = &tn[4 * (int64_t)f.nb];
+      T[nt].n[f.k] = f.nb;
+      // (relaxed atomics: in a parallel phase the ring tetrahedron may belong to no box, and then another
+      //  thread may be looking for ITS slot in it at the same time -- each of them only ever writes the
+      //  slot that faces its own cavity)
+      int32_t* back = T[f.nb].n;
       for (int m = 0; m < 4; ++m)
-        if (back[m] == f.t) {
-          back[m] = nt;
+        if (__atomic_load_n(&back[m], __ATOMIC_RELAXED) == f.t) {
+          __atomic_store_n(&back[m], nt, __ATOMIC_RELAXED);
           break;
         }
       if (w[0] != INF && w[1] != INF && w[2] != INF && w[3] != INF) {
@@ -541,7 +555,7 @@ struct Delaunay3 {
       c.newt.push_back(nt);
     }
     for (int32_t cc : c.cav) {
-      dead[cc] = 1;
+      T[cc].v[0] = DEAD;
       c.freelist.push_back(cc);
     }
     c.last = fin >= 0 ? fin : c.newt.back();
@@ -635,7 +649,7 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
       const int64_t from = m * j / parts;
       for (int64_t s = 0; s < m; ++s) {
         const int64_t t = from + s < m ? from + s : from + s - m;
-        if (!D.dead[t] && D.own((int32_t)t, j)) {
+        if (!D.is_dead(t) && D.own((int32_t)t, j)) {
           c.last = (int32_t)t;
           break;
         }
@@ -795,10 +809,10 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
       const double tr1 = now_s();
       for (int j = 0; j <= nth; ++j) failed = failed || ctx[j].failed;
       // the serial code starts its walk from a live tetrahedron
-      if (c0.last < 0 || D.dead[c0.last]) {
+      if (c0.last < 0 || D.is_dead(c0.last)) {
         c0.last = -1;
         for (int64_t t = 0; t < D.slots() && c0.last < 0; ++t)
-          if (!D.dead[t]) c0.last = (int32_t)t;
+          if (!D.is_dead(t)) c0.last = (int32_t)t;
       }
       for (size_t x = 0; x < pending.size() && !failed; ++x) serial(pending[x]);
       if (trace_on()) std::fprintf(stderr, "[dmh3d] round of %ld: parallel %.3f s, serial rest (%zu) %.3f s\n", (long)(r1 - r0), tr1 - tr0, pending.size(), now_s() - tr1);
@@ -814,7 +828,7 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   run_threads(nth, [&](int j) {
     int64_t k = 0;
     for (int64_t t = m * j / nth; t < m * (j + 1) / nth; ++t)
-      if (!D.dead[t] && D.inf_slot((int32_t)t) < 0) ++k;
+      if (!D.is_dead(t) && D.inf_slot((int32_t)t) < 0) ++k;
     cnt[j + 1] = k;
   });
   for (int j = 0; j < nth; ++j) cnt[j + 1] += cnt[j];
@@ -826,8 +840,8 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   run_threads(nth, [&](int j) {
     int64_t o = cnt[j];
     for (int64_t t = m * j / nth; t < m * (j + 1) / nth; ++t) {
-      if (D.dead[t] || D.inf_slot((int32_t)t) >= 0) continue;
-      for (int k = 0; k < 4; ++k) cells[4 * o + k] = ids[D.tv[4 * t + k]];
+      if (D.is_dead(t) || D.inf_slot((int32_t)t) >= 0) continue;
+      for (int k = 0; k < 4; ++k) cells[4 * o + k] = ids[D.T[t].v[k]];
       ++o;
     }
   });
