@@ -81,12 +81,14 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
  * this process may run on, at most 16; dmh_delaunay3d is this call with threads = 1).  The reference
  * has no counterpart: CGAL's insert behind delaunay_class3.cpp is single-threaded, and the 3-D
  * retriangulation is where its time-to-mesh goes (docs/source/usrman/overview.rst:116).
- * The large rounds of the insertion order are split into partitions along the Morton curve, one
- * thread each; a thread inserts a point only while the walk to it, its cavity and the tetrahedra
- * around the cavity have all their vertices in the thread's own partition, and otherwise hands the
- * point to the next pass (shifted partition bounds) and finally to the serial code.  No locks: two
- * threads never touch the same tetrahedron.  For points in general position the cell set is the one
- * dmh_delaunay3d returns; the output order is the same canonical order. */
+ * The points of a large round of the insertion order are divided among the boxes of a k-d tree, one
+ * thread each; a thread inserts a point only while the walk to it
+ * and its cavity consist of tetrahedra with all vertices in the thread's own box, and otherwise hands
+ * the point to the next pass (other cutting planes) and finally to the serial code.  No locks: no two
+ * threads ever modify or delete the same tetrahedron; tetrahedra with vertices of several boxes are
+ * frozen during a pass (only their neighbour slots facing a cavity are updated, each by one thread).
+ * For points in general position the cell set is the one dmh_delaunay3d returns; the output order is
+ * the same canonical order. */
 int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
                       int64_t* duplicates_out, int64_t* lost_out, int threads);
 

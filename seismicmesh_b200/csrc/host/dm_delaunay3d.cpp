@@ -232,7 +232,19 @@ constexpr int32_t INF = -1, DEAD = -2;
 constexpr int MAX_THREADS = 32;      // stamps of thread j are j + 1 + k * MAX_THREADS: unique over the whole run
 constexpr int64_t CHUNK = 512;       // tetrahedron slots a thread claims at a time
 constexpr int64_t PAR_MIN_ROUND = 8000;   // rounds smaller than this are inserted by one thread
-constexpr int64_t PAR_MIN_PER_THREAD = 1500;
+inline int64_t env_or(const char* name, int64_t dflt) {
+  const char* e = std::getenv(name);
+  return e != nullptr && std::atoll(e) > 0 ? std::atoll(e) : dflt;
+}
+// rows a box should hold at least: per round (number of boxes) and per pass (when to stop)
+inline int64_t par_round_rows() {
+  static const int64_t v = env_or("DM_HOST_ROUND_ROWS", 2000);
+  return v;
+}
+inline int64_t par_pass_rows() {
+  static const int64_t v = env_or("DM_HOST_PASS_ROWS", 1500);
+  return v;
+}
 constexpr int PAR_PASSES = 5;
 
 inline double now_s() {
@@ -574,6 +586,7 @@ int pick_threads(int threads) {
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) threads = std::min(threads > 0 ? threads : 1 << 20, CPU_COUNT(&set));
 #endif
+    if (threads >= 8) --threads;  // (one core left to the caller's other threads: measured faster on a 16-core box)
     threads = std::min(threads, 16);
   }
   return std::max(1, std::min(threads, MAX_THREADS - 1));
@@ -626,8 +639,9 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
     for (int64_t v = 0; v < n; v += stride) sample.push_back((int32_t)v);
   }
   for (int pass = 0; pass < PAR_PASSES; ++pass) {
-    if ((int64_t)pending.size() < 2 * PAR_MIN_PER_THREAD) break;
-    const int parts = std::min<int>((int)ctx.size(), nth + (pass >= 3 ? 1 : 0));
+    if ((int64_t)pending.size() < 2 * par_pass_rows()) break;
+    const int want = (int)std::max<int64_t>(2, std::min<int64_t>(nth, (int64_t)pending.size() / par_pass_rows()));
+    const int parts = std::min<int>((int)ctx.size(), want + (pass >= 3 ? 1 : 0));
     KdTree kd;
     kd.root = kd.build(D.P, sample.data(), sample.data() + sample.size(), parts, 0, pass % 3, pass % 3);
     run_threads(nth, [&](int j) {
@@ -795,7 +809,7 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
     D.owner.assign(N, 0);
     for (size_t g = 0; g + 1 < round_start.size() && !failed; ++g) {
       const int64_t r0 = round_start[g], r1 = round_start[g + 1];
-      const int use = (int)std::min<int64_t>(nth, (r1 - r0) / PAR_MIN_PER_THREAD);
+      const int use = (int)std::min<int64_t>(nth, (r1 - r0) / par_round_rows());
       if (r1 - r0 < PAR_MIN_ROUND || use < 2 || r0 < 64) {
         for (int64_t r = std::max<int64_t>(r0, 1); r < r1 && !failed; ++r) serial(r);
         continue;

@@ -28,7 +28,8 @@ def host_threads():
     except AttributeError:
         cores = os.cpu_count() or 1
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-    return max(1, min(16, cores // ranks))
+    mine = cores // ranks
+    return max(1, min(16, mine - 1 if mine >= 8 else mine))  # (one core left to the rest of the process)
 
 
 class QhullTriangulator:
