@@ -231,6 +231,7 @@ inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
 constexpr int32_t INF = -1, DEAD = -2;
 constexpr int MAX_THREADS = 32;      // stamps of thread j are j + 1 + k * MAX_THREADS: unique over the whole run
 constexpr int64_t CHUNK = 512;       // tetrahedron slots a thread claims at a time
+constexpr int PAR_PASSES = 6;
 constexpr int64_t PAR_MIN_ROUND = 8000;   // rounds smaller than this are inserted by one thread
 inline int64_t env_or(const char* name, int64_t dflt) {
   const char* e = std::getenv(name);
@@ -241,11 +242,14 @@ inline int64_t par_round_rows() {
   static const int64_t v = env_or("DM_HOST_ROUND_ROWS", 2000);
   return v;
 }
+inline int par_passes() {
+  static const int v = (int)env_or("DM_HOST_PASSES", PAR_PASSES);
+  return v;
+}
 inline int64_t par_pass_rows() {
   static const int64_t v = env_or("DM_HOST_PASS_ROWS", 1500);
   return v;
 }
-constexpr int PAR_PASSES = 5;
 
 inline double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -638,12 +642,13 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
     const int64_t stride = std::max<int64_t>(1, n / 32768);
     for (int64_t v = 0; v < n; v += stride) sample.push_back((int32_t)v);
   }
-  for (int pass = 0; pass < PAR_PASSES; ++pass) {
+  for (int pass = 0; pass < par_passes(); ++pass) {
     if ((int64_t)pending.size() < 2 * par_pass_rows()) break;
     const int want = (int)std::max<int64_t>(2, std::min<int64_t>(nth, (int64_t)pending.size() / par_pass_rows()));
-    const int parts = std::min<int>((int)ctx.size(), want + (pass >= 3 ? 1 : 0));
+    // (first axis, cutting rule, number of boxes: no two passes cut along the same planes)
+    const int parts = std::min<int>((int)ctx.size(), want + (pass / 3) % 2);
     KdTree kd;
-    kd.root = kd.build(D.P, sample.data(), sample.data() + sample.size(), parts, 0, pass % 3, pass % 3);
+    kd.root = kd.build(D.P, sample.data(), sample.data() + sample.size(), parts, 0, pass % 3, (pass + pass / 3) % 3);
     run_threads(nth, [&](int j) {
       const int64_t lo = n * j / nth, hi = n * (j + 1) / nth;
       for (int64_t v = lo; v < hi; ++v) D.owner[v] = (uint8_t)kd.box_of(D.pt((int32_t)v));
@@ -686,9 +691,10 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
       stop = stop || ctx[j].failed || ctx[j].exhausted;
     }
     std::sort(next.begin(), next.end());
+    const bool poor = 5 * next.size() > 4 * pending.size();  // less than a fifth inserted: the boxes have become too small
     pending.swap(next);
     if (trace_on()) std::fprintf(stderr, "[dmh3d] pass %d: %d parts, %zu -> %zu pending, %.3f s\n", pass, parts, before, pending.size(), now_s() - tp0);
-    if (stop) break;
+    if (stop || poor) break;
   }
 }
 

@@ -13,7 +13,7 @@ for h0,name in ((0.05,'ball005'),(0.035,'ball0035'),(0.02,'ball002')):
     p.tofile('/tmp/%s.bin'%name)
 PY
 g++ -O2 -std=c++17 -ffp-contract=off -pthread -Iinclude -Iseismicmesh_b200/csrc/host tools/host/delaunay3d_file_driver.cpp seismicmesh_b200/csrc/host/dm_delaunay3d.cpp -o /tmp/drvf
-for f in ball005 ball0035 ball002; do for th in 1 6 8 12 15; do for rr in 2000 4000 8000; do for pr in 750 1500; do
-  echo "== $f threads $th round_rows $rr pass_rows $pr: $(DM_HOST_ROUND_ROWS=$rr DM_HOST_PASS_ROWS=$pr /tmp/drvf /tmp/$f.bin $th 2>&1 | tail -1)"
+for f in ball005 ball0035 ball002; do for th in 1 8 12 15; do for rr in ${PASSES:-5 9}; do for pr in 1000 1500 2500; do
+  echo "== $f threads $th passes $rr pass_rows $pr: $(DM_HOST_PASSES=$rr DM_HOST_PASS_ROWS=$pr /tmp/drvf /tmp/$f.bin $th 2>&1 | tail -1)"
   [ $th = 1 ] && break 2
 done; done; done; done > gpurun_out/${TAG}_tune.log 2>&1
