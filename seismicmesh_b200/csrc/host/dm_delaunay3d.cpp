@@ -611,6 +611,18 @@ struct KdTree {
     if (cnt <= 1 || hi - lo < 2) return -(first + 1);
     int a = rule == 0 ? cnt / 2 : rule == 1 ? (3 * cnt + 4) / 8 : (5 * cnt + 3) / 8;
     a = std::max(1, std::min(cnt - 1, a));
+    // cut across the axis whose turn it is unless the box is thin in it (less than 0.6 of its longest
+    // extent: a cut there would leave two plates that are mostly border)
+    {
+      double ext[3];
+      for (int k = 0; k < 3; ++k) {
+        double mn = P[3 * (int64_t)*lo + k], mx = mn;
+        for (const int32_t* x = lo; x < hi; ++x) mn = std::min(mn, P[3 * (int64_t)*x + k]), mx = std::max(mx, P[3 * (int64_t)*x + k]);
+        ext[k] = mx - mn;
+      }
+      const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
+      for (int tries = 0; tries < 3 && ext[axis] < 0.6 * longest; ++tries) axis = (axis + 1) % 3;
+    }
     int32_t* mid = lo + (hi - lo) * (int64_t)a / cnt;
     std::nth_element(lo, mid, hi, [&](int32_t x, int32_t y) { return P[3 * (int64_t)x + axis] < P[3 * (int64_t)y + axis]; });
     const int me = (int)nodes.size();
@@ -642,9 +654,10 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
     const int64_t stride = std::max<int64_t>(1, n / 32768);
     for (int64_t v = 0; v < n; v += stride) sample.push_back((int32_t)v);
   }
+  int most = nth;  // boxes of a pass (halved whenever a pass inserted less than a fifth of its points: boxes too small)
   for (int pass = 0; pass < par_passes(); ++pass) {
     if ((int64_t)pending.size() < 2 * par_pass_rows()) break;
-    const int want = (int)std::max<int64_t>(2, std::min<int64_t>(nth, (int64_t)pending.size() / par_pass_rows()));
+    const int want = (int)std::max<int64_t>(2, std::min<int64_t>(most, (int64_t)pending.size() / par_pass_rows()));
     // (first axis, cutting rule, number of boxes: no two passes cut along the same planes)
     const int parts = std::min<int>((int)ctx.size(), want + (pass / 3) % 2);
     KdTree kd;
@@ -694,7 +707,8 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
     const bool poor = 5 * next.size() > 4 * pending.size();  // less than a fifth inserted: the boxes have become too small
     pending.swap(next);
     if (trace_on()) std::fprintf(stderr, "[dmh3d] pass %d: %d parts, %zu -> %zu pending, %.3f s\n", pass, parts, before, pending.size(), now_s() - tp0);
-    if (stop || poor) break;
+    if (stop || (poor && parts <= 2)) break;
+    if (poor) most = std::max(2, parts / 2);
   }
 }
 
