@@ -92,6 +92,15 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
 int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
                       int64_t* duplicates_out, int64_t* lost_out, int threads);
 
+/* Sorted unique rows of an int32 table `rows` (n, k), k = 2, 3 or 4, ids in [0, N): the ids of every row
+ * are sorted ascending, the rows put in lexicographic order and equal rows collapsed, in place; the
+ * *n_unique rows left are at the front, `counts` (n entries, may be NULL) holds how often each occurred.
+ * Replaces geometry.unique_rows of the row-wise sorted list (SeismicMesh/geometry/utils.py:141-172) where
+ * the reference's termination path and its boundary queries use it on cells, facets and edges (fix_mesh
+ * :204-246, get_boundary_edges / get_boundary_facets :310-361: a facet that occurs once is on the boundary).
+ * `threads` <= 0: 8. */
+int dmh_sort_unique_rows_i32(int32_t* rows, int64_t n, int k, int64_t N, int32_t* counts, int64_t* n_unique, int threads);
+
 /* The exact predicates, exported for the tests.
  * orient3d > 0: (a, b, c, d) positively oriented; insphere > 0: e strictly inside the sphere through a positively oriented (a, b, c, d). */
 double dmh_orient3d(const double* a, const double* b, const double* c, const double* d);

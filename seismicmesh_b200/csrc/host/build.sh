@@ -5,5 +5,5 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../../libdistmesh_host.so"
 "${CXX:-g++}" -O2 -std=c++17 -ffp-contract=off -fPIC -shared -pthread -Wall -I"$HERE/../../../include" \
-  "$HERE/dm_delaunay2d.cpp" "$HERE/dm_delaunay3d.cpp" -o "$OUT"
+  "$HERE/dm_delaunay2d.cpp" "$HERE/dm_delaunay3d.cpp" "$HERE/dm_rows.cpp" -o "$OUT"
 echo "built $OUT"

@@ -50,7 +50,7 @@ def simp_qual(p, t):
     return 2 * r / R
 
 
-def _unique_rows(a, return_index=False, return_inverse=False, return_counts=False):
+def _unique_rows(a, return_index=False, return_inverse=False, return_counts=False, rows_sorted=False):
     """`np.unique(a, axis=0, ...)` (rows in lexicographic order, index of the first occurrence,
     inverse, counts) without NumPy's structured-dtype sort, which dominates the termination step:
     integer rows are packed into one int64 key per row when they fit, everything else goes through
@@ -59,6 +59,24 @@ def _unique_rows(a, return_index=False, return_inverse=False, return_counts=Fals
     n, m = a.shape
     if n == 0:
         return np.unique(a, axis=0, return_index=return_index, return_inverse=return_inverse, return_counts=return_counts)
+    if rows_sorted and not (return_index or return_inverse) and a.dtype.kind in "iu" and m in (2, 3, 4) and n < 2**31:
+        # the termination path's case (cells / facets / edges with ascending ids per row): native code
+        lo, hi = int(a.min()), int(a.max())
+        if lo >= 0 and hi < 2**31 - 1:
+            import ctypes as C
+
+            from ._hostlib import lib as _host
+            from .triangulator import host_threads
+
+            rows = np.array(a, dtype=np.int32, order="C")  # (a copy: collapsed in place)
+            counts = np.empty(n, dtype=np.int32) if return_counts else None
+            nu = C.c_int64(0)
+            rc = _host().dmh_sort_unique_rows_i32(rows.ctypes.data, n, m, hi + 1, counts.ctypes.data if return_counts else None,
+                                                  C.byref(nu), host_threads())
+            if rc != 0:
+                raise RuntimeError(f"dmh_sort_unique_rows_i32 failed with code {rc}")
+            u = rows[: nu.value].astype(a.dtype, copy=False)
+            return (u, counts[: nu.value].astype(np.intp)) if return_counts else u
     bits = 63 // m
     if a.dtype.kind in "iu" and a.min() >= 0 and int(a.max()) < (1 << bits):
         key = a[:, 0].astype(np.int64)
@@ -92,7 +110,7 @@ def fix_mesh(p, t, ptol=2e-13, dim=2, delete_unused=False, fix_orientation=True)
     jx = np.asarray(jx).ravel()
     p = p[ix]
     t = jx[t]
-    t = _unique_rows(np.sort(t, axis=1))
+    t = _unique_rows(np.sort(t, axis=1), rows_sorted=True)
     if delete_unused:
         used, jx = np.unique(t, return_inverse=True)
         t = np.asarray(jx).reshape(t.shape)
@@ -114,7 +132,7 @@ def get_facets(t):
 
 
 def _once(rows, count):
-    u, c = _unique_rows(np.sort(rows, axis=1), return_counts=True)
+    u, c = _unique_rows(np.sort(rows, axis=1), return_counts=True, rows_sorted=True)
     return u[c == count]
 
 

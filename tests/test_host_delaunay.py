@@ -291,3 +291,28 @@ def test_get_triangulator_defaults():
         get_triangulator("bowyer-watson", 2)
     with pytest.raises(ValueError):
         get_triangulator("cgal", 2)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_sort_unique_rows_matches_numpy(hl, k):
+    """dmh_sort_unique_rows_i32 (the termination path's unique_rows of row-wise sorted cells / facets /
+    edges): rows, order and multiplicities of np.unique(np.sort(rows, 1), axis=0, return_counts=True),
+    below and above the size where it goes multi-threaded; bad ids are refused."""
+    rng = np.random.default_rng(k)
+    for n, N in ((0, 5), (1, 3), (500, 40), (150000, 3000)):
+        rows = rng.integers(0, N, (n, k)).astype(np.int32)
+        rows[: n // 3] = rows[n // 3: 2 * (n // 3)]  # plenty of duplicates
+        want, wc = (np.unique(np.sort(rows, axis=1), axis=0, return_counts=True) if n else (rows, np.empty(0, int)))
+        got = np.ascontiguousarray(rows.copy())
+        counts = np.empty(max(n, 1), np.int32)
+        nu = C.c_int64(-1)
+        assert hl.dmh_sort_unique_rows_i32(got.ctypes.data, n, k, N, counts.ctypes.data, C.byref(nu), 4) == 0
+        assert nu.value == len(want) and np.array_equal(got[: nu.value], want) and np.array_equal(counts[: nu.value], wc)
+        nu2 = C.c_int64(-1)
+        again = np.ascontiguousarray(rows.copy())
+        assert hl.dmh_sort_unique_rows_i32(again.ctypes.data, n, k, N, None, C.byref(nu2), 1) == 0
+        assert nu2.value == len(want) and np.array_equal(again[: nu2.value], want)
+    bad = np.array([[0, 1, 7][:k] + [0] * (k - 3)], dtype=np.int32)
+    bad[0, -1] = 9
+    assert hl.dmh_sort_unique_rows_i32(bad.ctypes.data, 1, k, 9, None, C.byref(nu), 1) == -1
+    assert hl.dmh_sort_unique_rows_i32(bad.ctypes.data, 1, 5, 10, None, C.byref(nu), 1) == -1
