@@ -20,7 +20,9 @@ The default invocation (N = 1) also carries, as sub-records of the same line:
   `time_to_mesh`  BASELINE.json's second metric: generate_mesh end to end (host Delaunay included) on
                   disk h0 = 0.01 and ball h0 = 0.05, 25 iterations, reference semantics and `ttol`.
 With N > 1 the step is the slab-decomposed one (one slab per GPU, ghosts chosen by dm_halo_select, one
-halo exchange per step), on the ball-sized cylinder slabs and, as a sub-record, on EAGE-shaped slabs.
+halo exchange per step), on the ball-sized cylinder slabs and, as a sub-record, on EAGE-shaped slabs; the
+`time_to_mesh` block is then generate_mesh(comm=...) over the N ranks (a box of N unit cubes at
+h0 = 0.031, and the EAGE-shaped hmin 150 m domain cut into N slabs).
 `--impl reference` times the reference's own CPU loop body (oracle port + the reference's compiled
 unique_edges) on the SAME configuration, without importing the product package.
 """
@@ -715,6 +717,44 @@ def time_to_mesh(cases, iters):
     return out
 
 
+def time_to_mesh_slabs(world, rank, iters):
+    """Time-to-mesh on N GPUs (BASELINE.json's metric names 1/2/4/8): generate_mesh(comm=...) end to end --
+    initial points, slab decomposition (decomp.blocker), per-iteration host Delaunay of every slab with the
+    host cores divided among the ranks, device loop, halo migration, gather on rank 0 -- on a box of
+    `world` unit cubes at h0 = 0.031 (33 k vertices per GPU, the size of the N = 1 block's ball: weak scaling)
+    and on the EAGE-shaped domain at hmin 150 m / 2 Hz (a fixed mesh cut into `world` slabs: strong scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    import seismicmesh_b200 as sm
+    from seismicmesh_b200 import meshutil
+    from seismicmesh_b200.parallel import TorchComm
+
+    comm = TorchComm()
+    vp, bbox = synth_vp("eage")
+    _, _, _, kw = sizing_kwargs("eage", vp, 150.0, 2.0)
+    ef = sm.get_sizing_function_from_segy(None, bbox, velocity_data=vp, **kw)
+    del vp
+    cases = ((f"box_of_{world}_unit_cubes_h0=0.031", sm.Cube((0.0, 1.0, 0.0, float(world), 0.0, 1.0)), 0.031, 1, "weak"),
+             ("eage_shaped_hmin=150_freq=2", sm.Cube(ef.bbox), ef, 1, "strong"))
+    out = {}
+    for name, dom, edge, axis, scaling in cases:
+        dist.barrier()
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        res = sm.generate_mesh(dom, edge, comm=comm, max_iter=iters, axis=axis, verbose=0)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - c0, float(sm.last_run_stats.get("delaunay", 0.0))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            pm, tm = res
+            qm = meshutil.simp_qual(pm, tm)
+            out[name] = {"wall_s_max_over_ranks": float(tt[0]), "delaunay_s_max_over_ranks": float(tt[1]), "ranks": world,
+                         "scaling": scaling, "vertices": int(len(pm)), "cells": int(len(tm)), "mean_quality": float(qm.mean()),
+                         "min_quality": float(qm.min()), "max_iter": iters, "triangulator": sm.last_run_stats.get("triangulator")}
+    return out if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -789,6 +829,8 @@ def main():
             extras["time_to_mesh"] = time_to_mesh(
                 (("disk_h0=0.01", sm.Disk([0.0, 0.0], 1.0), 0.01, (0.1, 0.3)),
                  ("ball_h0=0.05", sm.Ball([0.0, 0.0, 0.0], 1.0), 0.05, (0.1, 0.5)),
+                 # (the per-GPU workload of the N > 1 block's weak-scaling case: box of N unit cubes)
+                 ("box_of_1_unit_cubes_h0=0.031", sm.Cube((0.0, 1.0, 0.0, 1.0, 0.0, 1.0)), 0.031, ()),
                  ("eage_shaped_hmin=150_freq=2", sm.Cube(ef.bbox), ef, (0.5,))),
                 args.time_to_mesh)
             del ef
@@ -803,6 +845,12 @@ def main():
         except Exception as exc:  # never lose the headline line to a sub-record
             if rank == 0:
                 extras["workloads"] = {"eage_slabs": {"error": f"{type(exc).__name__}: {exc}"}}
+        if args.time_to_mesh > 1:
+            try:
+                extras["time_to_mesh"] = time_to_mesh_slabs(world, rank, args.time_to_mesh)
+            except Exception as exc:
+                if rank == 0:
+                    extras["time_to_mesh"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         out = {
