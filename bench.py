@@ -711,6 +711,19 @@ def time_to_mesh(cases, iters):
                          "vertices": int(len(pm)), "cells": int(len(tm)), "mean_quality": float(qm.mean()),
                          "min_quality": float(qm.min()),
                          "vertex_updates_per_s_wall": st_["nverts"] * st_["iterations"] / wall_m}
+        if name.startswith("ball"):
+            # BASELINE.json configs[1], second half: sliver_removal on the mesh just made (the reference-
+            # semantics points are regenerated: `pm` above belongs to the last ttol run)
+            pm, tm = sm.generate_mesh(dom, edge, max_iter=iters, verbose=0)
+            c0 = time.perf_counter()
+            ps, ts = sm.sliver_removal(points=pm, domain=dom, edge_length=edge, verbose=0)
+            wall_s = time.perf_counter() - c0
+            ss = dict(sm.last_run_stats)
+            dh = sm.geometry.calc_dihedral_angles(ps, ts)
+            res["sliver_removal"] = {"wall_s": wall_s, "delaunay_s": ss.get("delaunay"), "passes": ss.get("iterations"),
+                                     "vertices": int(len(ps)), "cells": int(len(ts)),
+                                     "min_dihedral_deg": float(np.min(dh) * 180 / np.pi),
+                                     "what": "sliver_removal(points=<the 25-iteration mesh>, min dihedral bound 10 deg, max_iter 50)"}
         res["max_iter"] = iters
         res["triangulator"] = st_["triangulator"]
         out[name] = res
