@@ -92,6 +92,22 @@ int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap,
 int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
                       int64_t* duplicates_out, int64_t* lost_out, int threads);
 
+/* A 3-D triangulation that stays around between calls.  dmh_dt3_build triangulates `points` (N,3) with
+ * `threads` threads (as dmh_delaunay3d_mt) and returns a handle (NULL on error, *rc_out = the code);
+ * dmh_dt3_cells writes its cells (conventions of dmh_delaunay3d; ids = rows in the order the points were
+ * given, first the N of the build, then every inserted batch); dmh_dt3_insert adds `more` (M,3) to the SAME
+ * triangulation by serial incremental insertion; dmh_dt3_points = rows so far; dmh_dt3_free releases it.
+ * This is the reference's use of its CGAL object in the slab-parallel loop: the owned vertices are
+ * triangulated, the cells decide which vertices a neighbour needs, the ghost vertices received in exchange
+ * are INSERTED (`dt.insert`, mesh_generator.py:466 with :715-731) and the cells read again -- one
+ * construction and a short insertion per iteration instead of two constructions.  A handle whose start was
+ * degenerate (fewer than four affinely independent points) is rebuilt from all points at the next insert. */
+void* dmh_dt3_build(const double* points, int64_t N, int threads, int* rc_out);
+int dmh_dt3_insert(void* handle, const double* more, int64_t M);
+int64_t dmh_dt3_points(void* handle);
+int dmh_dt3_cells(void* handle, int32_t* cells, int64_t cap, int64_t* T_out, int64_t* duplicates_out, int64_t* lost_out);
+void dmh_dt3_free(void* handle);
+
 /* Sorted unique rows of an int32 table `rows` (n, k), k = 2, 3 or 4, ids in [0, N): the ids of every row
  * are sorted ascending, the rows put in lexicographic order and equal rows collapsed, in place; the
  * *n_unique rows left are at the front, `counts` (n entries, may be NULL) holds how often each occurred.

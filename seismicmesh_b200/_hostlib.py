@@ -14,6 +14,11 @@ _SIGNATURES = {
     "dmh_delaunay3d_max_cells": (_I64, [_I64]),
     "dmh_delaunay3d": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "dmh_delaunay3d_mt": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.c_int]),
+    "dmh_dt3_build": (C.c_void_p, [_P, _I64, C.c_int, C.POINTER(C.c_int)]),
+    "dmh_dt3_insert": (C.c_int, [_P, _P, _I64]),
+    "dmh_dt3_points": (_I64, [_P]),
+    "dmh_dt3_cells": (C.c_int, [_P, _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "dmh_dt3_free": (None, [_P]),
     "dmh_sort_unique_rows_i32": (C.c_int, [_P, _I64, C.c_int, _I64, _P, C.POINTER(_I64), C.c_int]),
     "dmh_orient3d": (C.c_double, [_P, _P, _P, _P]),
     "dmh_insphere": (C.c_double, [_P, _P, _P, _P, _P]),

@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <limits>
 #include <thread>
+#include <utility>
 #include <vector>
 #if defined(__linux__)
 #include <sched.h>
@@ -712,23 +713,25 @@ void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& p
   }
 }
 
-}  // namespace
+// A triangulation that stays around between calls (dmh_dt3_*): the points in insertion order, the map back
+// to the caller's rows, the tetrahedra and the per-thread insertion state.
+struct Dt3 {
+  std::vector<double> sorted;
+  std::vector<int32_t> ids;
+  Delaunay3 D;
+  std::vector<Ctx> ctx;
+  int nth = 1;
+  int64_t N = 0;
+  bool built = false, failed = false;
+  double t_begin = 0.0, t_sorted = 0.0;
+};
 
-extern "C" {
-
-int64_t dmh_delaunay3d_max_cells(int64_t N) { return N < 4 ? 1 : 8 * N + 64; }
-
-int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
-                      int64_t* duplicates_out, int64_t* lost_out, int threads) {
-  if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
-      N > (int64_t)std::numeric_limits<int32_t>::max() / 64)
-    return DMH_ERR_ARG;
-  *T_out = 0;
-  if (duplicates_out != nullptr) *duplicates_out = 0;
-  if (lost_out != nullptr) *lost_out = N;
-  if (N < 4) return DMH_OK;
+// insertion of all N points; S.built stays false when there are not four affinely independent points
+int dt3_build(Dt3& S, const double* points, int64_t N, int threads) {
   int nth = pick_threads(threads);
   if (N < PAR_MIN_ROUND) nth = 1;
+  S.nth = nth;
+  S.N = N;
   const double t_begin = now_s();
 
   // ---- insertion order: rounds of growing size, Morton order within a round
@@ -780,8 +783,10 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   } else {
     std::sort(items.begin(), items.end(), less);
   }
-  std::vector<double> sorted(3 * N);
-  std::vector<int32_t> ids(N);
+  std::vector<double>& sorted = S.sorted;
+  std::vector<int32_t>& ids = S.ids;
+  sorted.assign(3 * N, 0.0);
+  ids.assign(N, 0);
   run_threads(nth, [&](int j) {
     for (int64_t r = N * j / nth; r < N * (j + 1) / nth; ++r) {
       ids[r] = items[r].id;
@@ -800,11 +805,12 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   items.shrink_to_fit();
 
   const double t_sorted = now_s();
-  Delaunay3 D;
+  Delaunay3& D = S.D;
   D.P = sorted.data();
   D.n = N;
   D.grow(7 * N + 64 + (nth > 1 ? (int64_t)nth * 4 * CHUNK + N : 0));
-  std::vector<Ctx> ctx(nth + 1);  // (a pass with shifted bounds has one partition more)
+  std::vector<Ctx>& ctx = S.ctx;
+  ctx.assign(nth + 1, Ctx());  // (a pass with shifted bounds has one partition more)
   for (int j = 0; j <= nth; ++j) ctx[j].stamp_next = j + 1;
   Ctx& c0 = ctx[0];
   // ---- four affinely independent points to start from
@@ -816,6 +822,7 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   for (int64_t r = 1; r < N && c >= 0 && d < 0; ++r)
     if (r != b && r != c && orient3d(D.pt(a), D.pt(b), D.pt(c), D.pt((int32_t)r)) != 0.0) d = (int32_t)r;
   if (d < 0) return DMH_OK;  // fewer than four affinely independent points: no cell, every row lost
+  S.built = true;
   D.init(c0, a, b, c, d);
   bool failed = false;
   auto serial = [&](int64_t r) {
@@ -852,7 +859,22 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
       if (trace_on()) std::fprintf(stderr, "[dmh3d] round of %ld: parallel %.3f s, serial rest (%zu) %.3f s\n", (long)(r1 - r0), tr1 - tr0, pending.size(), now_s() - tr1);
     }
   }
+  S.failed = failed;
+  S.t_begin = t_begin;
+  S.t_sorted = t_sorted;
+  return DMH_OK;
+}
+
+// the finite tetrahedra in the caller's numbering and the canonical output order
+int dt3_extract(Dt3& S, int32_t* cells, int64_t cap, int64_t* T_out, int64_t* duplicates_out, int64_t* lost_out) {
   const double t_built = now_s();
+  Delaunay3& D = S.D;
+  std::vector<Ctx>& ctx = S.ctx;
+  const std::vector<int32_t>& ids = S.ids;
+  const int nth = S.nth;
+  const int64_t N = S.N;
+  const bool failed = S.failed;
+  const double t_begin = S.t_begin, t_sorted = S.t_sorted;
   int64_t dups = 0, lost = 0;
   for (int j = 0; j <= nth; ++j) dups += ctx[j].dups, lost += ctx[j].lost;
   if (failed) lost += 1;
@@ -887,10 +909,139 @@ int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t c
   return DMH_OK;
 }
 
+// M more points (rows N .. N + M - 1 of the caller) into the triangulation that stands: serial insertion along
+// a Morton curve of their own.  What the reference does with the ghost vertices of a slab: `dt.insert` on the
+// CGAL triangulation that already holds the owned ones (mesh_generator.py:466, 715-731).
+int dt3_insert(Dt3& S, const double* more, int64_t M) {
+  if (M == 0) return DMH_OK;
+  double lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) lo[k] = std::numeric_limits<double>::infinity(), hi[k] = -lo[k];
+  for (int64_t i = 0; i < M; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const double v = more[3 * i + k];
+      if (!(v == v) || std::fabs(v) == std::numeric_limits<double>::infinity()) return DMH_ERR_ARG;
+      lo[k] = std::min(lo[k], v);
+      hi[k] = std::max(hi[k], v);
+    }
+  const int64_t N = S.N;
+  std::vector<std::pair<uint64_t, int32_t>> order((size_t)M);
+  for (int64_t i = 0; i < M; ++i) {
+    uint64_t q[3];
+    for (int k = 0; k < 3; ++k) {
+      const double w = hi[k] - lo[k];
+      q[k] = w > 0.0 ? (uint64_t)std::min(2097151.0, (more[3 * i + k] - lo[k]) / w * 2097152.0) : 0;
+    }
+    order[(size_t)i] = {spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2, (int32_t)i};
+  }
+  std::sort(order.begin(), order.end());
+  S.sorted.reserve(S.sorted.size() + 3 * M);
+  for (int64_t r = 0; r < M; ++r) {
+    const int64_t i = order[(size_t)r].second;
+    for (int k = 0; k < 3; ++k) S.sorted.push_back(more[3 * i + k]);
+    S.ids.push_back((int32_t)(N + i));
+  }
+  Delaunay3& D = S.D;
+  D.P = S.sorted.data();
+  D.n = N + M;
+  S.N = N + M;
+  Ctx& c0 = S.ctx[0];
+  if (c0.last < 0 || D.is_dead(c0.last)) {
+    c0.last = -1;
+    for (int64_t t = 0; t < D.slots() && c0.last < 0; ++t)
+      if (!D.is_dead(t)) c0.last = (int32_t)t;
+  }
+  for (int64_t r = N; r < N + M && !c0.failed; ++r) D.insert<false>(c0, (int32_t)r);
+  S.failed = S.failed || c0.failed;
+  return DMH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t dmh_delaunay3d_max_cells(int64_t N) { return N < 4 ? 1 : 8 * N + 64; }
+
+int dmh_delaunay3d_mt(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
+                      int64_t* duplicates_out, int64_t* lost_out, int threads) {
+  if (N < 0 || cap < 0 || T_out == nullptr || (N > 0 && points == nullptr) || (cap > 0 && cells == nullptr) ||
+      N > (int64_t)std::numeric_limits<int32_t>::max() / 64)
+    return DMH_ERR_ARG;
+  *T_out = 0;
+  if (duplicates_out != nullptr) *duplicates_out = 0;
+  if (lost_out != nullptr) *lost_out = N;
+  if (N < 4) return DMH_OK;
+  Dt3 S;
+  const int rc = dt3_build(S, points, N, threads);
+  if (rc != DMH_OK || !S.built) return rc;
+  return dt3_extract(S, cells, cap, T_out, duplicates_out, lost_out);
+}
+
 int dmh_delaunay3d(const double* points, int64_t N, int32_t* cells, int64_t cap, int64_t* T_out,
                    int64_t* duplicates_out, int64_t* lost_out) {
   return dmh_delaunay3d_mt(points, N, cells, cap, T_out, duplicates_out, lost_out, 1);
 }
+
+/* ---- a triangulation that stays around: build, read the cells, add points, read the cells again ---- */
+namespace {
+struct Dt3Handle {
+  std::unique_ptr<Dt3> s;
+  std::vector<double> all;  // every point so far, in the caller's order (a degenerate start is redone from these)
+  int threads = 0;
+  int64_t N = 0;
+  int rebuild() {
+    s.reset(new Dt3);
+    s->N = N;
+    return N >= 4 ? dt3_build(*s, all.data(), N, threads) : DMH_OK;
+  }
+};
+}  // namespace
+
+void* dmh_dt3_build(const double* points, int64_t N, int threads, int* rc_out) {
+  int rc = DMH_OK;
+  Dt3Handle* H = nullptr;
+  if (N < 0 || (N > 0 && points == nullptr) || N > (int64_t)std::numeric_limits<int32_t>::max() / 64) {
+    rc = DMH_ERR_ARG;
+  } else {
+    H = new Dt3Handle;
+    H->all.assign(points, points + 3 * N);
+    H->N = N;
+    H->threads = threads;
+    rc = H->rebuild();
+    if (rc != DMH_OK) {
+      delete H;
+      H = nullptr;
+    }
+  }
+  if (rc_out != nullptr) *rc_out = rc;
+  return H;
+}
+
+int dmh_dt3_insert(void* handle, const double* more, int64_t M) {
+  Dt3Handle* H = static_cast<Dt3Handle*>(handle);
+  if (H == nullptr || M < 0 || (M > 0 && more == nullptr) || H->N + M > (int64_t)std::numeric_limits<int32_t>::max() / 64)
+    return DMH_ERR_ARG;
+  if (M == 0) return DMH_OK;
+  for (int64_t i = 0; i < 3 * M; ++i)  // (refused before anything is recorded)
+    if (!(more[i] == more[i]) || std::fabs(more[i]) == std::numeric_limits<double>::infinity()) return DMH_ERR_ARG;
+  H->all.insert(H->all.end(), more, more + 3 * M);
+  H->N += M;
+  if (!H->s->built || H->s->failed) return H->rebuild();  // nothing sound to add to: start over with everything
+  return dt3_insert(*H->s, more, M);
+}
+
+int64_t dmh_dt3_points(void* handle) { return handle == nullptr ? -1 : static_cast<Dt3Handle*>(handle)->N; }
+
+int dmh_dt3_cells(void* handle, int32_t* cells, int64_t cap, int64_t* T_out, int64_t* duplicates_out, int64_t* lost_out) {
+  Dt3Handle* H = static_cast<Dt3Handle*>(handle);
+  if (H == nullptr || cap < 0 || T_out == nullptr || (cap > 0 && cells == nullptr)) return DMH_ERR_ARG;
+  *T_out = 0;
+  if (duplicates_out != nullptr) *duplicates_out = 0;
+  if (lost_out != nullptr) *lost_out = H->N;
+  if (!H->s->built) return DMH_OK;
+  return dt3_extract(*H->s, cells, cap, T_out, duplicates_out, lost_out);
+}
+
+void dmh_dt3_free(void* handle) { delete static_cast<Dt3Handle*>(handle); }
 
 double dmh_orient3d(const double* a, const double* b, const double* c, const double* d) { return orient3d(a, b, c, d); }
 double dmh_insphere(const double* a, const double* b, const double* c, const double* d, const double* e) {

@@ -402,7 +402,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
     from . import geometry
     from ._lib import check, lib
     from .engine import ForceLoop, Level
-    from .triangulator import get_triangulator
+    from .triangulator import _Rebuilt, get_triangulator
 
     rank, size_ = int(comm.rank), int(comm.size)
     group = getattr(comm, "group", None)
@@ -522,7 +522,8 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         start = time.time()
         n_own = len(p)
         t0 = time.perf_counter()
-        t_own = tri.triangulate(p)
+        dt = tri.build(p) if hasattr(tri, "build") else _Rebuilt(tri, p)  # (stays around: the ghosts are inserted into it below, as the reference does with its CGAL object)
+        t_own = dt.cells()
         stats["delaunay"] += time.perf_counter() - t0
         # ---- ghosts: export the vertices whose cells' circumballs reach a neighbour (enqueue + exchange)
         t1 = time.perf_counter()
@@ -538,7 +539,13 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
         ghosts = [g for g in (from_below, from_above) if len(g)]
         p_loc = np.ascontiguousarray(np.vstack([p] + ghosts)) if ghosts else p
         t0 = time.perf_counter()
-        t_loc = tri.triangulate(p_loc) if ghosts else t_own
+        if ghosts:
+            for g in ghosts:
+                dt.insert(g)
+            t_loc = dt.cells()
+        else:
+            t_loc = t_own
+        dt.close()
         stats["delaunay"] += time.perf_counter() - t0
         # cells with all their vertices outside this rank's extent belong to somebody else
         # (geometry.remove_external_entities, geometry/utils.py:57-94)

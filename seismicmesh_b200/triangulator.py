@@ -32,8 +32,29 @@ def host_threads():
     return max(1, min(16, mine - 1 if mine >= 8 else mine))  # (one core left to the rest of the process)
 
 
+class _Rebuilt:
+    """`tri.build(points)` for a triangulator without state: the cells are recomputed from all points."""
+
+    def __init__(self, tri, points):
+        self._tri = tri
+        self._p = np.ascontiguousarray(points, dtype=np.float64)
+
+    def insert(self, more):
+        if len(more):
+            self._p = np.ascontiguousarray(np.vstack((self._p, more)))
+
+    def cells(self):
+        return self._tri.triangulate(self._p)
+
+    def close(self):
+        pass
+
+
 class QhullTriangulator:
     name = "qhull (scipy.spatial.Delaunay)"
+
+    def build(self, points):
+        return _Rebuilt(self, points)
 
     def __init__(self, dim):
         self.dim = dim
@@ -61,6 +82,9 @@ class SweepHullTriangulator:
     """2-D Delaunay by ``dmh_delaunay2d`` (exact predicates, vertex ids = input rows)."""
 
     name = "sweep-hull (libdistmesh_host)"
+
+    def build(self, points):
+        return _Rebuilt(self, points)
 
     def __init__(self, dim):
         if dim != 2:
@@ -158,6 +182,13 @@ class BowyerWatsonTriangulator:
     def max_cells(self, n):
         return int(self._lib.dmh_delaunay3d_max_cells(n))
 
+    def build(self, points):
+        """A triangulation that stays around (dmh_dt3_*): ``.cells()``, then ``.insert(more)`` adds rows
+        len(points).. to the SAME triangulation (serial incremental insertion) and ``.cells()`` again -- what
+        the reference's slab ranks do with their ghost vertices (``dt.insert`` on the CGAL object that
+        already holds the owned ones, mesh_generator.py:466, 715-731) instead of triangulating twice."""
+        return _Dt3(self, points)
+
     def triangulate_into(self, points, cells):
         """Raw-buffer form: see SweepHullTriangulator.triangulate_into."""
         n = len(points)
@@ -171,6 +202,57 @@ class BowyerWatsonTriangulator:
             self.qhull_retries += 1
             return QhullTriangulator(3).triangulate_into(points, cells)
         return int(T.value)
+
+
+class _Dt3:
+    def __init__(self, tri, points):
+        self._tri = tri
+        self._lib = tri._lib
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise ValueError("points must be (N, 3)")
+        self._all = [p]
+        rc = C.c_int(0)
+        self._h = self._lib.dmh_dt3_build(p.ctypes.data, len(p), tri.threads, C.byref(rc))
+        if not self._h:
+            raise RuntimeError(f"dmh_dt3_build failed with code {rc.value}")
+
+    def insert(self, more):
+        q = np.ascontiguousarray(more, dtype=np.float64).reshape(-1, 3)
+        if len(q) == 0:
+            return
+        self._all.append(q)
+        rc = self._lib.dmh_dt3_insert(self._h, q.ctypes.data, len(q))
+        if rc != 0:
+            raise RuntimeError(f"dmh_dt3_insert failed with code {rc}")
+
+    def cells(self):
+        n = int(self._lib.dmh_dt3_points(self._h))
+        cap = self._tri.max_cells(n)
+        T, dups, lost = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        for _ in range(2):
+            cells = np.empty((cap, 4), dtype=np.int32)
+            rc = self._lib.dmh_dt3_cells(self._h, cells.ctypes.data, cap, C.byref(T), C.byref(dups), C.byref(lost))
+            if rc != -2:
+                break
+            cap = T.value
+        if rc != 0:
+            raise RuntimeError(f"dmh_dt3_cells failed with code {rc}")
+        if lost.value and n >= 4:  # as in triangulate(): not a clean triangulation of every distinct row
+            self._tri.qhull_retries += 1
+            return QhullTriangulator(3).triangulate(np.vstack(self._all))
+        return np.ascontiguousarray(cells[: T.value])
+
+    def close(self):
+        if self._h:
+            self._lib.dmh_dt3_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def get_triangulator(spec, dim):

@@ -365,3 +365,52 @@ def test_host_threads_split_among_ranks(monkeypatch):
     assert tr.host_threads() == want(cores // 8)
     monkeypatch.setenv("DM_HOST_THREADS", "5")
     assert tr.host_threads() == 5
+
+
+# ---- dmh_dt3_*: a triangulation that stays around (build, cells, insert more points, cells) ----------
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_incremental_insert_same_cells_as_rebuild(hl, threads):  # noqa: F811
+    """What a slab rank does every iteration: triangulate the owned vertices, read the cells, INSERT the
+    ghost vertices into the same triangulation, read the cells again.  Both cell lists must equal a
+    construction from scratch (points in general position), in the canonical output order."""
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator, get_triangulator
+
+    rng = np.random.default_rng(2)
+    own = rng.random((12000, 3))
+    ghosts = [rng.random((900, 3)) * [1.0, 0.12, 1.0] - [0.0, 0.12, 0.0], rng.random((700, 3)) * [1.0, 0.12, 1.0] + [0.0, 1.0, 0.0]]
+    tri = BowyerWatsonTriangulator(3, threads=threads)
+    dt = tri.build(own)
+    t_own = dt.cells()
+    assert _is_lex_sorted(t_own) and np.array_equal(_rows_sorted(t_own), _rows_sorted(tri.triangulate(own)))
+    for g in ghosts:
+        dt.insert(g)
+    dt.insert(np.empty((0, 3)))
+    t_loc = dt.cells()
+    allp = np.vstack([own] + ghosts)
+    assert t_loc.dtype == np.int32 and _is_lex_sorted(t_loc) and np.unique(t_loc).size == len(allp)
+    assert np.array_equal(_rows_sorted(t_loc), _rows_sorted(tri.triangulate(allp)))
+    dt.close()
+    dt.close()  # idempotent
+    # a start without four affinely independent points is redone from all points at the first insert
+    flat = np.ascontiguousarray(np.c_[rng.random((40, 2)), np.zeros(40)])
+    more = rng.random((300, 3))
+    T, dups, lost, rc = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+    h = hl.dmh_dt3_build(flat.ctypes.data, len(flat), threads, C.byref(rc))
+    assert h and rc.value == 0 and hl.dmh_dt3_points(h) == 40
+    out = np.empty((hl.dmh_delaunay3d_max_cells(340), 4), np.int32)
+    assert hl.dmh_dt3_cells(h, out.ctypes.data, len(out), C.byref(T), C.byref(dups), C.byref(lost)) == 0
+    assert (T.value, lost.value) == (0, 40)
+    assert hl.dmh_dt3_insert(h, more.ctypes.data, len(more)) == 0 and hl.dmh_dt3_points(h) == 340
+    assert hl.dmh_dt3_cells(h, out.ctypes.data, len(out), C.byref(T), C.byref(dups), C.byref(lost)) == 0 and lost.value == 0
+    assert np.array_equal(_rows_sorted(out[: T.value]), _rows_sorted(tri.triangulate(np.vstack((flat, more)))))
+    assert hl.dmh_dt3_cells(h, out.ctypes.data, 10, C.byref(T), None, None) == -2 and T.value > 10
+    bad = more.copy()
+    bad[3, 0] = np.nan
+    assert hl.dmh_dt3_insert(h, bad.ctypes.data, len(bad)) == -1 and hl.dmh_dt3_points(h) == 340  # nothing recorded
+    hl.dmh_dt3_free(h)
+    assert hl.dmh_dt3_insert(None, more.ctypes.data, 1) == -1
+    # triangulators without state answer the same calls by rebuilding
+    q = get_triangulator("qhull", 3).build(own[:400])
+    q.insert(ghosts[0][:40])
+    assert np.array_equal(_canon(q.cells()), _canon(tri.triangulate(np.vstack((own[:400], ghosts[0][:40])))))
