@@ -230,7 +230,7 @@ inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
 }
 
 constexpr int32_t INF = -1, DEAD = -2;
-constexpr int MAX_THREADS = 32;      // stamps of thread j are j + 1 + k * MAX_THREADS: unique over the whole run
+constexpr int MAX_THREADS = 32;      // (stamps of thread j are j + 1 + k * <threads of the call + 1>: unique over the whole run)
 constexpr int64_t CHUNK = 512;       // tetrahedron slots a thread claims at a time
 constexpr int PAR_PASSES = 6;
 constexpr int64_t PAR_MIN_ROUND = 8000;   // rounds smaller than this are inserted by one thread
@@ -306,6 +306,8 @@ struct Delaunay3 {
   std::vector<int32_t> mark;    // +stamp: in the cavity of that insertion, -stamp: tested and not in conflict
   std::vector<uint8_t> owner;   // partition of every vertex during a parallel phase
   std::atomic<int64_t> top{0};  // slots handed out so far
+  int32_t stamp_stride = 1;     // number of inserting contexts (a small stride keeps the stamps inside int32: at most
+                                // ~4 attempts per point and context even when every pass hands everything back)
   bool parallel = false;
 
   const double* pt(int32_t v) const { return P + 3 * (int64_t)v; }
@@ -497,7 +499,7 @@ struct Delaunay3 {
     }
     // ---- cavity: flood fill over the tetrahedra in conflict
     c.stamp = c.stamp_next;
-    c.stamp_next += MAX_THREADS;
+    c.stamp_next += stamp_stride;
     const int32_t stamp = c.stamp;
     c.cav.clear();
     c.bnd.clear();
@@ -811,6 +813,7 @@ int dt3_build(Dt3& S, const double* points, int64_t N, int threads) {
   D.grow(7 * N + 64 + (nth > 1 ? (int64_t)nth * 4 * CHUNK + N : 0));
   std::vector<Ctx>& ctx = S.ctx;
   ctx.assign(nth + 1, Ctx());  // (a pass with shifted bounds has one partition more)
+  D.stamp_stride = nth + 1;
   for (int j = 0; j <= nth; ++j) ctx[j].stamp_next = j + 1;
   Ctx& c0 = ctx[0];
   // ---- four affinely independent points to start from
