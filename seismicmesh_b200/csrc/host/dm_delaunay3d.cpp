@@ -650,10 +650,16 @@ struct KdTree {
 // Every pass cuts space into boxes along other planes, so that what a pass had to give back because it
 // touched a border of its box is inside a box of the next one; what is left after the last pass goes to
 // the serial code.
-void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& pending, int nth) {
+// `batch`: the points to insert are not spread like the points already in (ghost layers added to a slab): the
+// boxes are then cut from a sample of the pending points themselves, so that every thread gets its share.
+void parallel_round(Delaunay3& D, std::vector<Ctx>& ctx, std::vector<int32_t>& pending, int nth, bool batch = false) {
   const int64_t n = D.n;
+  if ((int64_t)D.owner.size() < n) D.owner.resize(n, 0);
   std::vector<int32_t> sample;
-  {
+  if (batch) {
+    const int64_t stride = std::max<int64_t>(1, (int64_t)pending.size() / 32768);
+    for (int64_t v = 0; v < (int64_t)pending.size(); v += stride) sample.push_back(pending[(size_t)v]);
+  } else {
     const int64_t stride = std::max<int64_t>(1, n / 32768);
     for (int64_t v = 0; v < n; v += stride) sample.push_back((int32_t)v);
   }
@@ -953,7 +959,30 @@ int dt3_insert(Dt3& S, const double* more, int64_t M) {
     for (int64_t t = 0; t < D.slots() && c0.last < 0; ++t)
       if (!D.is_dead(t)) c0.last = (int32_t)t;
   }
-  for (int64_t r = N; r < N + M && !c0.failed; ++r) D.insert<false>(c0, (int32_t)r);
+  // a large batch goes through the passes of a round (boxes cut from the batch itself), the rest serially
+  std::vector<int32_t> pending;
+  const int use = (int)std::min<int64_t>(S.nth, M / par_round_rows());
+  if (M >= PAR_MIN_ROUND && use >= 2) {
+    // one point in sixteen first, serially: a layer of points beyond a flat side of the hull starts with points
+    // that see the whole side (their cavity spans every box); once the side is broken up cavities are local
+    for (int64_t r = N; r < N + M; ++r) {
+      if ((r - N) % 16 == 0)
+        D.insert<false>(c0, (int32_t)r);
+      else
+        pending.push_back((int32_t)r);
+    }
+    D.grow(D.slots() + 8 * M + (int64_t)S.nth * 4 * CHUNK);  // (the arrays may not grow during a parallel phase)
+    parallel_round(D, S.ctx, pending, use, true);
+    for (size_t j = 0; j < S.ctx.size(); ++j) S.failed = S.failed || S.ctx[j].failed;
+    if (c0.last < 0 || D.is_dead(c0.last)) {
+      c0.last = -1;
+      for (int64_t t = 0; t < D.slots() && c0.last < 0; ++t)
+        if (!D.is_dead(t)) c0.last = (int32_t)t;
+    }
+    for (size_t x = 0; x < pending.size() && !S.failed && !c0.failed; ++x) D.insert<false>(c0, pending[x]);
+  } else {
+    for (int64_t r = N; r < N + M && !c0.failed; ++r) D.insert<false>(c0, (int32_t)r);
+  }
   S.failed = S.failed || c0.failed;
   return DMH_OK;
 }

@@ -392,6 +392,14 @@ def test_incremental_insert_same_cells_as_rebuild(hl, threads):  # noqa: F811
     assert np.array_equal(_rows_sorted(t_loc), _rows_sorted(tri.triangulate(allp)))
     dt.close()
     dt.close()  # idempotent
+    if threads > 1:  # batches large enough for the partitioned passes (two ghost layers beyond flat sides of the hull)
+        big = [rng.random((9000, 3)) * [1.0, 0.15, 1.0] - [0.0, 0.15, 0.0], rng.random((9000, 3)) * [1.0, 0.15, 1.0] + [0.0, 1.0, 0.0]]
+        dt = tri.build(own)
+        for g in big:
+            dt.insert(g)
+        t_big = dt.cells()
+        dt.close()
+        assert np.array_equal(_rows_sorted(t_big), _rows_sorted(tri.triangulate(np.vstack([own] + big))))
     # a start without four affinely independent points is redone from all points at the first insert
     flat = np.ascontiguousarray(np.c_[rng.random((40, 2)), np.zeros(40)])
     more = rng.random((300, 3))

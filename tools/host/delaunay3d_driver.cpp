@@ -23,4 +23,10 @@ int main(int argc,char**argv){
   bool same = T==T1;
   for(int64_t i=0;i<T && same;i++){ std::array<int,4> a{c[4*i],c[4*i+1],c[4*i+2],c[4*i+3]}, b{c1[4*i],c1[4*i+1],c1[4*i+2],c1[4*i+3]}; std::sort(a.begin(),a.end()); std::sort(b.begin(),b.end()); same = a==b; }
   printf("same as serial: %d\n",(int)same);
+  // the triangulation that stays around: 3/4 of the points built, the last quarter (shifted beyond a side of the
+  // hull: a ghost layer) inserted as one batch
+  { int64_t n0=3*n/4, m=n-n0; std::vector<double> q(p.begin()+3*n0,p.end()); for(int64_t i=0;i<m;i++) q[3*i+1]+=2.0;
+    int rc=0; void*h=dmh_dt3_build(p.data(),n0,nth,&rc); int rc2=dmh_dt3_insert(h,q.data(),m); int64_t T2=0;
+    int rc3=dmh_dt3_cells(h,c.data(),cap,&T2,&d,&l); dmh_dt3_free(h);
+    printf("build %ld + insert %ld: rc=%d/%d/%d T=%ld dups=%ld lost=%ld\n",n0,m,rc,rc2,rc3,T2,d,l); }
 }
