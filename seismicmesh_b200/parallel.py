@@ -402,7 +402,7 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
     from . import geometry
     from ._lib import check, lib
     from .engine import ForceLoop, Level
-    from .triangulator import _Rebuilt, get_triangulator
+    from .triangulator import _Rebuilt, get_triangulator, host_threads
 
     rank, size_ = int(comm.rank), int(comm.size)
     group = getattr(comm, "group", None)
@@ -573,7 +573,9 @@ def generate_mesh_parallel(domain, edge_length, comm, **kwargs):  # noqa: C901
             G.last_run_stats.update(stats)
             if rank != 0:
                 return True, True
-            gt = tri.triangulate(gp)
+            # (the other ranks are done: the final triangulation may use the threads they no longer need)
+            whole = get_triangulator(gen_opts["triangulator"], dim, threads=host_threads(ranks=1)) if not hasattr(gen_opts["triangulator"], "triangulate") else tri
+            gt = whole.triangulate(gp)
             t_kept = loop.kept_cells(D.to_dev(gp, torch.float64), D.to_dev(gt, torch.int32)).cpu().numpy()
             p_out, t_out = G._termination(gp, t_kept, gen_opts, dim, verbose=gen_opts["verbose"])
             p_out = G._level_set_newton(p_out, t_out, level0, deps, dim)

@@ -16,8 +16,9 @@ import ctypes as C
 import numpy as np
 
 
-def host_threads():
-    """Host threads one rank may use for the 3-D retriangulation."""
+def host_threads(ranks=None):
+    """Host threads one rank may use for the 3-D retriangulation (`ranks`: processes sharing the node,
+    default LOCAL_WORLD_SIZE)."""
     import os
 
     env = os.environ.get("DM_HOST_THREADS")
@@ -27,7 +28,8 @@ def host_threads():
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    if ranks is None:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
     mine = cores // ranks
     return max(1, min(16, mine - 1 if mine >= 8 else mine))  # (one core left to the rest of the process)
 
@@ -255,15 +257,15 @@ class _Dt3:
             pass
 
 
-def get_triangulator(spec, dim):
+def get_triangulator(spec, dim, threads=None):
     if spec is None or spec == "native":
-        return SweepHullTriangulator(dim) if dim == 2 else BowyerWatsonTriangulator(dim)
+        return SweepHullTriangulator(dim) if dim == 2 else BowyerWatsonTriangulator(dim, threads=threads)
     if spec == "qhull":
         return QhullTriangulator(dim)
     if spec == "sweephull":
         return SweepHullTriangulator(dim)
     if spec == "bowyer-watson":
-        return BowyerWatsonTriangulator(dim)
+        return BowyerWatsonTriangulator(dim, threads=threads)
     if hasattr(spec, "triangulate"):
         return spec
     raise ValueError(f"unknown triangulator {spec!r}")
