@@ -173,10 +173,18 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
                          int64_t nfix, const uint8_t* fixed, double* Ftot, cudaStream_t st) {
   const unsigned nb = nblk(pl->n_rows, VU_THREADS);  // vertices without a row (ghost copies) are not updated
   const double* pg = pad ? pl->p4 : p;
-#define DM_VU(H, P)                                                                                              \
-  launch_chain(vertex_update_kernel<DIM, H, P>, nb, VU_THREADS, st, f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr, \
-               pl->hslot, pl->hbar, pl->scalars, pl->n_rows, lv, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,     \
+  const bool fuse = lv.n > 0 && pl->n_rows < DM_FUSE_PROJECT_BELOW;  // (see DM_FUSE_PROJECT_BELOW)
+#define DM_VU_(H, P, F)                                                                                             \
+  launch_chain(vertex_update_kernel<DIM, H, P, F>, nb, VU_THREADS, st, f, p, pg, p_out, rows_of<DIM>(pl), pl->rowptr, \
+               pl->hslot, pl->hbar, pl->scalars, pl->n_rows, lv, L0mult, delta_t, deps, h0, nfix, fixed, Ftot,        \
                pl->partials, pl->sync + 2, pl->scalars, pl->esc, pl->counters + 5)
+#define DM_VU(H, P)      \
+  do {                   \
+    if (fuse)            \
+      DM_VU_(H, P, true); \
+    else                 \
+      DM_VU_(H, P, false); \
+  } while (0)
   if (DIM == 3 && pad) {
     switch (hmode) {
       case 0: DM_VU(0, true); break;
@@ -191,8 +199,9 @@ int launch_vertex_update(const DmPlan* pl, const double* p, bool pad, double* p_
     }
   }
 #undef DM_VU
+#undef DM_VU_
   mark("vertex_update+maxdp", st);
-  if (lv.n > 0) {  // Newton projection of the listed (escaped) vertices
+  if (lv.n > 0 && !fuse) {  // Newton projection of the listed (escaped) vertices
     launch_chain(project_list_kernel<DIM>, PJ_BLOCKS, PJ_THREADS, st, lv, deps, h0, pl->esc, pl->counters + 5,
                  pl->sync + 4, p_out);
     mark("project_escaped", st);

@@ -59,6 +59,13 @@ constexpr int HV_SMEM = 4608;    // heavy path: candidates sorted in shared memo
 #ifndef DM_VU_MINB
 #define DM_VU_MINB 8
 #endif
+// The Newton projection of the escaped vertices inside vertex_update (no list, no project_list launch) pays on
+// the small configurations, where a launch is a fifth of the step (disk h0=0.01 39.0 -> 36.8 us, EAGE-shaped hmin
+// 150 117 -> 112 us, BP2004-shaped hmin 75 56.3 -> 53.3 us), and costs on the large ones, where the escaped lanes
+// hold their warps (ball h0=0.02: vertex_update 75 -> 87 us for a 13 us launch): chosen by the number of rows.
+#ifndef DM_FUSE_PROJECT_BELOW
+#define DM_FUSE_PROJECT_BELOW 200000
+#endif
 #ifndef DM_AB_BARRIER
 #define DM_AB_BARRIER 0  // 1: block totals of stage B through a block barrier instead of an arrival counter
 #endif
@@ -1095,7 +1102,7 @@ __global__ void __launch_bounds__(PJ_THREADS) project_list_kernel(const Levels l
   }
 }
 
-template <int DIM, int HMODE, bool PAD>
+template <int DIM, int HMODE, bool PAD, bool FUSE>
 __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     const DmSizeFn f, const double* __restrict__ p, const double* __restrict__ pg, double* __restrict__ p_out,
     const Rows<DIM> R, const int32_t* __restrict__ rowptr, const double* __restrict__ hslot,
@@ -1188,14 +1195,22 @@ __global__ void __launch_bounds__(VU_THREADS, DM_VU_MINB) vertex_update_kernel(
     // only the few vertices that left a level set; doing it here would leave 1-2 lanes of nearly
     // every warp walking the finite-difference path while 30 wait, so those vertices are only
     // LISTED here (fd evaluated once per level, all lanes) and projected by project_list_kernel.
-    const double x0 = a0 + delta_t * F0, x1 = a1 + delta_t * F1, x2 = a2 + delta_t * F2;
-    store_pt<DIM>(p_out, v, x0, x1, x2);
+    double x0 = a0 + delta_t * F0, x1 = a1 + delta_t * F1, x2 = a2 + delta_t * F2;
     bool out = false;
     for (int l = 0; l < lv.n; ++l) {
       const double d = sdf_eval(lv.prog[l], DIM, x0, x1, x2);
       out = out || (l == 0 ? (d > 0.0) : (d > 0.0 && d < h0 / 1.5));
     }
-    if (out) esc[atomicAdd(esc_count, 1)] = (int32_t)v;
+    if (FUSE) {
+      // the escaped lanes walk the finite-difference path here, level after level as project_list_kernel does,
+      // while the rest of their warp waits
+      if (out)
+        for (int l = 0; l < lv.n; ++l) sdf_project(lv.prog[l], DIM, deps, h0, l, x0, x1, x2);
+      store_pt<DIM>(p_out, v, x0, x1, x2);
+    } else {
+      store_pt<DIM>(p_out, v, x0, x1, x2);
+      if (out) esc[atomicAdd(esc_count, 1)] = (int32_t)v;
+    }
   }
   // max |F|^2 without a block barrier (the warps of a block finish at different times: rows differ in length):
   // every warp leaves its maximum in shared memory, the warp that arrives last publishes the block's, and the
