@@ -387,7 +387,7 @@ struct SweepHull {
 
 extern "C" {
 
-const char* dmh_version(void) { return "distmesh_host 0.1"; }
+const char* dmh_version(void) { return "distmesh_host 0.2"; }
 
 int64_t dmh_delaunay2d_max_cells(int64_t N) { return N < 3 ? 1 : 2 * N - 5; }
 
