@@ -19,6 +19,7 @@
 #include <climits>
 #include <cstdint>
 #include <memory>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -32,8 +33,18 @@ inline void order_threads(int nth, F&& fn) {
   }
   std::vector<std::thread> th;
   th.reserve(nth - 1);
-  for (int j = 1; j < nth; ++j) th.emplace_back([&fn, j] { fn(j); });
+  int started = 1;
+  try {
+    for (int j = 1; j < nth; ++j) {
+      th.emplace_back([&fn, j] { fn(j); });
+      ++started;
+    }
+  } catch (const std::system_error&) {
+    // the process may not have another thread: the pieces that got none run here, one after the other
+    // (no piece ever waits for another)
+  }
   fn(0);
+  for (int j = started; j < nth; ++j) fn(j);
   for (auto& t : th) t.join();
 }
 
