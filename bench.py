@@ -821,6 +821,35 @@ def main():
     del wl
 
     extras = {}
+    backend = delaunay_backend(rec["config"]["dim"]) if rank == 0 else None  # (the record is rank 0's)
+
+    def final_line():
+        return {
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": rec["config"], "clocks": rec.get("clocks"), "e2e": rec["e2e"],
+            "gpu_launches": rec["gpu_launches"], "roofline": rec.get("roofline"), "cpu_baseline": rec.get("cpu_baseline"),
+            "row_reuse_step": rec.get("row_reuse_step"), "sliver_pass": rec.get("sliver_pass"),
+            "workloads": extras.get("workloads"), "time_to_mesh": extras.get("time_to_mesh"),
+            "delaunay_s": rec["delaunay_s"], "delaunay_backend": backend, "sizing_s": rec["sizing_s"],
+            "maxdp": rec["maxdp"], "wall_s_timed_region": rec.get("wall_s_timed_region"),
+        }
+
+    # The sub-records of a multi-rank run go through collectives: should one rank fail inside them the others
+    # would wait for ever and the headline line (measured above) would be lost with them.  A watchdog prints
+    # the line without the missing sub-records and ends the process instead.
+    watchdog = None
+    if default_run and world > 1:
+        def bail():
+            if rank == 0:
+                extras.setdefault("workloads", {"error": "sub-records timed out"})
+                extras.setdefault("time_to_mesh", {"error": "timed out"})
+                print(json.dumps(final_line()), flush=True)
+            os._exit(0)
+
+        watchdog = threading.Timer(float(os.environ.get("DM_BENCH_SUBRECORD_TIMEOUT", "420")), bail)
+        watchdog.daemon = True
+        watchdog.start()
     if default_run and world == 1:
         subs = {}
         for name, wk, h, fq in (("bp2004_hmin25_freq6", "bp2004", 25.0, 6.0), ("eage_hmin75_freq4", "eage", 75.0, 4.0)):
@@ -865,18 +894,10 @@ def main():
                 if rank == 0:
                     extras["time_to_mesh"] = {"error": f"{type(exc).__name__}: {exc}"}
 
+    if watchdog is not None:
+        watchdog.cancel()
     if rank == 0:
-        out = {
-            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": rec["config"], "clocks": rec.get("clocks"), "e2e": rec["e2e"],
-            "gpu_launches": rec["gpu_launches"], "roofline": rec.get("roofline"), "cpu_baseline": rec.get("cpu_baseline"),
-            "row_reuse_step": rec.get("row_reuse_step"), "sliver_pass": rec.get("sliver_pass"),
-            "workloads": extras.get("workloads"), "time_to_mesh": extras.get("time_to_mesh"),
-            "delaunay_s": rec["delaunay_s"], "delaunay_backend": delaunay_backend(rec["config"]["dim"]), "sizing_s": rec["sizing_s"],
-            "maxdp": rec["maxdp"], "wall_s_timed_region": rec.get("wall_s_timed_region"),
-        }
-        print(json.dumps(out), flush=True)
+        print(json.dumps(final_line()), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
