@@ -422,3 +422,41 @@ def test_incremental_insert_same_cells_as_rebuild(hl, threads):  # noqa: F811
     q = get_triangulator("qhull", 3).build(own[:400])
     q.insert(ghosts[0][:40])
     assert np.array_equal(_canon(q.cells()), _canon(tri.triangulate(np.vstack((own[:400], ghosts[0][:40])))))
+
+
+def test_incremental_insert_random_batches_and_duplicates(hl):  # noqa: F811
+    """Several batches of random size into one triangulation, some rows exact duplicates of rows already in
+    (a ghost vertex that coincides with an owned one), some on the hull's flat sides: after every batch the
+    cells are a valid Delaunay triangulation of the distinct points (exact checks) and, the points being in
+    general position apart from the duplicates, the cell SET of a construction from scratch."""
+    from seismicmesh_b200.triangulator import BowyerWatsonTriangulator
+
+    rng = np.random.default_rng(17)
+    tri = BowyerWatsonTriangulator(3, threads=3)
+    for trial in range(4):
+        pts = [rng.random((int(rng.integers(5, 400)), 3))]
+        dt = tri.build(pts[0])
+        for b in range(int(rng.integers(1, 5))):
+            q = rng.random((int(rng.integers(1, 300)), 3)) * [1.0, 0.3, 1.0] + [0.0, rng.choice([-0.3, 0.35, 1.0]), 0.0]
+            allp = np.vstack(pts)
+            k = min(len(q) // 4, len(allp))
+            if k:
+                q[:k] = allp[rng.choice(len(allp), k, replace=False)]  # exact duplicates of rows already in
+            dt.insert(q)
+            pts.append(np.ascontiguousarray(q))
+            allp = np.vstack(pts)
+            t = dt.cells()
+            assert _is_lex_sorted(t)
+            uniq = np.unique(allp, axis=0)
+            first = _first_occurrence_cells(allp, t)
+            _, fi = np.unique(allp, axis=0, return_index=True)
+            remap = -np.ones(len(allp), dtype=np.int64)
+            remap[np.sort(fi)] = np.arange(len(fi))
+            dense = remap[first]
+            assert (dense >= 0).all()
+            pd_ = allp[np.sort(fi)]
+            _check_triangulation(hl, pd_, _canon(dense).astype(np.int32), n_used=len(uniq))
+            ref = _first_occurrence_cells(allp, tri.triangulate(allp))
+            assert np.array_equal(_canon(first), _canon(ref))
+        dt.close()
+    assert tri.qhull_retries == 0
