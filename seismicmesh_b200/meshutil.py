@@ -62,7 +62,7 @@ def _unique_rows(a, return_index=False, return_inverse=False, return_counts=Fals
     if rows_sorted and not (return_index or return_inverse) and a.dtype.kind in "iu" and m in (2, 3, 4) and n < 2**31:
         # the termination path's case (cells / facets / edges with ascending ids per row): native code
         lo, hi = int(a.min()), int(a.max())
-        if lo >= 0 and hi < 2**31 - 1:
+        if lo >= 0 and hi < min(2**31 - 1, 64 * n + 4096):  # (ids about as dense as vertex ids are: the code buckets by id)
             import ctypes as C
 
             from ._hostlib import lib as _host
